@@ -1,0 +1,313 @@
+#!/usr/bin/env python
+"""bench.py -- DDPM samples/sec of the 1000-step reverse-diffusion loop on the CIFAR-shape U-Net (BASELINE.json).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N --steps K --warmup W
+
+A "step" is ONE reverse-diffusion step of the hot path over one batch: the whole U-Net evaluation (every launch of
+the forward program) + the fused posterior update, replayed as a CUDA graph, batch 256 per GPU, 3x32x32, dim 128,
+mults (1,2,2,2), groups 8, bf16 activations / fp32 accumulation, T = 1000.  samples/s = n_gpus * 256 / (1000 * s_per_step);
+consecutive steps touch > 500 MB of activations/weights per step, i.e. more than the 126 MB L2, so no explicit flush.
+
+JSON keys: see the task contract; `roofline` describes the dominant kernel (the tcgen05 implicit-GEMM conv) from a live
+CUDA-event pass over every launch of the step; `cpu_baseline` times the CPU oracle port on the host cores on a bounded
+sample; `e2e` is a complete `GaussianDiffusion.sample()` call (x_T from pinned host memory in, [0,1] images on the host out).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+CFG2 = dict(dim=128, dim_mults=[1, 2, 2, 2], channels=3, groups=8)
+IMAGE, BATCH, T = 32, 256, 1000
+FLOPS_PER_SAMPLE_EVAL = 5350096896           # BASELINE.md section 3 (torch FlopCounterMode on the reference U-Net)
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d.get("bf16_tflops_sustained", 1378.5), d.get("bf16_tflops", 1637.7), d.get("hbm_gbs", 6544.7), "measured"
+    return 1400.0, 1590.0, 6650.0, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu, self.rows, self.proc = gpu_index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200",
+                                          "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1]))
+                mx.append(float(r[2]))
+            except Exception:
+                continue
+            for name, col in (("hw_slowdown", 5), ("hw_thermal_slowdown", 6), ("sw_thermal_slowdown", 7), ("sw_power_cap", 8)):
+                if len(r) > col and r[col].lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def cpu_baseline(sample_batch=8, steps=3, warm=1):
+    """The CPU oracle port (oracle/ref_port.py == the reference's torch CPU arithmetic) on the host cores, bounded sample."""
+    from oracle import ref_port as O
+
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    sd = O.random_state_dict(CFG2, seed=0)
+    tb = O.ddpm_tables(T, "linear")
+    q = O.NoiseQueue(0)
+    x = q([sample_batch, 3, IMAGE, IMAGE])
+    dt = []
+    with torch.no_grad():
+        for i in range(warm + steps):
+            t = torch.full((sample_batch,), T - 1 - i, dtype=torch.long)
+            t0 = time.perf_counter()
+            eps = O.unet_forward(sd, CFG2, x, t.float())
+            x = O.ddpm_step(tb, x, t, eps, q(x.shape))
+            if i >= warm:
+                dt.append(time.perf_counter() - t0)
+    s_per_step = sum(dt) / len(dt)
+    return {"value": sample_batch / (s_per_step * T), "unit": "samples/s", "cores": cores, "kind": "port",
+            "sample": f"{steps} reverse steps at batch {sample_batch} (CIFAR-shape U-Net, fp32, torch CPU), extrapolated to T={T}",
+            "ms_per_step": s_per_step * 1e3}
+
+
+def run_reference(args):
+    """`--impl reference`: the reference's own CPU arithmetic on the host cores.  The reference is pure PyTorch with no
+    build of its own, so the arm times the oracle port (== the same aten CPU ops in the same order)
+    on a bounded sample: each step is one reverse-diffusion step (U-Net + posterior update) at batch 8."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import ref_port as O
+
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    sb = 8
+    sd = O.random_state_dict(CFG2, seed=0)
+    tb = O.ddpm_tables(T, "linear")
+    q = O.NoiseQueue(0)
+    x = q([sb, 3, IMAGE, IMAGE])
+    dt, budget0 = [], time.perf_counter()
+    with torch.no_grad():
+        for i in range(args.warmup + args.steps):
+            t = torch.full((sb,), T - 1 - (i % T), dtype=torch.long)
+            t0 = time.perf_counter()
+            eps = O.unet_forward(sd, CFG2, x, t.float())
+            x = O.ddpm_step(tb, x, t, eps, q(x.shape))
+            if i >= args.warmup:
+                dt.append(time.perf_counter() - t0)
+            if time.perf_counter() - budget0 > 150 and len(dt) >= 3:
+                break
+    ms = 1e3 * sum(dt) / len(dt)
+    val = sb / (ms * 1e-3 * T)
+    line = {"impl": "reference", "metric": "ddpm_samples_per_sec_32x32_unet_1000_steps", "value": val, "unit": "samples/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "configs[1]: DDPM 3x32x32 U-Net dim128 mults(1,2,2,2) groups8, T=1000; CPU arm: batch 8 per step"},
+            "cpu_baseline": {"value": val, "unit": "samples/s", "cores": cores, "kind": "port",
+                             "sample": f"{len(dt)} timed reverse steps at batch {sb} on {cores} host threads, extrapolated to T={T}"},
+            "e2e": {"value": val, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="b200")
+    ap.add_argument("--batch", type=int, default=BATCH)
+    ap.add_argument("--engine", default="tcgen05")
+    ap.add_argument("--dtype", default="bf16")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    args.warmup = max(args.warmup, 3)
+
+    import torch.distributed as dist
+    import diffusion_model_nemo_b200.modules as M
+    from diffusion_model_nemo_b200 import _lib as L, distributed as D
+    from diffusion_model_nemo_b200.modules import _runtime as R
+    from oracle import ref_port as O   # seeded synthetic weights (same as the parity tests) + cpu_baseline only
+
+    rank, ws, local = D.init("nccl")
+    dev = torch.device(f"cuda:{local}")
+    torch.cuda.set_device(dev)
+    B = args.batch
+
+    unet = M.Unet(None, dim=CFG2["dim"], dim_mults=CFG2["dim_mults"], channels=3, use_convnext=False, resnet_block_groups=8,
+                  compute_dtype=args.dtype, conv_engine=args.engine)
+    unet.load_state_dict(O.random_state_dict(CFG2, seed=0))
+    unet.to(dev)
+    sampler = M.GaussianDiffusion(T, "linear")
+    sampler.seed = 1234
+    ts = sampler._visit_order()
+    coef, times = sampler._loop_tables(ts, dev)
+    shape = [B, 3, IMAGE, IMAGE]
+    lib = L.lib()
+
+    # time a K-step prefix of the T-step schedule (same kernels, same shapes, same graph as the full run)
+    def timed(n_steps):
+        torch.cuda.synchronize(dev)
+        if ws > 1:
+            dist.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        res = R.run_native_loop(unet, kind=L.LOOP_DDPM, shape=shape, device=dev, times=times, coef=coef, seed=1234, use_graph=True,
+                                n_steps=n_steps)
+        e1.record()
+        torch.cuda.synchronize(dev)
+        return e0.elapsed_time(e1), res
+
+    timed(args.warmup)                       # builds the plan, uploads weights, captures the graph, warms clocks
+    plan = unet.plan(IMAGE, B, dev)
+    clk = ClockSampler(local)
+    clk.start()
+    ms_total, res = timed(args.steps)
+    clocks = clk.stop()
+    # the single collective of the job: all-gather of the final samples (timed once, amortised over T steps)
+    ag_ms = 0.0
+    if ws > 1:
+        torch.cuda.synchronize(dev)
+        dist.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        D.all_gather_samples(res.final, total=B * ws)
+        e1.record()
+        torch.cuda.synchronize(dev)
+        ag_ms = e0.elapsed_time(e1)
+    ms_step = ms_total / args.steps + ag_ms / T
+    if ws > 1:
+        tmax = torch.tensor([ms_step], device=dev)
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        ms_step = float(tmax.item())
+    value = ws * B / (ms_step * 1e-3 * T)
+
+    # ---- roofline of the dominant kernel: live CUDA-event pass over every launch of one step ----------------
+    ops = plan.op_table()
+    x_prof = res.final.clone()
+    row = torch.zeros(1, dtype=torch.int32, device=dev)
+    acc = [0.0] * len(ops)
+    n_prof = 3
+    plan.profile_forward(x_prof, row)
+    for _ in range(n_prof):
+        for i, v in enumerate(plan.profile_forward(x_prof, row)):
+            acc[i] += v / n_prof
+    sust, burst, hbm, src = measured_peaks()
+    groups = {}
+    for (name, kind, eng, fl, by), ms in zip(ops, acc):
+        key = {0: "memset", 1: "init_conv", 2: "conv_tcgen05" if eng else "conv_simt", 3: "gn_finalize", 4: "linattn_core",
+               5: "attn_core", 6: "final_proj"}[kind]
+        g = groups.setdefault(key, {"ms": 0.0, "flops": 0.0, "bytes": 0.0, "launches": 0})
+        g["ms"] += ms
+        g["flops"] += fl * B
+        g["bytes"] += by * B
+        g["launches"] += 1
+    step_prof_ms = sum(g["ms"] for g in groups.values())
+    dom = max(groups, key=lambda k: groups[k]["ms"])
+    gd = groups[dom]
+    if gd["flops"] > 0 and dom.startswith("conv"):
+        ach = gd["flops"] / (gd["ms"] * 1e-3) / 1e12
+        roof = {"kernel": dom, "bound": "tensor", "achieved": ach, "peak": sust, "unit": "TFLOP/s", "frac": ach / sust,
+                "peak_source": f"{src} bf16_tflops_sustained (kernel timed inside a long step)", "traffic": None,
+                "launches_per_step": gd["launches"], "avg_launch_ms": gd["ms"] / gd["launches"], "share_of_step": gd["ms"] / step_prof_ms}
+    else:
+        ach = gd["bytes"] / (gd["ms"] * 1e-3) / 1e9
+        roof = {"kernel": dom, "bound": "hbm", "achieved": ach, "peak": hbm, "unit": "GB/s", "frac": ach / hbm, "peak_source": src,
+                "traffic": None, "launches_per_step": gd["launches"], "avg_launch_ms": gd["ms"] / gd["launches"],
+                "share_of_step": gd["ms"] / step_prof_ms}
+    unet_tflops = FLOPS_PER_SAMPLE_EVAL * B / (ms_step * 1e-3) / 1e12
+    breakdown = {k: {"ms": round(v["ms"], 4), "launches": v["launches"],
+                     "tflops": round(v["flops"] / (v["ms"] * 1e-3) / 1e12, 2) if v["flops"] and v["ms"] > 0 else None,
+                     "gbs": round(v["bytes"] / (v["ms"] * 1e-3) / 1e9, 1) if v["ms"] > 0 else None} for k, v in groups.items()}
+
+    # ---- e2e: a complete sampler.sample()-style call: pinned host x_T in, [0,1] host images out -------------------
+    e2e = None
+    if not args.no_e2e:
+        proj_s = ms_step * 1e-3 * T
+        e2e_T = T if proj_s <= 60 else max(10, int(60 / (ms_step * 1e-3)))
+        s2 = M.GaussianDiffusion(e2e_T, "linear")
+        s2.seed = 99
+        x_host = torch.randn(shape).pin_memory()
+        torch.cuda.synchronize(dev)
+        if ws > 1:
+            dist.barrier()
+        t0 = time.perf_counter()
+        imgs = s2.p_sample_loop(unet, shape, device=dev, img=x_host.to(dev, non_blocking=True))
+        final_host = imgs[-1]
+        torch.cuda.synchronize(dev)
+        el = time.perf_counter() - t0
+        if ws > 1:
+            tmax = torch.tensor([el], device=dev)
+            dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+            el = float(tmax.item())
+        nbytes = final_host.numel() * 4
+        e2e = {"value": ws * B / el * (e2e_T / T), "unit": "samples/s", "h2d_bytes_per_step": nbytes / e2e_T,
+               "d2h_bytes_per_step": nbytes / e2e_T, "loop_steps": e2e_T, "wall_s": el,
+               "note": "one GaussianDiffusion.p_sample_loop(unet, shape, img=pinned x_T) call incl. H2D of x_T and D2H of the images"
+                       + ("" if e2e_T == T else f"; T shortened to {e2e_T} steps to bound the run, value scaled to T={T}")}
+
+    cpu = None
+    if rank == 0 and ws == 1 and not args.no_cpu_baseline:
+        cpu = cpu_baseline()
+        cpu.pop("ms_per_step", None)
+
+    loop_launches = getattr(plan, "last_loop_launches", 0)
+    if rank == 0:
+        line = {
+            "metric": "ddpm_samples_per_sec_32x32_unet_1000_steps", "value": value, "unit": "samples/s", "n_gpus": ws,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
+            "config": {"workload": "configs[1]: DDPM 3x32x32 U-Net dim128 mults(1,2,2,2) groups8, T=1000, batch 256 per GPU",
+                       "batch_per_gpu": B, "conv_engine": args.engine, "weights": "seeded random init (oracle.random_state_dict(seed=0))",
+                       "noise": "in-kernel Philox4x32-10, stream per rank", "l2": "per-step working set > 126 MB L2; no explicit flush",
+                       "parallelism": f"batch-sharded x{ws}, one all-gather of final samples"},
+            "unet_tflops": unet_tflops, "unet_frac_of_bf16_sustained": unet_tflops / sust, "unet_frac_of_bf16_burst": unet_tflops / burst,
+            "roofline": roof, "kernel_breakdown": breakdown, "allgather_ms": ag_ms,
+            "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(loop_launches), "clocks": clocks,
+        }
+        print(json.dumps(line), flush=True)
+    if ws > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

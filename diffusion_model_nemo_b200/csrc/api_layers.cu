@@ -1,0 +1,193 @@
+// api_layers.cu -- layer-level C ABI entry points (include/dmn_b200.h, "Layer-level entry points").
+// fp32 NCHW tensors at the boundary; converted to the engine's NHWC layout in caller-provided scratch.
+#include <vector>
+
+#include "../../include/dmn_b200.h"
+#include "common.cuh"
+#include "ops.h"
+
+using namespace dmn;
+
+namespace {
+size_t al(size_t v) { return (v + 255) / 256 * 256; }
+
+struct ConvScratch {
+  size_t x, y, w, w2, stats_in, stats_out, total;
+};
+ConvScratch conv_layout(const dmn_conv_args* a) {
+  const size_t esz = a->act == DMN_ACT_F32 ? 4 : 2;
+  const int hout = a->mode == CONV_DOWN ? a->hin / 2 : (a->mode == CONV_UP ? a->hin * 2 : a->hin);
+  const int wout = a->mode == CONV_DOWN ? a->win / 2 : (a->mode == CONV_UP ? a->win * 2 : a->win);
+  const int k = a->mode == CONV_SAME ? a->ksize : 4;
+  ConvScratch s;
+  size_t o = 0;
+  s.x = o; o += al((size_t)a->batch * a->hin * a->win * a->cin * esz);
+  s.y = o; o += al((size_t)a->batch * hout * wout * a->cout * esz);
+  s.w = o; o += al((size_t)a->cin * a->cout * k * k * 4);
+  s.w2 = o; o += al((size_t)a->cin * a->cout * k * k * 2);
+  s.stats_in = o; o += al((size_t)a->batch * 64 * 2 * 4);
+  s.stats_out = o; o += al((size_t)a->batch * 64 * 2 * 4);
+  s.total = o;
+  return s;
+}
+
+// per-(sample, group) sum / sum-of-squares of an NHWC tensor (test path only: one thread block per (b, g))
+template <typename T>
+__global__ void group_stats_kernel(const T* x, float* stats, int HW, int C, int G) {
+  const int b = blockIdx.x / G, g = blockIdx.x % G;
+  const int cpg = C / G;
+  float s = 0.f, ss = 0.f;
+  for (int i = threadIdx.x; i < HW * cpg; i += blockDim.x) {
+    const int pix = i / cpg, c = g * cpg + i % cpg;
+    const float v = to_f<T>(x[((long)b * HW + pix) * C + c]);
+    s += v;
+    ss += v * v;
+  }
+  __shared__ float rs[32], rss[32];
+  s = warp_sum(s);
+  ss = warp_sum(ss);
+  if ((threadIdx.x & 31) == 0) { rs[threadIdx.x >> 5] = s; rss[threadIdx.x >> 5] = ss; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float a = 0.f, c2 = 0.f;
+    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) { a += rs[i]; c2 += rss[i]; }
+    stats[2 * blockIdx.x] = a;
+    stats[2 * blockIdx.x + 1] = c2;
+  }
+}
+}  // namespace
+
+extern "C" {
+
+size_t dmn_conv_scratch_bytes(const dmn_conv_args* a) { return a ? conv_layout(a).total : 0; }
+
+int dmn_conv_forward(const dmn_conv_args* a, void* stream) {
+  if (!a) return fail(DMN_EINVAL, "null args");
+  DMN_REQUIRE(a->x && a->w && a->y && a->scratch_dev, "null tensor");
+  DMN_REQUIRE(a->mode >= 0 && a->mode <= 2, "mode");
+  DMN_REQUIRE(a->act == DMN_ACT_F32 || a->act == DMN_ACT_BF16, "act");
+  DMN_REQUIRE(a->engine == DMN_CONV_SIMT || a->act == DMN_ACT_BF16, "tcgen05 engine needs bf16 activations");
+  DMN_REQUIRE(a->gn_groups <= 64 && a->out_groups <= 64, "too many groups");
+  const ConvScratch L = conv_layout(a);
+  DMN_REQUIRE(a->scratch_bytes >= L.total, "scratch too small (dmn_conv_scratch_bytes)");
+  cudaStream_t st = (cudaStream_t)stream;
+  char* base = (char*)a->scratch_dev;
+  const int hout = a->mode == CONV_DOWN ? a->hin / 2 : (a->mode == CONV_UP ? a->hin * 2 : a->hin);
+  const int wout = a->mode == CONV_DOWN ? a->win / 2 : (a->mode == CONV_UP ? a->win * 2 : a->win);
+  const int k = a->mode == CONV_SAME ? a->ksize : 4;
+  int rc;
+  if ((rc = nchw_to_nhwc(a->x, base + L.x, a->batch, a->cin, a->hin * a->win, a->act, st))) return rc;
+
+  ConvP c;
+  c.src1 = base + L.x; c.C1 = a->cin; c.C2 = 0;
+  c.B = a->batch; c.Hin = a->hin; c.Win = a->win; c.Hout = hout; c.Wout = wout; c.Cout = a->cout;
+  c.mode = a->mode; c.ksize = a->ksize;
+  c.bias = a->bias;
+  if (a->gn_groups > 0) {
+    DMN_REQUIRE(a->gn_gamma && a->gn_beta, "GroupNorm prologue needs gamma/beta");
+    if (a->act == DMN_ACT_F32) group_stats_kernel<float><<<a->batch * a->gn_groups, 256, 0, st>>>((const float*)(base + L.x), (float*)(base + L.stats_in), a->hin * a->win, a->cin, a->gn_groups);
+    else group_stats_kernel<bf16><<<a->batch * a->gn_groups, 256, 0, st>>>((const bf16*)(base + L.x), (float*)(base + L.stats_in), a->hin * a->win, a->cin, a->gn_groups);
+    DMN_LAUNCH_CHECK("group_stats");
+    c.pro = PRO_GN | (a->silu ? PRO_SILU : 0) | (a->temb ? PRO_TEMB : 0);
+    c.pstats = (const float*)(base + L.stats_in); c.pgroups = a->gn_groups; c.pgamma = a->gn_gamma; c.pbeta = a->gn_beta;
+    if (a->temb) { c.temb = a->temb; c.temb_bstride = a->cin; }
+  }
+  c.out = base + L.y;
+  if (a->out_groups > 0) {
+    DMN_REQUIRE(a->out_stats, "out_stats is null");
+    DMN_CUDA_CHECK(cudaMemsetAsync(base + L.stats_out, 0, (size_t)a->batch * a->out_groups * 2 * 4, st));
+    c.ostats = (float*)(base + L.stats_out); c.ogroups = a->out_groups;
+  }
+  // weights: device fp32 in torch layout -> host repack -> device (validation path; sync copies are fine here)
+  const size_t nw = (size_t)a->cin * a->cout * k * k;
+  std::vector<float> hw(nw);
+  DMN_CUDA_CHECK(cudaMemcpyAsync(hw.data(), a->w, nw * 4, cudaMemcpyDeviceToHost, st));
+  DMN_CUDA_CHECK(cudaStreamSynchronize(st));
+  if (a->engine == DMN_CONV_TCGEN05) {
+    if (!conv_tcgen05_supported(c)) return fail(DMN_ENOTSUP, "conv shape not supported by the tcgen05 engine");
+    std::vector<char> img(conv_tcgen05_weight_bytes(a->mode, a->ksize, a->cin, a->cout));
+    conv_tcgen05_pack_weights(a->mode, a->ksize, a->cin, a->cout, hw.data(), img.data());
+    DMN_CUDA_CHECK(cudaMemcpyAsync(base + L.w2, img.data(), img.size(), cudaMemcpyHostToDevice, st));
+    DMN_CUDA_CHECK(cudaStreamSynchronize(st));
+    c.w = base + L.w2;
+    if ((rc = conv_tcgen05(c, st))) return rc;
+  } else {
+    std::vector<float> pw(nw);
+    conv_simt_pack_weights(a->mode, a->ksize, a->cin, a->cout, hw.data(), pw.data(), a->act == DMN_ACT_BF16);
+    DMN_CUDA_CHECK(cudaMemcpyAsync(base + L.w, pw.data(), nw * 4, cudaMemcpyHostToDevice, st));
+    DMN_CUDA_CHECK(cudaStreamSynchronize(st));
+    c.w = base + L.w;
+    if ((rc = conv_simt(c, a->act, st))) return rc;
+  }
+  if ((rc = nhwc_to_nchw(base + L.y, a->y, a->batch, a->cout, hout * wout, a->act, st))) return rc;
+  if (a->out_groups > 0) {
+    const int cpg = a->cout / a->out_groups;
+    if ((rc = stats_to_mean_rstd((const float*)(base + L.stats_out), a->out_stats, a->batch * a->out_groups,
+                                 1.f / (float)(hout * wout * cpg), st)))
+      return rc;
+  }
+  return 0;
+}
+
+static int attn_common(bool linear, const float* qkv, float* out, int batch, int heads, int dh, int n, int act, void* scratch,
+                       size_t scratch_bytes, void* stream) {
+  DMN_REQUIRE(qkv && out && scratch, "null tensor");
+  const size_t esz = act == DMN_ACT_F32 ? 4 : 2;
+  const size_t a_in = al((size_t)batch * n * 3 * heads * dh * esz), a_out = al((size_t)batch * n * heads * dh * esz);
+  DMN_REQUIRE(scratch_bytes >= a_in + a_out, "scratch too small: need batch*n*4*heads*dim_head elements (+512 B)");
+  cudaStream_t st = (cudaStream_t)stream;
+  char* base = (char*)scratch;
+  int rc;
+  if ((rc = nchw_to_nhwc(qkv, base, batch, 3 * heads * dh, n, act, st))) return rc;
+  rc = linear ? linattn_core(base, base + a_in, batch, heads, dh, n, act, st) : attn_core(base, base + a_in, batch, heads, dh, n, act, st);
+  if (rc) return rc;
+  return nhwc_to_nchw(base + a_in, out, batch, heads * dh, n, act, st);
+}
+
+int dmn_linear_attention_core(const float* qkv, float* out, int batch, int heads, int dim_head, int n_tokens, int act,
+                              void* scratch_dev, size_t scratch_bytes, void* stream) {
+  return attn_common(true, qkv, out, batch, heads, dim_head, n_tokens, act, scratch_dev, scratch_bytes, stream);
+}
+int dmn_attention_core(const float* qkv, float* out, int batch, int heads, int dim_head, int n_tokens, int act,
+                       void* scratch_dev, size_t scratch_bytes, void* stream) {
+  return attn_common(false, qkv, out, batch, heads, dim_head, n_tokens, act, scratch_dev, scratch_bytes, stream);
+}
+
+// plain GEMM through the tcgen05 engine: a 1x1 "convolution" over M pixels (H = M, W = 1)
+__global__ void bf16_to_f32_kernel(const bf16* in, float* out, long n) {
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = __bfloat162float(in[i]);
+}
+int dmn_selftest_umma_gemm(const void* a_bf16, const void* b_bf16, float* d, int M, int N, int K, void* stream) {
+  // b_bf16 must already be in the engine's blocked layout (host: conv_tcgen05_pack_weights via dmn_conv_forward);
+  // this entry point takes row-major B[N][K] bf16 on the DEVICE and repacks through the host for simplicity.
+  DMN_REQUIRE(a_bf16 && b_bf16 && d, "null tensor");
+  cudaStream_t st = (cudaStream_t)stream;
+  std::vector<bf16> hb((size_t)N * K);
+  DMN_CUDA_CHECK(cudaMemcpyAsync(hb.data(), b_bf16, hb.size() * 2, cudaMemcpyDeviceToHost, st));
+  DMN_CUDA_CHECK(cudaStreamSynchronize(st));
+  std::vector<float> hf(hb.size());
+  for (size_t i = 0; i < hb.size(); ++i) hf[i] = __bfloat162float(hb[i]);
+  std::vector<char> img(conv_tcgen05_weight_bytes(CONV_SAME, 1, K, N));
+  conv_tcgen05_pack_weights(CONV_SAME, 1, K, N, hf.data(), img.data());
+  void* wdev = nullptr;
+  void* odev = nullptr;
+  // self-test only: the one place the library allocates (and frees) device memory itself
+  DMN_CUDA_CHECK(cudaMalloc(&wdev, img.size()));
+  DMN_CUDA_CHECK(cudaMalloc(&odev, (size_t)M * N * 2));
+  DMN_CUDA_CHECK(cudaMemcpyAsync(wdev, img.data(), img.size(), cudaMemcpyHostToDevice, st));
+  ConvP c;
+  c.src1 = a_bf16; c.C1 = K; c.B = 1; c.Hin = M; c.Win = 1; c.Hout = M; c.Wout = 1; c.Cout = N;
+  c.mode = CONV_SAME; c.ksize = 1; c.w = wdev; c.out = odev;
+  int rc = conv_tcgen05(c, st);
+  if (!rc) {
+    bf16_to_f32_kernel<<<(unsigned)(((long)M * N + 255) / 256), 256, 0, st>>>((const bf16*)odev, d, (long)M * N);
+    cudaError_t e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) rc = fail(DMN_ECUDA, std::string("selftest: ") + cudaGetErrorString(e));
+  }
+  cudaFree(wdev);
+  cudaFree(odev);
+  return rc;
+}
+
+}  // extern "C"

@@ -1,0 +1,119 @@
+// common.cuh -- shared helpers for the sm_100a sampling-path kernels.
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+
+typedef __nv_bfloat16 bf16;
+
+namespace dmn {
+
+// ---- error plumbing (thread-local message behind dmn_last_error) ---------------------------------------
+void set_error(const std::string& msg);
+int fail(int code, const std::string& msg);
+
+#define DMN_CUDA_CHECK(expr)                                                                        \
+  do {                                                                                              \
+    cudaError_t _e = (expr);                                                                        \
+    if (_e != cudaSuccess)                                                                          \
+      return ::dmn::fail(-3, std::string(#expr) + ": " + cudaGetErrorString(_e));                   \
+  } while (0)
+
+#define DMN_LAUNCH_CHECK(name)                                                                      \
+  do {                                                                                              \
+    cudaError_t _e = cudaGetLastError();                                                            \
+    if (_e != cudaSuccess) return ::dmn::fail(-3, std::string(name) + ": " + cudaGetErrorString(_e)); \
+  } while (0)
+
+#define DMN_REQUIRE(cond, msg)                                                                      \
+  do {                                                                                              \
+    if (!(cond)) return ::dmn::fail(-1, std::string(msg) + " [" #cond "]");                         \
+  } while (0)
+
+// launch counter (bench.py's gpu_launches is derived from it)
+extern thread_local long g_launches;
+inline void count_launch(int n = 1) { g_launches += n; }
+
+// ---- element conversion --------------------------------------------------------------------------------
+template <typename T> __device__ __forceinline__ float to_f(T v);
+template <> __device__ __forceinline__ float to_f<float>(float v) { return v; }
+template <> __device__ __forceinline__ float to_f<bf16>(bf16 v) { return __bfloat162float(v); }
+template <typename T> __device__ __forceinline__ T from_f(float v);
+template <> __device__ __forceinline__ float from_f<float>(float v) { return v; }
+template <> __device__ __forceinline__ bf16 from_f<bf16>(float v) { return __float2bfloat16_rn(v); }
+
+// 4 consecutive elements <-> float4 (pointer must be aligned to 4 elements)
+template <typename T> __device__ __forceinline__ float4 load4(const T* p);
+template <> __device__ __forceinline__ float4 load4<float>(const float* p) {
+  return *reinterpret_cast<const float4*>(p);
+}
+template <> __device__ __forceinline__ float4 load4<bf16>(const bf16* p) {
+  uint2 u = *reinterpret_cast<const uint2*>(p);
+  float4 r;
+  r.x = __uint_as_float(u.x << 16);
+  r.y = __uint_as_float(u.x & 0xffff0000u);
+  r.z = __uint_as_float(u.y << 16);
+  r.w = __uint_as_float(u.y & 0xffff0000u);
+  return r;
+}
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+template <typename T> __device__ __forceinline__ void store4(T* p, float4 v);
+template <> __device__ __forceinline__ void store4<float>(float* p, float4 v) {
+  *reinterpret_cast<float4*>(p) = v;
+}
+template <> __device__ __forceinline__ void store4<bf16>(bf16* p, float4 v) {
+  uint2 u;
+  u.x = pack_bf16x2(v.x, v.y);
+  u.y = pack_bf16x2(v.z, v.w);
+  *reinterpret_cast<uint2*>(p) = u;
+}
+
+// 8 consecutive bf16 (one 16-byte item) <-> 8 floats
+__device__ __forceinline__ void unpack8(const uint4& u, float* f) {
+  f[0] = __uint_as_float(u.x << 16); f[1] = __uint_as_float(u.x & 0xffff0000u);
+  f[2] = __uint_as_float(u.y << 16); f[3] = __uint_as_float(u.y & 0xffff0000u);
+  f[4] = __uint_as_float(u.z << 16); f[5] = __uint_as_float(u.z & 0xffff0000u);
+  f[6] = __uint_as_float(u.w << 16); f[7] = __uint_as_float(u.w & 0xffff0000u);
+}
+__device__ __forceinline__ uint4 pack8(const float* f) {
+  uint4 u;
+  u.x = pack_bf16x2(f[0], f[1]); u.y = pack_bf16x2(f[2], f[3]);
+  u.z = pack_bf16x2(f[4], f[5]); u.w = pack_bf16x2(f[6], f[7]);
+  return u;
+}
+
+__device__ __forceinline__ float silu_f(float x) { return x / (1.0f + __expf(-x)); }
+// one MUFU per element: x*sigmoid(x) = hx + hx*tanh(hx), hx = x/2   (bf16 pipelines only)
+__device__ __forceinline__ float silu_fast(float x) {
+  float hx = 0.5f * x, t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(hx));
+  return fmaf(hx, t, hx);
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// GroupNorm statistics accumulated as {sum, sum of squares} per (sample, group) -> affine coefficients
+__device__ __forceinline__ void gn_mean_rstd(const float* stats2, float inv_count, float eps, float& mean, float& rstd) {
+  float s = stats2[0], ss = stats2[1];
+  mean = s * inv_count;
+  float var = fmaxf(ss * inv_count - mean * mean, 0.0f);
+  rstd = rsqrtf(var + eps);
+}
+
+constexpr float kGnEps = 1e-5f;   // torch.nn.GroupNorm default (parts/convnext.py:12, utils.py:89)
+
+}  // namespace dmn

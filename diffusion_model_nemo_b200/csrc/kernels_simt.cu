@@ -1,0 +1,647 @@
+// kernels_simt.cu -- CUDA-core kernels of the sampling path.
+//
+//  * conv_simt      : generic implicit-GEMM convolution with fp32 FMA accumulation.  It is the arithmetic of the
+//                     fp32 parity mode (1e-4 gate) and the cross-check for the tcgen05 engine; it carries the
+//                     same fused prologue (GroupNorm-apply + SiLU + time-embedding add of the *producer*) and
+//                     epilogue (bias, residual, GroupNorm statistics) as the tensor-core engine.
+//  * init_conv      : 7x7 stem reading the fp32 NCHW sampler state directly          (modules/unet.py:41)
+//  * gn_finalize    : y = SiLU(GroupNorm(raw)) + res, plus statistics for the next norm (parts/convnext.py:35-45,86)
+//  * final_proj     : GroupNorm + SiLU + 1x1 conv to out_dim, fp32 NCHW out            (modules/unet.py:112-116)
+//  * linattn_core / attn_core : parts/mha.py:44-58 / 16-29
+//  * time_table     : sinusoid -> Linear -> GELU -> Linear -> (SiLU -> Linear) x blocks (unet.py:61-66, convnext.py:68-72)
+#include <math.h>
+
+#include "common.cuh"
+#include "ops.h"
+
+namespace dmn {
+
+// =====================================================================================================
+// generic convolution
+// =====================================================================================================
+template <typename T>
+__global__ void __launch_bounds__(256) conv_simt_kernel(const ConvP p) {
+  constexpr int BM = 64, BN = 64, BK = 16;
+  __shared__ float As[BK][BM + 4];
+  __shared__ __align__(16) float Bs[BK][BN];
+
+  const int tid = threadIdx.x;
+  const int Cin = p.C1 + p.C2;
+  const int HWo = p.Hout * p.Wout;
+  const long M = (long)p.B * HWo;
+  const long m0 = (long)blockIdx.x * BM;
+  const int n0 = blockIdx.y * BN;
+
+  // A-loader role: one row (output pixel), 4 consecutive input channels
+  const int arow = tid >> 2, akq = (tid & 3) * 4;
+  const long am = m0 + arow;
+  const bool arow_ok = am < M;
+  int ab = 0, aoy = 0, aox = 0;
+  if (arow_ok) {
+    ab = (int)(am / HWo);
+    int r = (int)(am - (long)ab * HWo);
+    aoy = r / p.Wout;
+    aox = r - aoy * p.Wout;
+  }
+  // B-loader role
+  const int bk = tid >> 4, bn = (tid & 15) * 4;
+  // compute role
+  const int ty = tid >> 4, tx = tid & 15;
+
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+  const float* temb_row = nullptr;
+  if (p.pro & PRO_TEMB)
+    temb_row = p.temb + (p.d_row ? (long)(*p.d_row) * p.temb_rstride : 0) + (long)ab * p.temb_bstride;
+  const int cpg_in = (p.pro & PRO_GN) ? (p.C1 / p.pgroups) : 1;
+  const float inv_cnt = 1.f / (float)(p.Hin * p.Win * cpg_in);
+
+  const int kw_ = (p.mode == CONV_SAME) ? p.ksize : 4;
+  const int ntaps = kw_ * kw_;
+  for (int tap = 0; tap < ntaps; ++tap) {
+    const int ky = tap / kw_, kx = tap - ky * kw_;
+    int iy, ix;
+    bool ok = arow_ok;
+    if (p.mode == CONV_SAME) {
+      const int pad = p.ksize >> 1;
+      iy = aoy + ky - pad;
+      ix = aox + kx - pad;
+    } else if (p.mode == CONV_DOWN) {
+      iy = aoy * 2 - 1 + ky;
+      ix = aox * 2 - 1 + kx;
+    } else {  // transposed conv k4 s2 p1: oy = 2*iy - 1 + ky
+      const int ty_ = aoy + 1 - ky, tx_ = aox + 1 - kx;
+      ok = ok && !(ty_ & 1) && !(tx_ & 1) && ty_ >= 0 && tx_ >= 0;
+      iy = ty_ >> 1;
+      ix = tx_ >> 1;
+    }
+    ok = ok && iy >= 0 && iy < p.Hin && ix >= 0 && ix < p.Win;
+    const long pix = ((long)ab * p.Hin + iy) * p.Win + ix;
+
+    for (int c0 = 0; c0 < Cin; c0 += BK) {
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      const int c = c0 + akq;
+      if (ok && c < Cin) {
+        if (c < p.C1) v = load4<T>((const T*)p.src1 + pix * p.C1 + c);
+        else v = load4<T>((const T*)p.src2 + pix * p.C2 + (c - p.C1));
+        if (p.pro & PRO_GN) {
+          float mean, rstd;
+          gn_mean_rstd(p.pstats + ((long)ab * p.pgroups + c / cpg_in) * 2, inv_cnt, kGnEps, mean, rstd);
+          const float4 ga = *reinterpret_cast<const float4*>(p.pgamma + c);
+          const float4 be = *reinterpret_cast<const float4*>(p.pbeta + c);
+          v.x = (v.x - mean) * rstd * ga.x + be.x;
+          v.y = (v.y - mean) * rstd * ga.y + be.y;
+          v.z = (v.z - mean) * rstd * ga.z + be.z;
+          v.w = (v.w - mean) * rstd * ga.w + be.w;
+        }
+        if (p.pro & PRO_SILU) {
+          v.x = silu_f(v.x); v.y = silu_f(v.y); v.z = silu_f(v.z); v.w = silu_f(v.w);
+        }
+        if (p.pro & PRO_TEMB) {
+          const float4 te = *reinterpret_cast<const float4*>(temb_row + c);
+          v.x += te.x; v.y += te.y; v.z += te.z; v.w += te.w;
+        }
+      }
+      As[akq + 0][arow] = v.x;
+      As[akq + 1][arow] = v.y;
+      As[akq + 2][arow] = v.z;
+      As[akq + 3][arow] = v.w;
+
+      float4 w = make_float4(0.f, 0.f, 0.f, 0.f);
+      const int kk = c0 + bk;
+      if (kk < Cin && n0 + bn < p.Cout)
+        w = *reinterpret_cast<const float4*>((const float*)p.w + ((long)tap * Cin + kk) * p.Cout + n0 + bn);
+      *reinterpret_cast<float4*>(&Bs[bk][bn]) = w;
+      __syncthreads();
+#pragma unroll
+      for (int k = 0; k < BK; ++k) {
+        const float4 a = *reinterpret_cast<const float4*>(&As[k][ty * 4]);
+        const float4 b = *reinterpret_cast<const float4*>(&Bs[k][tx * 4]);
+        const float av[4] = {a.x, a.y, a.z, a.w};
+        const float bv[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+      }
+      __syncthreads();
+    }
+  }
+
+  // epilogue: bias, residual, store, GroupNorm statistics of the output
+  const int n = n0 + tx * 4;
+  if (n >= p.Cout) return;
+  float4 bias = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (p.bias) bias = *reinterpret_cast<const float4*>(p.bias + n);
+  const int cpg_out = p.ostats ? (p.Cout / p.ogroups) : 1;
+  float s = 0.f, ss = 0.f;
+  int sb = -1;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const long m = m0 + ty * 4 + i;
+    if (m >= M) break;
+    float4 o = make_float4(acc[i][0] + bias.x, acc[i][1] + bias.y, acc[i][2] + bias.z, acc[i][3] + bias.w);
+    if (p.res) {
+      const float4 r = load4<T>((const T*)p.res + m * p.Cout + n);
+      o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
+    }
+    store4<T>((T*)p.out + m * p.Cout + n, o);
+    if (p.ostats) {
+      const int b = (int)(m / HWo);
+      if (b != sb && sb >= 0) {
+        float* dst = p.ostats + ((long)sb * p.ogroups + n / cpg_out) * 2;
+        atomicAdd(dst, s);
+        atomicAdd(dst + 1, ss);
+        s = ss = 0.f;
+      }
+      sb = b;
+      s += o.x + o.y + o.z + o.w;
+      ss += o.x * o.x + o.y * o.y + o.z * o.z + o.w * o.w;
+    }
+  }
+  if (p.ostats && sb >= 0) {
+    float* dst = p.ostats + ((long)sb * p.ogroups + n / cpg_out) * 2;
+    atomicAdd(dst, s);
+    atomicAdd(dst + 1, ss);
+  }
+}
+
+int conv_simt(const ConvP& p, int act, cudaStream_t st) {
+  const int Cin = p.C1 + p.C2;
+  DMN_REQUIRE(p.C1 % 4 == 0 && p.C2 % 4 == 0 && p.Cout % 4 == 0 && Cin > 0, "conv_simt: channels must be multiples of 4");
+  DMN_REQUIRE(!(p.pro & PRO_GN) || (p.C2 == 0 && p.pgroups > 0 && (p.C1 / p.pgroups) % 4 == 0 && p.C1 % p.pgroups == 0),
+              "conv_simt: GroupNorm prologue needs a single source and channels-per-group % 4 == 0");
+  DMN_REQUIRE(!p.ostats || (p.ogroups > 0 && p.Cout % p.ogroups == 0 && (p.Cout / p.ogroups) % 4 == 0),
+              "conv_simt: output statistics need channels-per-group % 4 == 0");
+  DMN_REQUIRE(p.mode != CONV_SAME || p.ksize == 1 || p.ksize == 3, "conv_simt: ksize must be 1 or 3");
+  const long M = (long)p.B * p.Hout * p.Wout;
+  dim3 grid((unsigned)((M + 63) / 64), (unsigned)((p.Cout + 63) / 64));
+  if (act == ACT_F32) conv_simt_kernel<float><<<grid, 256, 0, st>>>(p);
+  else conv_simt_kernel<bf16><<<grid, 256, 0, st>>>(p);
+  count_launch();
+  DMN_LAUNCH_CHECK("conv_simt");
+  return 0;
+}
+
+void conv_simt_pack_weights(int mode, int ksize, int cin, int cout, const float* w, float* dst, bool round_bf16) {
+  const int k = (mode == CONV_SAME) ? ksize : 4;
+  for (int ky = 0; ky < k; ++ky)
+    for (int kx = 0; kx < k; ++kx)
+      for (int ci = 0; ci < cin; ++ci)
+        for (int co = 0; co < cout; ++co) {
+          // Conv2d weight [co][ci][ky][kx]; ConvTranspose2d weight [ci][co][ky][kx]
+          const long src = (mode == CONV_UP) ? ((((long)ci * cout + co) * k + ky) * k + kx)
+                                             : ((((long)co * cin + ci) * k + ky) * k + kx);
+          float v = w[src];
+          if (round_bf16) v = __bfloat162float(__float2bfloat16_rn(v));
+          dst[(((long)(ky * k + kx)) * cin + ci) * cout + co] = v;
+        }
+}
+
+// =====================================================================================================
+// init conv 7x7 (pad 3) on fp32 NCHW input
+// =====================================================================================================
+template <typename T>
+__global__ void init_conv_kernel(const InitConvP p) {
+  extern __shared__ float patch[];   // [7][S+6][Cin]
+  const int b = blockIdx.y, y = blockIdx.x, S = p.S, Cin = p.Cin;
+  const int PW = S + 6;
+  for (int i = threadIdx.x; i < 7 * PW * Cin; i += blockDim.x) {
+    const int ci = i % Cin;
+    const int px = (i / Cin) % PW;
+    const int r = i / (Cin * PW);
+    const int iy = y + r - 3, ix = px - 3;
+    float v = 0.f;
+    if (iy >= 0 && iy < S && ix >= 0 && ix < S) v = p.x[(((long)b * Cin + ci) * S + iy) * S + ix];
+    patch[i] = v;
+  }
+  __syncthreads();
+  int cls = p.pad_class;
+  if (p.cls_w && p.classes) cls = (int)p.classes[b];
+  for (int co = threadIdx.x; co < p.Cout; co += blockDim.x) {
+    float base = p.bias ? p.bias[co] : 0.f;
+    if (p.cls_w) base += p.cls_w[(long)cls * p.Cout + co];
+    for (int x0 = 0; x0 < S; x0 += 32) {
+      float acc[32];
+#pragma unroll
+      for (int i = 0; i < 32; ++i) acc[i] = 0.f;
+      for (int ky = 0; ky < 7; ++ky)
+        for (int kx = 0; kx < 7; ++kx)
+          for (int ci = 0; ci < Cin; ++ci) {
+            const float wv = p.w[((long)(ky * 7 + kx) * Cin + ci) * p.Cout + co];
+            const float* pr = patch + ((long)ky * PW + x0 + kx) * Cin + ci;
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              if (x0 + i < S) acc[i] = fmaf(pr[(long)i * Cin], wv, acc[i]);
+          }
+#pragma unroll
+      for (int i = 0; i < 32; ++i)
+        if (x0 + i < S) ((T*)p.out)[(((long)b * S + y) * S + x0 + i) * p.Cout + co] = from_f<T>(acc[i] + base);
+    }
+  }
+}
+
+int init_conv(const InitConvP& p, int act, cudaStream_t st) {
+  const size_t smem = (size_t)7 * (p.S + 6) * p.Cin * sizeof(float);
+  DMN_REQUIRE(smem <= 48 * 1024, "init_conv: input row patch does not fit in shared memory");
+  dim3 grid(p.S, p.B);
+  const int threads = p.Cout >= 128 ? 128 : (p.Cout >= 64 ? 64 : 32);
+  if (act == ACT_F32) init_conv_kernel<float><<<grid, threads, smem, st>>>(p);
+  else init_conv_kernel<bf16><<<grid, threads, smem, st>>>(p);
+  count_launch();
+  DMN_LAUNCH_CHECK("init_conv");
+  return 0;
+}
+
+// =====================================================================================================
+// GroupNorm finalize: y = act(GN(raw)) + res ; statistics of y for the next norm
+// grid = (blocks_per_image, B), 256 threads; the item stride is a multiple of C/4 so each thread keeps one
+// channel quad (=> one input group and one output group) for its whole loop.
+// =====================================================================================================
+template <typename T>
+__global__ void __launch_bounds__(256) gn_finalize_kernel(const FinalizeP p) {
+  __shared__ float sm_stats[2 * 64];
+  const int b = blockIdx.y;
+  const int C4 = p.C >> 2;
+  const long items = (long)p.HW * C4;
+  const int c = (threadIdx.x % C4) * 4;
+  const int cpg = p.C / p.groups;
+  float mean, rstd;
+  gn_mean_rstd(p.stats + ((long)b * p.groups + c / cpg) * 2, 1.f / (float)(p.HW * cpg), kGnEps, mean, rstd);
+  const float4 ga = *reinterpret_cast<const float4*>(p.gamma + c);
+  const float4 be = *reinterpret_cast<const float4*>(p.beta + c);
+  const float4 sc = make_float4(rstd * ga.x, rstd * ga.y, rstd * ga.z, rstd * ga.w);
+  const float4 sh = make_float4(be.x - mean * sc.x, be.y - mean * sc.y, be.z - mean * sc.z, be.w - mean * sc.w);
+  if (p.ostats) {
+    for (int i = threadIdx.x; i < 2 * p.ogroups; i += blockDim.x) sm_stats[i] = 0.f;
+    __syncthreads();
+  }
+  float s = 0.f, ss = 0.f;
+  const T* raw = (const T*)p.raw + (long)b * p.HW * p.C;
+  const T* res = p.res ? (const T*)p.res + (long)b * p.HW * p.C : nullptr;
+  T* out = (T*)p.out + (long)b * p.HW * p.C;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < items; i += (long)gridDim.x * blockDim.x) {
+    float4 v = load4<T>(raw + i * 4);
+    v.x = fmaf(v.x, sc.x, sh.x); v.y = fmaf(v.y, sc.y, sh.y); v.z = fmaf(v.z, sc.z, sh.z); v.w = fmaf(v.w, sc.w, sh.w);
+    if (p.silu) { v.x = silu_f(v.x); v.y = silu_f(v.y); v.z = silu_f(v.z); v.w = silu_f(v.w); }
+    if (res) {
+      const float4 r = load4<T>(res + i * 4);
+      v.x += r.x; v.y += r.y; v.z += r.z; v.w += r.w;
+    }
+    store4<T>(out + i * 4, v);
+    s += v.x + v.y + v.z + v.w;
+    ss += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+  }
+  if (p.ostats) {
+    const int og = c / (p.C / p.ogroups);
+    // threads of a warp that share og reduce through shared-memory atomics (few distinct og per warp)
+    atomicAdd(&sm_stats[og * 2], s);
+    atomicAdd(&sm_stats[og * 2 + 1], ss);
+    __syncthreads();
+    for (int i = threadIdx.x; i < 2 * p.ogroups; i += blockDim.x)
+      atomicAdd(p.ostats + (long)b * p.ogroups * 2 + i, sm_stats[i]);
+  }
+}
+
+int gn_finalize(const FinalizeP& p, int act, cudaStream_t st) {
+  const int C4 = p.C / 4;
+  DMN_REQUIRE(p.C % 4 == 0 && 256 % C4 == 0, "gn_finalize: C/4 must divide 256");
+  DMN_REQUIRE(p.C % p.groups == 0 && (p.C / p.groups) % 4 == 0, "gn_finalize: channels-per-group % 4");
+  DMN_REQUIRE(!p.ostats || (p.ogroups <= 64 && p.C % p.ogroups == 0 && (p.C / p.ogroups) % 4 == 0), "gn_finalize: ogroups");
+  const long items = (long)p.HW * C4;
+  int bpi = (int)((items + 256 * 4 - 1) / (256 * 4));
+  if (bpi < 1) bpi = 1;
+  if (bpi > 64) bpi = 64;
+  dim3 grid(bpi, p.B);
+  if (act == ACT_F32) gn_finalize_kernel<float><<<grid, 256, 0, st>>>(p);
+  else gn_finalize_kernel<bf16><<<grid, 256, 0, st>>>(p);
+  count_launch();
+  DMN_LAUNCH_CHECK("gn_finalize");
+  return 0;
+}
+
+// =====================================================================================================
+// final projection: eps[b][co][pix] = sum_c SiLU(GN(y))[b][pix][c] * w[co][c] + bias[co]
+// one warp per pixel
+// =====================================================================================================
+template <typename T>
+__global__ void __launch_bounds__(256) final_proj_kernel(const FinalProjP p) {
+  const int lane = threadIdx.x & 31;
+  const long wid = (long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const long total = (long)p.B * p.HW;
+  if (wid >= total) return;
+  const int b = (int)(wid / p.HW);
+  const int pix = (int)(wid - (long)b * p.HW);
+  const int cpg = p.C / p.groups;
+  const float inv = 1.f / (float)(p.HW * cpg);
+  const T* y = (const T*)p.y + wid * p.C;
+  float acc[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+  for (int c = lane; c < p.C; c += 32) {
+    float mean, rstd;
+    gn_mean_rstd(p.stats + ((long)b * p.groups + c / cpg) * 2, inv, kGnEps, mean, rstd);
+    float v = (to_f<T>(y[c]) - mean) * rstd * p.gamma[c] + p.beta[c];
+    v = silu_f(v);
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      if (j < p.Cout) acc[j] = fmaf(v, p.w[(long)j * p.C + c], acc[j]);
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    if (j < p.Cout) {
+      const float r = warp_sum(acc[j]);
+      if (lane == 0) p.out[((long)b * p.Cout + j) * p.HW + pix] = r + (p.bias ? p.bias[j] : 0.f);
+    }
+  }
+}
+
+int final_proj(const FinalProjP& p, int act, cudaStream_t st) {
+  DMN_REQUIRE(p.Cout <= 8, "final_proj: out_dim > 8 unsupported");
+  const long total = (long)p.B * p.HW;
+  const unsigned grid = (unsigned)((total + 7) / 8);
+  if (act == ACT_F32) final_proj_kernel<float><<<grid, 256, 0, st>>>(p);
+  else final_proj_kernel<bf16><<<grid, 256, 0, st>>>(p);
+  count_launch();
+  DMN_LAUNCH_CHECK("final_proj");
+  return 0;
+}
+
+// =====================================================================================================
+// LinearAttention core (parts/mha.py:44-58), dim_head = 32.  One block (256 threads) per (sample, head).
+//   q softmax over d (dim=-2), k softmax over n (dim=-1), q *= scale (after softmax),
+//   ctx[d][e] = sum_n k[d,n] v[e,n] ; out[e,n] = sum_d ctx[d][e] q[d,n]
+// qkv: [B][N][3*heads*32] (channel = which*heads*32 + head*32 + d);  out: [B][N][heads*32]
+// =====================================================================================================
+template <typename T>
+__global__ void __launch_bounds__(256) linattn_kernel(const T* __restrict__ qkv, T* __restrict__ out, int heads, int N) {
+  constexpr int D = 32;
+  __shared__ float red[8][D];
+  __shared__ float kmax[D], ksum[D];
+  __shared__ float ctx[D][D + 1];
+  const int b = blockIdx.x / heads, h = blockIdx.x % heads;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int C3 = 3 * heads * D;
+  const T* base = qkv + (long)b * N * C3;
+  const int qo = h * D, ko = heads * D + h * D, vo = 2 * heads * D + h * D;
+
+  // pass A: max over n of k[d, n]   (lane = d)
+  float m = -INFINITY;
+  for (int n = w; n < N; n += 8) m = fmaxf(m, to_f<T>(base[(long)n * C3 + ko + lane]));
+  red[w][lane] = m;
+  __syncthreads();
+  if (w == 0) {
+    float mm = red[0][lane];
+#pragma unroll
+    for (int i = 1; i < 8; ++i) mm = fmaxf(mm, red[i][lane]);
+    kmax[lane] = mm;
+  }
+  for (int i = threadIdx.x; i < D * (D + 1); i += 256) (&ctx[0][0])[i] = 0.f;
+  __syncthreads();
+
+  // pass B: p = exp(k - max); ksum[d] += p ; ctx[d][e] += p * v[e, n]
+  const float km = kmax[lane];
+  float acc[D];
+#pragma unroll
+  for (int e = 0; e < D; ++e) acc[e] = 0.f;
+  float psum = 0.f;
+  for (int n = w; n < N; n += 8) {
+    const float pk = __expf(to_f<T>(base[(long)n * C3 + ko + lane]) - km);
+    const float vv = to_f<T>(base[(long)n * C3 + vo + lane]);
+    psum += pk;
+#pragma unroll
+    for (int e = 0; e < D; ++e) acc[e] = fmaf(pk, __shfl_sync(0xffffffffu, vv, e), acc[e]);
+  }
+  red[w][lane] = psum;
+#pragma unroll
+  for (int e = 0; e < D; ++e) atomicAdd(&ctx[lane][e], acc[e]);
+  __syncthreads();
+  if (w == 0) {
+    float sacc = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) sacc += red[i][lane];
+    ksum[lane] = sacc;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < D * D; i += 256) {
+    const int d = i / D, e = i % D;
+    ctx[d][e] = ctx[d][e] / ksum[d];
+  }
+  __syncthreads();
+
+  // pass C: per token: softmax of q over d, scale, out[e] = sum_d ctx[d][e] * q[d]
+  const float scale = rsqrtf((float)D);
+  for (int n = threadIdx.x; n < N; n += 256) {
+    float q[D];
+    const T* qp = base + (long)n * C3 + qo;
+    float qm = -INFINITY;
+#pragma unroll
+    for (int d = 0; d < D; d += 4) {
+      const float4 t = load4<T>(qp + d);
+      q[d] = t.x; q[d + 1] = t.y; q[d + 2] = t.z; q[d + 3] = t.w;
+      qm = fmaxf(fmaxf(qm, fmaxf(t.x, t.y)), fmaxf(t.z, t.w));
+    }
+    float qs = 0.f;
+#pragma unroll
+    for (int d = 0; d < D; ++d) { q[d] = __expf(q[d] - qm); qs += q[d]; }
+    const float qn = scale / qs;
+    float o[D];
+#pragma unroll
+    for (int e = 0; e < D; ++e) o[e] = 0.f;
+#pragma unroll
+    for (int d = 0; d < D; ++d) {
+      const float qd = q[d] * qn;
+#pragma unroll
+      for (int e = 0; e < D; ++e) o[e] = fmaf(ctx[d][e], qd, o[e]);
+    }
+    T* op = out + ((long)b * N + n) * (heads * D) + h * D;
+#pragma unroll
+    for (int e = 0; e < D; e += 4) store4<T>(op + e, make_float4(o[e], o[e + 1], o[e + 2], o[e + 3]));
+  }
+}
+
+int linattn_core(const void* qkv, void* out, int B, int heads, int dh, int N, int act, cudaStream_t st) {
+  DMN_REQUIRE(dh == 32, "linattn_core: dim_head must be 32");
+  if (act == ACT_F32) linattn_kernel<float><<<B * heads, 256, 0, st>>>((const float*)qkv, (float*)out, heads, N);
+  else linattn_kernel<bf16><<<B * heads, 256, 0, st>>>((const bf16*)qkv, (bf16*)out, heads, N);
+  count_launch();
+  DMN_LAUNCH_CHECK("linattn_core");
+  return 0;
+}
+
+// =====================================================================================================
+// softmax Attention core (parts/mha.py:16-29), dim_head = 32.  One block per (sample, head), thread per query.
+// =====================================================================================================
+template <typename T>
+__global__ void attn_kernel(const T* __restrict__ qkv, T* __restrict__ out, int heads, int N) {
+  constexpr int D = 32;
+  extern __shared__ float kv[];   // k[N][D], v[N][D]
+  float* ks = kv;
+  float* vs = kv + (long)N * D;
+  const int b = blockIdx.x / heads, h = blockIdx.x % heads;
+  const int C3 = 3 * heads * D;
+  const T* base = qkv + (long)b * N * C3;
+  const int qo = h * D, ko = heads * D + h * D, vo = 2 * heads * D + h * D;
+  for (int i = threadIdx.x; i < N * D; i += blockDim.x) {
+    const int n = i / D, d = i % D;
+    ks[i] = to_f<T>(base[(long)n * C3 + ko + d]);
+    vs[i] = to_f<T>(base[(long)n * C3 + vo + d]);
+  }
+  __syncthreads();
+  const float scale = rsqrtf((float)D);
+  for (int i = threadIdx.x; i < N; i += blockDim.x) {
+    float q[D], o[D];
+#pragma unroll
+    for (int d = 0; d < D; ++d) { q[d] = to_f<T>(base[(long)i * C3 + qo + d]) * scale; o[d] = 0.f; }
+    float mx = -INFINITY, sum = 0.f;
+    for (int j = 0; j < N; ++j) {
+      float s = 0.f;
+#pragma unroll
+      for (int d = 0; d < D; ++d) s = fmaf(q[d], ks[j * D + d], s);
+      const float nm = fmaxf(mx, s);
+      const float corr = __expf(mx - nm);
+      const float pj = __expf(s - nm);
+      sum = sum * corr + pj;
+#pragma unroll
+      for (int d = 0; d < D; ++d) o[d] = fmaf(pj, vs[j * D + d], o[d] * corr);
+      mx = nm;
+    }
+    const float inv = 1.f / sum;
+    T* op = out + ((long)b * N + i) * (heads * D) + h * D;
+#pragma unroll
+    for (int d = 0; d < D; ++d) op[d] = from_f<T>(o[d] * inv);
+  }
+}
+
+int attn_core(const void* qkv, void* out, int B, int heads, int dh, int N, int act, cudaStream_t st) {
+  DMN_REQUIRE(dh == 32, "attn_core: dim_head must be 32");
+  const size_t smem = (size_t)2 * N * 32 * sizeof(float);
+  DMN_REQUIRE(smem <= 48 * 1024, "attn_core: too many tokens for the bottleneck attention kernel");
+  int threads = ((N + 31) / 32) * 32;
+  if (threads > 256) threads = 256;
+  if (act == ACT_F32) attn_kernel<float><<<B * heads, threads, smem, st>>>((const float*)qkv, (float*)out, heads, N);
+  else attn_kernel<bf16><<<B * heads, threads, smem, st>>>((const bf16*)qkv, (bf16*)out, heads, N);
+  count_launch();
+  DMN_LAUNCH_CHECK("attn_core");
+  return 0;
+}
+
+// =====================================================================================================
+// time path (fp32 throughout)
+// =====================================================================================================
+__global__ void sinusoid_kernel(const float* __restrict__ times, const float* __restrict__ freqs, float* __restrict__ out,
+                                int rows, int dim, int ld) {
+  const int half = dim >> 1;
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long)rows * half) return;
+  const int r = (int)(i / half), k = (int)(i % half);
+  const float a = times[r] * freqs[k];
+  out[(long)r * ld + k] = sinf(a);
+  out[(long)r * ld + half + k] = cosf(a);
+}
+
+// out[r][n] = act_out( sum_k in[r][k] * wT[k][n] + b[n] );  act_out: 0 none, 1 gelu(erf), 2 silu
+__global__ void __launch_bounds__(256) rows_linear_kernel(const float* __restrict__ in, int ld_in, int K, const float* __restrict__ wT,
+                                                          const float* __restrict__ bias, int N, float* __restrict__ out, int ld_out,
+                                                          int act_out) {
+  extern __shared__ float row[];
+  const int r = blockIdx.y;
+  for (int k = threadIdx.x; k < K; k += blockDim.x) row[k] = in[(long)r * ld_in + k];
+  __syncthreads();
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= N) return;
+  float acc = 0.f;
+  for (int k = 0; k < K; ++k) acc = fmaf(row[k], wT[(long)k * N + n], acc);
+  acc += bias[n];
+  if (act_out == 1) acc = 0.5f * acc * (1.0f + erff(acc * 0.70710678118654752440f));
+  else if (act_out == 2) acc = acc / (1.0f + expf(-acc));
+  out[(long)r * ld_out + n] = acc;
+}
+
+int time_table(const TimeP& p, cudaStream_t st) {
+  const int td = 4 * p.dim;
+  DMN_REQUIRE(p.rows > 0 && p.dim % 2 == 0, "time_table: bad shape");
+  float* e0 = p.tmp;                      // [rows][td] (first `dim` columns used)
+  float* h1 = p.tmp + (long)p.rows * td;  // [rows][td]
+  {
+    const long n = (long)p.rows * (p.dim / 2);
+    sinusoid_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(p.times, p.freqs, e0, p.rows, p.dim, td);
+    count_launch();
+    DMN_LAUNCH_CHECK("sinusoid");
+  }
+  dim3 g1((td + 255) / 256, p.rows);
+  rows_linear_kernel<<<g1, 256, p.dim * sizeof(float), st>>>(e0, td, p.dim, p.w1t, p.b1, td, h1, td, 1);
+  count_launch();
+  DMN_LAUNCH_CHECK("time_mlp.1");
+  // second Linear, then SiLU (the per-block mlp starts with SiLU, convnext.py:69) stored back into e0
+  rows_linear_kernel<<<g1, 256, td * sizeof(float), st>>>(h1, td, td, p.w3t, p.b3, td, e0, td, 2);
+  count_launch();
+  DMN_LAUNCH_CHECK("time_mlp.3");
+  dim3 g2((p.sumC + 255) / 256, p.rows);
+  rows_linear_kernel<<<g2, 256, td * sizeof(float), st>>>(e0, td, td, p.wct, p.bc, p.sumC, p.table, p.sumC, 0);
+  count_launch();
+  DMN_LAUNCH_CHECK("block_mlps");
+  return 0;
+}
+
+// =====================================================================================================
+// layout conversion (public-ABI boundary only; not on the loop's hot path)
+// =====================================================================================================
+template <typename T>
+__global__ void nchw_to_nhwc_kernel(const float* __restrict__ in, T* __restrict__ out, int C, int HW, long total) {
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int c = (int)(i % C);
+  const long bp = i / C;
+  const int pix = (int)(bp % HW);
+  const long b = bp / HW;
+  out[i] = from_f<T>(in[(b * C + c) * HW + pix]);
+}
+template <typename T>
+__global__ void nhwc_to_nchw_kernel(const T* __restrict__ in, float* __restrict__ out, int C, int HW, long total) {
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int pix = (int)(i % HW);
+  const long bc = i / HW;
+  const int c = (int)(bc % C);
+  const long b = bc / C;
+  out[i] = to_f<T>(in[(b * HW + pix) * C + c]);
+}
+int nchw_to_nhwc(const float* in, void* out, int B, int C, int HW, int act, cudaStream_t st) {
+  const long total = (long)B * C * HW;
+  const unsigned grid = (unsigned)((total + 255) / 256);
+  if (act == ACT_F32) nchw_to_nhwc_kernel<float><<<grid, 256, 0, st>>>(in, (float*)out, C, HW, total);
+  else nchw_to_nhwc_kernel<bf16><<<grid, 256, 0, st>>>(in, (bf16*)out, C, HW, total);
+  count_launch();
+  DMN_LAUNCH_CHECK("nchw_to_nhwc");
+  return 0;
+}
+int nhwc_to_nchw(const void* in, float* out, int B, int C, int HW, int act, cudaStream_t st) {
+  const long total = (long)B * C * HW;
+  const unsigned grid = (unsigned)((total + 255) / 256);
+  if (act == ACT_F32) nhwc_to_nchw_kernel<float><<<grid, 256, 0, st>>>((const float*)in, out, C, HW, total);
+  else nhwc_to_nchw_kernel<bf16><<<grid, 256, 0, st>>>((const bf16*)in, out, C, HW, total);
+  count_launch();
+  DMN_LAUNCH_CHECK("nhwc_to_nchw");
+  return 0;
+}
+__global__ void stats_to_mean_rstd_kernel(const float* __restrict__ stats, float* __restrict__ out, int n, float inv_count) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float mean, rstd;
+  gn_mean_rstd(stats + 2 * i, inv_count, kGnEps, mean, rstd);
+  out[2 * i] = mean;
+  out[2 * i + 1] = rstd;
+}
+int stats_to_mean_rstd(const float* stats, float* out, int n, float inv_count, cudaStream_t st) {
+  stats_to_mean_rstd_kernel<<<(n + 127) / 128, 128, 0, st>>>(stats, out, n, inv_count);
+  count_launch();
+  DMN_LAUNCH_CHECK("stats_to_mean_rstd");
+  return 0;
+}
+
+}  // namespace dmn

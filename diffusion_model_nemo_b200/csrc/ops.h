@@ -1,0 +1,119 @@
+// ops.h -- host-side launch interface of the engine kernels (internal; the public ABI is include/dmn_b200.h).
+//
+// Engine data layout: activations are NHWC ("pixel-major": [batch][H*W][C]) in fp32 or bf16; GroupNorm
+// statistics are {sum, sum-of-squares} per (sample, group) in fp32, accumulated by the producing kernel's
+// epilogue and turned into mean/rstd by the consumer's prologue.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace dmn {
+
+enum { ACT_F32 = 0, ACT_BF16 = 1 };
+enum { CONV_SAME = 0, CONV_DOWN = 1, CONV_UP = 2 };
+enum { PRO_NONE = 0, PRO_GN = 1, PRO_SILU = 2, PRO_TEMB = 4 };
+
+// One convolution (+ fused prologue on its input, + fused epilogue on its output).
+struct ConvP {
+  // sources: channel-concatenation of src1 (C1 channels) and src2 (C2 channels, 0 = none); never materialised
+  const void* src1 = nullptr;
+  const void* src2 = nullptr;
+  int C1 = 0, C2 = 0;
+  int B = 0, Hin = 0, Win = 0, Hout = 0, Wout = 0, Cout = 0;
+  int mode = CONV_SAME, ksize = 3;
+  // weights: SIMT engine  -> fp32 [tap][Cin][Cout];  tcgen05 engine -> bf16 blocked (see conv_tcgen05.cu)
+  const void* w = nullptr;
+  const float* bias = nullptr;
+  // prologue applied to src1 while loading (GroupNorm of the producer, SiLU, time-embedding add)
+  int pro = PRO_NONE;
+  const float* pstats = nullptr;   // [B][pgroups][2]
+  int pgroups = 0;
+  const float* pgamma = nullptr;
+  const float* pbeta = nullptr;
+  const float* temb = nullptr;     // effective row = temb + (d_row ? *d_row * temb_rstride : 0) + b * temb_bstride
+  long temb_bstride = 0, temb_rstride = 0;
+  const int* d_row = nullptr;
+  // epilogue
+  void* out = nullptr;             // raw conv output (+bias, +res)
+  const void* res = nullptr;       // optional residual added to the output (same layout as out)
+  float* ostats = nullptr;         // [B][ogroups][2] accumulated with atomics (must be zeroed beforehand)
+  int ogroups = 0;
+};
+
+int conv_simt(const ConvP& p, int act, cudaStream_t s);
+int conv_tcgen05(const ConvP& p, cudaStream_t s);              // bf16 activations only
+bool conv_tcgen05_supported(const ConvP& p);
+// bytes of the blocked bf16 weight image for the tcgen05 engine, and the host-side packer
+size_t conv_tcgen05_weight_bytes(int mode, int ksize, int cin, int cout);
+void conv_tcgen05_pack_weights(int mode, int ksize, int cin, int cout, const float* w_torch, void* dst_host);
+// SIMT packer: torch layout -> [tap][Cin][Cout] fp32 (optionally rounded to bf16 values)
+void conv_simt_pack_weights(int mode, int ksize, int cin, int cout, const float* w_torch, float* dst_host, bool round_bf16);
+
+// init_conv 7x7 pad 3 on the fp32 NCHW sampler state -> NHWC activations (+ class embedding)
+struct InitConvP {
+  const float* x = nullptr;        // [B][Cin][S][S]
+  const float* w = nullptr;        // [49*Cin][Cout] fp32
+  const float* bias = nullptr;
+  const float* cls_w = nullptr;    // [num_classes+1][Cout] or null
+  const int64_t* classes = nullptr;
+  int pad_class = 0;               // row used when classes == null
+  void* out = nullptr;
+  int B = 0, Cin = 0, S = 0, Cout = 0;
+};
+int init_conv(const InitConvP& p, int act, cudaStream_t s);
+
+// y = act(GroupNorm(raw)) [+ res];  optional statistics of y for the next norm
+struct FinalizeP {
+  const void* raw = nullptr;
+  const float* stats = nullptr;
+  int groups = 0;
+  const float* gamma = nullptr;
+  const float* beta = nullptr;
+  int silu = 0;
+  const void* res = nullptr;
+  void* out = nullptr;
+  float* ostats = nullptr;
+  int ogroups = 0;
+  int B = 0, HW = 0, C = 0;
+};
+int gn_finalize(const FinalizeP& p, int act, cudaStream_t s);
+
+// final_conv tail: eps = conv1x1(SiLU(GroupNorm(y)))  -> fp32 NCHW
+struct FinalProjP {
+  const void* y = nullptr;
+  const float* stats = nullptr;
+  int groups = 0;
+  const float* gamma = nullptr;
+  const float* beta = nullptr;
+  const float* w = nullptr;        // [Cout][C] fp32
+  const float* bias = nullptr;
+  float* out = nullptr;            // [B][Cout][HW]
+  int B = 0, HW = 0, C = 0, Cout = 0;
+};
+int final_proj(const FinalProjP& p, int act, cudaStream_t s);
+
+int linattn_core(const void* qkv, void* out, int B, int heads, int dh, int N, int act, cudaStream_t s);
+int attn_core(const void* qkv, void* out, int B, int heads, int dh, int N, int act, cudaStream_t s);
+
+// time path
+struct TimeP {
+  const float* times = nullptr;    // [rows]
+  const float* freqs = nullptr;    // [dim/2]
+  const float* w1t = nullptr;      // [dim][4dim]   (transposed Linear weights: [in][out])
+  const float* b1 = nullptr;
+  const float* w3t = nullptr;      // [4dim][4dim]
+  const float* b3 = nullptr;
+  const float* wct = nullptr;      // [4dim][sumC]  all ResnetBlock.mlp weights side by side
+  const float* bc = nullptr;       // [sumC]
+  float* tmp = nullptr;            // [rows][2*4dim] scratch
+  float* table = nullptr;          // [rows][sumC]
+  int rows = 0, dim = 0, sumC = 0;
+};
+int time_table(const TimeP& p, cudaStream_t s);
+
+// layout conversion at the public ABI boundary
+int nchw_to_nhwc(const float* in, void* out, int B, int C, int HW, int act, cudaStream_t s);
+int nhwc_to_nchw(const void* in, float* out, int B, int C, int HW, int act, cudaStream_t s);
+int stats_to_mean_rstd(const float* stats, float* out, int n, float inv_count, cudaStream_t s);
+
+}  // namespace dmn

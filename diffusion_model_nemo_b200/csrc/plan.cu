@@ -1,0 +1,904 @@
+// plan.cu -- the U-Net "plan": parameter table + weight packing + the static launch program of one
+// Unet.forward (modules/unet.py:131-168), the CUDA-graph loop driver and the C ABI around them.
+//
+// The launch program is built once from dmn_unet_cfg by mirroring Unet.__init__ (modules/unet.py:43-120):
+//   init_conv -> [ResnetBlock, ResnetBlock, Residual(PreNorm(LinearAttention)), Downsample] x levels
+//             -> ResnetBlock, Residual(PreNorm(Attention)), ResnetBlock
+//             -> [cat skip, ResnetBlock, ResnetBlock, Residual(PreNorm(LinearAttention)), Upsample] x (levels-1)
+//             -> ResnetBlock, GroupNorm, SiLU, Conv1x1
+// Fusion map (what each launch covers):
+//   conv (block1.proj)            : + bias, + GroupNorm statistics of its output
+//   conv (block2.proj)            : prologue = GroupNorm-apply(block1.norm) + SiLU + time-embedding add on the
+//                                   operand load; + bias, + statistics
+//   gn_finalize                   : SiLU(GroupNorm(block2)) + residual  (+ statistics for the following PreNorm)
+//   conv 1x1 (to_qkv)             : prologue = PreNorm GroupNorm(1) apply
+//   linattn_core / attn_core      : both softmaxes, scale and the two small contractions
+//   conv 1x1 (to_out)             : + bias (+ statistics of GroupNorm(1) | + residual for the bottleneck Attention)
+//   gn_finalize                   : GroupNorm(1) + residual
+//   concat                        : never materialised (two-source operand load)
+#include <cstring>
+#include <map>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "../../include/dmn_b200.h"
+#include "common.cuh"
+#include "ops.h"
+
+namespace dmn {
+
+static thread_local std::string g_err;
+thread_local long g_launches = 0;
+void set_error(const std::string& m) { g_err = m; }
+int fail(int code, const std::string& m) {
+  g_err = m;
+  return code;
+}
+
+int launch_advance_counter(int32_t* c, cudaStream_t st);
+int launch_set_counter(int32_t* c, int v, dmn_rng rng, cudaStream_t st);
+int launch_ddpm(const float* x, const float* eps, const float* z, float* out, long n, const float* coef, const int32_t* step_dev,
+                int step, dmn_rng rng, const dmn_rng* rng_dev, cudaStream_t st);
+int launch_learned(const float* x, const float* mo, const float* z, float* out, int batch, long chw, const float* coef,
+                   const int32_t* step_dev, int step, dmn_rng rng, const dmn_rng* rng_dev, cudaStream_t st);
+int launch_ddim(const float* x, const float* eps, const float* z, float* out, long n, const float* coef, const int32_t* step_dev,
+                int step, dmn_rng rng, const dmn_rng* rng_dev, cudaStream_t st);
+int launch_traj(const float* x, float* traj, long n, const int32_t* step_dev, int every, int n_steps, cudaStream_t st);
+int launch_langevin(const float* x, const float* mo, const float* z, float* out, float* mean_out, int batch, long chw,
+                    float snr, const float* coef, const int32_t* step_dev, int step, int draw, float* scratch, dmn_rng rng,
+                    const dmn_rng* rng_dev, cudaStream_t st);
+int launch_affine_noise(const float* x, const float* mo, const float* z, float* out, float* mean_out, long n, const float* coef,
+                        const int32_t* step_dev, int step, int draw, dmn_rng rng, const dmn_rng* rng_dev, cudaStream_t st);
+
+enum ParamKind {
+  PK_RAW,        // copied as is (bias, gamma, beta, final 1x1 weight, class embedding)
+  PK_CONV,       // convolution weight -> engine layout(s)
+  PK_INIT,       // init_conv weight [dim][ch][7][7] -> [49*ch][dim]
+  PK_LIN_T,      // Linear weight [out][in] -> [in][out]
+  PK_BLOCK_MLP_W,  // ResnetBlock.mlp.1.weight [cout][4dim] -> column slice of [4dim][sumC]
+  PK_BLOCK_MLP_B,  // ResnetBlock.mlp.1.bias -> slice of [sumC]
+};
+
+struct Param {
+  std::string name;
+  std::vector<int64_t> shape;
+  int kind = PK_RAW;
+  size_t off = 0;        // primary device region (bytes from weights base)
+  size_t off2 = 0;       // PK_CONV: tcgen05 image (0 = none)
+  bool has_simt = true;  // PK_CONV: SIMT image present
+  bool has_tc = false;   // PK_CONV: tcgen05 image present
+  int mode = 0, ksize = 0, cin = 0, cout = 0;   // PK_CONV
+  int col = 0;           // PK_BLOCK_MLP_*: column offset
+  bool loaded = false;
+  int64_t numel() const {
+    int64_t n = 1;
+    for (auto s : shape) n *= s;
+    return n;
+  }
+};
+
+enum OpKind { OP_MEMSET, OP_INIT, OP_CONV, OP_FINALIZE, OP_LINATTN, OP_ATTN, OP_FINALPROJ };
+
+// Buffers are addressed as (region id, so pointers can be resolved after bind)
+struct Buf {
+  size_t off = (size_t)-1;   // bytes from workspace base
+  bool valid() const { return off != (size_t)-1; }
+};
+
+struct Op {
+  int kind = OP_CONV;
+  std::string name;
+  // conv
+  int mode = 0, ksize = 3, C1 = 0, C2 = 0, Cout = 0, Hin = 0, Hout = 0;
+  Buf src1, src2, out, res;
+  int w = -1, bias = -1;            // param indices
+  int pro = 0, pgroups = 0, pgamma = -1, pbeta = -1;
+  Buf pstats, ostats;
+  int ogroups = 0;
+  int temb_col = -1;
+  bool tc = false;                  // tcgen05 engine for this conv
+  // finalize / final proj
+  int groups = 0, gamma = -1, beta = -1, silu = 0, C = 0, HW = 0;
+  Buf raw, stats;
+  // attention
+  int heads = 4, dh = 32, N = 0;
+};
+
+}  // namespace dmn
+
+using namespace dmn;
+
+struct dmn_plan {
+  dmn_unet_cfg cfg;
+  int act = 0, engine = 0;
+  size_t esz = 4;
+  std::vector<Param> params;
+  std::map<std::string, int> pidx;
+  std::vector<Op> ops;
+  size_t weights_bytes = 0, ws_bytes = 0;
+  char* wbase = nullptr;
+  char* wsbase = nullptr;
+  // time path
+  int sumC = 0;
+  size_t off_freqs = 0, off_wct = 0, off_bc = 0;
+  bool freqs_loaded = false;
+  Buf time_tmp, time_table;
+  // statistics arena
+  size_t stats_off = 0, stats_bytes = 0;
+  Buf out_nhwc_dummy;
+  int launches_per_forward = 0;
+  // loop state
+  Buf counters;   // int32[4]
+  struct GraphEntry {
+    cudaGraphExec_t exec = nullptr;
+    dmn_loop_desc key;
+  };
+  std::vector<GraphEntry> graphs;
+  ~dmn_plan() {
+    for (auto& g : graphs)
+      if (g.exec) cudaGraphExecDestroy(g.exec);
+  }
+};
+
+namespace dmn {
+
+static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+struct Builder {
+  dmn_plan& P;
+  size_t woff = 0, wsoff = 0;
+  explicit Builder(dmn_plan& p) : P(p) {}
+
+  size_t walloc(size_t bytes) {
+    size_t o = woff;
+    woff = align_up(woff + bytes, 256);
+    return o;
+  }
+  Buf wsalloc(size_t bytes) {
+    Buf b;
+    b.off = wsoff;
+    wsoff = align_up(wsoff + bytes, 256);
+    return b;
+  }
+  Buf act(int HW, int C) { return wsalloc((size_t)P.cfg.max_batch * HW * C * P.esz); }
+  Buf stats(int G) {
+    Buf b;
+    b.off = P.stats_off + P.stats_bytes;
+    P.stats_bytes += align_up((size_t)P.cfg.max_batch * G * 2 * sizeof(float), 256);
+    return b;
+  }
+
+  int add_param(const std::string& name, std::vector<int64_t> shape, int kind) {
+    Param q;
+    q.name = name;
+    q.shape = std::move(shape);
+    q.kind = kind;
+    if (kind == PK_RAW || kind == PK_INIT || kind == PK_LIN_T) q.off = walloc((size_t)q.numel() * sizeof(float));
+    P.params.push_back(q);
+    P.pidx[name] = (int)P.params.size() - 1;
+    return (int)P.params.size() - 1;
+  }
+  int add_conv_param(const std::string& name, int mode, int ksize, int cin, int cout, bool tc) {
+    Param q;
+    q.name = name;
+    const int k = (mode == CONV_SAME) ? ksize : 4;
+    if (mode == CONV_UP) q.shape = {cin, cout, k, k};
+    else q.shape = {cout, cin, k, k};
+    q.kind = PK_CONV;
+    q.mode = mode; q.ksize = ksize; q.cin = cin; q.cout = cout;
+    q.has_simt = !tc;
+    if (q.has_simt) q.off = walloc((size_t)q.numel() * sizeof(float));
+    q.has_tc = tc;
+    if (tc) q.off2 = walloc(conv_tcgen05_weight_bytes(mode, ksize, cin, cout));
+    P.params.push_back(q);
+    P.pidx[name] = (int)P.params.size() - 1;
+    return (int)P.params.size() - 1;
+  }
+
+  bool want_tc(int mode, int ksize, int C1, int C2, int Cout, int Hin, int pro, int pgroups, int ogroups) {
+    if (P.engine != DMN_CONV_TCGEN05) return false;
+    ConvP c;
+    c.mode = mode; c.ksize = ksize; c.C1 = C1; c.C2 = C2; c.Cout = Cout;
+    c.B = P.cfg.max_batch; c.Hin = c.Win = Hin;
+    c.Hout = c.Wout = (mode == CONV_DOWN) ? Hin / 2 : (mode == CONV_UP ? Hin * 2 : Hin);
+    c.pro = pro; c.pgroups = pgroups; c.ogroups = ogroups;
+    return conv_tcgen05_supported(c);
+  }
+
+  // conv op; returns op index
+  int conv(const std::string& pname, int mode, int ksize, Buf s1, int C1, Buf s2, int C2, int Cout, int Hin, Buf out,
+           bool has_bias, int ogroups, int pro = 0, int pgroups = 0, Buf pstats = Buf(), int pgamma = -1, int pbeta = -1,
+           int temb_col = -1, Buf res = Buf()) {
+    Op o;
+    o.kind = OP_CONV;
+    o.name = pname;
+    o.mode = mode; o.ksize = ksize; o.C1 = C1; o.C2 = C2; o.Cout = Cout; o.Hin = Hin;
+    o.Hout = (mode == CONV_DOWN) ? Hin / 2 : (mode == CONV_UP ? Hin * 2 : Hin);
+    o.src1 = s1; o.src2 = s2; o.out = out; o.res = res;
+    o.tc = want_tc(mode, ksize, C1, C2, Cout, Hin, pro, pgroups, ogroups);
+    o.w = add_conv_param(pname + ".weight", mode, ksize, C1 + C2, Cout, o.tc);
+    if (has_bias) o.bias = add_param(pname + ".bias", {Cout}, PK_RAW);
+    o.pro = pro; o.pgroups = pgroups; o.pstats = pstats; o.pgamma = pgamma; o.pbeta = pbeta; o.temb_col = temb_col;
+    o.ogroups = ogroups;
+    if (ogroups > 0) o.ostats = stats(ogroups);
+    P.ops.push_back(o);
+    return (int)P.ops.size() - 1;
+  }
+
+  // ResnetBlock (parts/convnext.py:63-86).  x_in: (s1,C1)+(s2,C2) -> out (Cout channels)
+  void resblock(const std::string& p, Buf s1, int C1, Buf s2, int C2, int Cout, int H, Buf h1, Buf h2, Buf rbuf, Buf out,
+                bool temb, int ostats_groups, Buf* ostats_out) {
+    const int G = P.cfg.groups;
+    const int Cin = C1 + C2;
+    int temb_col = -1;
+    if (temb && P.cfg.with_time_emb) {
+      temb_col = P.sumC;
+      Param w; w.name = p + ".mlp.1.weight"; w.shape = {Cout, 4 * P.cfg.dim}; w.kind = PK_BLOCK_MLP_W; w.col = temb_col;
+      P.params.push_back(w); P.pidx[w.name] = (int)P.params.size() - 1;
+      Param b; b.name = p + ".mlp.1.bias"; b.shape = {Cout}; b.kind = PK_BLOCK_MLP_B; b.col = temb_col;
+      P.params.push_back(b); P.pidx[b.name] = (int)P.params.size() - 1;
+      P.sumC += Cout;
+    }
+    // block1: conv -> (GroupNorm, SiLU deferred to the consumer)
+    int c1 = conv(p + ".block1.proj", CONV_SAME, 3, s1, C1, s2, C2, Cout, H, h1, true, G);
+    int g1w = add_param(p + ".block1.norm.weight", {Cout}, PK_RAW);
+    int g1b = add_param(p + ".block1.norm.bias", {Cout}, PK_RAW);
+    // block2: conv( SiLU(GN(h1)) + temb )
+    int pro = PRO_GN | PRO_SILU | (temb_col >= 0 ? PRO_TEMB : 0);
+    int c2 = conv(p + ".block2.proj", CONV_SAME, 3, h1, Cout, Buf(), 0, Cout, H, h2, true, G, pro, G, P.ops[c1].ostats, g1w, g1b,
+                  temb_col);
+    int g2w = add_param(p + ".block2.norm.weight", {Cout}, PK_RAW);
+    int g2b = add_param(p + ".block2.norm.bias", {Cout}, PK_RAW);
+    Buf res = s1;
+    if (Cin != Cout) {
+      conv(p + ".res_conv", CONV_SAME, 1, s1, C1, s2, C2, Cout, H, rbuf, true, 0);
+      res = rbuf;
+    }
+    Op f;
+    f.kind = OP_FINALIZE;
+    f.name = p + ".finalize";
+    f.raw = h2; f.stats = P.ops[c2].ostats; f.groups = G; f.gamma = g2w; f.beta = g2b; f.silu = 1;
+    f.res = res; f.out = out; f.C = Cout; f.HW = H * H;
+    f.ogroups = ostats_groups;
+    if (ostats_groups > 0) {
+      f.ostats = stats(ostats_groups);
+      if (ostats_out) *ostats_out = f.ostats;
+    }
+    P.ops.push_back(f);
+  }
+
+  // Residual(PreNorm(dim, LinearAttention | Attention))   (utils.py:68-93, parts/mha.py)
+  void attn_block(const std::string& p, bool linear, Buf x, Buf xstats, int C, int H, Buf qkv, Buf att, Buf oraw, Buf out) {
+    const int hidden = 128;
+    int nw = add_param(p + ".fn.norm.weight", {C}, PK_RAW);
+    int nb = add_param(p + ".fn.norm.bias", {C}, PK_RAW);
+    conv(p + ".fn.fn.to_qkv", CONV_SAME, 1, x, C, Buf(), 0, 3 * hidden, H, qkv, false, 0, PRO_GN, 1, xstats, nw, nb);
+    Op a;
+    a.kind = linear ? OP_LINATTN : OP_ATTN;
+    a.name = p + ".core";
+    a.src1 = qkv; a.out = att; a.N = H * H; a.heads = 4; a.dh = 32;
+    P.ops.push_back(a);
+    if (linear) {
+      int co = conv(p + ".fn.fn.to_out.0", CONV_SAME, 1, att, hidden, Buf(), 0, C, H, oraw, true, 1);
+      int gw = add_param(p + ".fn.fn.to_out.1.weight", {C}, PK_RAW);
+      int gb = add_param(p + ".fn.fn.to_out.1.bias", {C}, PK_RAW);
+      Op f;
+      f.kind = OP_FINALIZE;
+      f.name = p + ".finalize";
+      f.raw = oraw; f.stats = P.ops[co].ostats; f.groups = 1; f.gamma = gw; f.beta = gb; f.silu = 0;
+      f.res = x; f.out = out; f.C = C; f.HW = H * H;
+      P.ops.push_back(f);
+    } else {
+      conv(p + ".fn.fn.to_out", CONV_SAME, 1, att, hidden, Buf(), 0, C, H, out, true, 0, 0, 0, Buf(), -1, -1, -1, x);
+    }
+  }
+
+  int build() {
+    const dmn_unet_cfg& c = P.cfg;
+    const int dim = c.dim, n = c.n_mults, S = c.image_size, G = c.groups;
+    std::vector<int> dims = {dim};
+    for (int i = 0; i < n; ++i) dims.push_back(dim * c.dim_mults[i]);
+    // resolution of each level
+    std::vector<int> Hs(n);
+    int H = S;
+    for (int i = 0; i < n; ++i) {
+      Hs[i] = H;
+      if (i < n - 1) {
+        if (H % 2) return fail(DMN_EINVAL, "image_size must be divisible by 2^(levels-1)");
+        H /= 2;
+      }
+    }
+    // max per-sample activation size
+    size_t maxact = 0, maxqkv = 0, maxatt = 0;
+    for (int i = 0; i < n; ++i) {
+      size_t hw = (size_t)Hs[i] * Hs[i];
+      maxact = std::max(maxact, hw * std::max(dims[i], dims[i + 1]));
+      maxqkv = std::max(maxqkv, hw * 384);
+      maxatt = std::max(maxatt, hw * 128);
+    }
+    maxact = std::max(maxact, (size_t)S * S * dim);
+    auto actbuf = [&](size_t per_sample) { return wsalloc((size_t)c.max_batch * per_sample * P.esz); };
+
+    // statistics arena first (fixed offset); its size is known only after the program is built, so reserve generously
+    P.stats_off = wsoff;
+    const size_t stats_reserve = align_up((size_t)c.max_batch * 64 * 2 * sizeof(float), 256) * 160;
+    wsoff += stats_reserve;
+
+    Buf X[3] = {actbuf(maxact), actbuf(maxact), actbuf(maxact)};
+    Buf H1 = actbuf(maxact), H2 = actbuf(maxact), R = actbuf(maxact), O = actbuf(maxact);
+    Buf QKV = actbuf(maxqkv), ATT = actbuf(maxatt);
+    std::vector<Buf> skip(n);
+    for (int i = 0; i < n; ++i) skip[i] = actbuf((size_t)Hs[i] * Hs[i] * dims[i + 1]);
+
+    // parameters that are not attached to a conv op
+    add_param("init_conv.weight", {dim, c.channels, 7, 7}, PK_INIT);
+    add_param("init_conv.bias", {dim}, PK_RAW);
+    if (c.with_time_emb) {
+      add_param("time_mlp.1.weight", {4 * dim, dim}, PK_LIN_T);
+      add_param("time_mlp.1.bias", {4 * dim}, PK_RAW);
+      add_param("time_mlp.3.weight", {4 * dim, 4 * dim}, PK_LIN_T);
+      add_param("time_mlp.3.bias", {4 * dim}, PK_RAW);
+    }
+    if (c.num_classes >= 0) add_param("class_embed.weight", {c.num_classes + 1, dim}, PK_RAW);
+
+    Op m;
+    m.kind = OP_MEMSET;
+    m.name = "zero_stats";
+    P.ops.push_back(m);
+    Op ic;
+    ic.kind = OP_INIT;
+    ic.name = "init_conv";
+    ic.out = X[0];
+    P.ops.push_back(ic);
+
+    int cur = 0;   // index of the X buffer holding the current activation
+    Buf x = X[0];
+    for (int i = 0; i < n; ++i) {
+      const int ci = dims[i], co = dims[i + 1], Hh = Hs[i];
+      const std::string p = "downs." + std::to_string(i);
+      Buf o1 = X[(cur + 1) % 3];
+      resblock(p + ".0", x, ci, Buf(), 0, co, Hh, H1, H2, R, o1, true, 0, nullptr);
+      Buf o2 = X[(cur + 2) % 3];
+      Buf st;
+      resblock(p + ".1", o1, co, Buf(), 0, co, Hh, H1, H2, R, o2, true, 1, &st);
+      attn_block(p + ".2", true, o2, st, co, Hh, QKV, ATT, O, skip[i]);
+      if (i < n - 1) {
+        Buf o3 = X[cur % 3];
+        conv(p + ".3", CONV_DOWN, 4, skip[i], co, Buf(), 0, co, Hh, o3, true, 0);
+        x = o3;
+      } else {
+        x = skip[i];
+      }
+    }
+    const int mid = dims[n], Hm = Hs[n - 1];
+    {
+      Buf st;
+      Buf o1 = X[(cur + 1) % 3];
+      resblock("mid_block1", x, mid, Buf(), 0, mid, Hm, H1, H2, R, o1, true, 1, &st);
+      Buf o2 = X[(cur + 2) % 3];
+      attn_block("mid_attn", false, o1, st, mid, Hm, QKV, ATT, O, o2);
+      Buf o3 = X[cur % 3];
+      resblock("mid_block2", o2, mid, Buf(), 0, mid, Hm, H1, H2, R, o3, true, 0, nullptr);
+      x = o3;
+    }
+    // ups: reversed(in_out[1:])
+    int Hu = Hm;
+    for (int j = 0; j < n - 1; ++j) {
+      const int lvl = n - 1 - j;              // in_out[lvl] = (dims[lvl], dims[lvl+1])
+      const int ci = dims[lvl], co = dims[lvl + 1];
+      const std::string p = "ups." + std::to_string(j);
+      // input = cat(x [co channels], skip[lvl] [co channels])
+      Buf o1 = X[(cur + 1) % 3];
+      resblock(p + ".0", x, co, skip[lvl], co, ci, Hu, H1, H2, R, o1, true, 0, nullptr);
+      Buf o2 = X[(cur + 2) % 3];
+      Buf st;
+      resblock(p + ".1", o1, ci, Buf(), 0, ci, Hu, H1, H2, R, o2, true, 1, &st);
+      Buf o3 = X[cur % 3];
+      attn_block(p + ".2", true, o2, st, ci, Hu, QKV, ATT, O, o3);
+      Buf o4 = X[(cur + 1) % 3];
+      conv(p + ".3", CONV_UP, 4, o3, ci, Buf(), 0, ci, Hu, o4, true, 0);
+      x = o4;
+      cur = (cur + 1) % 3;
+      Hu *= 2;
+    }
+    if (Hu != S) return fail(DMN_EINVAL, "internal: resolution bookkeeping");
+    // final_conv = ResnetBlock(dim, dim) without time embedding, GroupNorm, SiLU, Conv1x1
+    {
+      Buf st;
+      Buf o1 = X[(cur + 1) % 3];
+      resblock("final_conv.0", x, dim, Buf(), 0, dim, S, H1, H2, R, o1, false, G, &st);
+      Op f;
+      f.kind = OP_FINALPROJ;
+      f.name = "final_conv.tail";
+      f.src1 = o1; f.stats = st; f.groups = G; f.C = dim; f.HW = S * S; f.Cout = c.out_dim;
+      f.gamma = add_param("final_conv.1.weight", {dim}, PK_RAW);
+      f.beta = add_param("final_conv.1.bias", {dim}, PK_RAW);
+      f.w = add_param("final_conv.3.weight", {c.out_dim, dim, 1, 1}, PK_RAW);
+      f.bias = add_param("final_conv.3.bias", {c.out_dim}, PK_RAW);
+      P.ops.push_back(f);
+    }
+    if (P.stats_bytes > stats_reserve) return fail(DMN_EINVAL, "internal: statistics arena overflow");
+
+    // time path storage
+    if (c.with_time_emb) {
+      P.off_freqs = walloc((size_t)(dim / 2) * sizeof(float));
+      P.off_wct = walloc((size_t)4 * dim * P.sumC * sizeof(float));
+      P.off_bc = walloc((size_t)P.sumC * sizeof(float));
+      P.time_tmp = wsalloc((size_t)c.max_time_rows * 8 * dim * sizeof(float));
+      P.time_table = wsalloc((size_t)c.max_time_rows * P.sumC * sizeof(float));
+    }
+    P.counters = wsalloc(256);
+    P.weights_bytes = woff;
+    P.ws_bytes = wsoff;
+    return 0;
+  }
+};
+
+static int run_forward(dmn_plan* P, const float* x_dev, const int32_t* row_dev, const int64_t* classes_dev, float* out_dev,
+                       int batch, cudaStream_t st, std::vector<cudaEvent_t>* evs = nullptr) {
+  const dmn_unet_cfg& c = P->cfg;
+  auto W = [&](int pi) -> const float* { return pi < 0 ? nullptr : (const float*)(P->wbase + P->params[pi].off); };
+  auto B = [&](const Buf& b) -> void* { return b.valid() ? (void*)(P->wsbase + b.off) : nullptr; };
+  const long launches0 = g_launches;
+  size_t op_i = 0;
+  if (evs) cudaEventRecord((*evs)[0], st);
+  for (const Op& o : P->ops) {
+    int rc = 0;
+    switch (o.kind) {
+      case OP_MEMSET: {
+        DMN_CUDA_CHECK(cudaMemsetAsync(P->wsbase + P->stats_off, 0, P->stats_bytes, st));
+        count_launch();
+        break;
+      }
+      case OP_INIT: {
+        InitConvP q;
+        q.x = x_dev;
+        q.w = W(P->pidx["init_conv.weight"]);
+        q.bias = W(P->pidx["init_conv.bias"]);
+        if (c.num_classes >= 0) {
+          q.cls_w = W(P->pidx["class_embed.weight"]);
+          q.classes = classes_dev;
+          q.pad_class = c.num_classes;
+        }
+        q.out = B(o.out);
+        q.B = batch; q.Cin = c.channels; q.S = c.image_size; q.Cout = c.dim;
+        rc = init_conv(q, P->act, st);
+        break;
+      }
+      case OP_CONV: {
+        ConvP q;
+        q.src1 = B(o.src1); q.src2 = B(o.src2); q.C1 = o.C1; q.C2 = o.C2;
+        q.B = batch; q.Hin = q.Win = o.Hin; q.Hout = q.Wout = o.Hout; q.Cout = o.Cout;
+        q.mode = o.mode; q.ksize = o.ksize;
+        const Param& wp = P->params[o.w];
+        q.w = o.tc ? (const void*)(P->wbase + wp.off2) : (const void*)(P->wbase + wp.off);
+        q.bias = W(o.bias);
+        q.pro = o.pro; q.pstats = (const float*)B(o.pstats); q.pgroups = o.pgroups;
+        q.pgamma = W(o.pgamma); q.pbeta = W(o.pbeta);
+        if (o.pro & PRO_TEMB) {
+          q.temb = (const float*)B(P->time_table) + o.temb_col;
+          if (row_dev) { q.d_row = row_dev; q.temb_rstride = P->sumC; q.temb_bstride = 0; }
+          else { q.d_row = nullptr; q.temb_rstride = 0; q.temb_bstride = P->sumC; }
+        }
+        q.out = B(o.out); q.res = B(o.res);
+        q.ostats = (float*)B(o.ostats); q.ogroups = o.ogroups;
+        rc = o.tc ? conv_tcgen05(q, st) : conv_simt(q, P->act, st);
+        break;
+      }
+      case OP_FINALIZE: {
+        FinalizeP q;
+        q.raw = B(o.raw); q.stats = (const float*)B(o.stats); q.groups = o.groups;
+        q.gamma = W(o.gamma); q.beta = W(o.beta); q.silu = o.silu;
+        q.res = B(o.res); q.out = B(o.out); q.ostats = (float*)B(o.ostats); q.ogroups = o.ogroups;
+        q.B = batch; q.HW = o.HW; q.C = o.C;
+        rc = gn_finalize(q, P->act, st);
+        break;
+      }
+      case OP_LINATTN:
+        rc = linattn_core(B(o.src1), B(o.out), batch, o.heads, o.dh, o.N, P->act, st);
+        break;
+      case OP_ATTN:
+        rc = attn_core(B(o.src1), B(o.out), batch, o.heads, o.dh, o.N, P->act, st);
+        break;
+      case OP_FINALPROJ: {
+        FinalProjP q;
+        q.y = B(o.src1); q.stats = (const float*)B(o.stats); q.groups = o.groups;
+        q.gamma = W(o.gamma); q.beta = W(o.beta); q.w = W(o.w); q.bias = W(o.bias);
+        q.out = out_dev; q.B = batch; q.HW = o.HW; q.C = o.C; q.Cout = o.Cout;
+        rc = final_proj(q, P->act, st);
+        break;
+      }
+    }
+    if (rc) {
+      set_error(o.name + ": " + g_err);
+      return rc;
+    }
+    ++op_i;
+    if (evs) cudaEventRecord((*evs)[op_i], st);
+  }
+  P->launches_per_forward = (int)(g_launches - launches0);
+  return 0;
+}
+
+static int check_ready(const dmn_plan* p) {
+  if (!p) return fail(DMN_EINVAL, "null plan");
+  if (!p->wbase || !p->wsbase) return fail(DMN_ESTATE, "plan is not bound to device memory (dmn_plan_bind)");
+  for (const auto& q : p->params)
+    if (!q.loaded) return fail(DMN_ESTATE, "parameter not loaded: " + q.name);
+  if (p->cfg.with_time_emb && !p->freqs_loaded) return fail(DMN_ESTATE, "sinusoid frequencies not loaded (dmn_plan_load_freqs)");
+  return 0;
+}
+
+}  // namespace dmn
+
+extern "C" {
+
+const char* dmn_last_error(void) { return g_err.c_str(); }
+int dmn_abi_version(void) { return DMN_ABI_VERSION; }
+
+int dmn_plan_create(const dmn_unet_cfg* cfg, dmn_plan** out) {
+  if (!cfg || !out) return fail(DMN_EINVAL, "null argument");
+  DMN_REQUIRE(cfg->n_mults >= 1 && cfg->n_mults <= 8, "n_mults out of range");
+  DMN_REQUIRE(cfg->dim >= 8 && cfg->dim % 8 == 0, "dim must be a multiple of 8");
+  DMN_REQUIRE(cfg->groups >= 1 && cfg->dim % cfg->groups == 0 && (cfg->dim / cfg->groups) % 4 == 0,
+              "resnet_block_groups must divide dim with at least 4 channels per group");
+  DMN_REQUIRE(cfg->channels >= 1 && cfg->channels <= 16 && cfg->out_dim >= 1 && cfg->out_dim <= 8, "channels / out_dim out of range");
+  DMN_REQUIRE(cfg->image_size >= 4 && cfg->max_batch >= 1, "image_size / max_batch out of range");
+  DMN_REQUIRE(cfg->act_dtype == DMN_ACT_F32 || cfg->act_dtype == DMN_ACT_BF16, "act_dtype");
+  DMN_REQUIRE(cfg->conv_engine == DMN_CONV_SIMT || (cfg->conv_engine == DMN_CONV_TCGEN05 && cfg->act_dtype == DMN_ACT_BF16),
+              "tcgen05 engine requires bf16 activations");
+  DMN_REQUIRE(cfg->with_time_emb == 1, "with_time_emb=False (WaveGradUNet) is not built yet");
+  for (int i = 0; i < cfg->n_mults; ++i) DMN_REQUIRE(cfg->dim_mults[i] >= 1, "dim_mults must be positive");
+  std::unique_ptr<dmn_plan> p(new dmn_plan());
+  p->cfg = *cfg;
+  if (p->cfg.max_time_rows < p->cfg.max_batch) p->cfg.max_time_rows = p->cfg.max_batch;
+  p->act = cfg->act_dtype;
+  p->engine = cfg->conv_engine;
+  p->esz = cfg->act_dtype == DMN_ACT_F32 ? 4 : 2;
+  Builder b(*p);
+  int rc = b.build();
+  if (rc) return rc;
+  *out = p.release();
+  return 0;
+}
+
+void dmn_plan_destroy(dmn_plan* p) { delete p; }
+size_t dmn_plan_weights_bytes(const dmn_plan* p) { return p ? p->weights_bytes : 0; }
+size_t dmn_plan_workspace_bytes(const dmn_plan* p) { return p ? p->ws_bytes : 0; }
+
+int dmn_plan_bind(dmn_plan* p, void* weights_dev, size_t weights_bytes, void* workspace_dev, size_t workspace_bytes) {
+  if (!p) return fail(DMN_EINVAL, "null plan");
+  DMN_REQUIRE(weights_dev && workspace_dev, "null device pointer");
+  DMN_REQUIRE(weights_bytes >= p->weights_bytes && workspace_bytes >= p->ws_bytes, "buffers smaller than dmn_plan_*_bytes()");
+  DMN_REQUIRE(((uintptr_t)weights_dev % 256) == 0 && ((uintptr_t)workspace_dev % 256) == 0, "device buffers must be 256-byte aligned");
+  p->wbase = (char*)weights_dev;
+  p->wsbase = (char*)workspace_dev;
+  for (auto& g : p->graphs)
+    if (g.exec) cudaGraphExecDestroy(g.exec);
+  p->graphs.clear();
+  return 0;
+}
+
+int dmn_plan_num_params(const dmn_plan* p) { return p ? (int)p->params.size() : 0; }
+const char* dmn_plan_param_name(const dmn_plan* p, int i) {
+  if (!p || i < 0 || i >= (int)p->params.size()) return nullptr;
+  return p->params[i].name.c_str();
+}
+int dmn_plan_param_shape(const dmn_plan* p, int i, int64_t shape_out[4]) {
+  if (!p || i < 0 || i >= (int)p->params.size()) return fail(DMN_EINVAL, "bad parameter index");
+  const auto& s = p->params[i].shape;
+  for (size_t k = 0; k < s.size() && k < 4; ++k) shape_out[k] = s[k];
+  return (int)s.size();
+}
+
+int dmn_plan_load_param(dmn_plan* p, const char* name, const float* host, int64_t numel, void* stream) {
+  if (!p || !name || !host) return fail(DMN_EINVAL, "null argument");
+  if (!p->wbase) return fail(DMN_ESTATE, "bind the plan before loading parameters");
+  auto it = p->pidx.find(name);
+  if (it == p->pidx.end()) return fail(DMN_EINVAL, std::string("unknown parameter: ") + name);
+  Param& q = p->params[it->second];
+  if (numel != q.numel()) return fail(DMN_EINVAL, std::string("size mismatch for ") + name);
+  cudaStream_t st = (cudaStream_t)stream;
+  const bool rb = p->act == DMN_ACT_BF16;
+  std::vector<float> tmp;
+  switch (q.kind) {
+    case PK_RAW:
+      DMN_CUDA_CHECK(cudaMemcpyAsync(p->wbase + q.off, host, numel * sizeof(float), cudaMemcpyHostToDevice, st));
+      break;
+    case PK_INIT: {
+      const int dim = (int)q.shape[0], ch = (int)q.shape[1];
+      tmp.resize(numel);
+      for (int co = 0; co < dim; ++co)
+        for (int ci = 0; ci < ch; ++ci)
+          for (int t = 0; t < 49; ++t) tmp[((long)t * ch + ci) * dim + co] = host[((long)co * ch + ci) * 49 + t];
+      DMN_CUDA_CHECK(cudaMemcpyAsync(p->wbase + q.off, tmp.data(), numel * sizeof(float), cudaMemcpyHostToDevice, st));
+      break;
+    }
+    case PK_LIN_T: {
+      const int no = (int)q.shape[0], ni = (int)q.shape[1];
+      tmp.resize(numel);
+      for (int o = 0; o < no; ++o)
+        for (int i = 0; i < ni; ++i) tmp[(long)i * no + o] = host[(long)o * ni + i];
+      DMN_CUDA_CHECK(cudaMemcpyAsync(p->wbase + q.off, tmp.data(), numel * sizeof(float), cudaMemcpyHostToDevice, st));
+      break;
+    }
+    case PK_BLOCK_MLP_W: {
+      const int co = (int)q.shape[0], td = (int)q.shape[1];
+      tmp.resize(numel);
+      for (int o = 0; o < co; ++o)
+        for (int i = 0; i < td; ++i) tmp[(long)i * co + o] = host[(long)o * td + i];
+      // strided destination: row i of [4dim][sumC], columns [col, col+co)
+      DMN_CUDA_CHECK(cudaMemcpy2DAsync(p->wbase + p->off_wct + (size_t)q.col * sizeof(float), (size_t)p->sumC * sizeof(float),
+                                       tmp.data(), (size_t)co * sizeof(float), (size_t)co * sizeof(float), td,
+                                       cudaMemcpyHostToDevice, st));
+      break;
+    }
+    case PK_BLOCK_MLP_B:
+      DMN_CUDA_CHECK(cudaMemcpyAsync(p->wbase + p->off_bc + (size_t)q.col * sizeof(float), host, numel * sizeof(float),
+                                     cudaMemcpyHostToDevice, st));
+      break;
+    case PK_CONV: {
+      if (q.has_simt) {
+        tmp.resize(numel);
+        conv_simt_pack_weights(q.mode, q.ksize, q.cin, q.cout, host, tmp.data(), rb);
+        DMN_CUDA_CHECK(cudaMemcpyAsync(p->wbase + q.off, tmp.data(), numel * sizeof(float), cudaMemcpyHostToDevice, st));
+      }
+      if (q.has_tc) {
+        const size_t nb = conv_tcgen05_weight_bytes(q.mode, q.ksize, q.cin, q.cout);
+        std::vector<char> img(nb);
+        conv_tcgen05_pack_weights(q.mode, q.ksize, q.cin, q.cout, host, img.data());
+        DMN_CUDA_CHECK(cudaMemcpyAsync(p->wbase + q.off2, img.data(), nb, cudaMemcpyHostToDevice, st));
+        DMN_CUDA_CHECK(cudaStreamSynchronize(st));
+      }
+      break;
+    }
+  }
+  DMN_CUDA_CHECK(cudaStreamSynchronize(st));   // staging buffers are stack-scoped
+  q.loaded = true;
+  return 0;
+}
+
+int dmn_plan_load_freqs(dmn_plan* p, const float* host_freqs, int n, void* stream) {
+  if (!p || !host_freqs) return fail(DMN_EINVAL, "null argument");
+  if (!p->wbase) return fail(DMN_ESTATE, "bind the plan before loading parameters");
+  DMN_REQUIRE(n == p->cfg.dim / 2, "expected dim/2 frequencies");
+  DMN_CUDA_CHECK(cudaMemcpyAsync(p->wbase + p->off_freqs, host_freqs, n * sizeof(float), cudaMemcpyHostToDevice, (cudaStream_t)stream));
+  DMN_CUDA_CHECK(cudaStreamSynchronize((cudaStream_t)stream));
+  p->freqs_loaded = true;
+  return 0;
+}
+
+int dmn_plan_ready(const dmn_plan* p) { return check_ready(p) == 0 ? 1 : 0; }
+
+int dmn_time_table(dmn_plan* p, const float* times_dev, int row0, int rows, void* stream) {
+  int rc = check_ready(p);
+  if (rc) return rc;
+  DMN_REQUIRE(times_dev && row0 >= 0 && rows > 0 && row0 + rows <= p->cfg.max_time_rows, "time table rows out of range");
+  const int dim = p->cfg.dim;
+  TimeP t;
+  t.times = times_dev;
+  t.freqs = (const float*)(p->wbase + p->off_freqs);
+  t.w1t = (const float*)(p->wbase + p->params[p->pidx["time_mlp.1.weight"]].off);
+  t.b1 = (const float*)(p->wbase + p->params[p->pidx["time_mlp.1.bias"]].off);
+  t.w3t = (const float*)(p->wbase + p->params[p->pidx["time_mlp.3.weight"]].off);
+  t.b3 = (const float*)(p->wbase + p->params[p->pidx["time_mlp.3.bias"]].off);
+  t.wct = (const float*)(p->wbase + p->off_wct);
+  t.bc = (const float*)(p->wbase + p->off_bc);
+  t.tmp = (float*)(p->wsbase + p->time_tmp.off) + (size_t)row0 * 8 * dim;
+  t.table = (float*)(p->wsbase + p->time_table.off) + (size_t)row0 * p->sumC;
+  t.rows = rows; t.dim = dim; t.sumC = p->sumC;
+  return time_table(t, (cudaStream_t)stream);
+}
+
+int dmn_unet_forward(dmn_plan* p, const float* x_dev, const int32_t* row_dev, const int64_t* classes_dev, float* out_dev,
+                     int batch, void* stream) {
+  int rc = check_ready(p);
+  if (rc) return rc;
+  DMN_REQUIRE(x_dev && out_dev, "null tensor");
+  DMN_REQUIRE(batch >= 1 && batch <= p->cfg.max_batch, "batch exceeds the plan's max_batch");
+  return run_forward(p, x_dev, row_dev, classes_dev, out_dev, batch, (cudaStream_t)stream);
+}
+
+int dmn_plan_launches_per_forward(const dmn_plan* p) { return p ? p->launches_per_forward : 0; }
+
+int dmn_plan_num_ops(const dmn_plan* p) { return p ? (int)p->ops.size() : 0; }
+
+int dmn_plan_op_info(const dmn_plan* p, int i, char* name_out, int name_cap, int32_t* kind, int32_t* engine,
+                     double* flops_per_sample, double* bytes_per_sample) {
+  if (!p || i < 0 || i >= (int)p->ops.size()) return fail(DMN_EINVAL, "bad op index");
+  const Op& o = p->ops[i];
+  const dmn_unet_cfg& c = p->cfg;
+  const double esz = (double)p->esz;
+  double fl = 0, by = 0;
+  switch (o.kind) {
+    case OP_MEMSET: by = (double)p->stats_bytes / c.max_batch; break;
+    case OP_INIT:
+      fl = 2.0 * c.image_size * c.image_size * 49.0 * c.channels * c.dim;
+      by = 4.0 * c.image_size * c.image_size * c.channels + esz * c.image_size * c.image_size * c.dim;
+      break;
+    case OP_CONV: {
+      const double cin = o.C1 + o.C2;
+      const double taps = o.mode == CONV_SAME ? o.ksize * o.ksize : 16.0;
+      const double mpix = o.mode == CONV_UP ? (double)o.Hin * o.Hin : (double)o.Hout * o.Hout;   // MACs counted on the strided side
+      fl = 2.0 * mpix * taps * cin * o.Cout;
+      by = esz * ((double)o.Hin * o.Hin * cin + (double)o.Hout * o.Hout * o.Cout * (o.res.valid() ? 2.0 : 1.0)) + 2.0 * taps * cin * o.Cout / c.max_batch;
+      break;
+    }
+    case OP_FINALIZE: by = esz * (double)o.HW * o.C * 3.0; break;
+    case OP_LINATTN: fl = 2.0 * 2.0 * o.heads * o.dh * o.dh * o.N; by = esz * (double)o.N * o.heads * o.dh * 4.0; break;
+    case OP_ATTN: fl = 2.0 * 2.0 * o.heads * o.dh * (double)o.N * o.N; by = esz * (double)o.N * o.heads * o.dh * 4.0; break;
+    case OP_FINALPROJ: fl = 2.0 * o.HW * o.C * o.Cout; by = esz * (double)o.HW * o.C + 4.0 * o.HW * o.Cout; break;
+  }
+  if (name_out && name_cap > 0) {
+    strncpy(name_out, o.name.c_str(), (size_t)name_cap - 1);
+    name_out[name_cap - 1] = 0;
+  }
+  if (kind) *kind = o.kind;
+  if (engine) *engine = (o.kind == OP_CONV && o.tc) ? 1 : 0;
+  if (flops_per_sample) *flops_per_sample = fl;
+  if (bytes_per_sample) *bytes_per_sample = by;
+  return 0;
+}
+
+int dmn_plan_profile_forward(dmn_plan* p, const float* x_dev, const int32_t* row_dev, const int64_t* classes_dev,
+                             float* out_dev, int batch, void* stream, float* ms_out, int max_ops) {
+  int rc = check_ready(p);
+  if (rc) return rc;
+  DMN_REQUIRE(x_dev && out_dev && ms_out, "null tensor");
+  DMN_REQUIRE(batch >= 1 && batch <= p->cfg.max_batch, "batch exceeds the plan's max_batch");
+  DMN_REQUIRE(max_ops >= (int)p->ops.size(), "ms_out too small (dmn_plan_num_ops)");
+  std::vector<cudaEvent_t> evs(p->ops.size() + 1);
+  for (auto& e : evs) DMN_CUDA_CHECK(cudaEventCreate(&e));
+  rc = run_forward(p, x_dev, row_dev, classes_dev, out_dev, batch, (cudaStream_t)stream, &evs);
+  if (!rc) {
+    cudaError_t e = cudaStreamSynchronize((cudaStream_t)stream);
+    if (e != cudaSuccess) rc = fail(DMN_ECUDA, std::string("profile_forward: ") + cudaGetErrorString(e));
+  }
+  if (!rc)
+    for (size_t i = 0; i < p->ops.size(); ++i) cudaEventElapsedTime(&ms_out[i], evs[i], evs[i + 1]);
+  for (auto& e : evs) cudaEventDestroy(e);
+  return rc;
+}
+
+}  // extern "C"
+
+// ---------------------------------------------------------------------------------------------------------
+// loop driver
+// ---------------------------------------------------------------------------------------------------------
+// One loop step.  `ctr` = device step counter (graph mode) or nullptr with host step `s` (injected-noise mode);
+// `z0` = this step's injected noise block (draws x n floats) or nullptr for in-kernel Philox with device rng state.
+static int enqueue_step(dmn_plan* p, const dmn_loop_desc* d, int32_t* ctr_dev, bool use_ctr, int s, const float* z0,
+                        cudaStream_t st) {
+  const dmn_unet_cfg& c = p->cfg;
+  const long chw = (long)c.channels * c.image_size * c.image_size;
+  const long n = (long)d->batch * chw;
+  const long n_out = (long)d->batch * c.out_dim * c.image_size * c.image_size;
+  float* mo = d->scratch_dev;              // model output
+  float* xmean = d->scratch_dev + n_out;   // PC: x_mean
+  float* lscr = xmean + n;                 // Langevin scratch: 2*batch + 2 floats
+  const int32_t* step_dev = use_ctr ? ctr_dev : nullptr;
+  const dmn_rng* rng_dev = z0 ? nullptr : reinterpret_cast<const dmn_rng*>(ctr_dev + 4);
+  int rc;
+  if (d->kind == DMN_LOOP_PC) {
+    for (int k = 0; k < d->n_corr; ++k) {
+      if ((rc = run_forward(p, d->state_dev, ctr_dev, d->classes_dev, mo, d->batch, st))) return rc;
+      const float* zk = z0 ? z0 + (long)k * n : nullptr;
+      if (d->corr_kind == 1)
+        rc = launch_affine_noise(d->state_dev, mo, zk, d->state_dev, xmean, n, d->coef2_dev, step_dev, s, k, d->rng, rng_dev, st);
+      else
+        rc = launch_langevin(d->state_dev, mo, zk, d->state_dev, xmean, d->batch, chw, d->snr, d->coef2_dev, step_dev, s, k, lscr,
+                             d->rng, rng_dev, st);
+      if (rc) return rc;
+    }
+    if ((rc = run_forward(p, d->state_dev, ctr_dev, d->classes_dev, mo, d->batch, st))) return rc;
+    const float* zp = z0 ? z0 + (long)d->n_corr * n : nullptr;
+    if ((rc = launch_affine_noise(d->state_dev, mo, zp, d->state_dev, xmean, n, d->coef_dev, step_dev, s, 7, d->rng, rng_dev, st)))
+      return rc;
+  } else {
+    if ((rc = run_forward(p, d->state_dev, ctr_dev, d->classes_dev, mo, d->batch, st))) return rc;
+    if (d->kind == DMN_LOOP_DDPM)
+      rc = launch_ddpm(d->state_dev, mo, z0, d->state_dev, n, d->coef_dev, step_dev, s, d->rng, rng_dev, st);
+    else if (d->kind == DMN_LOOP_LEARNED)
+      rc = launch_learned(d->state_dev, mo, z0, d->state_dev, d->batch, chw, d->coef_dev, step_dev, s, d->rng, rng_dev, st);
+    else
+      rc = launch_ddim(d->state_dev, mo, z0, d->state_dev, n, d->coef_dev, step_dev, s, d->rng, rng_dev, st);
+    if (rc) return rc;
+  }
+  if (d->traj_dev && d->traj_every > 0)
+    if ((rc = launch_traj(d->state_dev, d->traj_dev, n, ctr_dev, d->traj_every, d->n_steps, st))) return rc;
+  return launch_advance_counter(ctr_dev, st);
+}
+
+// the graph bakes in every pointer and scalar below; the RNG seed is NOT baked (it lives in device memory)
+static bool same_graph_key(const dmn_loop_desc& a, const dmn_loop_desc& b) {
+  const bool traj = a.traj_dev || b.traj_dev;   // only the trajectory kernel bakes n_steps in
+  return a.kind == b.kind && (!traj || a.n_steps == b.n_steps) && a.batch == b.batch && a.n_corr == b.n_corr && a.snr == b.snr &&
+         a.corr_kind == b.corr_kind && a.coef_dev == b.coef_dev && a.coef2_dev == b.coef2_dev && a.classes_dev == b.classes_dev &&
+         a.state_dev == b.state_dev && a.scratch_dev == b.scratch_dev && a.traj_dev == b.traj_dev && a.traj_every == b.traj_every;
+}
+
+extern "C" {
+
+int dmn_sample_loop(dmn_plan* p, const dmn_loop_desc* d, void* stream) {
+  int rc = check_ready(p);
+  if (rc) return rc;
+  if (!d) return fail(DMN_EINVAL, "null descriptor");
+  const dmn_unet_cfg& c = p->cfg;
+  DMN_REQUIRE(d->kind >= DMN_LOOP_DDPM && d->kind <= DMN_LOOP_PC, "unknown loop kind");
+  DMN_REQUIRE(d->batch >= 1 && d->batch <= c.max_batch, "batch exceeds the plan's max_batch");
+  DMN_REQUIRE(d->n_steps >= 1 && d->n_steps <= c.max_time_rows, "n_steps exceeds the plan's time table");
+  DMN_REQUIRE(d->state_dev && d->scratch_dev && d->coef_dev, "null device pointer in loop descriptor");
+  DMN_REQUIRE(d->kind != DMN_LOOP_PC || d->n_corr == 0 || d->coef2_dev, "PC loop needs corrector coefficients");
+  DMN_REQUIRE(d->n_corr >= 0 && d->n_corr <= 6, "n_corr out of range (0..6)");
+  if (d->kind == DMN_LOOP_LEARNED) DMN_REQUIRE(c.out_dim == 2 * c.channels, "learned-variance loop needs a U-Net with 2*channels outputs");
+  else DMN_REQUIRE(c.out_dim == c.channels, "U-Net out_dim must equal channels for this sampler");
+  const long chw = (long)c.channels * c.image_size * c.image_size;
+  const long n = (long)d->batch * chw;
+  const long n_out = (long)d->batch * c.out_dim * c.image_size * c.image_size;
+  DMN_REQUIRE(d->scratch_bytes >= (size_t)(n_out + n + 2 * d->batch + 16) * sizeof(float), "loop scratch too small");
+  cudaStream_t st = (cudaStream_t)stream;
+  int32_t* ctr = (int32_t*)(p->wsbase + p->counters.off);
+  float* xmean = d->scratch_dev + n_out;
+  if ((rc = launch_set_counter(ctr, 0, d->rng, st))) return rc;
+
+  if (d->noise_dev) {
+    // parity mode: injected noise => per-step pointers differ, plain launches with the host step index
+    const int draws = (d->kind == DMN_LOOP_PC) ? d->n_corr + 1 : 1;
+    for (int s = 0; s < d->n_steps; ++s)
+      if ((rc = enqueue_step(p, d, ctr, false, s, d->noise_dev + (long)s * draws * n, st))) return rc;
+  } else if (!d->use_graph) {
+    for (int s = 0; s < d->n_steps; ++s)
+      if ((rc = enqueue_step(p, d, ctr, true, 0, nullptr, st))) return rc;
+  } else {
+    cudaGraphExec_t exec = nullptr;
+    for (auto& g : p->graphs)
+      if (same_graph_key(g.key, *d)) exec = g.exec;
+    if (!exec) {
+      cudaStream_t cs;
+      DMN_CUDA_CHECK(cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking));
+      cudaGraph_t graph = nullptr;
+      cudaError_t e = cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal);
+      if (e != cudaSuccess) {
+        cudaStreamDestroy(cs);
+        return fail(DMN_ECUDA, std::string("begin capture: ") + cudaGetErrorString(e));
+      }
+      rc = enqueue_step(p, d, ctr, true, 0, nullptr, cs);
+      e = cudaStreamEndCapture(cs, &graph);
+      cudaStreamDestroy(cs);
+      if (rc) {
+        if (graph) cudaGraphDestroy(graph);
+        return rc;
+      }
+      if (e != cudaSuccess) return fail(DMN_ECUDA, std::string("end capture: ") + cudaGetErrorString(e));
+      e = cudaGraphInstantiate(&exec, graph, 0);
+      cudaGraphDestroy(graph);
+      if (e != cudaSuccess) return fail(DMN_ECUDA, std::string("graph instantiate: ") + cudaGetErrorString(e));
+      if (p->graphs.size() >= 8) {
+        cudaGraphExecDestroy(p->graphs.front().exec);
+        p->graphs.erase(p->graphs.begin());
+      }
+      dmn_plan::GraphEntry ge;
+      ge.exec = exec;
+      ge.key = *d;
+      p->graphs.push_back(ge);
+    }
+    for (int s = 0; s < d->n_steps; ++s) DMN_CUDA_CHECK(cudaGraphLaunch(exec, st));
+    count_launch((int)((long)d->n_steps * dmn_loop_launches_per_step(p, d)));
+  }
+  if (d->kind == DMN_LOOP_PC && d->aux_dev)
+    DMN_CUDA_CHECK(cudaMemcpyAsync(d->aux_dev, xmean, n * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  return 0;
+}
+
+int dmn_loop_launches_per_step(const dmn_plan* p, const dmn_loop_desc* d) {
+  if (!p || !d) return 0;
+  const int per_fwd = (int)p->ops.size() - 1;   // kernels only: the statistics memset is not counted
+  int n = 0;
+  if (d->kind == DMN_LOOP_PC) n = (d->n_corr + 1) * per_fwd + d->n_corr * (d->corr_kind == 1 ? 1 : 3) + 1;
+  else n = per_fwd + 1;
+  if (d->traj_dev && d->traj_every > 0) n += 1;
+  return n + 1;   // + advance_counter
+}
+
+}  // extern "C"

@@ -1,0 +1,389 @@
+// sampler.cu -- the per-step posterior / score updates as single vectorised, coalesced elementwise kernels.
+//
+// Algorithmic traffic per element (fp32): read x, model output, z (parity mode) and write x  = 16 B;
+// with in-kernel Philox noise = 12 B.  These kernels are HBM/launch bound (about 2 us at B = 256, 3x32x32).
+#include "../../include/dmn_b200.h"
+#include "common.cuh"
+
+namespace dmn {
+
+// ---- Philox4x32-10, counter = (quad index lo, quad index hi, step word, stream id), key = seed ----------
+struct Philox {
+  __device__ static inline uint4 gen(uint64_t seed, uint64_t stream_id, uint32_t step_word, uint64_t quad) {
+    uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+    uint32_t c0 = (uint32_t)quad, c1 = (uint32_t)(quad >> 32), c2 = step_word, c3 = (uint32_t)stream_id ^ (uint32_t)(stream_id >> 32) * 0x9E3779B9u;
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+      const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+      const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+      const uint32_t n0 = hi1 ^ c1 ^ k0, n1 = lo1, n2 = hi0 ^ c3 ^ k1, n3 = lo0;
+      c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+      k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    return make_uint4(c0, c1, c2, c3);
+  }
+  __device__ static inline float4 normal4(uint64_t seed, uint64_t stream_id, uint32_t step_word, uint64_t quad) {
+    const uint4 r = gen(seed, stream_id, step_word, quad);
+    // Box-Muller on two pairs; u in (0,1]
+    const float u0 = ((float)r.x + 1.0f) * 2.3283064365386963e-10f;
+    const float u1 = (float)r.y * 2.3283064365386963e-10f;
+    const float u2 = ((float)r.z + 1.0f) * 2.3283064365386963e-10f;
+    const float u3 = (float)r.w * 2.3283064365386963e-10f;
+    const float ra = sqrtf(-2.0f * __logf(u0)), rb = sqrtf(-2.0f * __logf(u2));
+    float s0, c0, s1, c1;
+    __sincosf(6.283185307179586f * u1, &s0, &c0);
+    __sincosf(6.283185307179586f * u3, &s1, &c1);
+    return make_float4(ra * c0, ra * s0, rb * c1, rb * s1);
+  }
+};
+
+__device__ __forceinline__ const float* coef_row(const float* coef, const int32_t* step_dev, int step) {
+  return coef + (long)(step_dev ? *step_dev : step) * DMN_COEF_STRIDE;
+}
+__device__ __forceinline__ uint32_t step_word(const int32_t* step_dev, int step, int draw) {
+  return (uint32_t)((step_dev ? *step_dev : step) + 1) * 8u + (uint32_t)draw;
+}
+__device__ __forceinline__ dmn_rng pick_rng(const dmn_rng& by_value, const dmn_rng* dev) { return dev ? *dev : by_value; }
+__device__ __forceinline__ float clamp1(float v) { return fminf(fmaxf(v, -1.0f), 1.0f); }
+
+// generic 4-wide element loop helpers: n must be a multiple of 4 (C*H*W of images always is here; checked on host)
+
+__global__ void __launch_bounds__(256) ddpm_step_kernel(const float* __restrict__ x, const float* __restrict__ eps,
+                                                        const float* __restrict__ z, float* __restrict__ out, long n4,
+                                                        const float* __restrict__ coef, const int32_t* step_dev, int step,
+                                                        dmn_rng rng_v, const dmn_rng* rng_dev) {
+  const dmn_rng rng = pick_rng(rng_v, rng_dev);
+  const float* c = coef_row(coef, step_dev, step);
+  const float c0 = c[0], c1 = c[1], c2 = c[2], c3 = c[3], c4 = c[4];
+  const bool pred_x0 = c[5] != 0.f;
+  const uint32_t sw = step_word(step_dev, step, 0);
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long)gridDim.x * blockDim.x) {
+    const float4 xv = reinterpret_cast<const float4*>(x)[i];
+    const float4 ev = reinterpret_cast<const float4*>(eps)[i];
+    const float4 zv = z ? reinterpret_cast<const float4*>(z)[i] : Philox::normal4(rng.seed, rng.stream_id, sw, (uint64_t)i);
+    float4 o;
+#define DMN_DDPM(f)                                                    \
+  {                                                                    \
+    float x0 = pred_x0 ? ev.f : (c0 * xv.f - c1 * ev.f);               \
+    x0 = clamp1(x0);                                                   \
+    const float mean = c2 * x0 + c3 * xv.f;                            \
+    o.f = mean + c4 * zv.f;                                            \
+  }
+    DMN_DDPM(x) DMN_DDPM(y) DMN_DDPM(z) DMN_DDPM(w)
+#undef DMN_DDPM
+    reinterpret_cast<float4*>(out)[i] = o;
+  }
+}
+
+__global__ void __launch_bounds__(256) learned_step_kernel(const float* __restrict__ x, const float* __restrict__ mo,
+                                                           const float* __restrict__ z, float* __restrict__ out, long chw4,
+                                                           long n4, const float* __restrict__ coef, const int32_t* step_dev,
+                                                           int step, dmn_rng rng_v, const dmn_rng* rng_dev) {
+  const dmn_rng rng = pick_rng(rng_v, rng_dev);
+  const float* c = coef_row(coef, step_dev, step);
+  const float c0 = c[0], c1 = c[1], c2 = c[2], c3 = c[3], mask = c[4], min_log = c[5], max_log = c[6];
+  const uint32_t sw = step_word(step_dev, step, 0);
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long)gridDim.x * blockDim.x) {
+    const long b = i / chw4, r = i - b * chw4;
+    const float4 xv = reinterpret_cast<const float4*>(x)[i];
+    const float4 ev = reinterpret_cast<const float4*>(mo)[b * 2 * chw4 + r];
+    const float4 vv = reinterpret_cast<const float4*>(mo)[b * 2 * chw4 + chw4 + r];
+    const float4 zv = z ? reinterpret_cast<const float4*>(z)[i] : Philox::normal4(rng.seed, rng.stream_id, sw, (uint64_t)i);
+    float4 o;
+#define DMN_LRN(f)                                                     \
+  {                                                                    \
+    const float frac = (vv.f + 1.0f) * 0.5f;                           \
+    const float logvar = frac * max_log + (1.0f - frac) * min_log;     \
+    float x0 = clamp1(c0 * xv.f - c1 * ev.f);                          \
+    const float mean = c2 * x0 + c3 * xv.f;                            \
+    o.f = mean + mask * expf(0.5f * logvar) * zv.f;                    \
+  }
+    DMN_LRN(x) DMN_LRN(y) DMN_LRN(z) DMN_LRN(w)
+#undef DMN_LRN
+    reinterpret_cast<float4*>(out)[i] = o;
+  }
+}
+
+__global__ void __launch_bounds__(256) ddim_step_kernel(const float* __restrict__ x, const float* __restrict__ eps,
+                                                        const float* __restrict__ z, float* __restrict__ out, long n4,
+                                                        const float* __restrict__ coef, const int32_t* step_dev, int step,
+                                                        dmn_rng rng_v, const dmn_rng* rng_dev) {
+  const dmn_rng rng = pick_rng(rng_v, rng_dev);
+  // row: {sqrt(1-a_t), sqrt(a_t), sqrt(a_next), c1, c2, pred_x0}
+  const float* c = coef_row(coef, step_dev, step);
+  const float s1m = c[0], sa = c[1], san = c[2], k1 = c[3], k2 = c[4];
+  const bool pred_x0 = c[5] != 0.f;
+  const bool need_z = k1 != 0.f;
+  const uint32_t sw = step_word(step_dev, step, 0);
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long)gridDim.x * blockDim.x) {
+    const float4 xv = reinterpret_cast<const float4*>(x)[i];
+    const float4 ev = reinterpret_cast<const float4*>(eps)[i];
+    float4 zv = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (z) zv = reinterpret_cast<const float4*>(z)[i];
+    else if (need_z) zv = Philox::normal4(rng.seed, rng.stream_id, sw, (uint64_t)i);
+    float4 o;
+#define DMN_DDIM(f)                                                    \
+  {                                                                    \
+    float x0 = pred_x0 ? ev.f : (xv.f - ev.f * s1m) / sa;              \
+    x0 = clamp1(x0);                                                   \
+    o.f = san * x0 + k1 * zv.f + k2 * ev.f;                            \
+  }
+    DMN_DDIM(x) DMN_DDIM(y) DMN_DDIM(z) DMN_DDIM(w)
+#undef DMN_DDIM
+    reinterpret_cast<float4*>(out)[i] = o;
+  }
+}
+
+__global__ void __launch_bounds__(256) affine_noise_kernel(const float* __restrict__ x, const float* __restrict__ mo,
+                                                           const float* __restrict__ z, float* __restrict__ out,
+                                                           float* __restrict__ mean_out, long n4, const float* __restrict__ coef,
+                                                           const int32_t* step_dev, int step, int draw, dmn_rng rng_v, const dmn_rng* rng_dev) {
+  const dmn_rng rng = pick_rng(rng_v, rng_dev);
+  const float* c = coef_row(coef, step_dev, step);
+  const float a = c[0], b = c[1], g = c[2];
+  const uint32_t sw = step_word(step_dev, step, draw);
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long)gridDim.x * blockDim.x) {
+    const float4 xv = reinterpret_cast<const float4*>(x)[i];
+    const float4 mv = reinterpret_cast<const float4*>(mo)[i];
+    const float4 zv = z ? reinterpret_cast<const float4*>(z)[i] : Philox::normal4(rng.seed, rng.stream_id, sw, (uint64_t)i);
+    float4 m, o;
+    m.x = a * xv.x + b * mv.x; m.y = a * xv.y + b * mv.y; m.z = a * xv.z + b * mv.z; m.w = a * xv.w + b * mv.w;
+    o.x = m.x + g * zv.x; o.y = m.y + g * zv.y; o.z = m.z + g * zv.z; o.w = m.w + g * zv.w;
+    if (mean_out) reinterpret_cast<float4*>(mean_out)[i] = m;
+    reinterpret_cast<float4*>(out)[i] = o;
+  }
+}
+
+// Langevin: per-sample sums of squares of g = scale*model_out and z  -> ssq[b][2]
+__global__ void __launch_bounds__(256) langevin_sumsq_kernel(const float* __restrict__ mo, const float* __restrict__ z,
+                                                             float* __restrict__ ssq, long chw4, const float* __restrict__ coef,
+                                                             const int32_t* step_dev, int step, int draw, dmn_rng rng_v, const dmn_rng* rng_dev) {
+  const dmn_rng rng = pick_rng(rng_v, rng_dev);
+  __shared__ float red[2][8];
+  const int b = blockIdx.y;
+  const float scale = coef_row(coef, step_dev, step)[0];
+  const uint32_t sw = step_word(step_dev, step, draw);
+  float sg = 0.f, sz = 0.f;
+  for (long r = (long)blockIdx.x * blockDim.x + threadIdx.x; r < chw4; r += (long)gridDim.x * blockDim.x) {
+    const long i = (long)b * chw4 + r;
+    float4 g = reinterpret_cast<const float4*>(mo)[i];
+    g.x *= scale; g.y *= scale; g.z *= scale; g.w *= scale;
+    const float4 zv = z ? reinterpret_cast<const float4*>(z)[i] : Philox::normal4(rng.seed, rng.stream_id, sw, (uint64_t)i);
+    sg += g.x * g.x + g.y * g.y + g.z * g.z + g.w * g.w;
+    sz += zv.x * zv.x + zv.y * zv.y + zv.z * zv.z + zv.w * zv.w;
+  }
+  sg = warp_sum(sg);
+  sz = warp_sum(sz);
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane == 0) { red[0][w] = sg; red[1][w] = sz; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float a = 0.f, c = 0.f;
+    for (int i = 0; i < 8; ++i) { a += red[0][i]; c += red[1][i]; }
+    atomicAdd(ssq + 2 * b, a);
+    atomicAdd(ssq + 2 * b + 1, c);
+  }
+}
+// batch means of the per-sample norms  -> means[0] = mean ||g_b||, means[1] = mean ||z_b||
+__global__ void langevin_means_kernel(const float* __restrict__ ssq, float* __restrict__ means, int B) {
+  float a = 0.f, c = 0.f;
+  for (int b = threadIdx.x; b < B; b += 32) { a += sqrtf(ssq[2 * b]); c += sqrtf(ssq[2 * b + 1]); }
+  a = warp_sum(a);
+  c = warp_sum(c);
+  if (threadIdx.x == 0) { means[0] = a / (float)B; means[1] = c / (float)B; }
+}
+__global__ void __launch_bounds__(256) langevin_apply_kernel(const float* __restrict__ x, const float* __restrict__ mo,
+                                                             const float* __restrict__ z, float* __restrict__ out,
+                                                             float* __restrict__ mean_out, long n4, float snr,
+                                                             const float* __restrict__ means, const float* __restrict__ coef,
+                                                             const int32_t* step_dev, int step, int draw, dmn_rng rng_v, const dmn_rng* rng_dev) {
+  const dmn_rng rng = pick_rng(rng_v, rng_dev);
+  const float* c = coef_row(coef, step_dev, step);
+  const float scale = c[0], alpha = c[1];
+  const float ratio = snr * means[1] / means[0];
+  const float ss = ratio * ratio * 2.0f * alpha;
+  const float nz = sqrtf(ss * 2.0f);
+  const uint32_t sw = step_word(step_dev, step, draw);
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long)gridDim.x * blockDim.x) {
+    const float4 xv = reinterpret_cast<const float4*>(x)[i];
+    float4 g = reinterpret_cast<const float4*>(mo)[i];
+    g.x *= scale; g.y *= scale; g.z *= scale; g.w *= scale;
+    const float4 zv = z ? reinterpret_cast<const float4*>(z)[i] : Philox::normal4(rng.seed, rng.stream_id, sw, (uint64_t)i);
+    float4 m, o;
+    m.x = xv.x + ss * g.x; m.y = xv.y + ss * g.y; m.z = xv.z + ss * g.z; m.w = xv.w + ss * g.w;
+    o.x = m.x + nz * zv.x; o.y = m.y + nz * zv.y; o.z = m.z + nz * zv.z; o.w = m.w + nz * zv.w;
+    if (mean_out) reinterpret_cast<float4*>(mean_out)[i] = m;
+    reinterpret_cast<float4*>(out)[i] = o;
+  }
+}
+
+__global__ void __launch_bounds__(256) unnormalize_kernel(const float* __restrict__ x, float* __restrict__ out, long n) {
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x)
+    out[i] = (x[i] + 1.0f) * 0.5f;
+}
+__global__ void __launch_bounds__(256) axpby_kernel(const float* __restrict__ x, const float* __restrict__ y, float a, float b,
+                                                    float* __restrict__ out, long n) {
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x)
+    out[i] = a * x[i] + b * y[i];
+}
+__global__ void __launch_bounds__(256) randn_kernel(float* __restrict__ out, long n4, dmn_rng rng, uint32_t sw) {
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long)gridDim.x * blockDim.x)
+    reinterpret_cast<float4*>(out)[i] = Philox::normal4(rng.seed, rng.stream_id, sw, (uint64_t)i);
+}
+__global__ void advance_counter_kernel(int32_t* c) { *c += 1; }
+// loop state: int32 step counter at [0], dmn_rng at byte offset 16
+__global__ void set_counter_kernel(int32_t* c, int v, dmn_rng rng) {
+  *c = v;
+  *reinterpret_cast<dmn_rng*>(c + 4) = rng;
+}
+// copy every `every`-th step's state into the trajectory buffer (device-side decision => graph friendly)
+__global__ void __launch_bounds__(256) traj_kernel(const float* __restrict__ x, float* __restrict__ traj, long n4,
+                                                   const int32_t* step_dev, int every, int n_steps) {
+  const int s = *step_dev;
+  if (((s + 1) % every) != 0 || s >= n_steps) return;
+  const long slot = (long)((s + 1) / every - 1);
+  float4* dst = reinterpret_cast<float4*>(traj) + slot * n4;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long)gridDim.x * blockDim.x)
+    dst[i] = reinterpret_cast<const float4*>(x)[i];
+}
+
+static inline unsigned grid_for(long n, int per_block = 256, int cap = 148 * 8) {
+  long g = (n + per_block - 1) / per_block;
+  if (g < 1) g = 1;
+  if (g > cap) g = cap;
+  return (unsigned)g;
+}
+
+int launch_advance_counter(int32_t* c, cudaStream_t st) {
+  advance_counter_kernel<<<1, 1, 0, st>>>(c);
+  count_launch();
+  DMN_LAUNCH_CHECK("advance_counter");
+  return 0;
+}
+int launch_set_counter(int32_t* c, int v, dmn_rng rng, cudaStream_t st) {
+  set_counter_kernel<<<1, 1, 0, st>>>(c, v, rng);
+  count_launch();
+  DMN_LAUNCH_CHECK("set_counter");
+  return 0;
+}
+int launch_traj(const float* x, float* traj, long n, const int32_t* step_dev, int every, int n_steps, cudaStream_t st) {
+  traj_kernel<<<grid_for(n / 4), 256, 0, st>>>(x, traj, n / 4, step_dev, every, n_steps);
+  count_launch();
+  DMN_LAUNCH_CHECK("traj");
+  return 0;
+}
+int launch_langevin(const float* x, const float* mo, const float* z, float* out, float* mean_out, int batch, long chw,
+                    float snr, const float* coef, const int32_t* step_dev, int step, int draw, float* scratch, dmn_rng rng,
+                    const dmn_rng* rng_dev, cudaStream_t st) {
+  DMN_REQUIRE(chw % 4 == 0, "langevin: C*H*W must be a multiple of 4");
+  float* ssq = scratch;                 // [batch][2]
+  float* means = scratch + 2 * batch;   // [2]
+  DMN_CUDA_CHECK(cudaMemsetAsync(ssq, 0, sizeof(float) * 2 * batch, st));
+  count_launch();
+  int bps = (int)((chw / 4 + 255) / 256);
+  if (bps > 8) bps = 8;
+  langevin_sumsq_kernel<<<dim3(bps, batch), 256, 0, st>>>(mo, z, ssq, chw / 4, coef, step_dev, step, draw, rng, rng_dev);
+  count_launch();
+  DMN_LAUNCH_CHECK("langevin_sumsq");
+  langevin_means_kernel<<<1, 32, 0, st>>>(ssq, means, batch);
+  count_launch();
+  DMN_LAUNCH_CHECK("langevin_means");
+  const long n4 = (long)batch * chw / 4;
+  langevin_apply_kernel<<<grid_for(n4), 256, 0, st>>>(x, mo, z, out, mean_out, n4, snr, means, coef, step_dev, step, draw, rng,
+                                                      rng_dev);
+  count_launch();
+  DMN_LAUNCH_CHECK("langevin_apply");
+  return 0;
+}
+int launch_affine_noise(const float* x, const float* mo, const float* z, float* out, float* mean_out, long n, const float* coef,
+                        const int32_t* step_dev, int step, int draw, dmn_rng rng, const dmn_rng* rng_dev, cudaStream_t st) {
+  DMN_REQUIRE(n % 4 == 0, "affine_noise: element count must be a multiple of 4");
+  affine_noise_kernel<<<grid_for(n / 4), 256, 0, st>>>(x, mo, z, out, mean_out, n / 4, coef, step_dev, step, draw, rng, rng_dev);
+  count_launch();
+  DMN_LAUNCH_CHECK("affine_noise");
+  return 0;
+}
+
+int launch_ddpm(const float* x, const float* eps, const float* z, float* out, long n, const float* coef, const int32_t* step_dev,
+                int step, dmn_rng rng, const dmn_rng* rng_dev, cudaStream_t st) {
+  DMN_REQUIRE(n % 4 == 0 && n > 0, "ddpm_step: element count must be a positive multiple of 4");
+  ddpm_step_kernel<<<grid_for(n / 4), 256, 0, st>>>(x, eps, z, out, n / 4, coef, step_dev, step, rng, rng_dev);
+  count_launch();
+  DMN_LAUNCH_CHECK("ddpm_step");
+  return 0;
+}
+int launch_learned(const float* x, const float* mo, const float* z, float* out, int batch, long chw, const float* coef,
+                   const int32_t* step_dev, int step, dmn_rng rng, const dmn_rng* rng_dev, cudaStream_t st) {
+  DMN_REQUIRE(chw % 4 == 0 && chw > 0 && batch > 0, "learned_step: C*H*W must be a positive multiple of 4");
+  const long n4 = (long)batch * chw / 4;
+  learned_step_kernel<<<grid_for(n4), 256, 0, st>>>(x, mo, z, out, chw / 4, n4, coef, step_dev, step, rng, rng_dev);
+  count_launch();
+  DMN_LAUNCH_CHECK("learned_step");
+  return 0;
+}
+int launch_ddim(const float* x, const float* eps, const float* z, float* out, long n, const float* coef, const int32_t* step_dev,
+                int step, dmn_rng rng, const dmn_rng* rng_dev, cudaStream_t st) {
+  DMN_REQUIRE(n % 4 == 0 && n > 0, "ddim_step: element count must be a positive multiple of 4");
+  ddim_step_kernel<<<grid_for(n / 4), 256, 0, st>>>(x, eps, z, out, n / 4, coef, step_dev, step, rng, rng_dev);
+  count_launch();
+  DMN_LAUNCH_CHECK("ddim_step");
+  return 0;
+}
+
+}  // namespace dmn
+
+using namespace dmn;
+
+extern "C" {
+
+int dmn_ddpm_step(const float* x, const float* eps, const float* z_dev, float* x_out, int64_t n, const float* coef_dev,
+                  const int32_t* step_dev, int step, dmn_rng rng, void* stream) {
+  return launch_ddpm(x, eps, z_dev, x_out, n, coef_dev, step_dev, step, rng, nullptr, (cudaStream_t)stream);
+}
+
+int dmn_learned_step(const float* x, const float* model_out, const float* z_dev, float* x_out, int batch, int64_t chw,
+                     const float* coef_dev, const int32_t* step_dev, int step, dmn_rng rng, void* stream) {
+  return launch_learned(x, model_out, z_dev, x_out, batch, chw, coef_dev, step_dev, step, rng, nullptr, (cudaStream_t)stream);
+}
+
+int dmn_ddim_step(const float* x, const float* eps, const float* z_dev, float* x_out, int64_t n, const float* coef_dev,
+                  const int32_t* step_dev, int step, dmn_rng rng, void* stream) {
+  return launch_ddim(x, eps, z_dev, x_out, n, coef_dev, step_dev, step, rng, nullptr, (cudaStream_t)stream);
+}
+
+int dmn_affine_noise_step(const float* x, const float* model_out, const float* z_dev, float* x_out, float* x_mean_out, int64_t n,
+                          const float* coef_dev, const int32_t* step_dev, int step, dmn_rng rng, void* stream) {
+  return launch_affine_noise(x, model_out, z_dev, x_out, x_mean_out, n, coef_dev, step_dev, step, 7, rng, nullptr,
+                             (cudaStream_t)stream);
+}
+
+int dmn_langevin_step(const float* x, const float* model_out, const float* z_dev, float* x_out, float* x_mean_out, int batch,
+                      int64_t chw, float snr, const float* coef_dev, const int32_t* step_dev, int step, float* scratch_dev,
+                      dmn_rng rng, void* stream) {
+  return launch_langevin(x, model_out, z_dev, x_out, x_mean_out, batch, chw, snr, coef_dev, step_dev, step, 0, scratch_dev, rng,
+                         nullptr, (cudaStream_t)stream);
+}
+
+int dmn_unnormalize(const float* x, float* out, int64_t n, void* stream) {
+  unnormalize_kernel<<<grid_for(n), 256, 0, (cudaStream_t)stream>>>(x, out, n);
+  count_launch();
+  DMN_LAUNCH_CHECK("unnormalize");
+  return 0;
+}
+
+int dmn_randn(float* out, int64_t n, dmn_rng rng, int step, void* stream) {
+  DMN_REQUIRE(n % 4 == 0 && n > 0, "randn: element count must be a positive multiple of 4");
+  randn_kernel<<<grid_for(n / 4), 256, 0, (cudaStream_t)stream>>>(out, n / 4, rng, (uint32_t)(step + 1) * 8u);
+  count_launch();
+  DMN_LAUNCH_CHECK("randn");
+  return 0;
+}
+
+int dmn_axpby(const float* x, const float* y, float a, float b, float* out, int64_t n, void* stream) {
+  axpby_kernel<<<grid_for(n), 256, 0, (cudaStream_t)stream>>>(x, y, a, b, out, n);
+  count_launch();
+  DMN_LAUNCH_CHECK("axpby");
+  return 0;
+}
+
+}  // extern "C"
