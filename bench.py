@@ -156,6 +156,7 @@ def main():
     ap.add_argument("--dtype", default="bf16")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--dump-ops", default="", help="write the per-launch table of one step (name, ms, TFLOP/s, GB/s) to this file")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -240,6 +241,12 @@ def main():
         g["flops"] += fl * B
         g["bytes"] += by * B
         g["launches"] += 1
+    if args.dump_ops and rank == 0:
+        with open(args.dump_ops, "w") as f:
+            for (name, kind, eng, fl, by), ms in zip(ops, acc):
+                tf = fl * B / (ms * 1e-3) / 1e12 if ms > 0 else 0.0
+                gb = by * B / (ms * 1e-3) / 1e9 if ms > 0 else 0.0
+                f.write(f"{name:34s} kind={kind} tc={eng} ms={ms:8.4f} tflops={tf:8.1f} gbs={gb:8.1f}\n")
     step_prof_ms = sum(g["ms"] for g in groups.values())
     dom = max(groups, key=lambda k: groups[k]["ms"])
     gd = groups[dom]

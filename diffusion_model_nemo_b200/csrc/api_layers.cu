@@ -25,15 +25,15 @@ ConvScratch conv_layout(const dmn_conv_args* a) {
   s.y = o; o += al((size_t)a->batch * hout * wout * a->cout * esz);
   s.w = o; o += al((size_t)a->cin * a->cout * k * k * 4);
   s.w2 = o; o += al((size_t)a->cin * a->cout * k * k * 2);
-  s.stats_in = o; o += al((size_t)a->batch * 64 * 2 * 4);
-  s.stats_out = o; o += al((size_t)a->batch * 64 * 2 * 4);
+  s.stats_in = o; o += al((size_t)a->batch * 64 * 2 * 8);
+  s.stats_out = o; o += al((size_t)a->batch * 64 * 2 * 8);
   s.total = o;
   return s;
 }
 
 // per-(sample, group) sum / sum-of-squares of an NHWC tensor (test path only: one thread block per (b, g))
 template <typename T>
-__global__ void group_stats_kernel(const T* x, float* stats, int HW, int C, int G) {
+__global__ void group_stats_kernel(const T* x, stat_t* stats, int HW, int C, int G) {
   const int b = blockIdx.x / G, g = blockIdx.x % G;
   const int cpg = C / G;
   float s = 0.f, ss = 0.f;
@@ -51,8 +51,8 @@ __global__ void group_stats_kernel(const T* x, float* stats, int HW, int C, int 
   if (threadIdx.x == 0) {
     float a = 0.f, c2 = 0.f;
     for (int i = 0; i < (int)(blockDim.x >> 5); ++i) { a += rs[i]; c2 += rss[i]; }
-    stats[2 * blockIdx.x] = a;
-    stats[2 * blockIdx.x + 1] = c2;
+    stats[2 * blockIdx.x] = __float2ll_rn(a * kStatScaleSum);
+    stats[2 * blockIdx.x + 1] = __float2ll_rn(c2 * kStatScaleSq);
   }
 }
 }  // namespace
@@ -85,18 +85,18 @@ int dmn_conv_forward(const dmn_conv_args* a, void* stream) {
   c.bias = a->bias;
   if (a->gn_groups > 0) {
     DMN_REQUIRE(a->gn_gamma && a->gn_beta, "GroupNorm prologue needs gamma/beta");
-    if (a->act == DMN_ACT_F32) group_stats_kernel<float><<<a->batch * a->gn_groups, 256, 0, st>>>((const float*)(base + L.x), (float*)(base + L.stats_in), a->hin * a->win, a->cin, a->gn_groups);
-    else group_stats_kernel<bf16><<<a->batch * a->gn_groups, 256, 0, st>>>((const bf16*)(base + L.x), (float*)(base + L.stats_in), a->hin * a->win, a->cin, a->gn_groups);
+    if (a->act == DMN_ACT_F32) group_stats_kernel<float><<<a->batch * a->gn_groups, 256, 0, st>>>((const float*)(base + L.x), (stat_t*)(base + L.stats_in), a->hin * a->win, a->cin, a->gn_groups);
+    else group_stats_kernel<bf16><<<a->batch * a->gn_groups, 256, 0, st>>>((const bf16*)(base + L.x), (stat_t*)(base + L.stats_in), a->hin * a->win, a->cin, a->gn_groups);
     DMN_LAUNCH_CHECK("group_stats");
     c.pro = PRO_GN | (a->silu ? PRO_SILU : 0) | (a->temb ? PRO_TEMB : 0);
-    c.pstats = (const float*)(base + L.stats_in); c.pgroups = a->gn_groups; c.pgamma = a->gn_gamma; c.pbeta = a->gn_beta;
+    c.pstats = (const stat_t*)(base + L.stats_in); c.pgroups = a->gn_groups; c.pgamma = a->gn_gamma; c.pbeta = a->gn_beta;
     if (a->temb) { c.temb = a->temb; c.temb_bstride = a->cin; }
   }
   c.out = base + L.y;
   if (a->out_groups > 0) {
     DMN_REQUIRE(a->out_stats, "out_stats is null");
-    DMN_CUDA_CHECK(cudaMemsetAsync(base + L.stats_out, 0, (size_t)a->batch * a->out_groups * 2 * 4, st));
-    c.ostats = (float*)(base + L.stats_out); c.ogroups = a->out_groups;
+    DMN_CUDA_CHECK(cudaMemsetAsync(base + L.stats_out, 0, (size_t)a->batch * a->out_groups * 2 * 8, st));
+    c.ostats = (stat_t*)(base + L.stats_out); c.ogroups = a->out_groups;
   }
   // weights: device fp32 in torch layout -> host repack -> device (validation path; sync copies are fine here)
   const size_t nw = (size_t)a->cin * a->cout * k * k;
@@ -122,7 +122,7 @@ int dmn_conv_forward(const dmn_conv_args* a, void* stream) {
   if ((rc = nhwc_to_nchw(base + L.y, a->y, a->batch, a->cout, hout * wout, a->act, st))) return rc;
   if (a->out_groups > 0) {
     const int cpg = a->cout / a->out_groups;
-    if ((rc = stats_to_mean_rstd((const float*)(base + L.stats_out), a->out_stats, a->batch * a->out_groups,
+    if ((rc = stats_to_mean_rstd((const stat_t*)(base + L.stats_out), a->out_stats, a->batch * a->out_groups,
                                  1.f / (float)(hout * wout * cpg), st)))
       return rc;
   }

@@ -106,12 +106,27 @@ __device__ __forceinline__ float warp_max(float v) {
   return v;
 }
 
-// GroupNorm statistics accumulated as {sum, sum of squares} per (sample, group) -> affine coefficients
-__device__ __forceinline__ void gn_mean_rstd(const float* stats2, float inv_count, float eps, float& mean, float& rstd) {
-  float s = stats2[0], ss = stats2[1];
-  mean = s * inv_count;
-  float var = fmaxf(ss * inv_count - mean * mean, 0.0f);
-  rstd = rsqrtf(var + eps);
+// GroupNorm statistics are accumulated per (sample, group) as {sum, sum of squares} in 64-bit FIXED POINT with integer
+// atomics: integer addition is associative, so the result does not depend on the order in which CTAs / warps arrive and the
+// whole sampling loop is bit-reproducible run to run (graph replay == plain launches == any other GPU with the same seed).
+typedef long long stat_t;
+constexpr float kStatScaleSum = 16777216.0f;   // 2^24
+constexpr float kStatScaleSq = 1048576.0f;     // 2^20
+__device__ __forceinline__ void stat_add(stat_t* dst, float s, float ss) {
+  atomicAdd(reinterpret_cast<unsigned long long*>(dst), (unsigned long long)__float2ll_rn(s * kStatScaleSum));
+  atomicAdd(reinterpret_cast<unsigned long long*>(dst + 1), (unsigned long long)__float2ll_rn(ss * kStatScaleSq));
+}
+__device__ __forceinline__ void stat_add_fixed(stat_t* dst, long long s, long long ss) {
+  atomicAdd(reinterpret_cast<unsigned long long*>(dst), (unsigned long long)s);
+  atomicAdd(reinterpret_cast<unsigned long long*>(dst + 1), (unsigned long long)ss);
+}
+__device__ __forceinline__ void gn_mean_rstd(const stat_t* stats2, float inv_count, float eps, float& mean, float& rstd) {
+  const double m = (double)stats2[0] * (1.0 / 16777216.0) * (double)inv_count;
+  const double q = (double)stats2[1] * (1.0 / 1048576.0) * (double)inv_count;
+  double var = q - m * m;
+  if (var < 0.0) var = 0.0;
+  mean = (float)m;
+  rstd = rsqrtf((float)var + eps);
 }
 
 constexpr float kGnEps = 1e-5f;   // torch.nn.GroupNorm default (parts/convnext.py:12, utils.py:89)

@@ -2,28 +2,37 @@
 //
 // D[m][n] = sum_{tap, ci} A[m + delta(tap)][ci] * W[n][tap][ci]       (bf16 operands, fp32 accumulate in TMEM)
 //
-// "Shifted-view" formulation.  The NHWC activation tensor is addressed through a FLAT padded pixel index
-//   f = img * S + (y + pad) * Wp + (x + pad),   Wp = W + pad, S = (H + pad) * Wp,  pad = 1 for 3x3, 0 for 1x1
-// in which one zero column / zero row is shared by neighbouring rows / images, so that every filter tap is a
-// constant offset delta = (ky-1)*Wp + (kx-1) in f.  A CTA owns 256 consecutive flat positions (two 128-row
-// accumulators).  Its input window [m0 - halo, m0 + 256 + halo) is loaded ONCE per 32-channel pass into
-// shared memory by the producer warps -- which also apply the fused prologue (GroupNorm-apply of the producing
-// conv, SiLU, time-embedding add; zero padding stays zero) -- in the UMMA K-major, no-swizzle canonical layout
+// "Shifted-view" formulation.  Every convolution of the U-Net is expressed over a VIRTUAL image addressed by a flat
+// pixel index f = img * S + row * Wv + col in which each filter tap is a constant offset delta in f:
+//
+//   GEO_SAME  3x3 pad 1 : Wv = W+1, S = (H+1)*Wv; row 0 / col 0 of every image block are zero pads SHARED with the
+//             (1x1 pad 0)  neighbouring row / image, delta = (ky-1)*Wv + (kx-1).  1x1: Wv = W, S = H*W, delta = 0.
+//   GEO_DOWN  Conv k4 s2 p1 == 2x2 stride-1 conv over the shifted space-to-depth image: virtual pixel (u,v) holds the
+//             2x2 input patch rows (2u-1, 2u) x cols (2v-1, 2v) as 4*C channels; Wv = W/2+1, delta = du*Wv + dv.
+//   GEO_UP    ConvTranspose k4 s2 p1 == four sub-pixel phases (py,px); each phase is a 2x2 conv over the padded input
+//             (layout of GEO_SAME 3x3) with its own 4 taps/weights; the phase is folded into the N-tile index.
+//   GEO_INIT  7x7 pad 3 stem on the fp32 NCHW sampler state: the kx direction is packed into channels
+//             (virtual channel = kx*Cin + ch, 7*Cin <= 32), 3 zero rows shared between images, delta = (ky-3)*W.
+//
+// A CTA owns 256 consecutive flat positions (two 128-row accumulators).  Its input window is loaded ONCE per
+// 32-channel pass into shared memory by the producer warps -- which also apply the fused prologue (GroupNorm-apply of
+// the producing conv, SiLU, time-embedding add; padding stays zero) -- in the UMMA K-major, no-swizzle canonical layout
 //   A_smem[kchunk (8 channels = 16 B)][pixel]      (LBO = PA*16 B between k-chunks, SBO = 128 B between 8-row groups)
-// so the operand of tap t is the same buffer with the start address advanced by delta*16 B: nine MMAs per
-// k-step read one resident tile; nothing is re-fetched from L2.  Weights are pre-blocked on the host into
-// [n_tile][pass][tap][kchunk][n] 16-byte items and streamed with 1-D bulk async copies (cp.async.bulk ->
-// UBLKCP, the TMA engine's non-tensor mode) through a 6-stage mbarrier ring.
+// so the operand of tap t is the same buffer with the start address advanced by delta*16 B: all taps of a k-step read
+// one resident tile and nothing is re-fetched from L2.  Weights are pre-blocked on the host into
+// [n_tile][pass][tap][kchunk][n] 16-byte items and streamed with 1-D bulk async copies (cp.async.bulk -> UBLKCP, the TMA
+// engine's non-tensor mode) through a 6-stage mbarrier ring.
 //
 // Warp roles (192 threads): warps 0-3 operand producers, then epilogue (TMEM -> registers -> +bias, +residual,
 // GroupNorm statistics, bf16 -> global); warp 4 weight loader; warp 5 TMEM allocator + single-thread MMA issuer.
-// Resources per CTA: <= 100 KB shared memory and 256 TMEM columns, so two CTAs share an SM and one CTA's
+// Resources per CTA: <= 113 KB shared memory and 256 TMEM columns, so two CTAs share an SM and one CTA's
 // epilogue / operand ramp overlaps the other's MMA main loop.
 //
 // Garbage rows: flat positions that fall on a pad column/row are computed and discarded (1 - HW/S of the MMA
-// work: 6 % at 32x32, 11 % at 16x16, 21 % at 8x8, 36 % at 4x4).
+// work for 3x3: 6 % at 32x32, 11 % at 16x16, 21 % at 8x8, 36 % at 4x4).
 #include <cstdlib>
 #include <cstring>
+#include <vector>
 
 #include "common.cuh"
 #include "ops.h"
@@ -31,26 +40,34 @@
 namespace dmn {
 namespace tc {
 
+enum { GEO_SAME = 0, GEO_DOWN = 1, GEO_UP = 2, GEO_INIT = 3 };
+
 constexpr int kThreads = 192;
 constexpr int kProducerThreads = 128;
 constexpr int kMT = 2;                 // 128-row accumulators per CTA
 constexpr int kMcta = 128 * kMT;
 constexpr int kCk = 32;                // channels per pass (4 k-chunks of 8)
 constexpr int kStagesB = 6;
-constexpr int kMaxItems = 13;          // 16-byte operand items per producer thread per pass
+constexpr int kMaxItems = 13;          // 16-byte operand items per producer thread per pass (P <= 416)
 constexpr int kNimgMax = 20;           // images a 256-position window may touch
 constexpr int kGroupsMax = 32;         // GroupNorm groups of the prologue
 constexpr int kOgMax = 16;             // output-statistics groups per N tile
 
 struct Params {
   ConvP c;
-  int S, Wp, pad, halo, P, PA, HW;
-  int ksize, ntap, NT, n_pass;
+  int geo;
+  int S, Wv, pad, halo_lo, P, PA, n_abuf;
+  int H, W, HW;            // input image
+  int ksize, ntap, NT, n_pass, tiles_per_phase;
   long total_flat;
   uint32_t lbo_a, sbo_a, lbo_b, sbo_b;   // bytes
   uint32_t tmem_cols;
   int cpg_in, cpg_out;
   float inv_cnt_in;
+  // GEO_INIT extras
+  const float* cls_w;
+  const int64_t* classes;
+  int pad_class;
 };
 
 // ---------------------------------------------------------------------------------------------------
@@ -138,38 +155,58 @@ __device__ __forceinline__ uint32_t make_idesc(int M, int N) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
-struct FlatPos {
-  int img, pix;     // pix < 0: padding / out of range
+// flat virtual position -> (image, virtual row, virtual col); img < 0 when out of range
+struct VPos {
+  int img, row, col;
 };
-__device__ __forceinline__ FlatPos decode(long f, const Params& p) {
-  FlatPos r;
+__device__ __forceinline__ VPos vdecode(long f, const Params& p) {
+  VPos r;
   r.img = -1;
-  r.pix = -1;
+  r.row = r.col = 0;
   if (f < 0 || f >= p.total_flat) return r;
   const int img = (int)(f / p.S);
   const int rem = (int)(f - (long)img * p.S);
-  const int row = rem / p.Wp, col = rem - row * p.Wp;
   r.img = img;
-  if (row >= p.pad && col >= p.pad) r.pix = (row - p.pad) * (p.Wp - p.pad) + (col - p.pad);
+  r.row = rem / p.Wv;
+  r.col = rem - r.row * p.Wv;
   return r;
+}
+// tap offset in flat positions
+template <int GEO>
+__device__ __forceinline__ int tap_delta(const Params& p, int t, int phase) {
+  if (GEO == GEO_SAME) {
+    const int kh = p.ksize >> 1, ky = t / p.ksize, kx = t - ky * p.ksize;
+    return (ky - kh) * p.Wv + (kx - kh);
+  } else if (GEO == GEO_DOWN) {
+    return (t >> 1) * p.Wv + (t & 1);
+  } else if (GEO == GEO_UP) {
+    const int py = phase >> 1, px = phase & 1, a = t >> 1, b = t & 1;
+    const int dy = py ? (a ? 0 : 1) : (a ? -1 : 0);
+    const int dx = px ? (b ? 0 : 1) : (b ? -1 : 0);
+    return dy * p.Wv + dx;
+  } else {
+    return (t - 3) * p.Wv;
+  }
 }
 
 // ---------------------------------------------------------------------------------------------------
 // kernel
 // ---------------------------------------------------------------------------------------------------
+template <int GEO>
 __global__ void __launch_bounds__(kThreads, 2) conv_tcgen05_kernel(const Params p) {
   extern __shared__ __align__(128) uint8_t smem[];
   const int tid = threadIdx.x;
   const int warp = tid >> 5, lane = tid & 31;
   const long m0 = (long)blockIdx.x * kMcta;
   const int n_tile = blockIdx.y;
-  const int n0 = n_tile * p.NT;
+  const int phase = (GEO == GEO_UP) ? n_tile / p.tiles_per_phase : 0;
+  const int n0 = (GEO == GEO_UP ? n_tile % p.tiles_per_phase : n_tile) * p.NT;
 
   // ---- shared memory carve-up ----
   const uint32_t a_bytes = 4u * p.PA * 16u;           // one A buffer (4 k-chunks)
   const uint32_t b_bytes = 4u * p.NT * 16u;           // one B stage
   uint8_t* sA = smem;
-  uint8_t* sB = sA + 2 * a_bytes;
+  uint8_t* sB = sA + p.n_abuf * a_bytes;
   uint64_t* bars = reinterpret_cast<uint64_t*>(sB + kStagesB * b_bytes);
   uint64_t* full_b = bars;
   uint64_t* empty_b = bars + kStagesB;
@@ -178,11 +215,10 @@ __global__ void __launch_bounds__(kThreads, 2) conv_tcgen05_kernel(const Params 
   uint64_t* acc_full = empty_a + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 1);
   float* s_bias = reinterpret_cast<float*>(tmem_slot + 2);
-  float2* s_gn = reinterpret_cast<float2*>(s_bias + 128);               // [kNimgMax][kGroupsMax] (mean, rstd)
-  float* s_ost = reinterpret_cast<float*>(s_gn + kNimgMax * kGroupsMax);  // [kNimgMax][kOgMax][2]
+  float2* s_gn = reinterpret_cast<float2*>(s_bias + 128);                                   // [kNimgMax][kGroupsMax] (mean, rstd)
+  unsigned long long* s_ost = reinterpret_cast<unsigned long long*>(s_gn + kNimgMax * kGroupsMax);   // [kNimgMax][kOgMax][2]
 
-  // images touched by this CTA's window
-  long f_lo = m0 - p.halo;
+  long f_lo = m0 - p.halo_lo;
   if (f_lo < 0) f_lo = 0;
   const int img_lo = (int)(f_lo / p.S);
 
@@ -194,11 +230,11 @@ __global__ void __launch_bounds__(kThreads, 2) conv_tcgen05_kernel(const Params 
     fence_barrier_init();
   }
   if (warp == 5) tmem_alloc(smem_u32(tmem_slot), p.tmem_cols);
-  // zero both operand buffers once: padding positions are never written again
-  for (uint32_t i = tid; i < 2 * a_bytes / 16; i += kThreads) reinterpret_cast<uint4*>(sA)[i] = make_uint4(0, 0, 0, 0);
+  // zero both operand buffers once: padding positions are never written again (GEO_DOWN writes its own zeros)
+  for (uint32_t i = tid; i < p.n_abuf * a_bytes / 16; i += kThreads) reinterpret_cast<uint4*>(sA)[i] = make_uint4(0, 0, 0, 0);
   for (int i = tid; i < p.NT; i += kThreads) s_bias[i] = p.c.bias ? p.c.bias[n0 + i] : 0.f;
-  for (int i = tid; i < kNimgMax * kOgMax * 2; i += kThreads) s_ost[i] = 0.f;
-  if (p.c.pro & PRO_GN) {
+  for (int i = tid; i < kNimgMax * kOgMax * 2; i += kThreads) s_ost[i] = 0ull;
+  if (GEO == GEO_SAME && (p.c.pro & PRO_GN)) {
     for (int i = tid; i < kNimgMax * p.c.pgroups; i += kThreads) {
       const int il = i / p.c.pgroups, g = i - il * p.c.pgroups;
       const int img = img_lo + il;
@@ -216,82 +252,126 @@ __global__ void __launch_bounds__(kThreads, 2) conv_tcgen05_kernel(const Params 
   if (warp < 4) {
     // =============================== operand producers ===============================
     const int kc = tid & 3;
-    int goff[kMaxItems];      // img*HW + pix, or -1
-    int imgl[kMaxItems];
+    if (GEO == GEO_INIT) {
+      // one pass: virtual channel vc = kx*Cin + ch  (7*Cin <= 32); source is the fp32 NCHW sampler state
+      const float* x = (const float*)p.c.src1;
+      const int Cin = p.c.C1;
+      for (int pixel = tid >> 2; pixel < p.P; pixel += 32) {
+        const VPos v = vdecode(m0 - p.halo_lo + pixel, p);
+        if (v.img < 0 || v.row < 3) continue;          // shared zero rows
+        const int iy = v.row - 3;
+        float f[8];
 #pragma unroll
-    for (int j = 0; j < kMaxItems; ++j) {
-      const int pixel = (tid >> 2) + 32 * j;
-      goff[j] = -1;
-      imgl[j] = 0;
-      if (pixel < p.P) {
-        const FlatPos fp = decode(m0 - p.halo + pixel, p);
-        if (fp.pix >= 0) {
-          goff[j] = fp.img * p.HW + fp.pix;
-          imgl[j] = fp.img - img_lo;
+        for (int e = 0; e < 8; ++e) {
+          const int vc = kc * 8 + e;
+          const int kx = vc / Cin, ch = vc - kx * Cin;
+          const int ix = v.col + kx - 3;
+          f[e] = (kx < 7 && ix >= 0 && ix < p.W) ? __ldg(x + (((long)v.img * Cin + ch) * p.H + iy) * p.W + ix) : 0.f;
         }
-      }
-    }
-    const bf16* src1 = (const bf16*)p.c.src1;
-    const bf16* src2 = (const bf16*)p.c.src2;
-    const float* temb_base = nullptr;
-    if (p.c.pro & PRO_TEMB) temb_base = p.c.temb + (p.c.d_row ? (long)(*p.c.d_row) * p.c.temb_rstride : 0);
-
-    for (int c = 0; c < p.n_pass; ++c) {
-      const int buf = c & 1;
-      mbar_wait(smem_u32(&empty_a[buf]), ((c >> 1) & 1) ^ 1);
-      const int cb = c * kCk + kc * 8;        // first channel of this thread's k-chunk
-      const bf16* src;
-      int Cs, cofs;
-      if (cb < p.c.C1) { src = src1; Cs = p.c.C1; cofs = cb; }
-      else { src = src2; Cs = p.c.C2; cofs = cb - p.c.C1; }
-      uint4 raw[kMaxItems];
-#pragma unroll
-      for (int j = 0; j < kMaxItems; ++j)
-        if (goff[j] >= 0) raw[j] = __ldg(reinterpret_cast<const uint4*>(src + (long)goff[j] * Cs + cofs));
-      uint8_t* dstbase = sA + buf * a_bytes + (uint32_t)kc * p.lbo_a;
-      if (p.c.pro == PRO_NONE) {
-#pragma unroll
-        for (int j = 0; j < kMaxItems; ++j)
-          if (goff[j] >= 0) *reinterpret_cast<uint4*>(dstbase + ((tid >> 2) + 32 * j) * 16) = raw[j];
-      } else {
-        float ga[8], be[8], te[8];
-        {
-          const float4 g0 = *reinterpret_cast<const float4*>(p.c.pgamma + cb), g1 = *reinterpret_cast<const float4*>(p.c.pgamma + cb + 4);
-          const float4 b0 = *reinterpret_cast<const float4*>(p.c.pbeta + cb), b1 = *reinterpret_cast<const float4*>(p.c.pbeta + cb + 4);
-          ga[0] = g0.x; ga[1] = g0.y; ga[2] = g0.z; ga[3] = g0.w; ga[4] = g1.x; ga[5] = g1.y; ga[6] = g1.z; ga[7] = g1.w;
-          be[0] = b0.x; be[1] = b0.y; be[2] = b0.z; be[3] = b0.w; be[4] = b1.x; be[5] = b1.y; be[6] = b1.z; be[7] = b1.w;
-        }
-        const bool temb_shared = (p.c.pro & PRO_TEMB) && p.c.temb_bstride == 0;
-#pragma unroll
-        for (int e = 0; e < 8; ++e) te[e] = 0.f;
-        if (temb_shared) {
-          const float4 t0 = *reinterpret_cast<const float4*>(temb_base + cb), t1 = *reinterpret_cast<const float4*>(temb_base + cb + 4);
-          te[0] = t0.x; te[1] = t0.y; te[2] = t0.z; te[3] = t0.w; te[4] = t1.x; te[5] = t1.y; te[6] = t1.z; te[7] = t1.w;
-        }
-        const int g = cb / p.cpg_in;
-#pragma unroll
-        for (int j = 0; j < kMaxItems; ++j) {
-          if (goff[j] < 0) continue;
-          const float2 mr = s_gn[imgl[j] * kGroupsMax + g];
-          if ((p.c.pro & PRO_TEMB) && !temb_shared) {
-            const float* tp = temb_base + (long)(img_lo + imgl[j]) * p.c.temb_bstride + cb;
-            const float4 t0 = *reinterpret_cast<const float4*>(tp), t1 = *reinterpret_cast<const float4*>(tp + 4);
-            te[0] = t0.x; te[1] = t0.y; te[2] = t0.z; te[3] = t0.w; te[4] = t1.x; te[5] = t1.y; te[6] = t1.z; te[7] = t1.w;
-          }
-          float v[8];
-          unpack8(raw[j], v);
-#pragma unroll
-          for (int e = 0; e < 8; ++e) {
-            float t = (v[e] - mr.x) * mr.y;
-            t = fmaf(t, ga[e], be[e]);
-            if (p.c.pro & PRO_SILU) t = silu_fast(t);
-            v[e] = t + te[e];
-          }
-          *reinterpret_cast<uint4*>(dstbase + ((tid >> 2) + 32 * j) * 16) = pack8(v);
-        }
+        *reinterpret_cast<uint4*>(sA + (uint32_t)kc * p.lbo_a + pixel * 16) = pack8(f);
       }
       fence_proxy_async();
-      mbar_arrive(smem_u32(&full_a[buf]));
+      mbar_arrive(smem_u32(&full_a[0]));
+    } else {
+      // per-thread item table: smem pixel (tid>>2) + 32 j, k-chunk kc
+      int goff[kMaxItems];      // SAME/UP: img*HW + pix (or -1); DOWN: packed (img, u, v) (or -1)
+      int imgl[kMaxItems];
+#pragma unroll
+      for (int j = 0; j < kMaxItems; ++j) {
+        const int pixel = (tid >> 2) + 32 * j;
+        goff[j] = -1;
+        imgl[j] = 0;
+        if (pixel < p.P) {
+          const VPos v = vdecode(m0 - p.halo_lo + pixel, p);
+          if (v.img >= 0) {
+            if (GEO == GEO_DOWN) {
+              goff[j] = (v.img << 14) | (v.row << 7) | v.col;
+            } else if (v.row >= p.pad && v.col >= p.pad) {
+              goff[j] = v.img * p.HW + (v.row - p.pad) * p.W + (v.col - p.pad);
+              imgl[j] = v.img - img_lo;
+            }
+          }
+        }
+      }
+      const bf16* src1 = (const bf16*)p.c.src1;
+      const bf16* src2 = (const bf16*)p.c.src2;
+      const float* temb_base = nullptr;
+      if (GEO == GEO_SAME && (p.c.pro & PRO_TEMB)) temb_base = p.c.temb + (p.c.d_row ? (long)(*p.c.d_row) * p.c.temb_rstride : 0);
+
+      for (int c = 0; c < p.n_pass; ++c) {
+        const int buf = c & 1;
+        mbar_wait(smem_u32(&empty_a[buf]), ((c >> 1) & 1) ^ 1);
+        int cb = c * kCk + kc * 8;        // first (virtual) channel of this thread's k-chunk
+        int sy = 0, sx = 0;
+        if (GEO == GEO_DOWN) {            // virtual channel = sub * C + ci, sub = sy*2 + sx
+          const int sub = cb / p.c.C1;
+          cb -= sub * p.c.C1;
+          sy = sub >> 1;
+          sx = sub & 1;
+        }
+        const bf16* src;
+        int Cs, cofs;
+        if (cb < p.c.C1) { src = src1; Cs = p.c.C1; cofs = cb; }
+        else { src = src2; Cs = p.c.C2; cofs = cb - p.c.C1; }
+        uint4 raw[kMaxItems];
+#pragma unroll
+        for (int j = 0; j < kMaxItems; ++j) {
+          raw[j] = make_uint4(0, 0, 0, 0);
+          if (goff[j] >= 0) {
+            if (GEO == GEO_DOWN) {
+              const int img = goff[j] >> 14, iy = 2 * ((goff[j] >> 7) & 127) - 1 + sy, ix = 2 * (goff[j] & 127) - 1 + sx;
+              if (iy >= 0 && iy < p.H && ix >= 0 && ix < p.W)
+                raw[j] = __ldg(reinterpret_cast<const uint4*>(src + ((long)img * p.HW + iy * p.W + ix) * Cs + cofs));
+            } else {
+              raw[j] = __ldg(reinterpret_cast<const uint4*>(src + (long)goff[j] * Cs + cofs));
+            }
+          }
+        }
+        uint8_t* dstbase = sA + buf * a_bytes + (uint32_t)kc * p.lbo_a;
+        if (GEO != GEO_SAME || p.c.pro == PRO_NONE) {
+#pragma unroll
+          for (int j = 0; j < kMaxItems; ++j)
+            if (goff[j] >= 0) *reinterpret_cast<uint4*>(dstbase + ((tid >> 2) + 32 * j) * 16) = raw[j];
+        } else {
+          float ga[8], be[8], te[8];
+          {
+            const float4 g0 = *reinterpret_cast<const float4*>(p.c.pgamma + cb), g1 = *reinterpret_cast<const float4*>(p.c.pgamma + cb + 4);
+            const float4 b0 = *reinterpret_cast<const float4*>(p.c.pbeta + cb), b1 = *reinterpret_cast<const float4*>(p.c.pbeta + cb + 4);
+            ga[0] = g0.x; ga[1] = g0.y; ga[2] = g0.z; ga[3] = g0.w; ga[4] = g1.x; ga[5] = g1.y; ga[6] = g1.z; ga[7] = g1.w;
+            be[0] = b0.x; be[1] = b0.y; be[2] = b0.z; be[3] = b0.w; be[4] = b1.x; be[5] = b1.y; be[6] = b1.z; be[7] = b1.w;
+          }
+          const bool temb_shared = (p.c.pro & PRO_TEMB) && p.c.temb_bstride == 0;
+#pragma unroll
+          for (int e = 0; e < 8; ++e) te[e] = 0.f;
+          if (temb_shared) {
+            const float4 t0 = *reinterpret_cast<const float4*>(temb_base + cb), t1 = *reinterpret_cast<const float4*>(temb_base + cb + 4);
+            te[0] = t0.x; te[1] = t0.y; te[2] = t0.z; te[3] = t0.w; te[4] = t1.x; te[5] = t1.y; te[6] = t1.z; te[7] = t1.w;
+          }
+          const int g = cb / p.cpg_in;
+#pragma unroll
+          for (int j = 0; j < kMaxItems; ++j) {
+            if (goff[j] < 0) continue;
+            const float2 mr = s_gn[imgl[j] * kGroupsMax + g];
+            if ((p.c.pro & PRO_TEMB) && !temb_shared) {
+              const float* tp = temb_base + (long)(img_lo + imgl[j]) * p.c.temb_bstride + cb;
+              const float4 t0 = *reinterpret_cast<const float4*>(tp), t1 = *reinterpret_cast<const float4*>(tp + 4);
+              te[0] = t0.x; te[1] = t0.y; te[2] = t0.z; te[3] = t0.w; te[4] = t1.x; te[5] = t1.y; te[6] = t1.z; te[7] = t1.w;
+            }
+            float v[8];
+            unpack8(raw[j], v);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              float t = (v[e] - mr.x) * mr.y;
+              t = fmaf(t, ga[e], be[e]);
+              if (p.c.pro & PRO_SILU) t = silu_fast(t);
+              v[e] = t + te[e];
+            }
+            *reinterpret_cast<uint4*>(dstbase + ((tid >> 2) + 32 * j) * 16) = pack8(v);
+          }
+        }
+        fence_proxy_async();
+        mbar_arrive(smem_u32(&full_a[buf]));
+      }
     }
 
     // =============================== epilogue ===============================
@@ -302,11 +382,30 @@ __global__ void __launch_bounds__(kThreads, 2) conv_tcgen05_kernel(const Params 
 #pragma unroll 1
     for (int mt = 0; mt < kMT; ++mt) {
       const int row = warp * 32 + lane;
-      const FlatPos fp = decode(m0 + mt * 128 + row, p);
-      const bool valid = fp.pix >= 0;
-      const long orow = valid ? ((long)fp.img * p.HW + fp.pix) * p.c.Cout + n0 : 0;
+      const VPos v = vdecode(m0 + mt * 128 + row, p);
+      bool valid = v.img >= 0;
+      long opix = 0;      // output pixel index (img * HWout + pix)
+      if (valid) {
+        if (GEO == GEO_SAME) {
+          valid = v.row >= p.pad && v.col >= p.pad;
+          opix = (long)v.img * p.HW + (v.row - p.pad) * p.W + (v.col - p.pad);
+        } else if (GEO == GEO_DOWN) {
+          valid = v.row < (p.H >> 1) && v.col < (p.W >> 1);
+          opix = (long)v.img * (p.HW >> 2) + v.row * (p.W >> 1) + v.col;
+        } else if (GEO == GEO_UP) {
+          valid = v.row >= 1 && v.col >= 1;
+          opix = (long)v.img * (p.HW << 2) + (2 * (v.row - 1) + (phase >> 1)) * (2 * p.W) + 2 * (v.col - 1) + (phase & 1);
+        } else {
+          valid = v.row >= 3;
+          opix = (long)v.img * p.HW + (v.row - 3) * p.W + v.col;
+        }
+      }
+      const long orow = valid ? opix * p.c.Cout + n0 : 0;
+      const float* cls_row = nullptr;
+      if (GEO == GEO_INIT && p.cls_w && valid)
+        cls_row = p.cls_w + (long)(p.classes ? (int)p.classes[v.img] : p.pad_class) * p.c.Cout + n0;
       // statistics bookkeeping: is the warp inside one image?
-      const int my_img = valid ? fp.img - img_lo : -1;
+      const int my_img = valid ? v.img - img_lo : -1;
       const int ref_img = __reduce_max_sync(0xffffffffu, my_img);
       const bool uniform = __all_sync(0xffffffffu, my_img == ref_img || my_img < 0);
       int cur_g = -1;
@@ -317,21 +416,25 @@ __global__ void __launch_bounds__(kThreads, 2) conv_tcgen05_kernel(const Params 
         if (uniform) {
           const float a = warp_sum(s), b = warp_sum(ss);
           if (lane == 0 && ref_img >= 0) {
-            atomicAdd(&s_ost[(ref_img * kOgMax + gl) * 2], a);
-            atomicAdd(&s_ost[(ref_img * kOgMax + gl) * 2 + 1], b);
+            atomicAdd(&s_ost[(ref_img * kOgMax + gl) * 2], (unsigned long long)__float2ll_rn(a * kStatScaleSum));
+            atomicAdd(&s_ost[(ref_img * kOgMax + gl) * 2 + 1], (unsigned long long)__float2ll_rn(b * kStatScaleSq));
           }
         } else if (valid) {
-          atomicAdd(&s_ost[(my_img * kOgMax + gl) * 2], s);
-          atomicAdd(&s_ost[(my_img * kOgMax + gl) * 2 + 1], ss);
+          atomicAdd(&s_ost[(my_img * kOgMax + gl) * 2], (unsigned long long)__float2ll_rn(s * kStatScaleSum));
+          atomicAdd(&s_ost[(my_img * kOgMax + gl) * 2 + 1], (unsigned long long)__float2ll_rn(ss * kStatScaleSq));
         }
         s = ss = 0.f;
       };
       for (int ch = 0; ch < p.NT / 32; ++ch) {
         uint32_t r[32];
         tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(mt * p.NT + ch * 32), r);
-        float v[32];
+        float vv[32];
 #pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) + s_bias[ch * 32 + j];
+        for (int j = 0; j < 32; ++j) vv[j] = __uint_as_float(r[j]) + s_bias[ch * 32 + j];
+        if (GEO == GEO_INIT && cls_row) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) vv[j] += __ldg(cls_row + ch * 32 + j);
+        }
         if (res && valid) {
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
@@ -339,12 +442,12 @@ __global__ void __launch_bounds__(kThreads, 2) conv_tcgen05_kernel(const Params 
             float rf[8];
             unpack8(rr, rf);
 #pragma unroll
-            for (int e = 0; e < 8; ++e) v[q * 8 + e] += rf[e];
+            for (int e = 0; e < 8; ++e) vv[q * 8 + e] += rf[e];
           }
         }
         if (valid) {
 #pragma unroll
-          for (int q = 0; q < 4; ++q) *reinterpret_cast<uint4*>(out + orow + ch * 32 + q * 8) = pack8(v + q * 8);
+          for (int q = 0; q < 4; ++q) *reinterpret_cast<uint4*>(out + orow + ch * 32 + q * 8) = pack8(vv + q * 8);
         }
         if (p.c.ostats) {
 #pragma unroll
@@ -353,7 +456,7 @@ __global__ void __launch_bounds__(kThreads, 2) conv_tcgen05_kernel(const Params 
             if (g != cur_g) { flush(); cur_g = g; }
             if (valid) {
 #pragma unroll
-              for (int e = 0; e < 8; ++e) { s += v[q * 8 + e]; ss += v[q * 8 + e] * v[q * 8 + e]; }
+              for (int e = 0; e < 8; ++e) { s += vv[q * 8 + e]; ss += vv[q * 8 + e] * vv[q * 8 + e]; }
             }
           }
         }
@@ -377,7 +480,6 @@ __global__ void __launch_bounds__(kThreads, 2) conv_tcgen05_kernel(const Params 
     // =============================== MMA issuer ===============================
     if (lane == 0) {
       const uint32_t idesc = make_idesc(128, p.NT);
-      const int kh = p.ksize >> 1;
       int s = 0;
       for (int c = 0; c < p.n_pass; ++c) {
         const int buf = c & 1;
@@ -388,8 +490,7 @@ __global__ void __launch_bounds__(kThreads, 2) conv_tcgen05_kernel(const Params 
           const int st = s % kStagesB;
           mbar_wait(smem_u32(&full_b[st]), (s / kStagesB) & 1);
           tc_fence_after();
-          const int ky = t / p.ksize, kx = t - ky * p.ksize;
-          const int delta = (ky - kh) * p.Wp + (kx - kh);
+          const int delta = tap_delta<GEO>(p, t, phase);
           const uint32_t bbase = smem_u32(sB + st * b_bytes);
 #pragma unroll
           for (int k16 = 0; k16 < 2; ++k16) {
@@ -397,7 +498,7 @@ __global__ void __launch_bounds__(kThreads, 2) conv_tcgen05_kernel(const Params 
 #pragma unroll
             for (int mt = 0; mt < kMT; ++mt) {
               const uint64_t adesc =
-                  make_desc(abase + 2 * k16 * p.lbo_a + (uint32_t)(p.halo + mt * 128 + delta) * 16u, p.lbo_a, p.sbo_a);
+                  make_desc(abase + 2 * k16 * p.lbo_a + (uint32_t)(p.halo_lo + mt * 128 + delta) * 16u, p.lbo_a, p.sbo_a);
               umma_bf16(tmem_base + (uint32_t)(mt * p.NT), adesc, bdesc, idesc, (c | t | k16) ? 1u : 0u);
             }
           }
@@ -410,18 +511,14 @@ __global__ void __launch_bounds__(kThreads, 2) conv_tcgen05_kernel(const Params 
   }
 
   __syncthreads();
-  // flush the CTA's GroupNorm statistics
+  // flush the CTA's GroupNorm statistics (fixed point, integer atomics: deterministic)
   if (p.c.ostats) {
     const int og_tile = (p.NT + p.cpg_out - 1) / p.cpg_out;
     for (int i = tid; i < kNimgMax * og_tile; i += kThreads) {
       const int il = i / og_tile, gl = i - il * og_tile;
       const int img = img_lo + il;
-      const float a = s_ost[(il * kOgMax + gl) * 2], b = s_ost[(il * kOgMax + gl) * 2 + 1];
-      if (img < p.c.B && (a != 0.f || b != 0.f)) {
-        float* dst = p.c.ostats + ((long)img * p.c.ogroups + n0 / p.cpg_out + gl) * 2;
-        atomicAdd(dst, a);
-        atomicAdd(dst + 1, b);
-      }
+      const unsigned long long a = s_ost[(il * kOgMax + gl) * 2], b = s_ost[(il * kOgMax + gl) * 2 + 1];
+      if (img < p.c.B && (a | b)) stat_add_fixed(p.c.ostats + ((long)img * p.c.ogroups + n0 / p.cpg_out + gl) * 2, (long long)a, (long long)b);
     }
   }
   if (warp == 5) {
@@ -432,25 +529,58 @@ __global__ void __launch_bounds__(kThreads, 2) conv_tcgen05_kernel(const Params 
 
 static int pick_nt(int cout) { return cout % 128 == 0 ? 128 : (cout % 64 == 0 ? 64 : (cout % 32 == 0 ? 32 : 0)); }
 
-static bool fill_params(const ConvP& c, Params& p) {
-  if (c.mode != CONV_SAME || (c.ksize != 1 && c.ksize != 3)) return false;
-  if (c.C1 <= 0 || c.C1 % kCk || c.C2 % kCk) return false;
+static bool fill_params(const ConvP& c, int geo, Params& p) {
+  p = Params();
+  p.c = c;
+  p.geo = geo;
   p.NT = pick_nt(c.Cout);
   if (!p.NT) return false;
-  p.c = c;
+  p.H = c.Hin; p.W = c.Win; p.HW = c.Hin * c.Win;
   p.ksize = c.ksize;
-  p.ntap = c.ksize * c.ksize;
-  p.pad = c.ksize == 3 ? 1 : 0;
-  p.Wp = c.Win + p.pad;
-  p.S = (c.Hin + p.pad) * p.Wp;
-  p.HW = c.Hin * c.Win;
-  p.halo = c.ksize == 3 ? p.Wp + 1 : 0;
-  p.P = kMcta + 2 * p.halo;
+  p.tiles_per_phase = c.Cout / p.NT;
+  int halo_hi = 0;
+  if (geo == GEO_SAME) {
+    if (c.ksize != 1 && c.ksize != 3) return false;
+    if (c.C1 <= 0 || c.C1 % kCk || c.C2 % kCk) return false;
+    p.ntap = c.ksize * c.ksize;
+    p.pad = c.ksize == 3 ? 1 : 0;
+    p.Wv = c.Win + p.pad;
+    p.S = (c.Hin + p.pad) * p.Wv;
+    p.halo_lo = halo_hi = c.ksize == 3 ? p.Wv + 1 : 0;
+    p.n_pass = (c.C1 + c.C2) / kCk;
+  } else if (geo == GEO_DOWN) {
+    if (c.C2 != 0 || c.C1 % kCk || (c.Hin & 1) || (c.Win & 1) || c.pro != PRO_NONE || c.ostats || c.res) return false;
+    if (c.Hin / 2 + 1 > 127 || c.B >= (1 << 17)) return false;
+    p.ntap = 4;
+    p.pad = 0;
+    p.Wv = c.Win / 2 + 1;
+    p.S = (c.Hin / 2 + 1) * p.Wv;
+    p.halo_lo = 0;
+    halo_hi = p.Wv + 1;
+    p.n_pass = 4 * c.C1 / kCk;
+  } else if (geo == GEO_UP) {
+    if (c.C2 != 0 || c.C1 % kCk || c.pro != PRO_NONE || c.ostats || c.res) return false;
+    p.ntap = 4;
+    p.pad = 1;
+    p.Wv = c.Win + 1;
+    p.S = (c.Hin + 1) * p.Wv;
+    p.halo_lo = halo_hi = p.Wv + 1;
+    p.n_pass = c.C1 / kCk;
+  } else {
+    if (7 * c.C1 > kCk || c.C2 != 0) return false;
+    p.ntap = 7;
+    p.pad = 0;
+    p.Wv = c.Win;
+    p.S = (c.Hin + 3) * p.Wv;
+    p.halo_lo = halo_hi = 3 * p.Wv;
+    p.n_pass = 1;
+  }
+  p.n_abuf = (geo == GEO_INIT) ? 1 : 2;
+  p.P = kMcta + p.halo_lo + halo_hi;
   p.PA = p.P;
   while (p.PA % 8 != 2) ++p.PA;
-  if ((4 * p.P + kProducerThreads - 1) / kProducerThreads > kMaxItems) return false;
+  if (geo != GEO_INIT && (4 * p.P + kProducerThreads - 1) / kProducerThreads > kMaxItems) return false;
   if (kMcta / p.S + 3 > kNimgMax) return false;
-  p.n_pass = (c.C1 + c.C2) / kCk;
   p.total_flat = (long)c.B * p.S;
   p.lbo_a = (uint32_t)p.PA * 16u;
   p.sbo_a = 128u;
@@ -461,7 +591,7 @@ static bool fill_params(const ConvP& c, Params& p) {
   p.cpg_in = 1;
   p.inv_cnt_in = 0.f;
   if (c.pro & PRO_GN) {
-    if (c.C2 != 0 || c.pgroups <= 0 || c.pgroups > kGroupsMax || c.C1 % c.pgroups) return false;
+    if (geo != GEO_SAME || c.C2 != 0 || c.pgroups <= 0 || c.pgroups > kGroupsMax || c.C1 % c.pgroups) return false;
     p.cpg_in = c.C1 / c.pgroups;
     if (p.cpg_in % 8) return false;
     p.inv_cnt_in = 1.f / (float)(p.HW * p.cpg_in);
@@ -481,64 +611,139 @@ static bool fill_params(const ConvP& c, Params& p) {
 }
 
 static size_t smem_bytes(const Params& p) {
-  return (size_t)2 * 4 * p.PA * 16 + (size_t)kStagesB * 4 * p.NT * 16 + (2 * kStagesB + 5) * 8 + 16 + 128 * 4 +
-         (size_t)kNimgMax * kGroupsMax * 8 + (size_t)kNimgMax * kOgMax * 2 * 4 + 128;
+  return (size_t)p.n_abuf * 4 * p.PA * 16 + (size_t)kStagesB * 4 * p.NT * 16 + (2 * kStagesB + 5) * 8 + 16 + 128 * 4 +
+         (size_t)kNimgMax * kGroupsMax * 8 + (size_t)kNimgMax * kOgMax * 2 * 8 + 128;
+}
+
+static int geo_of(const ConvP& c) { return c.mode == CONV_SAME ? GEO_SAME : (c.mode == CONV_DOWN ? GEO_DOWN : GEO_UP); }
+
+template <int GEO>
+static int launch(const Params& p, cudaStream_t st) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    DMN_CUDA_CHECK(cudaFuncSetAttribute(conv_tcgen05_kernel<GEO>, cudaFuncAttributeMaxDynamicSharedMemorySize, 113 * 1024));
+    attr_set = true;
+  }
+  const unsigned gy = (unsigned)((GEO == GEO_UP ? 4 : 1) * (p.c.Cout / p.NT));
+  dim3 grid((unsigned)((p.total_flat + kMcta - 1) / kMcta), gy);
+  conv_tcgen05_kernel<GEO><<<grid, kThreads, smem_bytes(p), st>>>(p);
+  count_launch();
+  DMN_LAUNCH_CHECK("conv_tcgen05");
+  return 0;
 }
 
 }  // namespace tc
 
 bool conv_tcgen05_supported(const ConvP& c) {
   tc::Params p;
-  if (!tc::fill_params(c, p)) return false;
+  if (!tc::fill_params(c, tc::geo_of(c), p)) return false;
   return tc::smem_bytes(p) <= 113 * 1024;
+}
+bool init_conv_tcgen05_supported(int Cin, int S, int Cout, int B) {
+  ConvP c;
+  c.C1 = Cin; c.Hin = c.Win = S; c.Cout = Cout; c.B = B;
+  tc::Params p;
+  return tc::fill_params(c, tc::GEO_INIT, p) && tc::smem_bytes(p) <= 113 * 1024;
 }
 
 size_t conv_tcgen05_weight_bytes(int mode, int ksize, int cin, int cout) {
   const int taps = (mode == CONV_SAME) ? ksize * ksize : 16;
   return (size_t)cout * cin * taps * 2;
 }
+size_t init_conv_tcgen05_weight_bytes(int cout) { return (size_t)cout * 7 * tc::kCk * 2; }
 
-// [n_tile][pass][tap][kchunk 0..3][n 0..NT-1][8 channels] bf16
+// blocked bf16 weight image [n_tile][pass][tap][kchunk 0..3][n 0..NT-1][8 channels]
 void conv_tcgen05_pack_weights(int mode, int ksize, int cin, int cout, const float* w, void* dst_host) {
-  (void)mode;
   const int NT = tc::pick_nt(cout);
-  const int taps = ksize * ksize;
-  const int n_pass = cin / tc::kCk;
+  bf16* dst = (bf16*)dst_host;
+  size_t o = 0;
+  if (mode == CONV_SAME) {
+    const int taps = ksize * ksize;
+    for (int nt = 0; nt < cout / NT; ++nt)
+      for (int c = 0; c < cin / tc::kCk; ++c)
+        for (int t = 0; t < taps; ++t)
+          for (int kc = 0; kc < 4; ++kc)
+            for (int n = 0; n < NT; ++n)
+              for (int e = 0; e < 8; ++e) {
+                const int co = nt * NT + n, ci = c * tc::kCk + kc * 8 + e;
+                dst[o++] = __float2bfloat16_rn(w[((long)co * cin + ci) * taps + t]);
+              }
+  } else if (mode == CONV_DOWN) {
+    // Conv2d weight [co][ci][ky][kx], k4 s2 p1.  virtual channel = sub*C + ci, sub = sy*2+sx; tap t = du*2+dv;
+    // ky = 2*du + sy, kx = 2*dv + sx
+    for (int nt = 0; nt < cout / NT; ++nt)
+      for (int c = 0; c < 4 * cin / tc::kCk; ++c)
+        for (int t = 0; t < 4; ++t)
+          for (int kc = 0; kc < 4; ++kc)
+            for (int n = 0; n < NT; ++n)
+              for (int e = 0; e < 8; ++e) {
+                const int vc = c * tc::kCk + kc * 8 + e, sub = vc / cin, ci = vc % cin;
+                const int ky = 2 * (t >> 1) + (sub >> 1), kx = 2 * (t & 1) + (sub & 1);
+                const int co = nt * NT + n;
+                dst[o++] = __float2bfloat16_rn(w[(((long)co * cin + ci) * 4 + ky) * 4 + kx]);
+              }
+  } else {
+    // ConvTranspose2d weight [ci][co][ky][kx], k4 s2 p1.  n_tile = phase*(cout/NT) + ct, phase = py*2+px;
+    // tap t = a*2+b: dy = py ? (a ? 0 : +1) : (a ? -1 : 0) (dx likewise); ky = py + 1 - 2*dy
+    for (int ph = 0; ph < 4; ++ph)
+      for (int ct = 0; ct < cout / NT; ++ct)
+        for (int c = 0; c < cin / tc::kCk; ++c)
+          for (int t = 0; t < 4; ++t) {
+            const int py = ph >> 1, px = ph & 1, a = t >> 1, b = t & 1;
+            const int dy = py ? (a ? 0 : 1) : (a ? -1 : 0), dx = px ? (b ? 0 : 1) : (b ? -1 : 0);
+            const int ky = py + 1 - 2 * dy, kx = px + 1 - 2 * dx;
+            for (int kc = 0; kc < 4; ++kc)
+              for (int n = 0; n < NT; ++n)
+                for (int e = 0; e < 8; ++e) {
+                  const int ci = c * tc::kCk + kc * 8 + e, co = ct * NT + n;
+                  dst[o++] = __float2bfloat16_rn(w[(((long)ci * cout + co) * 4 + ky) * 4 + kx]);
+                }
+          }
+  }
+}
+
+// init conv weight [co][ch][7][7] -> [n_tile][tap ky][kchunk][n][8], virtual channel vc = kx*Cin + ch
+void init_conv_tcgen05_pack_weights(int cin, int cout, const float* w, void* dst_host) {
+  const int NT = tc::pick_nt(cout);
   bf16* dst = (bf16*)dst_host;
   size_t o = 0;
   for (int nt = 0; nt < cout / NT; ++nt)
-    for (int c = 0; c < n_pass; ++c)
-      for (int t = 0; t < taps; ++t)
-        for (int kc = 0; kc < 4; ++kc)
-          for (int n = 0; n < NT; ++n)
-            for (int e = 0; e < 8; ++e) {
-              const int co = nt * NT + n, ci = c * tc::kCk + kc * 8 + e;
-              dst[o++] = __float2bfloat16_rn(w[((long)co * cin + ci) * taps + t]);
-            }
+    for (int ky = 0; ky < 7; ++ky)
+      for (int kc = 0; kc < 4; ++kc)
+        for (int n = 0; n < NT; ++n)
+          for (int e = 0; e < 8; ++e) {
+            const int vc = kc * 8 + e, kx = vc / cin, ch = vc % cin, co = nt * NT + n;
+            dst[o++] = __float2bfloat16_rn(kx < 7 ? w[(((long)co * cin + ch) * 7 + ky) * 7 + kx] : 0.f);
+          }
 }
 
 int conv_tcgen05(const ConvP& c, cudaStream_t st) {
   tc::Params p;
-  if (!tc::fill_params(c, p)) return fail(-2, "conv_tcgen05: unsupported convolution shape");
+  const int geo = tc::geo_of(c);
+  if (!tc::fill_params(c, geo, p)) return fail(-2, "conv_tcgen05: unsupported convolution shape");
   static const bool swap = [] {
     const char* e = getenv("DMN_UMMA_SWAP_LBO_SBO");
     return e && e[0] == '1';
   }();
-  if (swap) {
+  if (swap) {   // negative control for the descriptor encoding (tests only)
     std::swap(p.lbo_a, p.sbo_a);
     std::swap(p.lbo_b, p.sbo_b);
   }
-  const size_t smem = tc::smem_bytes(p);
-  static bool attr_set = false;
-  if (!attr_set) {
-    DMN_CUDA_CHECK(cudaFuncSetAttribute(tc::conv_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 113 * 1024));
-    attr_set = true;
-  }
-  dim3 grid((unsigned)((p.total_flat + tc::kMcta - 1) / tc::kMcta), (unsigned)(c.Cout / p.NT));
-  tc::conv_tcgen05_kernel<<<grid, tc::kThreads, smem, st>>>(p);
-  count_launch();
-  DMN_LAUNCH_CHECK("conv_tcgen05");
-  return 0;
+  if (geo == tc::GEO_SAME) return tc::launch<tc::GEO_SAME>(p, st);
+  if (geo == tc::GEO_DOWN) return tc::launch<tc::GEO_DOWN>(p, st);
+  return tc::launch<tc::GEO_UP>(p, st);
+}
+
+int init_conv_tcgen05(const InitConvP& q, cudaStream_t st) {
+  ConvP c;
+  c.src1 = q.x; c.C1 = q.Cin; c.B = q.B; c.Hin = c.Win = q.S; c.Hout = c.Wout = q.S; c.Cout = q.Cout;
+  c.w = q.w; c.bias = q.bias; c.out = q.out;
+  tc::Params p;
+  if (!tc::fill_params(c, tc::GEO_INIT, p)) return fail(-2, "init_conv_tcgen05: unsupported shape");
+  p.cls_w = q.cls_w;
+  p.classes = q.classes;
+  p.pad_class = q.pad_class;
+  return tc::launch<tc::GEO_INIT>(p, st);
 }
 
 }  // namespace dmn

@@ -153,9 +153,7 @@ __global__ void __launch_bounds__(256) conv_simt_kernel(const ConvP p) {
     if (p.ostats) {
       const int b = (int)(m / HWo);
       if (b != sb && sb >= 0) {
-        float* dst = p.ostats + ((long)sb * p.ogroups + n / cpg_out) * 2;
-        atomicAdd(dst, s);
-        atomicAdd(dst + 1, ss);
+        stat_add(p.ostats + ((long)sb * p.ogroups + n / cpg_out) * 2, s, ss);
         s = ss = 0.f;
       }
       sb = b;
@@ -163,11 +161,7 @@ __global__ void __launch_bounds__(256) conv_simt_kernel(const ConvP p) {
       ss += o.x * o.x + o.y * o.y + o.z * o.z + o.w * o.w;
     }
   }
-  if (p.ostats && sb >= 0) {
-    float* dst = p.ostats + ((long)sb * p.ogroups + n / cpg_out) * 2;
-    atomicAdd(dst, s);
-    atomicAdd(dst + 1, ss);
-  }
+  if (p.ostats && sb >= 0) stat_add(p.ostats + ((long)sb * p.ogroups + n / cpg_out) * 2, s, ss);
 }
 
 int conv_simt(const ConvP& p, int act, cudaStream_t st) {
@@ -258,67 +252,115 @@ int init_conv(const InitConvP& p, int act, cudaStream_t st) {
 }
 
 // =====================================================================================================
-// GroupNorm finalize: y = act(GN(raw)) + res ; statistics of y for the next norm
-// grid = (blocks_per_image, B), 256 threads; the item stride is a multiple of C/4 so each thread keeps one
-// channel quad (=> one input group and one output group) for its whole loop.
+// GroupNorm finalize: y = act(GN(raw)) + res ; statistics of y for the next norm.  HBM-bound: 3 x esz bytes / element.
+// grid = (blocks_per_image, B), 256 threads, 16-byte accesses (8 bf16 / 4 fp32 channels per thread); the item stride is a
+// multiple of C/VEC so each thread keeps one channel vector (=> one input group, one output group) for its whole loop.
 // =====================================================================================================
-template <typename T>
+template <typename T, int V> struct VecIO;
+template <> struct VecIO<float, 4> {
+  static constexpr int N = 4;
+  static __device__ __forceinline__ void load(const float* p, float* v) {
+    const float4 t = *reinterpret_cast<const float4*>(p);
+    v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+  }
+  static __device__ __forceinline__ void store(float* p, const float* v) { *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]); }
+};
+template <> struct VecIO<bf16, 4> {
+  static constexpr int N = 4;
+  static __device__ __forceinline__ void load(const bf16* p, float* v) {
+    const float4 t = load4<bf16>(p);
+    v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+  }
+  static __device__ __forceinline__ void store(bf16* p, const float* v) { store4<bf16>(p, make_float4(v[0], v[1], v[2], v[3])); }
+};
+template <> struct VecIO<bf16, 8> {
+  static constexpr int N = 8;
+  static __device__ __forceinline__ void load(const bf16* p, float* v) { unpack8(*reinterpret_cast<const uint4*>(p), v); }
+  static __device__ __forceinline__ void store(bf16* p, const float* v) { *reinterpret_cast<uint4*>(p) = pack8(v); }
+};
+
+template <typename T, int V>
 __global__ void __launch_bounds__(256) gn_finalize_kernel(const FinalizeP p) {
-  __shared__ float sm_stats[2 * 64];
+  __shared__ unsigned long long sm_stats[2 * 64];
   const int b = blockIdx.y;
-  const int C4 = p.C >> 2;
-  const long items = (long)p.HW * C4;
-  const int c = (threadIdx.x % C4) * 4;
+  const int CV = p.C / V;
+  const long items = (long)p.HW * CV;
+  const int c = (threadIdx.x % CV) * V;
   const int cpg = p.C / p.groups;
   float mean, rstd;
   gn_mean_rstd(p.stats + ((long)b * p.groups + c / cpg) * 2, 1.f / (float)(p.HW * cpg), kGnEps, mean, rstd);
-  const float4 ga = *reinterpret_cast<const float4*>(p.gamma + c);
-  const float4 be = *reinterpret_cast<const float4*>(p.beta + c);
-  const float4 sc = make_float4(rstd * ga.x, rstd * ga.y, rstd * ga.z, rstd * ga.w);
-  const float4 sh = make_float4(be.x - mean * sc.x, be.y - mean * sc.y, be.z - mean * sc.z, be.w - mean * sc.w);
+  float sc[V], sh[V];
+#pragma unroll
+  for (int e = 0; e < V; ++e) {
+    sc[e] = rstd * p.gamma[c + e];
+    sh[e] = p.beta[c + e] - mean * sc[e];
+  }
   if (p.ostats) {
-    for (int i = threadIdx.x; i < 2 * p.ogroups; i += blockDim.x) sm_stats[i] = 0.f;
+    for (int i = threadIdx.x; i < 2 * p.ogroups; i += blockDim.x) sm_stats[i] = 0ull;
     __syncthreads();
   }
   float s = 0.f, ss = 0.f;
   const T* raw = (const T*)p.raw + (long)b * p.HW * p.C;
   const T* res = p.res ? (const T*)p.res + (long)b * p.HW * p.C : nullptr;
   T* out = (T*)p.out + (long)b * p.HW * p.C;
-  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < items; i += (long)gridDim.x * blockDim.x) {
-    float4 v = load4<T>(raw + i * 4);
-    v.x = fmaf(v.x, sc.x, sh.x); v.y = fmaf(v.y, sc.y, sh.y); v.z = fmaf(v.z, sc.z, sh.z); v.w = fmaf(v.w, sc.w, sh.w);
-    if (p.silu) { v.x = silu_f(v.x); v.y = silu_f(v.y); v.z = silu_f(v.z); v.w = silu_f(v.w); }
+  const long stride = (long)gridDim.x * blockDim.x;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < items; i += 2 * stride) {
+    const bool two = i + stride < items;
+    float v0[V], v1[V], r0[V], r1[V];
+    VecIO<T, V>::load(raw + i * V, v0);
+    if (two) VecIO<T, V>::load(raw + (i + stride) * V, v1);
     if (res) {
-      const float4 r = load4<T>(res + i * 4);
-      v.x += r.x; v.y += r.y; v.z += r.z; v.w += r.w;
+      VecIO<T, V>::load(res + i * V, r0);
+      if (two) VecIO<T, V>::load(res + (i + stride) * V, r1);
     }
-    store4<T>(out + i * 4, v);
-    s += v.x + v.y + v.z + v.w;
-    ss += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+#pragma unroll
+    for (int e = 0; e < V; ++e) {
+      float t = fmaf(v0[e], sc[e], sh[e]);
+      if (p.silu) t = silu_f(t);
+      if (res) t += r0[e];
+      v0[e] = t;
+      s += t;
+      ss += t * t;
+    }
+    VecIO<T, V>::store(out + i * V, v0);
+    if (two) {
+#pragma unroll
+      for (int e = 0; e < V; ++e) {
+        float t = fmaf(v1[e], sc[e], sh[e]);
+        if (p.silu) t = silu_f(t);
+        if (res) t += r1[e];
+        v1[e] = t;
+        s += t;
+        ss += t * t;
+      }
+      VecIO<T, V>::store(out + (i + stride) * V, v1);
+    }
   }
   if (p.ostats) {
     const int og = c / (p.C / p.ogroups);
-    // threads of a warp that share og reduce through shared-memory atomics (few distinct og per warp)
-    atomicAdd(&sm_stats[og * 2], s);
-    atomicAdd(&sm_stats[og * 2 + 1], ss);
+    // fixed-point integer atomics: order independent => deterministic
+    atomicAdd(&sm_stats[og * 2], (unsigned long long)__float2ll_rn(s * kStatScaleSum));
+    atomicAdd(&sm_stats[og * 2 + 1], (unsigned long long)__float2ll_rn(ss * kStatScaleSq));
     __syncthreads();
     for (int i = threadIdx.x; i < 2 * p.ogroups; i += blockDim.x)
-      atomicAdd(p.ostats + (long)b * p.ogroups * 2 + i, sm_stats[i]);
+      atomicAdd(reinterpret_cast<unsigned long long*>(p.ostats) + (long)b * p.ogroups * 2 + i, sm_stats[i]);
   }
 }
 
 int gn_finalize(const FinalizeP& p, int act, cudaStream_t st) {
-  const int C4 = p.C / 4;
-  DMN_REQUIRE(p.C % 4 == 0 && 256 % C4 == 0, "gn_finalize: C/4 must divide 256");
-  DMN_REQUIRE(p.C % p.groups == 0 && (p.C / p.groups) % 4 == 0, "gn_finalize: channels-per-group % 4");
-  DMN_REQUIRE(!p.ostats || (p.ogroups <= 64 && p.C % p.ogroups == 0 && (p.C / p.ogroups) % 4 == 0), "gn_finalize: ogroups");
-  const long items = (long)p.HW * C4;
+  int V = act == ACT_F32 ? 4 : 8;
+  if (V == 8 && ((p.C / p.groups) % 8 || (p.ostats && (p.C / p.ogroups) % 8) || 256 % (p.C / 8))) V = 4;
+  DMN_REQUIRE(p.C % V == 0 && 256 % (p.C / V) == 0, "gn_finalize: C/vector must divide 256");
+  DMN_REQUIRE(p.C % p.groups == 0 && (p.C / p.groups) % V == 0, "gn_finalize: channels-per-group must be a multiple of the vector width");
+  DMN_REQUIRE(!p.ostats || (p.ogroups <= 64 && p.C % p.ogroups == 0 && (p.C / p.ogroups) % V == 0), "gn_finalize: ogroups");
+  const long items = (long)p.HW * (p.C / V);
   int bpi = (int)((items + 256 * 4 - 1) / (256 * 4));
   if (bpi < 1) bpi = 1;
   if (bpi > 64) bpi = 64;
   dim3 grid(bpi, p.B);
-  if (act == ACT_F32) gn_finalize_kernel<float><<<grid, 256, 0, st>>>(p);
-  else gn_finalize_kernel<bf16><<<grid, 256, 0, st>>>(p);
+  if (act == ACT_F32) gn_finalize_kernel<float, 4><<<grid, 256, 0, st>>>(p);
+  else if (V == 8) gn_finalize_kernel<bf16, 8><<<grid, 256, 0, st>>>(p);
+  else gn_finalize_kernel<bf16, 4><<<grid, 256, 0, st>>>(p);
   count_launch();
   DMN_LAUNCH_CHECK("gn_finalize");
   return 0;
@@ -372,102 +414,147 @@ int final_proj(const FinalProjP& p, int act, cudaStream_t st) {
 }
 
 // =====================================================================================================
-// LinearAttention core (parts/mha.py:44-58), dim_head = 32.  One block (256 threads) per (sample, head).
+// LinearAttention core (parts/mha.py:44-58), heads = 4, dim_head = 32.  One block (256 threads) per SAMPLE (all heads):
 //   q softmax over d (dim=-2), k softmax over n (dim=-1), q *= scale (after softmax),
-//   ctx[d][e] = sum_n k[d,n] v[e,n] ; out[e,n] = sum_d ctx[d][e] q[d,n]
-// qkv: [B][N][3*heads*32] (channel = which*heads*32 + head*32 + d);  out: [B][N][heads*32]
+//   ctx[h][d][e] = sum_n k[d,n] v[e,n] ; out[e,n] = sum_d ctx[d][e] q[d,n]
+// qkv: [B][N][384] (channel = which*128 + head*32 + d);  out: [B][N][128].
+// Tokens stream through shared-memory tiles with coalesced 256-byte rows; every reduction has a fixed order (deterministic).
 // =====================================================================================================
 template <typename T>
-__global__ void __launch_bounds__(256) linattn_kernel(const T* __restrict__ qkv, T* __restrict__ out, int heads, int N) {
-  constexpr int D = 32;
-  __shared__ float red[8][D];
-  __shared__ float kmax[D], ksum[D];
-  __shared__ float ctx[D][D + 1];
-  const int b = blockIdx.x / heads, h = blockIdx.x % heads;
-  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  const int C3 = 3 * heads * D;
-  const T* base = qkv + (long)b * N * C3;
-  const int qo = h * D, ko = heads * D + h * D, vo = 2 * heads * D + h * D;
+__global__ void __launch_bounds__(256) linattn_kernel(const T* __restrict__ qkv, T* __restrict__ out, int N) {
+  constexpr int HD = 128, TN = 32, LD = HD + 4;     // row padding keeps float4 rows 16-byte aligned and spreads banks
+  extern __shared__ __align__(16) float lsm[];
+  float (*tP)[LD] = reinterpret_cast<float (*)[LD]>(lsm);                       // exp(k - max) | q tile rows [0,32)
+  float (*tV)[LD] = reinterpret_cast<float (*)[LD]>(lsm + TN * LD);             // v            | q tile rows [32,64)
+  float (*ctx)[32][32] = reinterpret_cast<float (*)[32][32]>(lsm + 2 * TN * LD);   // [head][d][e]
+  float (*red)[HD] = reinterpret_cast<float (*)[HD]>(lsm + 2 * TN * LD + 4 * 32 * 32);
+  float* kmax = lsm + 2 * TN * LD + 4 * 32 * 32 + 2 * HD;
+  float* kinv = kmax + HD;
+  const int b = blockIdx.x, t = threadIdx.x;
+  const T* base = qkv + (long)b * N * 384;
 
-  // pass A: max over n of k[d, n]   (lane = d)
-  float m = -INFINITY;
-  for (int n = w; n < N; n += 8) m = fmaxf(m, to_f<T>(base[(long)n * C3 + ko + lane]));
-  red[w][lane] = m;
-  __syncthreads();
-  if (w == 0) {
-    float mm = red[0][lane];
-#pragma unroll
-    for (int i = 1; i < 8; ++i) mm = fmaxf(mm, red[i][lane]);
-    kmax[lane] = mm;
+  // phase 1: max over tokens of k, per channel  (thread = (channel, half))
+  {
+    const int c = t & 127, half = t >> 7;
+    float m = -INFINITY;
+    for (int n = half; n < N; n += 2) m = fmaxf(m, to_f<T>(base[(long)n * 384 + 128 + c]));
+    red[half][c] = m;
+    __syncthreads();
+    if (t < HD) kmax[t] = fmaxf(red[0][t], red[1][t]);
+    __syncthreads();
   }
-  for (int i = threadIdx.x; i < D * (D + 1); i += 256) (&ctx[0][0])[i] = 0.f;
-  __syncthreads();
-
-  // pass B: p = exp(k - max); ksum[d] += p ; ctx[d][e] += p * v[e, n]
-  const float km = kmax[lane];
-  float acc[D];
+  // phase 2: ctx accumulation.  thread -> head h = t/64, 4x4 patch (d0, e0) of the 32x32 context
+  const int h = t >> 6, pd = ((t & 63) >> 3) * 4, pe = (t & 7) * 4;
+  float acc[4][4];
 #pragma unroll
-  for (int e = 0; e < D; ++e) acc[e] = 0.f;
-  float psum = 0.f;
-  for (int n = w; n < N; n += 8) {
-    const float pk = __expf(to_f<T>(base[(long)n * C3 + ko + lane]) - km);
-    const float vv = to_f<T>(base[(long)n * C3 + vo + lane]);
-    psum += pk;
+  for (int i = 0; i < 4; ++i)
 #pragma unroll
-    for (int e = 0; e < D; ++e) acc[e] = fmaf(pk, __shfl_sync(0xffffffffu, vv, e), acc[e]);
-  }
-  red[w][lane] = psum;
-#pragma unroll
-  for (int e = 0; e < D; ++e) atomicAdd(&ctx[lane][e], acc[e]);
-  __syncthreads();
-  if (w == 0) {
-    float sacc = 0.f;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) sacc += red[i][lane];
-    ksum[lane] = sacc;
-  }
-  __syncthreads();
-  for (int i = threadIdx.x; i < D * D; i += 256) {
-    const int d = i / D, e = i % D;
-    ctx[d][e] = ctx[d][e] / ksum[d];
-  }
-  __syncthreads();
-
-  // pass C: per token: softmax of q over d, scale, out[e] = sum_d ctx[d][e] * q[d]
-  const float scale = rsqrtf((float)D);
-  for (int n = threadIdx.x; n < N; n += 256) {
-    float q[D];
-    const T* qp = base + (long)n * C3 + qo;
-    float qm = -INFINITY;
-#pragma unroll
-    for (int d = 0; d < D; d += 4) {
-      const float4 t = load4<T>(qp + d);
-      q[d] = t.x; q[d + 1] = t.y; q[d + 2] = t.z; q[d + 3] = t.w;
-      qm = fmaxf(fmaxf(qm, fmaxf(t.x, t.y)), fmaxf(t.z, t.w));
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  float ksum = 0.f;                                  // threads 0..127: running sum of exp for channel t
+  for (int n0 = 0; n0 < N; n0 += TN) {
+    // load tile: TN tokens x (k 128 + v 128) channels, 4 channels per thread-iteration
+    for (int i = t; i < TN * 64; i += 256) {
+      const int r = i >> 6, q4 = (i & 63) * 4;       // q4 in [0,256): [0,128) -> k, [128,256) -> v
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      const bool ok = n0 + r < N;
+      if (ok) v = load4<T>(base + (long)(n0 + r) * 384 + 128 + q4);
+      if (q4 < 128) {
+        if (ok) {
+          v.x = __expf(v.x - kmax[q4]); v.y = __expf(v.y - kmax[q4 + 1]); v.z = __expf(v.z - kmax[q4 + 2]); v.w = __expf(v.w - kmax[q4 + 3]);
+        }
+        *reinterpret_cast<float4*>(&tP[r][q4]) = v;
+      } else {
+        *reinterpret_cast<float4*>(&tV[r][q4 - 128]) = v;
+      }
     }
-    float qs = 0.f;
-#pragma unroll
-    for (int d = 0; d < D; ++d) { q[d] = __expf(q[d] - qm); qs += q[d]; }
-    const float qn = scale / qs;
-    float o[D];
-#pragma unroll
-    for (int e = 0; e < D; ++e) o[e] = 0.f;
-#pragma unroll
-    for (int d = 0; d < D; ++d) {
-      const float qd = q[d] * qn;
-#pragma unroll
-      for (int e = 0; e < D; ++e) o[e] = fmaf(ctx[d][e], qd, o[e]);
+    __syncthreads();
+    if (t < HD) {
+#pragma unroll 8
+      for (int r = 0; r < TN; ++r) ksum += tP[r][t];
     }
-    T* op = out + ((long)b * N + n) * (heads * D) + h * D;
+#pragma unroll 4
+    for (int r = 0; r < TN; ++r) {
+      const float4 pk = *reinterpret_cast<const float4*>(&tP[r][h * 32 + pd]);
+      const float4 vv = *reinterpret_cast<const float4*>(&tV[r][h * 32 + pe]);
+      const float pa[4] = {pk.x, pk.y, pk.z, pk.w}, va[4] = {vv.x, vv.y, vv.z, vv.w};
 #pragma unroll
-    for (int e = 0; e < D; e += 4) store4<T>(op + e, make_float4(o[e], o[e + 1], o[e + 2], o[e + 3]));
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(pa[i], va[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+  if (t < HD) kinv[t] = 1.f / ksum;
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) ctx[h][pd + i][pe + j] = acc[i][j] * kinv[h * 32 + pd + i];
+  __syncthreads();
+
+  // phase 3: per token softmax of q over d, scale, out[e] = sum_d ctx[d][e] * q[d].  thread = (token r = t%64.., head)
+  const float scale = rsqrtf(32.f);
+  for (int n0 = 0; n0 < N; n0 += 2 * TN) {
+    // q tile of 64 tokens: rows [0,32) in tP, [32,64) in tV
+    for (int i = t; i < 2 * TN * 32; i += 256) {
+      const int r = i >> 5, q4 = (i & 31) * 4;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (n0 + r < N) v = load4<T>(base + (long)(n0 + r) * 384 + q4);
+      float* dst = r < TN ? &tP[r][q4] : &tV[r - TN][q4];
+      *reinterpret_cast<float4*>(dst) = v;
+    }
+    __syncthreads();
+    {
+      const int r = t & 63, hh = t >> 6;
+      const float* qrow = (r < TN ? &tP[r][0] : &tV[r - TN][0]) + hh * 32;
+      float q[32];
+      float qm = -INFINITY;
+#pragma unroll
+      for (int d = 0; d < 32; d += 4) {
+        const float4 v = *reinterpret_cast<const float4*>(qrow + d);
+        q[d] = v.x; q[d + 1] = v.y; q[d + 2] = v.z; q[d + 3] = v.w;
+        qm = fmaxf(fmaxf(qm, fmaxf(v.x, v.y)), fmaxf(v.z, v.w));
+      }
+      float qs = 0.f;
+#pragma unroll
+      for (int d = 0; d < 32; ++d) { q[d] = __expf(q[d] - qm); qs += q[d]; }
+      const float qn = scale / qs;
+      T* op = out + ((long)b * N + n0 + r) * HD + hh * 32;
+#pragma unroll
+      for (int eh = 0; eh < 32; eh += 16) {
+        float o[16];
+#pragma unroll
+        for (int e = 0; e < 16; ++e) o[e] = 0.f;
+#pragma unroll
+        for (int d = 0; d < 32; ++d) {
+          const float qd = q[d] * qn;
+#pragma unroll
+          for (int e = 0; e < 16; e += 4) {
+            const float4 cv = *reinterpret_cast<const float4*>(&ctx[hh][d][eh + e]);
+            o[e] = fmaf(cv.x, qd, o[e]); o[e + 1] = fmaf(cv.y, qd, o[e + 1]); o[e + 2] = fmaf(cv.z, qd, o[e + 2]); o[e + 3] = fmaf(cv.w, qd, o[e + 3]);
+          }
+        }
+        if (n0 + r < N) {
+#pragma unroll
+          for (int e = 0; e < 16; e += 4) store4<T>(op + eh + e, make_float4(o[e], o[e + 1], o[e + 2], o[e + 3]));
+        }
+      }
+    }
+    __syncthreads();
   }
 }
 
 int linattn_core(const void* qkv, void* out, int B, int heads, int dh, int N, int act, cudaStream_t st) {
-  DMN_REQUIRE(dh == 32, "linattn_core: dim_head must be 32");
-  if (act == ACT_F32) linattn_kernel<float><<<B * heads, 256, 0, st>>>((const float*)qkv, (float*)out, heads, N);
-  else linattn_kernel<bf16><<<B * heads, 256, 0, st>>>((const bf16*)qkv, (bf16*)out, heads, N);
+  DMN_REQUIRE(dh == 32 && heads == 4, "linattn_core: heads must be 4 and dim_head 32");
+  const size_t smem = (size_t)(2 * 32 * 132 + 4 * 32 * 32 + 4 * 128) * sizeof(float);
+  static bool attr = false;
+  if (!attr) {
+    DMN_CUDA_CHECK(cudaFuncSetAttribute(linattn_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    DMN_CUDA_CHECK(cudaFuncSetAttribute(linattn_kernel<bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr = true;
+  }
+  if (act == ACT_F32) linattn_kernel<float><<<B, 256, smem, st>>>((const float*)qkv, (float*)out, N);
+  else linattn_kernel<bf16><<<B, 256, smem, st>>>((const bf16*)qkv, (bf16*)out, N);
   count_launch();
   DMN_LAUNCH_CHECK("linattn_core");
   return 0;
@@ -629,7 +716,7 @@ int nhwc_to_nchw(const void* in, float* out, int B, int C, int HW, int act, cuda
   DMN_LAUNCH_CHECK("nhwc_to_nchw");
   return 0;
 }
-__global__ void stats_to_mean_rstd_kernel(const float* __restrict__ stats, float* __restrict__ out, int n, float inv_count) {
+__global__ void stats_to_mean_rstd_kernel(const stat_t* __restrict__ stats, float* __restrict__ out, int n, float inv_count) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   float mean, rstd;
@@ -637,7 +724,7 @@ __global__ void stats_to_mean_rstd_kernel(const float* __restrict__ stats, float
   out[2 * i] = mean;
   out[2 * i + 1] = rstd;
 }
-int stats_to_mean_rstd(const float* stats, float* out, int n, float inv_count, cudaStream_t st) {
+int stats_to_mean_rstd(const stat_t* stats, float* out, int n, float inv_count, cudaStream_t st) {
   stats_to_mean_rstd_kernel<<<(n + 127) / 128, 128, 0, st>>>(stats, out, n, inv_count);
   count_launch();
   DMN_LAUNCH_CHECK("stats_to_mean_rstd");

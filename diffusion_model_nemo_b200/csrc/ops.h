@@ -9,6 +9,8 @@
 
 namespace dmn {
 
+typedef long long stat_t;   // fixed-point GroupNorm statistics (common.cuh)
+
 enum { ACT_F32 = 0, ACT_BF16 = 1 };
 enum { CONV_SAME = 0, CONV_DOWN = 1, CONV_UP = 2 };
 enum { PRO_NONE = 0, PRO_GN = 1, PRO_SILU = 2, PRO_TEMB = 4 };
@@ -26,7 +28,7 @@ struct ConvP {
   const float* bias = nullptr;
   // prologue applied to src1 while loading (GroupNorm of the producer, SiLU, time-embedding add)
   int pro = PRO_NONE;
-  const float* pstats = nullptr;   // [B][pgroups][2]
+  const stat_t* pstats = nullptr;  // [B][pgroups][2]
   int pgroups = 0;
   const float* pgamma = nullptr;
   const float* pbeta = nullptr;
@@ -36,7 +38,7 @@ struct ConvP {
   // epilogue
   void* out = nullptr;             // raw conv output (+bias, +res)
   const void* res = nullptr;       // optional residual added to the output (same layout as out)
-  float* ostats = nullptr;         // [B][ogroups][2] accumulated with atomics (must be zeroed beforehand)
+  stat_t* ostats = nullptr;        // [B][ogroups][2] accumulated with integer atomics (must be zeroed beforehand)
   int ogroups = 0;
 };
 
@@ -61,18 +63,23 @@ struct InitConvP {
   int B = 0, Cin = 0, S = 0, Cout = 0;
 };
 int init_conv(const InitConvP& p, int act, cudaStream_t s);
+// tensor-core stem (bf16 activations): w = blocked bf16 image from init_conv_tcgen05_pack_weights
+int init_conv_tcgen05(const InitConvP& p, cudaStream_t s);
+bool init_conv_tcgen05_supported(int Cin, int S, int Cout, int B);
+size_t init_conv_tcgen05_weight_bytes(int cout);
+void init_conv_tcgen05_pack_weights(int cin, int cout, const float* w_torch, void* dst_host);
 
 // y = act(GroupNorm(raw)) [+ res];  optional statistics of y for the next norm
 struct FinalizeP {
   const void* raw = nullptr;
-  const float* stats = nullptr;
+  const stat_t* stats = nullptr;
   int groups = 0;
   const float* gamma = nullptr;
   const float* beta = nullptr;
   int silu = 0;
   const void* res = nullptr;
   void* out = nullptr;
-  float* ostats = nullptr;
+  stat_t* ostats = nullptr;
   int ogroups = 0;
   int B = 0, HW = 0, C = 0;
 };
@@ -81,7 +88,7 @@ int gn_finalize(const FinalizeP& p, int act, cudaStream_t s);
 // final_conv tail: eps = conv1x1(SiLU(GroupNorm(y)))  -> fp32 NCHW
 struct FinalProjP {
   const void* y = nullptr;
-  const float* stats = nullptr;
+  const stat_t* stats = nullptr;
   int groups = 0;
   const float* gamma = nullptr;
   const float* beta = nullptr;
@@ -114,6 +121,6 @@ int time_table(const TimeP& p, cudaStream_t s);
 // layout conversion at the public ABI boundary
 int nchw_to_nhwc(const float* in, void* out, int B, int C, int HW, int act, cudaStream_t s);
 int nhwc_to_nchw(const void* in, float* out, int B, int C, int HW, int act, cudaStream_t s);
-int stats_to_mean_rstd(const float* stats, float* out, int n, float inv_count, cudaStream_t s);
+int stats_to_mean_rstd(const stat_t* stats, float* out, int n, float inv_count, cudaStream_t s);
 
 }  // namespace dmn

@@ -128,6 +128,7 @@ struct dmn_plan {
   size_t stats_off = 0, stats_bytes = 0;
   Buf out_nhwc_dummy;
   int launches_per_forward = 0;
+  bool init_tc = false;            // stem on the tensor-core engine
   // loop state
   Buf counters;   // int32[4]
   struct GraphEntry {
@@ -165,7 +166,7 @@ struct Builder {
   Buf stats(int G) {
     Buf b;
     b.off = P.stats_off + P.stats_bytes;
-    P.stats_bytes += align_up((size_t)P.cfg.max_batch * G * 2 * sizeof(float), 256);
+    P.stats_bytes += align_up((size_t)P.cfg.max_batch * G * 2 * sizeof(stat_t), 256);
     return b;
   }
 
@@ -322,7 +323,7 @@ struct Builder {
 
     // statistics arena first (fixed offset); its size is known only after the program is built, so reserve generously
     P.stats_off = wsoff;
-    const size_t stats_reserve = align_up((size_t)c.max_batch * 64 * 2 * sizeof(float), 256) * 160;
+    const size_t stats_reserve = align_up((size_t)c.max_batch * 64 * 2 * sizeof(stat_t), 256) * 160;
     wsoff += stats_reserve;
 
     Buf X[3] = {actbuf(maxact), actbuf(maxact), actbuf(maxact)};
@@ -332,7 +333,14 @@ struct Builder {
     for (int i = 0; i < n; ++i) skip[i] = actbuf((size_t)Hs[i] * Hs[i] * dims[i + 1]);
 
     // parameters that are not attached to a conv op
-    add_param("init_conv.weight", {dim, c.channels, 7, 7}, PK_INIT);
+    {
+      const int pi = add_param("init_conv.weight", {dim, c.channels, 7, 7}, PK_INIT);
+      P.init_tc = P.engine == DMN_CONV_TCGEN05 && init_conv_tcgen05_supported(c.channels, S, dim, c.max_batch);
+      if (P.init_tc) {
+        P.params[pi].has_tc = true;
+        P.params[pi].off2 = walloc(init_conv_tcgen05_weight_bytes(dim));
+      }
+    }
     add_param("init_conv.bias", {dim}, PK_RAW);
     if (c.with_time_emb) {
       add_param("time_mlp.1.weight", {4 * dim, dim}, PK_LIN_T);
@@ -463,7 +471,12 @@ static int run_forward(dmn_plan* P, const float* x_dev, const int32_t* row_dev, 
         }
         q.out = B(o.out);
         q.B = batch; q.Cin = c.channels; q.S = c.image_size; q.Cout = c.dim;
-        rc = init_conv(q, P->act, st);
+        if (P->init_tc) {
+          q.w = (const float*)(P->wbase + P->params[P->pidx["init_conv.weight"]].off2);
+          rc = init_conv_tcgen05(q, st);
+        } else {
+          rc = init_conv(q, P->act, st);
+        }
         break;
       }
       case OP_CONV: {
@@ -474,7 +487,7 @@ static int run_forward(dmn_plan* P, const float* x_dev, const int32_t* row_dev, 
         const Param& wp = P->params[o.w];
         q.w = o.tc ? (const void*)(P->wbase + wp.off2) : (const void*)(P->wbase + wp.off);
         q.bias = W(o.bias);
-        q.pro = o.pro; q.pstats = (const float*)B(o.pstats); q.pgroups = o.pgroups;
+        q.pro = o.pro; q.pstats = (const stat_t*)B(o.pstats); q.pgroups = o.pgroups;
         q.pgamma = W(o.pgamma); q.pbeta = W(o.pbeta);
         if (o.pro & PRO_TEMB) {
           q.temb = (const float*)B(P->time_table) + o.temb_col;
@@ -482,15 +495,15 @@ static int run_forward(dmn_plan* P, const float* x_dev, const int32_t* row_dev, 
           else { q.d_row = nullptr; q.temb_rstride = 0; q.temb_bstride = P->sumC; }
         }
         q.out = B(o.out); q.res = B(o.res);
-        q.ostats = (float*)B(o.ostats); q.ogroups = o.ogroups;
+        q.ostats = (stat_t*)B(o.ostats); q.ogroups = o.ogroups;
         rc = o.tc ? conv_tcgen05(q, st) : conv_simt(q, P->act, st);
         break;
       }
       case OP_FINALIZE: {
         FinalizeP q;
-        q.raw = B(o.raw); q.stats = (const float*)B(o.stats); q.groups = o.groups;
+        q.raw = B(o.raw); q.stats = (const stat_t*)B(o.stats); q.groups = o.groups;
         q.gamma = W(o.gamma); q.beta = W(o.beta); q.silu = o.silu;
-        q.res = B(o.res); q.out = B(o.out); q.ostats = (float*)B(o.ostats); q.ogroups = o.ogroups;
+        q.res = B(o.res); q.out = B(o.out); q.ostats = (stat_t*)B(o.ostats); q.ogroups = o.ogroups;
         q.B = batch; q.HW = o.HW; q.C = o.C;
         rc = gn_finalize(q, P->act, st);
         break;
@@ -503,7 +516,7 @@ static int run_forward(dmn_plan* P, const float* x_dev, const int32_t* row_dev, 
         break;
       case OP_FINALPROJ: {
         FinalProjP q;
-        q.y = B(o.src1); q.stats = (const float*)B(o.stats); q.groups = o.groups;
+        q.y = B(o.src1); q.stats = (const stat_t*)B(o.stats); q.groups = o.groups;
         q.gamma = W(o.gamma); q.beta = W(o.beta); q.w = W(o.w); q.bias = W(o.bias);
         q.out = out_dev; q.B = batch; q.HW = o.HW; q.C = o.C; q.Cout = o.Cout;
         rc = final_proj(q, P->act, st);
@@ -613,6 +626,12 @@ int dmn_plan_load_param(dmn_plan* p, const char* name, const float* host, int64_
         for (int ci = 0; ci < ch; ++ci)
           for (int t = 0; t < 49; ++t) tmp[((long)t * ch + ci) * dim + co] = host[((long)co * ch + ci) * 49 + t];
       DMN_CUDA_CHECK(cudaMemcpyAsync(p->wbase + q.off, tmp.data(), numel * sizeof(float), cudaMemcpyHostToDevice, st));
+      if (q.has_tc) {
+        std::vector<char> img(init_conv_tcgen05_weight_bytes(dim));
+        init_conv_tcgen05_pack_weights(ch, dim, host, img.data());
+        DMN_CUDA_CHECK(cudaMemcpyAsync(p->wbase + q.off2, img.data(), img.size(), cudaMemcpyHostToDevice, st));
+        DMN_CUDA_CHECK(cudaStreamSynchronize(st));
+      }
       break;
     }
     case PK_LIN_T: {
@@ -735,7 +754,7 @@ int dmn_plan_op_info(const dmn_plan* p, int i, char* name_out, int name_cap, int
     name_out[name_cap - 1] = 0;
   }
   if (kind) *kind = o.kind;
-  if (engine) *engine = (o.kind == OP_CONV && o.tc) ? 1 : 0;
+  if (engine) *engine = ((o.kind == OP_CONV && o.tc) || (o.kind == OP_INIT && p->init_tc)) ? 1 : 0;
   if (flops_per_sample) *flops_per_sample = fl;
   if (bytes_per_sample) *bytes_per_sample = by;
   return 0;

@@ -39,12 +39,26 @@ def test_conv_tcgen05_vs_torch(k, cin, cout, h, b):
     w = _bf(_rand(cout, cin, k, k, seed=2) / (cin * k * k) ** 0.5)
     bias = _rand(cout, seed=3) * 0.1
     ref = F.conv2d(x, w, bias, padding=k // 2)
-    og = min(8, cout // 8)                     # the engine needs >= 8 channels per statistics group
+    og = cout // 32                            # 32 channels per statistics group (the engine needs a multiple of 8)
     y, st = conv_forward(x.to(DEV), w.to(DEV), bias.to(DEV), ksize=k, out_groups=og, act=L.ACT_BF16, engine=L.CONV_TCGEN05)
     assert rel_l2(y.cpu(), ref) <= 4e-3
     g = ref.reshape(b, og, -1)
     assert torch.allclose(st[..., 0].cpu(), g.mean(-1), atol=2e-3)
     assert torch.allclose(st[..., 1].cpu(), (g.var(-1, unbiased=False) + 1e-5).rsqrt(), rtol=5e-3)
+
+
+@pytest.mark.parametrize("mode,cin,cout,h,b", [(1, 32, 32, 8, 3), (1, 128, 128, 32, 2), (1, 256, 256, 16, 3), (1, 64, 64, 14, 2),
+                                               (2, 32, 32, 4, 5), (2, 256, 256, 8, 2), (2, 128, 128, 16, 2), (2, 64, 64, 7, 3)])
+def test_conv_tcgen05_down_up_vs_torch(mode, cin, cout, h, b):
+    """Downsample (Conv k4 s2 p1 as a 2x2 conv over the space-to-depth image) and Upsample (ConvTranspose k4 s2 p1 as four
+    sub-pixel phases) on the tensor-core engine (reference utils.py:77-82)."""
+    x = _bf(_rand(b, cin, h, h, seed=1))
+    w = _bf(_rand(*((cin, cout, 4, 4) if mode == 2 else (cout, cin, 4, 4)), seed=2) / (cin * 8) ** 0.5)
+    bias = _rand(cout, seed=3) * 0.1
+    ref = F.conv2d(x, w, bias, stride=2, padding=1) if mode == 1 else F.conv_transpose2d(x, w, bias, stride=2, padding=1)
+    y, _ = conv_forward(x.to(DEV), w.to(DEV), bias.to(DEV), mode=mode, ksize=4, act=L.ACT_BF16, engine=L.CONV_TCGEN05)
+    assert y.shape == ref.shape
+    assert rel_l2(y.cpu(), ref) <= 4e-3
 
 
 def test_conv_tcgen05_prologue_and_gn1_stats():

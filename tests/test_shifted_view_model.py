@@ -91,3 +91,167 @@ def test_garbage_row_fraction_is_as_documented():
     # MMA rows spent on pad positions = 1 - HW/S
     for hw, frac in ((32, 0.06), (16, 0.114), (8, 0.21), (4, 0.36)):
         assert abs((1 - hw * hw / (hw + 1) ** 2) - frac) < 0.005
+
+
+# ---- the other geometries of conv_tcgen05.cu: GEO_DOWN (k4 s2 p1), GEO_UP (ConvTranspose k4 s2 p1), GEO_INIT (7x7 stem) ----
+def _run_generic(B, S, Wv, halo_lo, halo_hi, n_pass, ntap, NT, n_tiles, fill_a, delta_of, wblock, store):
+    """The CTA loop of the kernel with geometry-specific callbacks."""
+    P = MCTA + halo_lo + halo_hi
+    total = B * S
+    for m0 in range(0, total, MCTA):
+        for nt in range(n_tiles):
+            acc = np.zeros((MCTA, NT), np.float32)
+            for c in range(n_pass):
+                A = np.zeros((4, P + 8, 8), np.float32)
+                for pixel in range(P):
+                    f = m0 - halo_lo + pixel
+                    if 0 <= f < total:
+                        img, rem = divmod(f, S)
+                        row, col = divmod(rem, Wv)
+                        v = fill_a(img, row, col, c)
+                        if v is not None:
+                            A[:, pixel, :] = v.reshape(4, 8)
+                for t in range(ntap):
+                    d = delta_of(t, nt)
+                    Bt = wblock(nt, c, t)                    # [4][NT][8]
+                    for k16 in range(2):
+                        for mt in range(2):
+                            r0 = halo_lo + mt * 128 + d
+                            a = A[2 * k16:2 * k16 + 2, r0:r0 + 128, :].transpose(1, 0, 2).reshape(128, 16)
+                            b = Bt[2 * k16:2 * k16 + 2].transpose(1, 0, 2).reshape(NT, 16)
+                            acc[mt * 128:(mt + 1) * 128] += a @ b.T
+            for r in range(MCTA):
+                f = m0 + r
+                if f < total:
+                    img, rem = divmod(f, S)
+                    row, col = divmod(rem, Wv)
+                    store(img, row, col, nt, acc[r])
+
+
+@pytest.mark.parametrize("B,H,C,Cout", [(3, 8, 32, 32), (2, 16, 64, 64), (5, 4, 32, 64)])
+def test_down_as_space_to_depth_2x2(B, H, C, Cout):
+    W = H
+    g = torch.Generator().manual_seed(1)
+    x = torch.randn(B, C, H, W, generator=g)
+    w = torch.randn(Cout, C, 4, 4, generator=g) / (C * 16) ** 0.5
+    ref = F.conv2d(x, w, stride=2, padding=1).permute(0, 2, 3, 1).numpy()
+    xn, wn = x.permute(0, 2, 3, 1).numpy(), w.numpy()
+    NT = 64 if Cout % 64 == 0 else 32
+    Wv = W // 2 + 1
+    S = (H // 2 + 1) * Wv
+    out = np.zeros((B, H // 2, W // 2, Cout), np.float32)
+
+    def fill_a(img, u, v, c):
+        vals = np.zeros(32, np.float32)
+        for i in range(32):
+            vc = c * 32 + i
+            sub, ci = divmod(vc, C)
+            iy, ix = 2 * u - 1 + (sub >> 1), 2 * v - 1 + (sub & 1)
+            if 0 <= iy < H and 0 <= ix < W:
+                vals[i] = xn[img, iy, ix, ci]
+        return vals
+
+    def wblock(nt, c, t):
+        blk = np.zeros((4, NT, 8), np.float32)
+        for kc in range(4):
+            for e in range(8):
+                vc = c * 32 + kc * 8 + e
+                sub, ci = divmod(vc, C)
+                ky, kx = 2 * (t >> 1) + (sub >> 1), 2 * (t & 1) + (sub & 1)
+                blk[kc, :, e] = wn[nt * NT:(nt + 1) * NT, ci, ky, kx]
+        return blk
+
+    def store(img, u, v, nt, row):
+        if u < H // 2 and v < W // 2:
+            out[img, u, v, nt * NT:(nt + 1) * NT] = row
+
+    _run_generic(B, S, Wv, 0, Wv + 1, 4 * C // 32, 4, NT, Cout // NT, fill_a, lambda t, nt: (t >> 1) * Wv + (t & 1), wblock, store)
+    assert np.abs(out - ref).max() < 1e-4
+
+
+@pytest.mark.parametrize("B,H,C,Cout", [(3, 4, 32, 32), (2, 8, 64, 32), (1, 16, 32, 64)])
+def test_up_as_four_subpixel_phases(B, H, C, Cout):
+    W = H
+    g = torch.Generator().manual_seed(2)
+    x = torch.randn(B, C, H, W, generator=g)
+    w = torch.randn(C, Cout, 4, 4, generator=g) / (C * 4) ** 0.5
+    ref = F.conv_transpose2d(x, w, stride=2, padding=1).permute(0, 2, 3, 1).numpy()
+    xn, wn = x.permute(0, 2, 3, 1).numpy(), w.numpy()
+    NT = 64 if Cout % 64 == 0 else 32
+    tpp = Cout // NT
+    Wv = W + 1
+    S = (H + 1) * Wv
+    out = np.zeros((B, 2 * H, 2 * W, Cout), np.float32)
+
+    def dydx(t, ph):
+        py, px, a, b = ph >> 1, ph & 1, t >> 1, t & 1
+        dy = (0 if a else 1) if py else (-1 if a else 0)
+        dx = (0 if b else 1) if px else (-1 if b else 0)
+        return dy, dx
+
+    def fill_a(img, row, col, c):
+        if row >= 1 and col >= 1:
+            return xn[img, row - 1, col - 1, c * 32:(c + 1) * 32].copy()
+        return None
+
+    def wblock(nt, c, t):
+        ph, ct = divmod(nt, tpp)
+        dy, dx = dydx(t, ph)
+        ky, kx = (ph >> 1) + 1 - 2 * dy, (ph & 1) + 1 - 2 * dx
+        blk = np.zeros((4, NT, 8), np.float32)
+        for kc in range(4):
+            for e in range(8):
+                blk[kc, :, e] = wn[c * 32 + kc * 8 + e, ct * NT:(ct + 1) * NT, ky, kx]
+        return blk
+
+    def delta(t, nt):
+        dy, dx = dydx(t, nt // tpp)
+        return dy * Wv + dx
+
+    def store(img, row, col, nt, vals):
+        ph, ct = divmod(nt, tpp)
+        if row >= 1 and col >= 1:
+            out[img, 2 * (row - 1) + (ph >> 1), 2 * (col - 1) + (ph & 1), ct * NT:(ct + 1) * NT] = vals
+
+    _run_generic(B, S, Wv, Wv + 1, Wv + 1, C // 32, 4, NT, 4 * tpp, fill_a, delta, wblock, store)
+    assert np.abs(out - ref).max() < 1e-4
+
+
+@pytest.mark.parametrize("B,H,Cin,Cout", [(2, 8, 3, 32), (3, 16, 1, 32), (1, 32, 3, 64)])
+def test_stem_7x7_with_kx_packed_into_channels(B, H, Cin, Cout):
+    W = H
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(B, Cin, H, W, generator=g)
+    w = torch.randn(Cout, Cin, 7, 7, generator=g) / (Cin * 49) ** 0.5
+    ref = F.conv2d(x, w, padding=3).permute(0, 2, 3, 1).numpy()
+    xn, wn = x.numpy(), w.numpy()
+    NT = 64 if Cout % 64 == 0 else 32
+    Wv, S = W, (H + 3) * W
+    out = np.zeros((B, H, W, Cout), np.float32)
+
+    def fill_a(img, row, col, c):
+        if row < 3:
+            return None
+        vals = np.zeros(32, np.float32)
+        for vc in range(32):
+            kx, ch = divmod(vc, Cin)
+            ix = col + kx - 3
+            if kx < 7 and 0 <= ix < W:
+                vals[vc] = xn[img, ch, row - 3, ix]
+        return vals
+
+    def wblock(nt, c, t):
+        blk = np.zeros((4, NT, 8), np.float32)
+        for kc in range(4):
+            for e in range(8):
+                kx, ch = divmod(kc * 8 + e, Cin)
+                if kx < 7:
+                    blk[kc, :, e] = wn[nt * NT:(nt + 1) * NT, ch, t, kx]
+        return blk
+
+    def store(img, row, col, nt, vals):
+        if row >= 3:
+            out[img, row - 3, col, nt * NT:(nt + 1) * NT] = vals
+
+    _run_generic(B, S, Wv, 3 * Wv, 3 * Wv, 1, 7, NT, Cout // NT, fill_a, lambda t, nt: (t - 3) * Wv, wblock, store)
+    assert np.abs(out - ref).max() < 1e-4
