@@ -57,7 +57,12 @@ __global__ void group_stats_kernel(const T* x, stat_t* stats, int HW, int C, int
 }
 }  // namespace
 
+namespace dmn { int conv_tcgen05_read_trace(long long* out, int n); }
+
 extern "C" {
+
+/* debug only (not part of the documented ABI): timeline of one CTA of the last tcgen05 conv launched with DMN_TC_TRACE=1 */
+int dmn_debug_conv_trace(long long* out, int n) { return conv_tcgen05_read_trace(out, n); }
 
 size_t dmn_conv_scratch_bytes(const dmn_conv_args* a) { return a ? conv_layout(a).total : 0; }
 

@@ -338,9 +338,19 @@ __global__ void __launch_bounds__(256) gn_finalize_kernel(const FinalizeP p) {
   }
   if (p.ostats) {
     const int og = c / (p.C / p.ogroups);
-    // fixed-point integer atomics: order independent => deterministic
-    atomicAdd(&sm_stats[og * 2], (unsigned long long)__float2ll_rn(s * kStatScaleSum));
-    atomicAdd(&sm_stats[og * 2 + 1], (unsigned long long)__float2ll_rn(ss * kStatScaleSq));
+    // lanes that share the output group form aligned power-of-two classes: butterfly over them, then one fixed-point integer
+    // atomic per class (order independent => deterministic)
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const int og2 = __shfl_xor_sync(0xffffffffu, og, o);
+      const float s2 = __shfl_xor_sync(0xffffffffu, s, o), ss2 = __shfl_xor_sync(0xffffffffu, ss, o);
+      if (og2 == og) { s += s2; ss += ss2; }
+    }
+    const unsigned peers = __match_any_sync(0xffffffffu, og);
+    if ((threadIdx.x & 31) == __ffs(peers) - 1) {
+      atomicAdd(&sm_stats[og * 2], (unsigned long long)__float2ll_rn(s * kStatScaleSum));
+      atomicAdd(&sm_stats[og * 2 + 1], (unsigned long long)__float2ll_rn(ss * kStatScaleSq));
+    }
     __syncthreads();
     for (int i = threadIdx.x; i < 2 * p.ogroups; i += blockDim.x)
       atomicAdd(reinterpret_cast<unsigned long long*>(p.ostats) + (long)b * p.ogroups * 2 + i, sm_stats[i]);
@@ -367,47 +377,57 @@ int gn_finalize(const FinalizeP& p, int act, cudaStream_t st) {
 }
 
 // =====================================================================================================
-// final projection: eps[b][co][pix] = sum_c SiLU(GN(y))[b][pix][c] * w[co][c] + bias[co]
-// one warp per pixel
+// final projection: eps[b][co][pix] = sum_c SiLU(GN(y))[b][pix][c] * w[co][c] + bias[co]      (fp32 NCHW out)
+// one thread per pixel (the output is pixel-contiguous per channel => coalesced fp32 stores); GroupNorm coefficients and
+// the tiny weight matrix live in shared memory.  HBM-bound: esz*C bytes read + 4*Cout written per pixel.
 // =====================================================================================================
 template <typename T>
-__global__ void __launch_bounds__(256) final_proj_kernel(const FinalProjP p) {
-  const int lane = threadIdx.x & 31;
-  const long wid = (long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  const long total = (long)p.B * p.HW;
-  if (wid >= total) return;
-  const int b = (int)(wid / p.HW);
-  const int pix = (int)(wid - (long)b * p.HW);
+__global__ void __launch_bounds__(128) final_proj_kernel(const FinalProjP p) {
+  extern __shared__ float fsm[];
+  float* s_sc = fsm;                 // [C] rstd*gamma
+  float* s_sh = fsm + p.C;           // [C] beta - mean*rstd*gamma
+  float* s_w = fsm + 2 * p.C;        // [Cout][C]
+  const int b = blockIdx.y;
   const int cpg = p.C / p.groups;
   const float inv = 1.f / (float)(p.HW * cpg);
-  const T* y = (const T*)p.y + wid * p.C;
+  for (int c = threadIdx.x; c < p.C; c += blockDim.x) {
+    float mean, rstd;
+    gn_mean_rstd(p.stats + ((long)b * p.groups + c / cpg) * 2, inv, kGnEps, mean, rstd);
+    const float sc = rstd * p.gamma[c];
+    s_sc[c] = sc;
+    s_sh[c] = p.beta[c] - mean * sc;
+  }
+  for (int i = threadIdx.x; i < p.Cout * p.C; i += blockDim.x) s_w[i] = p.w[i];
+  __syncthreads();
+  const int pix = blockIdx.x * blockDim.x + threadIdx.x;
+  if (pix >= p.HW) return;
+  const T* y = (const T*)p.y + ((long)b * p.HW + pix) * p.C;
   float acc[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) acc[j] = 0.f;
-  for (int c = lane; c < p.C; c += 32) {
-    float mean, rstd;
-    gn_mean_rstd(p.stats + ((long)b * p.groups + c / cpg) * 2, inv, kGnEps, mean, rstd);
-    float v = (to_f<T>(y[c]) - mean) * rstd * p.gamma[c] + p.beta[c];
-    v = silu_f(v);
+  for (int c = 0; c < p.C; c += 4) {
+    const float4 t = load4<T>(y + c);
+    const float v[4] = {t.x, t.y, t.z, t.w};
 #pragma unroll
-    for (int j = 0; j < 8; ++j)
-      if (j < p.Cout) acc[j] = fmaf(v, p.w[(long)j * p.C + c], acc[j]);
-  }
+    for (int e = 0; e < 4; ++e) {
+      const float a = silu_f(fmaf(v[e], s_sc[c + e], s_sh[c + e]));
 #pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    if (j < p.Cout) {
-      const float r = warp_sum(acc[j]);
-      if (lane == 0) p.out[((long)b * p.Cout + j) * p.HW + pix] = r + (p.bias ? p.bias[j] : 0.f);
+      for (int j = 0; j < 8; ++j)
+        if (j < p.Cout) acc[j] = fmaf(a, s_w[j * p.C + c + e], acc[j]);
     }
   }
+#pragma unroll
+  for (int j = 0; j < 8; ++j)
+    if (j < p.Cout) p.out[((long)b * p.Cout + j) * p.HW + pix] = acc[j] + (p.bias ? p.bias[j] : 0.f);
 }
 
 int final_proj(const FinalProjP& p, int act, cudaStream_t st) {
-  DMN_REQUIRE(p.Cout <= 8, "final_proj: out_dim > 8 unsupported");
-  const long total = (long)p.B * p.HW;
-  const unsigned grid = (unsigned)((total + 7) / 8);
-  if (act == ACT_F32) final_proj_kernel<float><<<grid, 256, 0, st>>>(p);
-  else final_proj_kernel<bf16><<<grid, 256, 0, st>>>(p);
+  DMN_REQUIRE(p.Cout <= 8 && p.C % 4 == 0, "final_proj: out_dim > 8 or C % 4 != 0 unsupported");
+  const size_t smem = (size_t)(2 + p.Cout) * p.C * sizeof(float);
+  DMN_REQUIRE(smem <= 48 * 1024, "final_proj: channel count too large");
+  dim3 grid((unsigned)((p.HW + 127) / 128), (unsigned)p.B);
+  if (act == ACT_F32) final_proj_kernel<float><<<grid, 128, smem, st>>>(p);
+  else final_proj_kernel<bf16><<<grid, 128, smem, st>>>(p);
   count_launch();
   DMN_LAUNCH_CHECK("final_proj");
   return 0;
