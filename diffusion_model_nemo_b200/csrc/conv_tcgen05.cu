@@ -14,19 +14,23 @@
 //   GEO_INIT  7x7 pad 3 stem on the fp32 NCHW sampler state: the kx direction is packed into channels
 //             (virtual channel = kx*Cin + ch, 7*Cin <= 32), 3 zero rows shared between images, delta = (ky-3)*W.
 //
-// A CTA owns 256 consecutive flat positions (two 128-row accumulators).  Its input window is loaded ONCE per
-// 32-channel pass into shared memory by the producer warps -- which also apply the fused prologue (GroupNorm-apply of
-// the producing conv, SiLU, time-embedding add; padding stays zero) -- in the UMMA K-major, no-swizzle canonical layout
+// A tile is 256 (or 128) consecutive flat positions x one N tile (two / one 128-row accumulators).  Its input window is
+// loaded ONCE per 32-channel pass into shared memory by the producer warps -- which also apply the fused prologue
+// (GroupNorm-apply of the producing conv, SiLU, time-embedding add; padding is written as zero) -- in the UMMA K-major,
+// no-swizzle canonical layout
 //   A_smem[kchunk (8 channels = 16 B)][pixel]      (LBO = PA*16 B between k-chunks, SBO = 128 B between 8-row groups)
 // so the operand of tap t is the same buffer with the start address advanced by delta*16 B: all taps of a k-step read
 // one resident tile and nothing is re-fetched from L2.  Weights are pre-blocked on the host into
 // [n_tile][pass][tap][kchunk][n] 16-byte items and streamed with 1-D bulk async copies (cp.async.bulk -> UBLKCP, the TMA
-// engine's non-tensor mode) through a 6-stage mbarrier ring.
+// engine's non-tensor mode) through an mbarrier ring.
 //
-// Warp roles (192 threads): warps 0-3 operand producers, then epilogue (TMEM -> registers -> +bias, +residual,
-// GroupNorm statistics, bf16 -> global); warp 4 weight loader; warp 5 TMEM allocator + single-thread MMA issuer.
-// Resources per CTA: <= 113 KB shared memory and 256 TMEM columns, so two CTAs share an SM and one CTA's
-// epilogue / operand ramp overlaps the other's MMA main loop.
+// PERSISTENT, warp-specialised CTA (one per SM, 576 threads), tiles assigned round-robin:
+//   warps 0-7   operand producers (global -> prologue transform -> shared), run ahead across tiles (2 operand buffers)
+//   warps 8-15  epilogue (TMEM -> registers -> +bias, +residual, GroupNorm statistics, bf16 -> global); two warps per TMEM
+//               lane quarter, each taking half of the tile's columns
+//   warp 16     weight loader (one lane), warp 17 TMEM allocator + single-thread MMA issuer
+// The accumulators are double buffered in TMEM (2 x mt x NT <= 512 columns), so the epilogue of tile i overlaps the main
+// loop of tile i+1 and the per-CTA setup is paid once per launch.
 //
 // Garbage rows: flat positions that fall on a pad column/row are computed and discarded (1 - HW/S of the MMA
 // work for 3x3: 6 % at 32x32, 11 % at 16x16, 21 % at 8x8, 36 % at 4x4).
@@ -42,30 +46,33 @@ namespace tc {
 
 enum { GEO_SAME = 0, GEO_DOWN = 1, GEO_UP = 2, GEO_INIT = 3 };
 
-constexpr int kThreads = 192;
-constexpr int kProducerThreads = 128;
-constexpr int kMTmax = 2;              // 128-row accumulators per CTA: 2, or 1 when two would leave most SMs idle
+constexpr int kProdWarps = 8, kEpiWarps = 8;
+constexpr int kProdThreads = kProdWarps * 32, kEpiThreads = kEpiWarps * 32;
+constexpr int kLoaderWarp = kProdWarps + kEpiWarps, kMmaWarp = kLoaderWarp + 1;
+constexpr int kThreads = (kMmaWarp + 1) * 32;     // 576
+constexpr int kMTmax = 2;              // 128-row accumulators per tile: 2, or 1 when two would leave most SMs idle
 constexpr int kMcta = 128 * kMTmax;    // table sizing
 constexpr int kCk = 32;                // channels per pass (4 k-chunks of 8)
-constexpr int kStagesMax = 8;         // weight-ring depth is chosen per launch (4..8) to fit shared memory
-constexpr int kMaxItems = 13;          // 16-byte operand items per producer thread per pass (P <= 416)
+constexpr int kStagesMax = 12;         // weight-ring depth (chosen per launch to fit shared memory)
+constexpr int kMaxItems = 7;           // 16-byte operand items per producer thread per pass (P <= 448)
 constexpr int kNimgMax = 20;           // images a 256-position window may touch
 constexpr int kGroupsMax = 32;         // GroupNorm groups of the prologue
-constexpr int kOgMax = 16;             // output-statistics groups per N tile
+constexpr int kOgMax = 8;              // output-statistics groups per N tile (>= 16 channels each)
 constexpr int kSegMax = 4;             // images a warp's 32 consecutive rows may touch (S >= 16)
+constexpr int kSlots = kMTmax * kEpiWarps;   // statistics slot owners per tile: (mt, epilogue warp)
 
 struct Params {
   ConvP c;
   int geo;
-  int S, Wv, pad, halo_lo, P, PA, n_abuf, mt, mcta;
+  int S, Wv, pad, halo_lo, P, PA, mt, mcta;
   int H, W, HW;            // input image
-  int ksize, ntap, NT, n_pass, tiles_per_phase;
+  int ksize, ntap, NT, n_pass, tiles_per_phase, n_tiles_n, m_tiles, total_tiles;
   long total_flat;
   uint32_t lbo_a, sbo_a, lbo_b, sbo_b;   // bytes
   uint32_t tmem_cols;
   int cpg_in, cpg_out, cpg_in_shift, cpg_out_shift, nstage, nt_shift;
   float inv_cnt_in;
-  long long* trace;        // debug: per-role clock64 timeline of CTA (trace_cta, 0); null in production
+  long long* trace;        // debug timeline (null in production)
   int trace_cta;
   // GEO_INIT extras
   const float* cls_w;
@@ -158,15 +165,18 @@ __device__ __forceinline__ uint32_t make_idesc(int M, int N) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
-// debug timeline (DMN_TC_TRACE=1): slot layout documented in tools/trace_conv.py
+
+// debug timeline (DMN_TC_TRACE=1): CTA `trace_cta` records clock64 per role and tile: slot = 16*tile_iter + k
+//   k: 0 producer tile start, 1 producer tables done, 2 producer last pass filled, 4 MMA got accumulators, 5 MMA first operand,
+//      6 MMA tile issued, 8 epilogue tables done, 9 epilogue accumulators ready, 10 epilogue TMEM drained, 11 epilogue tile done
 __device__ long long g_trace[1024];
-#define TRACE(slot)                                                                     \
-  do {                                                                                  \
-    if (p.trace && blockIdx.x == (unsigned)p.trace_cta && blockIdx.y == 0) p.trace[(slot)] = clock64(); \
+#define TRACE(it, k)                                                                                       \
+  do {                                                                                                     \
+    if (p.trace && blockIdx.x == (unsigned)p.trace_cta && (it) < 60) p.trace[16 * (it) + (k)] = clock64(); \
   } while (0)
 
 // flat virtual position -> (image, virtual row, virtual col); img < 0 when out of range.  32-bit arithmetic only
-// (the host guarantees total_flat < 2^30): 64-bit divisions here used to cost ~7 us per CTA.
+// (the host guarantees total_flat < 2^30).
 struct VPos {
   int img, row, col;
 };
@@ -207,169 +217,149 @@ __device__ __forceinline__ void mbar_wait_relaxed(uint32_t bar, uint32_t parity)
   const long long t0 = clock64();
   int n = 0;
   while (!mbar_try_wait(bar, parity)) {
-    __nanosleep(64);
+    __nanosleep(40);
     if ((++n & 1023) == 0 && clock64() - t0 > 4000000000LL) __trap();
   }
+}
+__device__ __forceinline__ void bar_sync_named(int id, int threads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
 }
 
 // ---------------------------------------------------------------------------------------------------
 // kernel
 // ---------------------------------------------------------------------------------------------------
 template <int GEO>
-__global__ void __launch_bounds__(kThreads, 2) conv_tcgen05_kernel(const Params p) {
+__global__ void __launch_bounds__(kThreads, 1) conv_tcgen05_kernel(const Params p) {
   extern __shared__ __align__(128) uint8_t smem[];
   const int tid = threadIdx.x;
   const int warp = tid >> 5, lane = tid & 31;
-  const int m0 = (int)blockIdx.x * p.mcta;
-  const int n_tile = blockIdx.y;
-  const int phase = (GEO == GEO_UP) ? n_tile / p.tiles_per_phase : 0;
-  const int n0 = (GEO == GEO_UP ? n_tile % p.tiles_per_phase : n_tile) * p.NT;
   const int nst = p.nstage;
 
   // ---- shared memory carve-up ----
   const uint32_t a_bytes = 4u * p.PA * 16u;           // one A buffer (4 k-chunks)
   const uint32_t b_bytes = 4u * p.NT * 16u;           // one B stage
   uint8_t* sA = smem;
-  uint8_t* sB = sA + p.n_abuf * a_bytes;
+  uint8_t* sB = sA + 2 * a_bytes;
   uint64_t* bars = reinterpret_cast<uint64_t*>(sB + nst * b_bytes);
   uint64_t* full_b = bars;
   uint64_t* empty_b = bars + kStagesMax;
   uint64_t* full_a = bars + 2 * kStagesMax;
   uint64_t* empty_a = full_a + 2;
   uint64_t* acc_full = empty_a + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 1);
-  int* s_delta = reinterpret_cast<int*>(tmem_slot + 2);                                     // [16] tap offsets
-  float* s_bias = reinterpret_cast<float*>(s_delta + 16);
+  uint64_t* acc_empty = acc_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+  int* s_delta = reinterpret_cast<int*>(tmem_slot + 2);                                     // [4 phases][16 taps]
+  float* s_bias = reinterpret_cast<float*>(s_delta + 64);                                   // [128]
   float2* s_gn = reinterpret_cast<float2*>(s_bias + 128);                                   // [kNimgMax][kGroupsMax] (mean, rstd)
-  float* s_part = reinterpret_cast<float*>(s_gn + kNimgMax * kGroupsMax);                   // [8 (mt,warp)][kSegMax][kOgMax][2]
-  int* s_partkey = reinterpret_cast<int*>(s_part + 8 * kSegMax * kOgMax * 2);               // [8][kSegMax] image key or -1
-  int* s_opix = s_partkey + 8 * kSegMax;                                                    // [256] output pixel or -1
+  float* s_part = reinterpret_cast<float*>(s_gn + kNimgMax * kGroupsMax);                   // [kSlots][kSegMax][kOgMax][2]
+  int* s_partkey = reinterpret_cast<int*>(s_part + kSlots * kSegMax * kOgMax * 2);          // [kSlots][kSegMax] image key or -1
+  int* s_opix = s_partkey + kSlots * kSegMax;                                               // [256] output pixel or -1
   int* s_oimg = s_opix + kMcta;                                                             // [256] image - img_lo (clamped)
   int* s_pix = s_oimg + kMcta;                                                              // [P] operand source or -1
   int* s_pimg = s_pix + p.P;                                                                // [P] image - img_lo
 
-  int f_lo = m0 - p.halo_lo;
-  if (f_lo < 0) f_lo = 0;
-  const int img_lo = f_lo / p.S;
-
-  if (tid == 0) TRACE(0);
   // ---- one-time setup ----
-  if (warp == 4) {          // one lane per barrier
+  if (warp == kLoaderWarp) {          // one lane per barrier
     if (lane < nst) { mbar_init(smem_u32(&full_b[lane]), 1); mbar_init(smem_u32(&empty_b[lane]), 1); }
-    if (lane >= 8 && lane < 10) { mbar_init(smem_u32(&full_a[lane - 8]), kProducerThreads); mbar_init(smem_u32(&empty_a[lane - 8]), 1); }
-    if (lane == 10) mbar_init(smem_u32(acc_full), 1);
+    if (lane >= 16 && lane < 18) { mbar_init(smem_u32(&full_a[lane - 16]), kProdThreads); mbar_init(smem_u32(&empty_a[lane - 16]), 1); }
+    if (lane >= 18 && lane < 20) { mbar_init(smem_u32(&acc_full[lane - 18]), 1); mbar_init(smem_u32(&acc_empty[lane - 18]), kEpiThreads); }
     fence_barrier_init();
-    if (lane >= 16 && lane < 16 + p.ntap) s_delta[lane - 16] = tap_delta<GEO>(p, lane - 16, phase);
   }
-  if (warp == 5) tmem_alloc(smem_u32(tmem_slot), p.tmem_cols);
-  // zero the operand buffers once: padding positions are never written again (GEO_DOWN writes its own zeros)
-  for (uint32_t i = tid; i < p.n_abuf * a_bytes / 16; i += kThreads) reinterpret_cast<uint4*>(sA)[i] = make_uint4(0, 0, 0, 0);
-  for (int i = tid; i < p.NT; i += kThreads) s_bias[i] = p.c.bias ? p.c.bias[n0 + i] : 0.f;
-  for (int i = tid; i < 8 * kSegMax; i += kThreads) s_partkey[i] = -1;
-  // operand source table (one decode per window pixel instead of one per thread-item)
-  if (GEO != GEO_INIT) {
-    for (int pixel = tid; pixel < p.P; pixel += kThreads) {
-      const VPos v = vdecode(m0 - p.halo_lo + pixel, p);
-      int g = -1, il = 0;
-      if (v.img >= 0) {
-        if (GEO == GEO_DOWN) {
-          g = (v.img << 14) | (v.row << 7) | v.col;
-        } else if (v.row >= p.pad && v.col >= p.pad) {
-          g = v.img * p.HW + (v.row - p.pad) * p.W + (v.col - p.pad);
-          il = v.img - img_lo;
-        }
-      }
-      s_pix[pixel] = g;
-      s_pimg[pixel] = il;
-    }
+  if (warp == kMmaWarp) tmem_alloc(smem_u32(tmem_slot), p.tmem_cols);
+  if (tid < 64) {
+    const int ph = tid >> 4, t = tid & 15;
+    s_delta[tid] = t < p.ntap ? tap_delta<GEO>(p, t, ph) : 0;
   }
-  // output row table
-  for (int r = tid; r < p.mcta; r += kThreads) {
-    const VPos v = vdecode(m0 + r, p);
-    bool valid = v.img >= 0;
-    int opix = -1;
-    if (valid) {
-      if (GEO == GEO_SAME) {
-        valid = v.row >= p.pad && v.col >= p.pad;
-        opix = v.img * p.HW + (v.row - p.pad) * p.W + (v.col - p.pad);
-      } else if (GEO == GEO_DOWN) {
-        valid = v.row < (p.H >> 1) && v.col < (p.W >> 1);
-        opix = v.img * (p.HW >> 2) + v.row * (p.W >> 1) + v.col;
-      } else if (GEO == GEO_UP) {
-        valid = v.row >= 1 && v.col >= 1;
-        opix = v.img * (p.HW << 2) + (2 * (v.row - 1) + (phase >> 1)) * (2 * p.W) + 2 * (v.col - 1) + (phase & 1);
-      } else {
-        valid = v.row >= 3;
-        opix = v.img * p.HW + (v.row - 3) * p.W + v.col;
-      }
-    }
-    int il = (v.img >= 0 ? v.img : p.c.B - 1) - img_lo;
-    il = il < 0 ? 0 : (il >= kNimgMax ? kNimgMax - 1 : il);
-    s_opix[r] = valid ? opix : -1;
-    s_oimg[r] = il;
-  }
-  if (GEO == GEO_SAME && (p.c.pro & PRO_GN)) {
-    for (int i = tid; i < kNimgMax * p.c.pgroups; i += kThreads) {
-      const int il = i / p.c.pgroups, g = i - il * p.c.pgroups;
-      const int img = img_lo + il;
-      float mean = 0.f, rstd = 0.f;
-      if (img < p.c.B) gn_mean_rstd(p.c.pstats + ((long)img * p.c.pgroups + g) * 2, p.inv_cnt_in, kGnEps, mean, rstd);
-      s_gn[il * kGroupsMax + g] = make_float2(mean, rstd);
-    }
-  }
-  fence_proxy_async();      // the zero fill must be visible to the tensor-core (async) proxy
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  if (tid == 0) TRACE(1);
 
-  if (warp < 4) {
+  if (warp < kProdWarps) {
     // =============================== operand producers ===============================
-    const int kc = tid & 3;
-    if (GEO == GEO_INIT) {
-      // one pass: virtual channel vc = kx*Cin + ch  (7*Cin <= 32); source is the fp32 NCHW sampler state
-      const float* x = (const float*)p.c.src1;
-      const int Cin = p.c.C1;
-      for (int pixel = tid >> 2; pixel < p.P; pixel += 32) {
-        const VPos v = vdecode(m0 - p.halo_lo + pixel, p);
-        if (v.img < 0 || v.row < 3) continue;          // shared zero rows
-        const int iy = v.row - 3;
-        float f[8];
+    const int kc = tid & 3, px0 = tid >> 2;          // k-chunk, first window pixel of this thread (step 64)
+    const bf16* src1 = (const bf16*)p.c.src1;
+    const bf16* src2 = (const bf16*)p.c.src2;
+    const float* temb_base = nullptr;
+    if (GEO == GEO_SAME && (p.c.pro & PRO_TEMB)) temb_base = p.c.temb + (p.c.d_row ? (long)(*p.c.d_row) * p.c.temb_rstride : 0);
+    int gpass = 0;                                     // passes issued so far (operand-buffer ring position)
+    int pit = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++pit) {
+      if (tid == 0) TRACE(pit, 0);
+      const int m0 = (tile / p.n_tiles_n) * p.mcta;
+      int f_lo = m0 - p.halo_lo;
+      if (f_lo < 0) f_lo = 0;
+      const int img_lo = f_lo / p.S;
+      if (GEO == GEO_INIT) {
+        // one pass: virtual channel vc = kx*Cin + ch  (7*Cin <= 32); source is the fp32 NCHW sampler state
+        const float* x = (const float*)p.c.src1;
+        const int Cin = p.c.C1;
+        const int buf = gpass & 1;
+        mbar_wait_relaxed(smem_u32(&empty_a[buf]), ((gpass >> 1) & 1) ^ 1);
+        for (int pixel = px0; pixel < p.P; pixel += kProdThreads / 4) {
+          const VPos v = vdecode(m0 - p.halo_lo + pixel, p);
+          float f[8];
 #pragma unroll
-        for (int e = 0; e < 8; ++e) {
-          const int vc = kc * 8 + e;
-          const int kx = vc / Cin, ch = vc - kx * Cin;
-          const int ix = v.col + kx - 3;
-          f[e] = (kx < 7 && ix >= 0 && ix < p.W) ? __ldg(x + (((long)v.img * Cin + ch) * p.H + iy) * p.W + ix) : 0.f;
+          for (int e = 0; e < 8; ++e) f[e] = 0.f;
+          if (v.img >= 0 && v.row >= 3) {              // rows 0..2 of every block are the shared zero rows
+            const int iy = v.row - 3;
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              const int vc = kc * 8 + e;
+              const int kx = vc / Cin, ch = vc - kx * Cin;
+              const int ix = v.col + kx - 3;
+              if (kx < 7 && ix >= 0 && ix < p.W) f[e] = __ldg(x + (((long)v.img * Cin + ch) * p.H + iy) * p.W + ix);
+            }
+          }
+          *reinterpret_cast<uint4*>(sA + buf * a_bytes + (uint32_t)kc * p.lbo_a + pixel * 16) = pack8(f);
         }
-        *reinterpret_cast<uint4*>(sA + (uint32_t)kc * p.lbo_a + pixel * 16) = pack8(f);
+        fence_proxy_async();
+        mbar_arrive(smem_u32(&full_a[buf]));
+        ++gpass;
+        continue;
       }
-      fence_proxy_async();
-      mbar_arrive(smem_u32(&full_a[0]));
-    } else {
-      // per-thread item table: smem pixel (tid>>2) + 32 j, k-chunk kc
-      int goff[kMaxItems];      // SAME/UP: img*HW + pix (or -1); DOWN: packed (img, u, v) (or -1)
+      // ---- per-tile tables: operand source per window pixel, GroupNorm (mean, rstd) per touched image ----
+      bar_sync_named(2, kProdThreads);                 // everyone is done with the previous tile's tables
+      for (int pixel = tid; pixel < p.P; pixel += kProdThreads) {
+        const VPos v = vdecode(m0 - p.halo_lo + pixel, p);
+        int g = -1, il = 0;
+        if (v.img >= 0) {
+          if (GEO == GEO_DOWN) {
+            g = (v.img << 14) | (v.row << 7) | v.col;
+          } else if (v.row >= p.pad && v.col >= p.pad) {
+            g = v.img * p.HW + (v.row - p.pad) * p.W + (v.col - p.pad);
+            il = v.img - img_lo;
+          }
+        }
+        s_pix[pixel] = g;
+        s_pimg[pixel] = il;
+      }
+      if (GEO == GEO_SAME && (p.c.pro & PRO_GN)) {
+        for (int i = tid; i < kNimgMax * p.c.pgroups; i += kProdThreads) {
+          const int il = i / p.c.pgroups, g = i - il * p.c.pgroups;
+          const int img = img_lo + il;
+          float mean = 0.f, rstd = 0.f;
+          if (img < p.c.B) gn_mean_rstd(p.c.pstats + ((long)img * p.c.pgroups + g) * 2, p.inv_cnt_in, kGnEps, mean, rstd);
+          s_gn[il * kGroupsMax + g] = make_float2(mean, rstd);
+        }
+      }
+      bar_sync_named(2, kProdThreads);
+      if (tid == 0) TRACE(pit, 1);
+      int goff[kMaxItems];      // SAME/UP: img*HW + pix (or -1 = padding); DOWN: packed (img, u, v) (or -1); -2 = outside the window
       int imgl[kMaxItems];
 #pragma unroll
       for (int j = 0; j < kMaxItems; ++j) {
-        const int pixel = (tid >> 2) + 32 * j;
-        goff[j] = -1;
+        const int pixel = px0 + (kProdThreads / 4) * j;
+        goff[j] = -2;
         imgl[j] = 0;
         if (pixel < p.P) {
           goff[j] = s_pix[pixel];
           imgl[j] = s_pimg[pixel];
         }
       }
-      const bf16* src1 = (const bf16*)p.c.src1;
-      const bf16* src2 = (const bf16*)p.c.src2;
-      const float* temb_base = nullptr;
-      if (GEO == GEO_SAME && (p.c.pro & PRO_TEMB)) temb_base = p.c.temb + (p.c.d_row ? (long)(*p.c.d_row) * p.c.temb_rstride : 0);
-
-      for (int c = 0; c < p.n_pass; ++c) {
-        const int buf = c & 1;
-        mbar_wait_relaxed(smem_u32(&empty_a[buf]), ((c >> 1) & 1) ^ 1);
-        if (tid == 0 && c < 64) TRACE(16 + 4 * c);
+      for (int c = 0; c < p.n_pass; ++c, ++gpass) {
+        const int buf = gpass & 1;
+        mbar_wait_relaxed(smem_u32(&empty_a[buf]), ((gpass >> 1) & 1) ^ 1);
         int cb = c * kCk + kc * 8;        // first (virtual) channel of this thread's k-chunk
         int sy = 0, sx = 0;
         if (GEO == GEO_DOWN) {            // virtual channel = sub * C + ci, sub = sy*2 + sx
@@ -400,7 +390,7 @@ __global__ void __launch_bounds__(kThreads, 2) conv_tcgen05_kernel(const Params 
         if (GEO != GEO_SAME || p.c.pro == PRO_NONE) {
 #pragma unroll
           for (int j = 0; j < kMaxItems; ++j)
-            if (goff[j] >= 0) *reinterpret_cast<uint4*>(dstbase + ((tid >> 2) + 32 * j) * 16) = raw[j];
+            if (goff[j] >= -1) *reinterpret_cast<uint4*>(dstbase + (px0 + (kProdThreads / 4) * j) * 16) = raw[j];   // padding -> zeros
         } else {
           float ga[8], be[8], te[8];
           {
@@ -419,181 +409,254 @@ __global__ void __launch_bounds__(kThreads, 2) conv_tcgen05_kernel(const Params 
           const int g = cb >> p.cpg_in_shift;
 #pragma unroll
           for (int j = 0; j < kMaxItems; ++j) {
-            if (goff[j] < 0) continue;
-            const float2 mr = s_gn[imgl[j] * kGroupsMax + g];
-            if ((p.c.pro & PRO_TEMB) && !temb_shared) {
-              const float* tp = temb_base + (long)(img_lo + imgl[j]) * p.c.temb_bstride + cb;
-              const float4 t0 = *reinterpret_cast<const float4*>(tp), t1 = *reinterpret_cast<const float4*>(tp + 4);
-              te[0] = t0.x; te[1] = t0.y; te[2] = t0.z; te[3] = t0.w; te[4] = t1.x; te[5] = t1.y; te[6] = t1.z; te[7] = t1.w;
-            }
-            float v[8];
-            unpack8(raw[j], v);
-            const float sc = mr.y, sh = -mr.x * mr.y;
+            if (goff[j] < -1) continue;
+            uint4 o = make_uint4(0, 0, 0, 0);          // padding stays zero AFTER the transform
+            if (goff[j] >= 0) {
+              const float2 mr = s_gn[imgl[j] * kGroupsMax + g];
+              if ((p.c.pro & PRO_TEMB) && !temb_shared) {
+                const float* tp = temb_base + (long)(img_lo + imgl[j]) * p.c.temb_bstride + cb;
+                const float4 t0 = *reinterpret_cast<const float4*>(tp), t1 = *reinterpret_cast<const float4*>(tp + 4);
+                te[0] = t0.x; te[1] = t0.y; te[2] = t0.z; te[3] = t0.w; te[4] = t1.x; te[5] = t1.y; te[6] = t1.z; te[7] = t1.w;
+              }
+              float v[8];
+              unpack8(raw[j], v);
+              const float sc = mr.y, sh = -mr.x * mr.y;
 #pragma unroll
-            for (int e = 0; e < 8; ++e) {
-              float t = fmaf(v[e], sc, sh);
-              t = fmaf(t, ga[e], be[e]);
-              if (p.c.pro & PRO_SILU) t = silu_fast(t);
-              v[e] = t + te[e];
+              for (int e = 0; e < 8; ++e) {
+                float t = fmaf(v[e], sc, sh);
+                t = fmaf(t, ga[e], be[e]);
+                if (p.c.pro & PRO_SILU) t = silu_fast(t);
+                v[e] = t + te[e];
+              }
+              o = pack8(v);
             }
-            *reinterpret_cast<uint4*>(dstbase + ((tid >> 2) + 32 * j) * 16) = pack8(v);
+            *reinterpret_cast<uint4*>(dstbase + (px0 + (kProdThreads / 4) * j) * 16) = o;
           }
         }
         fence_proxy_async();
         mbar_arrive(smem_u32(&full_a[buf]));
-        if (tid == 0 && c < 64) TRACE(17 + 4 * c);
       }
+      if (tid == 0) TRACE(pit, 2);
     }
-
+  } else if (warp < kLoaderWarp) {
     // =============================== epilogue ===============================
-    if (tid == 0) TRACE(2);
-    mbar_wait_relaxed(smem_u32(acc_full), 0);
-    tc_fence_after();
-    if (tid == 0) TRACE(3);
+    const int ew = warp - kProdWarps;                 // 0..7
+    const int et = tid - kProdThreads;                // 0..255
+    const int quarter = ew & 3, half = ew >> 2;       // TMEM lane quarter, column half of the tile
     bf16* out = (bf16*)p.c.out;
     const bf16* res = (const bf16*)p.c.res;
-    // The operand / weight buffers are dead once the accumulators are complete: reuse them as a staging tile so that the
-    // global stores are full 256-byte rows (row stride padded by 16 B => conflict-free 16-byte shared stores).
-    const uint32_t rs = (uint32_t)p.NT * 2u + 16u;
-#pragma unroll 1
-    for (int mt = 0; mt < p.mt; ++mt) {
-      uint8_t* stage = smem + (uint32_t)mt * 128u * rs;
-      const int row = mt * 128 + warp * 32 + lane;
-      const int opix = s_opix[row];
-      const bool valid = opix >= 0;
-      const long orow = valid ? (long)opix * p.c.Cout + n0 : 0;
-      const float* cls_row = nullptr;
-      if (GEO == GEO_INIT && p.cls_w && valid)
-        cls_row = p.cls_w + (long)(p.classes ? (int)p.classes[img_lo + s_oimg[row]] : p.pad_class) * p.c.Cout + n0;
-      // statistics: segmented warp reduction keyed by image (rows of a warp are consecutive flat positions, so the key is
-      // non-decreasing); the last lane of every segment stores the partial into a slot owned by (mt, warp, segment):
-      // no atomics, fixed summation order => deterministic
-      const int key = s_oimg[row];
-      unsigned segmask = 0;
-#pragma unroll
-      for (int i = 0; i < 5; ++i) {
-        const int k2 = __shfl_up_sync(0xffffffffu, key, 1 << i);
-        if (lane >= (1 << i) && k2 == key) segmask |= 1u << i;
-      }
-      const int knext = __shfl_down_sync(0xffffffffu, key, 1);
-      const bool tail = (lane == 31) || (knext != key);
-      const unsigned tails = __ballot_sync(0xffffffffu, tail);
-      int seg = __popc(tails & ((1u << lane) - 1u));
-      seg = seg < kSegMax ? seg : kSegMax - 1;
-      // per-thread partial sums per 16-channel pair (statistics groups have >= 16 channels): 16 independent chains
-      float sa[8], qa[8];
-#pragma unroll
-      for (int i = 0; i < 8; ++i) sa[i] = qa[i] = 0.f;
-#pragma unroll
-      for (int ch = 0; ch < 4; ++ch) {
-        if (ch < (p.NT >> 5)) {
-          uint32_t r[32];
-          if (tid == 0) TRACE(300 + (mt * 4 + ch) * 4);
-          tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(mt * p.NT + ch * 32), r);
-          if (tid == 0) TRACE(301 + (mt * 4 + ch) * 4);
-          float vv[32];
-#pragma unroll
-          for (int j = 0; j < 32; ++j) vv[j] = __uint_as_float(r[j]) + s_bias[ch * 32 + j];
-          if (GEO == GEO_INIT && cls_row) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) vv[j] += __ldg(cls_row + ch * 32 + j);
+    // columns owned by this warp: half of the tile (64 / 32); with NT = 32 only the first warp of each lane quarter works
+    const bool active = p.NT >= 64 || half == 0;
+    const int ncol = p.NT >= 64 ? (p.NT >> 1) : p.NT;
+    const int col0 = p.NT >= 64 ? half * ncol : 0;
+    int it = 0, last_ntile = -1;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+      const int n_tile = tile % p.n_tiles_n;
+      const int m0 = (tile / p.n_tiles_n) * p.mcta;
+      const int phase = (GEO == GEO_UP) ? n_tile / p.tiles_per_phase : 0;
+      const int n0 = (GEO == GEO_UP ? n_tile % p.tiles_per_phase : n_tile) * p.NT;
+      int f_lo = m0 - p.halo_lo;
+      if (f_lo < 0) f_lo = 0;
+      const int img_lo = f_lo / p.S;
+      // ---- per-tile tables (epilogue owned) ----
+      for (int r = et; r < p.mcta; r += kEpiThreads) {
+        const VPos v = vdecode(m0 + r, p);
+        bool valid = v.img >= 0;
+        int opix = -1;
+        if (valid) {
+          if (GEO == GEO_SAME) {
+            valid = v.row >= p.pad && v.col >= p.pad;
+            opix = v.img * p.HW + (v.row - p.pad) * p.W + (v.col - p.pad);
+          } else if (GEO == GEO_DOWN) {
+            valid = v.row < (p.H >> 1) && v.col < (p.W >> 1);
+            opix = v.img * (p.HW >> 2) + v.row * (p.W >> 1) + v.col;
+          } else if (GEO == GEO_UP) {
+            valid = v.row >= 1 && v.col >= 1;
+            opix = v.img * (p.HW << 2) + (2 * (v.row - 1) + (phase >> 1)) * (2 * p.W) + 2 * (v.col - 1) + (phase & 1);
+          } else {
+            valid = v.row >= 3;
+            opix = v.img * p.HW + (v.row - 3) * p.W + v.col;
           }
-          if (res && valid) {
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              const uint4 rr = *reinterpret_cast<const uint4*>(res + orow + ch * 32 + q * 8);
-              float rf[8];
-              unpack8(rr, rf);
-#pragma unroll
-              for (int e = 0; e < 8; ++e) vv[q * 8 + e] += rf[e];
-            }
-          }
-#pragma unroll
-          for (int q = 0; q < 4; ++q)
-            *reinterpret_cast<uint4*>(stage + (uint32_t)(warp * 32 + lane) * rs + (uint32_t)(ch * 64 + q * 16)) = pack8(vv + q * 8);
-          if (tid == 0) TRACE(302 + (mt * 4 + ch) * 4);
-          if (p.c.ostats && valid) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              sa[ch * 2 + (j >> 4)] += vv[j];
-              qa[ch * 2 + (j >> 4)] = fmaf(vv[j], vv[j], qa[ch * 2 + (j >> 4)]);
-            }
-          }
-          if (tid == 0) TRACE(303 + (mt * 4 + ch) * 4);
         }
+        int il = (v.img >= 0 ? v.img : p.c.B - 1) - img_lo;
+        il = il < 0 ? 0 : (il >= kNimgMax ? kNimgMax - 1 : il);
+        s_opix[r] = valid ? opix : -1;
+        s_oimg[r] = il;
       }
-      if (tid == 0) TRACE(400 + mt * 4);
-      if (p.c.ostats) {
-        // one segmented scan for all 16 partials (independent shuffle chains), then the segment tails combine the pairs into
-        // groups and store them into the slot owned by (mt, warp, segment): no atomics, fixed order => deterministic
+      if (n_tile != last_ntile) {
+        for (int i = et; i < p.NT; i += kEpiThreads) s_bias[i] = p.c.bias ? p.c.bias[n0 + i] : 0.f;
+        last_ntile = n_tile;
+      }
+      for (int i = et; i < kSlots * kSegMax; i += kEpiThreads) s_partkey[i] = -1;
+      bar_sync_named(1, kEpiThreads);
+      if (et == 0) TRACE(it, 8);
+
+      const int as = it & 1;
+      mbar_wait_relaxed(smem_u32(&acc_full[as]), (it >> 1) & 1);
+      tc_fence_after();
+      if (et == 0) TRACE(it, 9);
+      const uint32_t tacc = tmem_base + (uint32_t)(as * p.mt * p.NT);
+      if (!active) {
+        tc_fence_before();
+        mbar_arrive(smem_u32(&acc_empty[as]));
+      }
+#pragma unroll 1
+      for (int mt = 0; active && mt < p.mt; ++mt) {
+        const int row = mt * 128 + quarter * 32 + lane;
+        const int opix = s_opix[row];
+        const bool valid = opix >= 0;
+        const long orow = valid ? (long)opix * p.c.Cout + n0 + col0 : 0;
+        const float* cls_row = nullptr;
+        if (GEO == GEO_INIT && p.cls_w && valid)
+          cls_row = p.cls_w + (long)(p.classes ? (int)p.classes[img_lo + s_oimg[row]] : p.pad_class) * p.c.Cout + n0 + col0;
+        // statistics: segmented warp reduction keyed by image (rows of a warp are consecutive flat positions, so the key is
+        // non-decreasing); the last lane of every segment stores the partial into a slot owned by (mt, warp, segment)
+        const int key = s_oimg[row];
+        unsigned segmask = 0;
 #pragma unroll
         for (int i = 0; i < 5; ++i) {
-          const bool take = segmask & (1u << i);
-#pragma unroll
-          for (int k = 0; k < 8; ++k) {
-            const float ta = __shfl_up_sync(0xffffffffu, sa[k], 1 << i), tb = __shfl_up_sync(0xffffffffu, qa[k], 1 << i);
-            if (take) { sa[k] += ta; qa[k] += tb; }
-          }
+          const int k2 = __shfl_up_sync(0xffffffffu, key, 1 << i);
+          if (lane >= (1 << i) && k2 == key) segmask |= 1u << i;
         }
-        if (tail) {
-          const int sidx = (mt * 4 + warp) * kSegMax + seg;
-          float* slot = s_part + sidx * kOgMax * 2;
-          s_partkey[sidx] = key;
-          const int sh = p.cpg_out_shift;
-          if (sh <= 4) {
+        const int knext = __shfl_down_sync(0xffffffffu, key, 1);
+        const bool tail = (lane == 31) || (knext != key);
+        const unsigned tails = __ballot_sync(0xffffffffu, tail);
+        int seg = __popc(tails & ((1u << lane) - 1u));
+        seg = seg < kSegMax ? seg : kSegMax - 1;
+        // per-thread partial sums per 16-channel pair (statistics groups have >= 16 channels): independent chains
+        float sa[4], qa[4];
 #pragma unroll
-            for (int g = 0; g < 8; ++g) { slot[g * 2] = sa[g]; slot[g * 2 + 1] = qa[g]; }
-          } else if (sh == 5) {
+        for (int i = 0; i < 4; ++i) sa[i] = qa[i] = 0.f;
 #pragma unroll
-            for (int g = 0; g < 4; ++g) { slot[g * 2] = sa[2 * g] + sa[2 * g + 1]; slot[g * 2 + 1] = qa[2 * g] + qa[2 * g + 1]; }
-          } else if (sh == 6) {
-#pragma unroll
-            for (int g = 0; g < 2; ++g) {
-              slot[g * 2] = (sa[4 * g] + sa[4 * g + 1]) + (sa[4 * g + 2] + sa[4 * g + 3]);
-              slot[g * 2 + 1] = (qa[4 * g] + qa[4 * g + 1]) + (qa[4 * g + 2] + qa[4 * g + 3]);
+        for (int ch = 0; ch < 2; ++ch) {
+          if (ch * 32 < ncol) {
+            uint32_t r[32];
+            tmem_ld32(tacc + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(mt * p.NT + col0 + ch * 32), r);
+            if (mt == p.mt - 1 && (ch + 1) * 32 >= ncol) {     // last TMEM read of this tile: hand the accumulators back
+              tc_fence_before();
+              mbar_arrive(smem_u32(&acc_empty[as]));
+              if (et == 0) TRACE(it, 10);
             }
-          } else {
-            slot[0] = ((sa[0] + sa[1]) + (sa[2] + sa[3])) + ((sa[4] + sa[5]) + (sa[6] + sa[7]));
-            slot[1] = ((qa[0] + qa[1]) + (qa[2] + qa[3])) + ((qa[4] + qa[5]) + (qa[6] + qa[7]));
+            const int nv = ncol < 32 ? ncol : 32;              // valid columns in this chunk (16 when NT = 32)
+            float vv[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) vv[j] = __uint_as_float(r[j]) + s_bias[col0 + ch * 32 + (j < nv ? j : 0)];
+            if (GEO == GEO_INIT && cls_row) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (j < nv) vv[j] += __ldg(cls_row + ch * 32 + j);
+            }
+            if (res && valid) {
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                if (q * 8 < nv) {
+                  const uint4 rr = *reinterpret_cast<const uint4*>(res + orow + ch * 32 + q * 8);
+                  float rf[8];
+                  unpack8(rr, rf);
+#pragma unroll
+                  for (int e = 0; e < 8; ++e) vv[q * 8 + e] += rf[e];
+                }
+              }
+            }
+            if (valid) {
+#pragma unroll
+              for (int q = 0; q < 4; ++q)
+                if (q * 8 < nv) *reinterpret_cast<uint4*>(out + orow + ch * 32 + q * 8) = pack8(vv + q * 8);
+            }
+            if (p.c.ostats && valid) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) {
+                if (j < nv) {
+                  sa[ch * 2 + (j >> 4)] += vv[j];
+                  qa[ch * 2 + (j >> 4)] = fmaf(vv[j], vv[j], qa[ch * 2 + (j >> 4)]);
+                }
+              }
+            }
+          }
+        }
+        if (p.c.ostats) {
+          // one segmented scan for all partials (independent shuffle chains), then the segment tails combine the pairs into
+          // groups and store them into the slot owned by (mt, warp, segment): no atomics, fixed order => deterministic
+#pragma unroll
+          for (int i = 0; i < 5; ++i) {
+            const bool take = segmask & (1u << i);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const float ta = __shfl_up_sync(0xffffffffu, sa[k], 1 << i), tb = __shfl_up_sync(0xffffffffu, qa[k], 1 << i);
+              if (take) { sa[k] += ta; qa[k] += tb; }
+            }
+          }
+          if (tail) {
+            const int sidx = (mt * kEpiWarps + ew) * kSegMax + seg;
+            float* slot = s_part + sidx * kOgMax * 2;
+            s_partkey[sidx] = key;
+            // group index local to the N tile of the first pair of this warp: (col0 >> 4) pairs in
+            const int sh = p.cpg_out_shift, pair0 = col0 >> 4;
+            if (sh <= 4) {
+#pragma unroll
+              for (int k = 0; k < 4; ++k) { slot[(pair0 + k) * 2] = sa[k]; slot[(pair0 + k) * 2 + 1] = qa[k]; }
+            } else if (sh == 5) {
+#pragma unroll
+              for (int k = 0; k < 2; ++k) { slot[((pair0 >> 1) + k) * 2] = sa[2 * k] + sa[2 * k + 1]; slot[((pair0 >> 1) + k) * 2 + 1] = qa[2 * k] + qa[2 * k + 1]; }
+            } else {
+              // >= 64 channels per group: this warp's (<= 64) columns belong to one group; its two halves are separate slots
+              slot[(pair0 >> (sh - 4)) * 2] = (sa[0] + sa[1]) + (sa[2] + sa[3]);
+              slot[(pair0 >> (sh - 4)) * 2 + 1] = (qa[0] + qa[1]) + (qa[2] + qa[3]);
+            }
           }
         }
       }
-      // copy-out: every thread hands ITS OWN staged row (NT*2 contiguous bytes in shared and in global memory) to the bulk
-      // copy engine: no barrier, no copy loop, full-line global writes
-      if (tid == 0) TRACE(401 + mt * 4);
-      fence_proxy_async();
-      if (tid == 0) TRACE(402 + mt * 4);
-      if (valid) {
-        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(out + orow),
-                     "r"(smem_u32(stage + (uint32_t)(warp * 32 + lane) * rs)), "r"((uint32_t)p.NT * 2u)
-                     : "memory");
-        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+      // ---- flush the tile's GroupNorm statistics: fixed-order sum over the slots, then one fixed-point integer atomic per
+      // (image, group) => deterministic ----
+      bar_sync_named(1, kEpiThreads);
+      if (p.c.ostats) {
+        const int sh = p.cpg_out_shift;
+        const int og_tile = (p.NT + (1 << sh) - 1) >> sh;
+        for (int i = et; i < kNimgMax * og_tile; i += kEpiThreads) {
+          const int il = i / og_tile, gl = i - il * og_tile;
+          const int img = img_lo + il;
+          float a = 0.f, b = 0.f;
+          bool any = false;
+          for (int k = 0; k < kSlots * kSegMax; ++k) {
+            if (s_partkey[k] == il) {
+              // a slot only holds the groups its warp's columns cover
+              const int half_k = ((k / kSegMax) % kEpiWarps) >> 2;
+              const int pair0 = (half_k * (p.NT >> 1)) >> 4, pairs = (p.NT >> 1) >> 4;
+              const int g_lo = sh <= 4 ? pair0 : (pair0 >> (sh - 4));
+              const int g_hi = sh <= 4 ? pair0 + (pairs > 0 ? pairs : 1) - 1 : ((pair0 + (pairs > 0 ? pairs : 1) - 1) >> (sh - 4));
+              if (gl >= g_lo && gl <= g_hi) {
+                a += s_part[(k * kOgMax + gl) * 2];
+                b += s_part[(k * kOgMax + gl) * 2 + 1];
+                any = true;
+              }
+            }
+          }
+          if (any && img < p.c.B) stat_add(p.c.ostats + ((long)img * p.c.ogroups + (n0 >> sh) + gl) * 2, a, b);
+        }
       }
-      if (tid == 0) TRACE(403 + mt * 4);
+      bar_sync_named(1, kEpiThreads);       // tables / slots are rewritten by the next tile
+      if (et == 0) TRACE(it, 11);
     }
-    asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
-    if (tid == 0) TRACE(408);
-    if (tid == 0) TRACE(4);
-    tc_fence_before();
-  } else if (warp == 4) {
+  } else if (warp == kLoaderWarp) {
     // =============================== weight loader ===============================
     if (lane == 0) {
-      const uint8_t* wsrc = (const uint8_t*)p.c.w + (size_t)n_tile * p.n_pass * p.ntap * b_bytes;
-      const int total = p.n_pass * p.ntap;
       int st = 0, ph = 1;
-      for (int s = 0; s < total; ++s) {
-        mbar_wait_relaxed(smem_u32(&empty_b[st]), ph);
-        mbar_arrive_expect_tx(smem_u32(&full_b[st]), b_bytes);
-        bulk_g2s(smem_u32(sB + st * b_bytes), wsrc + (size_t)s * b_bytes, b_bytes, smem_u32(&full_b[st]));
-        if (s == 0) TRACE(5);
-        if (s == total - 1) TRACE(6);
-        if (++st == nst) { st = 0; ph ^= 1; }
+      const int per_tile = p.n_pass * p.ntap;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        const int n_tile = tile % p.n_tiles_n;
+        const uint8_t* wsrc = (const uint8_t*)p.c.w + (size_t)n_tile * per_tile * b_bytes;
+        for (int s = 0; s < per_tile; ++s) {
+          mbar_wait_relaxed(smem_u32(&empty_b[st]), ph);
+          mbar_arrive_expect_tx(smem_u32(&full_b[st]), b_bytes);
+          bulk_g2s(smem_u32(sB + st * b_bytes), wsrc + (size_t)s * b_bytes, b_bytes, smem_u32(&full_b[st]));
+          if (++st == nst) { st = 0; ph ^= 1; }
+        }
       }
     }
   } else {
     // =============================== MMA issuer ===============================
     // One thread feeds the tensor core; its instruction stream is the critical path, so everything that does not depend on
-    // the stage is hoisted: descriptor high words, LBO fields, the four (k16, mt) operand offsets.
+    // the stage is hoisted: descriptor high words, LBO fields, operand offsets.
     if (lane == 0) {
       const uint32_t idesc = make_idesc(128, p.NT);
       const uint32_t hi_a = (p.sbo_a >> 4) | (1u << 14), hi_b = (p.sbo_b >> 4) | (1u << 14);
@@ -602,90 +665,94 @@ __global__ void __launch_bounds__(kThreads, 2) conv_tcgen05_kernel(const Params 
       const uint32_t a_buf_units = a_bytes >> 4;
       const uint32_t a_k16 = 2u * (p.lbo_a >> 4);
       const uint32_t b_units0 = smem_u32(sB) >> 4, b_stage_units = b_bytes >> 4, b_k16 = 2u * (p.lbo_b >> 4);
-      const uint32_t d1 = tmem_base + (uint32_t)p.NT;
       const bool two = p.mt == 2;
-      int st = 0, ph = 0;
-      for (int c = 0; c < p.n_pass; ++c) {
-        const int buf = c & 1;
-        mbar_wait(smem_u32(&full_a[buf]), (c >> 1) & 1);
+      int st = 0, ph = 0, gpass = 0, it = 0;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+        const int n_tile = tile % p.n_tiles_n;
+        const int phase = (GEO == GEO_UP) ? n_tile / p.tiles_per_phase : 0;
+        const int* deltas = s_delta + phase * 16;
+        const int as = it & 1;
+        mbar_wait(smem_u32(&acc_empty[as]), ((it >> 1) & 1) ^ 1);      // epilogue has drained this accumulator set
         tc_fence_after();
-        if (c < 64) TRACE(18 + 4 * c);
-        const uint32_t au = a_units0 + (uint32_t)buf * a_buf_units;
-        for (int t = 0; t < p.ntap; ++t) {
-          mbar_wait(smem_u32(&full_b[st]), ph);
+        TRACE(it, 4);
+        const uint32_t d0 = tmem_base + (uint32_t)(as * p.mt * p.NT), d1 = d0 + (uint32_t)p.NT;
+        long long wa = 0, wb = 0;
+        for (int c = 0; c < p.n_pass; ++c, ++gpass) {
+          const int buf = gpass & 1;
+          long long tw = p.trace ? clock64() : 0;
+          mbar_wait(smem_u32(&full_a[buf]), (gpass >> 1) & 1);
+          if (p.trace) wa += clock64() - tw;
           tc_fence_after();
-          const uint32_t a0 = au + (uint32_t)s_delta[t];
-          const uint32_t b0 = b_units0 + (uint32_t)st * b_stage_units;
-          const uint32_t acc = (c | t) ? 1u : 0u;
-          {
-            const uint64_t bd = ((uint64_t)hi_b << 32) | ((b0 & 0x3FFFu) | lbo_b_f);
-            const uint64_t ad0 = ((uint64_t)hi_a << 32) | ((a0 & 0x3FFFu) | lbo_a_f);
-            const uint64_t ad1 = ((uint64_t)hi_a << 32) | (((a0 + 128u) & 0x3FFFu) | lbo_a_f);
-            umma_bf16(tmem_base, ad0, bd, idesc, acc);
-            if (two) umma_bf16(d1, ad1, bd, idesc, acc);
+          if (c == 0) TRACE(it, 5);
+          const uint32_t au = a_units0 + (uint32_t)buf * a_buf_units;
+          for (int t = 0; t < p.ntap; ++t) {
+            tw = p.trace ? clock64() : 0;
+            mbar_wait(smem_u32(&full_b[st]), ph);
+            if (p.trace) wb += clock64() - tw;
+            tc_fence_after();
+            const uint32_t a0 = au + (uint32_t)deltas[t];
+            const uint32_t b0 = b_units0 + (uint32_t)st * b_stage_units;
+            const uint32_t acc = (c | t) ? 1u : 0u;
+            {
+              const uint64_t bd = ((uint64_t)hi_b << 32) | ((b0 & 0x3FFFu) | lbo_b_f);
+              const uint64_t ad0 = ((uint64_t)hi_a << 32) | ((a0 & 0x3FFFu) | lbo_a_f);
+              const uint64_t ad1 = ((uint64_t)hi_a << 32) | (((a0 + 128u) & 0x3FFFu) | lbo_a_f);
+              umma_bf16(d0, ad0, bd, idesc, acc);
+              if (two) umma_bf16(d1, ad1, bd, idesc, acc);
+            }
+            {
+              const uint64_t bd = ((uint64_t)hi_b << 32) | (((b0 + b_k16) & 0x3FFFu) | lbo_b_f);
+              const uint64_t ad0 = ((uint64_t)hi_a << 32) | (((a0 + a_k16) & 0x3FFFu) | lbo_a_f);
+              const uint64_t ad1 = ((uint64_t)hi_a << 32) | (((a0 + a_k16 + 128u) & 0x3FFFu) | lbo_a_f);
+              umma_bf16(d0, ad0, bd, idesc, 1u);
+              if (two) umma_bf16(d1, ad1, bd, idesc, 1u);
+            }
+            umma_commit(smem_u32(&empty_b[st]));     // frees the weight stage once these MMAs retire
+            if (++st == nst) { st = 0; ph ^= 1; }
           }
-          {
-            const uint64_t bd = ((uint64_t)hi_b << 32) | (((b0 + b_k16) & 0x3FFFu) | lbo_b_f);
-            const uint64_t ad0 = ((uint64_t)hi_a << 32) | (((a0 + a_k16) & 0x3FFFu) | lbo_a_f);
-            const uint64_t ad1 = ((uint64_t)hi_a << 32) | (((a0 + a_k16 + 128u) & 0x3FFFu) | lbo_a_f);
-            umma_bf16(tmem_base, ad0, bd, idesc, 1u);
-            if (two) umma_bf16(d1, ad1, bd, idesc, 1u);
-          }
-          umma_commit(smem_u32(&empty_b[st]));     // frees the weight stage once these MMAs retire
-          if (++st == nst) { st = 0; ph ^= 1; }
+          umma_commit(smem_u32(&empty_a[buf]));      // frees the operand buffer
         }
-        umma_commit(smem_u32(&empty_a[buf]));      // frees the operand buffer
-        if (c < 64) TRACE(19 + 4 * c);
+        umma_commit(smem_u32(&acc_full[as]));        // accumulators of this tile complete -> epilogue
+        TRACE(it, 6);
+        if (p.trace && blockIdx.x == (unsigned)p.trace_cta && it < 60) { p.trace[16 * it + 12] = wa; p.trace[16 * it + 13] = wb; }
       }
-      umma_commit(smem_u32(acc_full));
     }
   }
 
+  tc_fence_before();
   __syncthreads();
-  // flush the CTA's GroupNorm statistics: fixed-order sum over the (mt, warp, segment) slots, then one fixed-point
-  // integer atomic per (image, group) => deterministic
-  if (p.c.ostats) {
-    const int og_tile = (p.NT + (1 << p.cpg_out_shift) - 1) >> p.cpg_out_shift;
-    for (int i = tid; i < kNimgMax * og_tile; i += kThreads) {
-      const int il = i / og_tile, gl = i - il * og_tile;
-      const int img = img_lo + il;
-      float a = 0.f, b = 0.f;
-      bool any = false;
-#pragma unroll 4
-      for (int k = 0; k < 8 * kSegMax; ++k) {
-        if (s_partkey[k] == il) {
-          a += s_part[(k * kOgMax + gl) * 2];
-          b += s_part[(k * kOgMax + gl) * 2 + 1];
-          any = true;
-        }
-      }
-      if (any && img < p.c.B) stat_add(p.c.ostats + ((long)img * p.c.ogroups + (n0 >> p.cpg_out_shift) + gl) * 2, a, b);
-    }
-  }
-  if (warp == 5) {
+  if (warp == kMmaWarp) {
     tc_fence_after();
     tmem_dealloc(tmem_base, p.tmem_cols);
   }
-  if (tid == 0) TRACE(7);
 }
 
 static size_t smem_fixed_bytes(const Params& p) {
-  return (size_t)p.n_abuf * 4 * p.PA * 16 + (2 * kStagesMax + 5) * 8 + 16 + 16 * 4 + 128 * 4 + (size_t)kNimgMax * kGroupsMax * 8 +
-         (size_t)8 * kSegMax * kOgMax * 2 * 4 + 8 * kSegMax * 4 + 2 * kMcta * 4 + 2 * (size_t)p.P * 4 + 128;
+  return (size_t)2 * 4 * p.PA * 16 + (2 * kStagesMax + 8) * 8 + 16 + 64 * 4 + 128 * 4 + (size_t)kNimgMax * kGroupsMax * 8 +
+         (size_t)kSlots * kSegMax * kOgMax * 2 * 4 + kSlots * kSegMax * 4 + 2 * kMcta * 4 + 2 * (size_t)p.P * 4 + 128;
 }
 static size_t smem_bytes(const Params& p) { return smem_fixed_bytes(p) + (size_t)p.nstage * 4 * p.NT * 16; }
-constexpr size_t kSmemLimit = 113 * 1024;
-// deepest weight ring (<= kStagesMax, >= 4) that still lets two CTAs share an SM
+constexpr size_t kSmemLimit = 200 * 1024;
 static bool pick_stages(Params& p) {
   const size_t fixed = smem_fixed_bytes(p), stage = (size_t)4 * p.NT * 16;
   if (fixed + 4 * stage > kSmemLimit) return false;
   int n = (int)((kSmemLimit - fixed) / stage);
   p.nstage = n > kStagesMax ? kStagesMax : n;
-  // the epilogue stages both 128-row output tiles in the (then dead) operand + weight buffers
-  return (size_t)p.mt * 128 * (p.NT * 2 + 16) <= (size_t)p.n_abuf * 4 * p.PA * 16 + (size_t)p.nstage * stage;
+  return true;
 }
 
 static int pick_nt(int cout) { return cout % 128 == 0 ? 128 : (cout % 64 == 0 ? 64 : (cout % 32 == 0 ? 32 : 0)); }
+
+static int num_sms() {
+  static int n = 0;
+  if (!n) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
 
 static bool fill_params(const ConvP& c, int geo, Params& p) {
   p = Params();
@@ -696,6 +763,7 @@ static bool fill_params(const ConvP& c, int geo, Params& p) {
   p.H = c.Hin; p.W = c.Win; p.HW = c.Hin * c.Win;
   p.ksize = c.ksize;
   p.tiles_per_phase = c.Cout / p.NT;
+  p.n_tiles_n = (geo == GEO_UP ? 4 : 1) * p.tiles_per_phase;
   p.nt_shift = p.NT == 128 ? 7 : (p.NT == 64 ? 6 : 5);
   int halo_hi = 0;
   if (geo == GEO_SAME) {
@@ -734,27 +802,27 @@ static bool fill_params(const ConvP& c, int geo, Params& p) {
     p.halo_lo = halo_hi = 3 * p.Wv;
     p.n_pass = 1;
   }
-  p.n_abuf = (geo == GEO_INIT) ? 1 : 2;
+  p.total_flat = (long)c.B * p.S;
+  if (p.total_flat + 4096 >= (1L << 30) || (long)c.B * 4 * p.HW >= (1L << 30)) return false;   // 32-bit index arithmetic
   {
-    // two accumulators (256 rows) per CTA halve the weight traffic per FLOP; with few tiles one accumulator keeps more SMs busy
-    const long tiles2 = ((long)c.B * p.S + 255) / 256 * (geo == GEO_UP ? 4 : 1) * (c.Cout / p.NT);
-    p.mt = tiles2 >= 240 ? 2 : 1;
+    // two accumulators (256 rows) per tile halve the weight traffic per FLOP; with few tiles one accumulator keeps more SMs busy
+    const long tiles2 = (p.total_flat + 255) / 256 * p.n_tiles_n;
+    p.mt = tiles2 >= num_sms() ? 2 : 1;
     p.mcta = 128 * p.mt;
   }
+  p.m_tiles = (int)((p.total_flat + p.mcta - 1) / p.mcta);
+  p.total_tiles = p.m_tiles * p.n_tiles_n;
   p.P = p.mcta + p.halo_lo + halo_hi;
   p.PA = p.P;
   while (p.PA % 8 != 2) ++p.PA;
-  if (geo != GEO_INIT && (4 * p.P + kProducerThreads - 1) / kProducerThreads > kMaxItems) return false;
-  if (geo == GEO_INIT) p.P = p.P;   // (the stem's producer loops over the window; no per-thread item table)
+  if (geo != GEO_INIT && (4 * p.P + kProdThreads - 1) / kProdThreads > kMaxItems) return false;
   if (kMcta / p.S + 3 > kNimgMax || p.S < 16) return false;
-  p.total_flat = (long)c.B * p.S;
   p.lbo_a = (uint32_t)p.PA * 16u;
   p.sbo_a = 128u;
   p.lbo_b = (uint32_t)p.NT * 16u;
   p.sbo_b = 128u;
-  p.tmem_cols = (uint32_t)(p.mt * p.NT);
-  if (p.tmem_cols < 32) p.tmem_cols = 32;
-  if (p.total_flat + 4096 >= (1L << 30) || (long)c.B * 4 * p.HW >= (1L << 30)) return false;   // 32-bit index arithmetic
+  p.tmem_cols = 32;
+  while (p.tmem_cols < (uint32_t)(2 * p.mt * p.NT)) p.tmem_cols <<= 1;    // double-buffered accumulators, power of two
   p.cpg_in = 1;
   p.cpg_in_shift = p.cpg_out_shift = 0;
   p.inv_cnt_in = 0.f;
@@ -774,8 +842,7 @@ static bool fill_params(const ConvP& c, int geo, Params& p) {
     if (p.cpg_out % 16 || (p.cpg_out & (p.cpg_out - 1))) return false;
     while ((1 << p.cpg_out_shift) < p.cpg_out) ++p.cpg_out_shift;
     if ((p.NT + p.cpg_out - 1) / p.cpg_out > kOgMax) return false;
-    if (p.cpg_out < p.NT && p.NT % p.cpg_out) return false;
-    if (p.cpg_out > p.NT && p.cpg_out % p.NT) return false;
+    if (p.NT < 64) return false;     // each epilogue warp must own whole 16-channel pairs
   }
   return pick_stages(p);
 }
@@ -791,17 +858,16 @@ static int launch(Params p, cudaStream_t st) {
   if (trace_on) {
     void* sym = nullptr;
     DMN_CUDA_CHECK(cudaGetSymbolAddress(&sym, g_trace));
+    DMN_CUDA_CHECK(cudaMemsetAsync(sym, 0, sizeof(long long) * 1024, st));
     p.trace = (long long*)sym;
-    const long nx = (p.total_flat + p.mcta - 1) / p.mcta;
-    p.trace_cta = (int)(nx / 2);
+    p.trace_cta = 3;
   }
   static bool attr_set = false;
   if (!attr_set) {
     DMN_CUDA_CHECK(cudaFuncSetAttribute(conv_tcgen05_kernel<GEO>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemLimit));
     attr_set = true;
   }
-  const unsigned gy = (unsigned)((GEO == GEO_UP ? 4 : 1) * (p.c.Cout / p.NT));
-  dim3 grid((unsigned)((p.total_flat + p.mcta - 1) / p.mcta), gy);
+  const int grid = p.total_tiles < num_sms() ? p.total_tiles : num_sms();
   conv_tcgen05_kernel<GEO><<<grid, kThreads, smem_bytes(p), st>>>(p);
   count_launch();
   DMN_LAUNCH_CHECK("conv_tcgen05");
@@ -892,7 +958,6 @@ void init_conv_tcgen05_pack_weights(int cin, int cout, const float* w, void* dst
           }
 }
 
-// debug: copy the trace of the last traced launch to the host (DMN_TC_TRACE=1)
 int conv_tcgen05_read_trace(long long* out, int n) {
   if (n > 1024) n = 1024;
   DMN_CUDA_CHECK(cudaDeviceSynchronize());

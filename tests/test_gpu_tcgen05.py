@@ -39,9 +39,11 @@ def test_conv_tcgen05_vs_torch(k, cin, cout, h, b):
     w = _bf(_rand(cout, cin, k, k, seed=2) / (cin * k * k) ** 0.5)
     bias = _rand(cout, seed=3) * 0.1
     ref = F.conv2d(x, w, bias, padding=k // 2)
-    og = cout // 32                            # 32 channels per statistics group (the engine needs a multiple of 8)
+    og = cout // 32 if cout >= 64 else 0       # 32 channels per statistics group; fused statistics need an N tile >= 64
     y, st = conv_forward(x.to(DEV), w.to(DEV), bias.to(DEV), ksize=k, out_groups=og, act=L.ACT_BF16, engine=L.CONV_TCGEN05)
     assert rel_l2(y.cpu(), ref) <= 4e-3
+    if og == 0:
+        return
     g = ref.reshape(b, og, -1)
     assert torch.allclose(st[..., 0].cpu(), g.mean(-1), atol=2e-3)
     assert torch.allclose(st[..., 1].cpu(), (g.var(-1, unbiased=False) + 1e-5).rsqrt(), rtol=5e-3)

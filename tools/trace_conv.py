@@ -1,14 +1,14 @@
-"""Debug aid: per-role clock64 timeline of one CTA of the tcgen05 conv kernel (DMN_TC_TRACE=1).
-
-slots: 0 start, 1 setup done, 2 producers done, 3 accumulators ready, 4 epilogue done, 5 first B copy issued, 6 last B copy
-issued, 7 CTA end; per pass c: 16+4c producer got the buffer, 17+4c producer filled it, 18+4c MMA got it, 19+4c MMA issued it."""
+"""Debug aid: per-role clock64 timeline of one persistent CTA of the tcgen05 conv kernel (DMN_TC_TRACE=1).
+slot = 16*tile_iter + k;  k: 0 producer tile start, 1 producer tables done, 2 producer last pass filled, 4 MMA got accumulators,
+5 MMA first operand, 6 MMA tile issued, 8 epilogue tables done, 9 accumulators ready, 10 TMEM drained, 11 epilogue tile done"""
 import ctypes as C
 import os
 import sys
 
 os.environ["DMN_TC_TRACE"] = "1"
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
 import torch
 from diffusion_model_nemo_b200 import _lib as L
 from gpu_helpers import conv_forward
@@ -32,21 +32,17 @@ def run(k, cin, cout, h, b, gn, mode=0):
     buf = (C.c_longlong * 1024)()
     lib.dmn_debug_conv_trace(buf, 1024)
     t = list(buf)
-    t0 = t[0]
+    t0 = min(v for v in t if v)
     rel = lambda v: (v - t0) if v else None
-    n_pass = (4 * cin if mode == 1 else cin) // 32
-    print(f"== k{k} mode{mode} {cin}->{cout} @{h}x{h} B={b} gn={gn}: passes={n_pass}")
-    print("   setup", rel(t[1]), " firstB", rel(t[5]), " lastB", rel(t[6]), " prod_done", rel(t[2]), " acc_ready", rel(t[3]),
-          " epi_done", rel(t[4]), " end", rel(t[7]))
-    print("   epilogue chunks (ld_issue, ld_done, stored, stats_done):")
-    for i in range(8):
-        print("     ", [rel(t[300 + i * 4 + k]) for k in range(4)])
-    print("   per mt (chunks_done, scan_done, fence_done, bulk_issued):", [rel(t[400 + k]) for k in range(8)], " wait_group_done", rel(t[408]))
-    for c in range(min(n_pass, 1)):
-        print(f"   pass {c}: prod_get {rel(t[16+4*c])} prod_fill {rel(t[17+4*c])}  mma_get {rel(t[18+4*c])} mma_issued {rel(t[19+4*c])}")
+    print(f"== k{k} mode{mode} {cin}->{cout} @{h}x{h} B={b} gn={gn}")
+    for it in range(10):
+        row = t[16 * it:16 * it + 16]
+        if not any(row):
+            break
+        print(f"   tile {it}: prod start {rel(row[0])} tables {rel(row[1])} filled {rel(row[2])} | mma acc {rel(row[4])} firstA {rel(row[5])} "
+              f"issued {rel(row[6])} (waitA {row[12]} waitB {row[13]}) | epi tables {rel(row[8])} ready {rel(row[9])} drained {rel(row[10])} done {rel(row[11])}")
 
 
 if __name__ == "__main__":
-    run(3, 128, 128, 32, 64, False)
-    run(3, 256, 256, 4, 256, False)
-    run(1, 128, 384, 32, 64, False)
+    run(3, 128, 128, 32, 256, False)
+    run(3, 256, 256, 16, 256, True)
