@@ -54,7 +54,10 @@ constexpr int kThreads = (kMmaWarp + 1) * 32;     // 576
 constexpr int kMTmax = 2;              // 128-row accumulators per tile: 2, or 1 when two would leave most SMs idle
 constexpr int kMcta = 128 * kMTmax;    // table sizing
 constexpr int kCk = 32;                // channels per pass (4 k-chunks of 8)
-constexpr int kStagesMax = 12;         // weight-ring depth (chosen per launch to fit shared memory)
+constexpr int kStagesMax = 8;          // weight-ring depth (chosen per launch to fit shared memory); one stage = G taps
+constexpr int kABuf = 3;               // operand (A) buffers: the producers run up to kABuf passes ahead of the MMA issuer
+constexpr int kDepth = 1;              // passes a producer thread keeps in flight (cp.async groups) before it finishes the oldest;
+                                       // kABuf >= kDepth + 2, else finishing pass c would wait for the MMAs of pass c-1
 constexpr int kMaxItems = 7;           // 16-byte operand items per producer thread per pass (P <= 448)
 constexpr int kNimgMax = 20;           // images a 256-position window may touch
 constexpr int kGroupsMax = 32;         // GroupNorm groups of the prologue
@@ -72,6 +75,9 @@ struct Params {
   uint32_t lbo_a, sbo_a, lbo_b, sbo_b;   // bytes
   uint32_t tmem_cols;
   int cpg_in, cpg_out, cpg_in_shift, cpg_out_shift, nstage, nt_shift;
+  int G, stages_per_pass;  // taps per weight stage, ntap / G
+  uint32_t stage_bytes;    // G * 4 * NT * 16
+  int delta[64];           // [4 phases][16 taps] tap offsets in flat positions (constant bank => uniform registers in the issuer)
   float inv_cnt_in;
   long long* trace;        // debug timeline (null in production)
   int trace_cta;
@@ -109,15 +115,14 @@ __device__ __forceinline__ VPos vdecode(int f, const Params& p) {
   r.col = (int)(rem - row * uW);
   return r;
 }
-// tap offset in flat positions
-template <int GEO>
-__device__ __forceinline__ int tap_delta(const Params& p, int t, int phase) {
-  if (GEO == GEO_SAME) {
+// tap offset in flat positions (host: the table is passed in the kernel parameters = constant bank)
+static int tap_delta(const Params& p, int geo, int t, int phase) {
+  if (geo == GEO_SAME) {
     const int kh = p.ksize >> 1, ky = t / p.ksize, kx = t - ky * p.ksize;
     return (ky - kh) * p.Wv + (kx - kh);
-  } else if (GEO == GEO_DOWN) {
+  } else if (geo == GEO_DOWN) {
     return (t >> 1) * p.Wv + (t & 1);
-  } else if (GEO == GEO_UP) {
+  } else if (geo == GEO_UP) {
     const int py = phase >> 1, px = phase & 1, a = t >> 1, b = t & 1;
     const int dy = py ? (a ? 0 : 1) : (a ? -1 : 0);
     const int dx = px ? (b ? 0 : 1) : (b ? -1 : 0);
@@ -133,24 +138,25 @@ template <int GEO>
 __global__ void __launch_bounds__(kThreads, 1) conv_tcgen05_kernel(const Params p) {
   extern __shared__ __align__(128) uint8_t smem[];
   const int tid = threadIdx.x;
-  const int warp = tid >> 5, lane = tid & 31;
+  // broadcast => ptxas knows the role branches below are warp-uniform and may use the uniform datapath inside them
+  const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0), lane = tid & 31;
   const int nst = p.nstage;
 
   // ---- shared memory carve-up ----
   const uint32_t a_bytes = 4u * p.PA * 16u;           // one A buffer (4 k-chunks)
-  const uint32_t b_bytes = 4u * p.NT * 16u;           // one B stage
+  const uint32_t tap_bytes = 4u * p.NT * 16u;         // weights of one tap of one pass
+  const uint32_t b_bytes = p.stage_bytes;             // one B stage (G taps)
   uint8_t* sA = smem;
-  uint8_t* sB = sA + 2 * a_bytes;
+  uint8_t* sB = sA + kABuf * a_bytes;
   uint64_t* bars = reinterpret_cast<uint64_t*>(sB + nst * b_bytes);
   uint64_t* full_b = bars;
   uint64_t* empty_b = bars + kStagesMax;
   uint64_t* full_a = bars + 2 * kStagesMax;
-  uint64_t* empty_a = full_a + 2;
-  uint64_t* acc_full = empty_a + 2;
+  uint64_t* empty_a = full_a + kABuf;
+  uint64_t* acc_full = empty_a + kABuf;
   uint64_t* acc_empty = acc_full + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
-  int* s_delta = reinterpret_cast<int*>(tmem_slot + 2);                                     // [4 phases][16 taps]
-  float* s_bias = reinterpret_cast<float*>(s_delta + 64);                                   // [128]
+  float* s_bias = reinterpret_cast<float*>(tmem_slot + 2);                                  // [128]
   float2* s_gn = reinterpret_cast<float2*>(s_bias + 128);                                   // [kNimgMax][kGroupsMax] (mean, rstd)
   float* s_part = reinterpret_cast<float*>(s_gn + kNimgMax * kGroupsMax);                   // [kSlots][kSegMax][kOgMax][2]
   int* s_partkey = reinterpret_cast<int*>(s_part + kSlots * kSegMax * kOgMax * 2);          // [kSlots][kSegMax] image key or -1
@@ -162,15 +168,11 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tcgen05_kernel(const Params 
   // ---- one-time setup ----
   if (warp == kLoaderWarp) {          // one lane per barrier
     if (lane < nst) { mbar_init(smem_u32(&full_b[lane]), 1); mbar_init(smem_u32(&empty_b[lane]), 1); }
-    if (lane >= 16 && lane < 18) { mbar_init(smem_u32(&full_a[lane - 16]), kProdThreads); mbar_init(smem_u32(&empty_a[lane - 16]), 1); }
-    if (lane >= 18 && lane < 20) { mbar_init(smem_u32(&acc_full[lane - 18]), 1); mbar_init(smem_u32(&acc_empty[lane - 18]), kEpiThreads); }
+    if (lane >= 16 && lane < 16 + kABuf) { mbar_init(smem_u32(&full_a[lane - 16]), kProdThreads); mbar_init(smem_u32(&empty_a[lane - 16]), 1); }
+    if (lane >= 24 && lane < 26) { mbar_init(smem_u32(&acc_full[lane - 24]), 1); mbar_init(smem_u32(&acc_empty[lane - 24]), kEpiThreads); }
     fence_barrier_init();
   }
   if (warp == kMmaWarp) tmem_alloc(smem_u32(tmem_slot), p.tmem_cols);
-  if (tid < 64) {
-    const int ph = tid >> 4, t = tid & 15;
-    s_delta[tid] = t < p.ntap ? tap_delta<GEO>(p, t, ph) : 0;
-  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -178,12 +180,20 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tcgen05_kernel(const Params 
 
   if (warp < kProdWarps) {
     // =============================== operand producers ===============================
+    // Each thread owns up to kMaxItems 16-byte items (pixel, k-chunk) of every pass.  A pass is ISSUED as cp.async (LDGSTS)
+    // copies straight into the operand buffer (padding is stored as zeros), and FINISHED kDepth passes later: wait for the
+    // thread's own copies, apply the fused prologue in place (GroupNorm-apply, SiLU, time-embedding add), make the writes
+    // visible to the tensor core (async proxy) and arrive on the buffer's barrier.  Global latency is thereby covered by
+    // kDepth passes in flight without staging the raw data in registers.
     const int kc = tid & 3, px0 = tid >> 2;          // k-chunk, first window pixel of this thread (step 64)
     const bf16* src1 = (const bf16*)p.c.src1;
     const bf16* src2 = (const bf16*)p.c.src2;
     const float* temb_base = nullptr;
     if (GEO == GEO_SAME && (p.c.pro & PRO_TEMB)) temb_base = p.c.temb + (p.c.d_row ? (long)(*p.c.d_row) * p.c.temb_rstride : 0);
-    int gpass = 0;                                     // passes issued so far (operand-buffer ring position)
+    const bool has_pro = GEO == GEO_SAME && p.c.pro != PRO_NONE;
+    const uint32_t sA_u = smem_u32(sA);
+    int ibuf = 0, fbuf = 0;
+    uint32_t iph = 1;                                  // parity of the "buffer is free" wait; flips when the ring wraps
     int pit = 0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++pit) {
       if (tid == 0) TRACE(pit, 0);
@@ -195,8 +205,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tcgen05_kernel(const Params 
         // one pass: virtual channel vc = kx*Cin + ch  (7*Cin <= 32); source is the fp32 NCHW sampler state
         const float* x = (const float*)p.c.src1;
         const int Cin = p.c.C1;
-        const int buf = gpass & 1;
-        mbar_wait_relaxed(smem_u32(&empty_a[buf]), ((gpass >> 1) & 1) ^ 1);
+        mbar_wait_relaxed(smem_u32(&empty_a[ibuf]), iph);
         for (int pixel = px0; pixel < p.P; pixel += kProdThreads / 4) {
           const VPos v = vdecode(m0 - p.halo_lo + pixel, p);
           float f[8];
@@ -212,11 +221,12 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tcgen05_kernel(const Params 
               if (kx < 7 && ix >= 0 && ix < p.W) f[e] = __ldg(x + (((long)v.img * Cin + ch) * p.H + iy) * p.W + ix);
             }
           }
-          *reinterpret_cast<uint4*>(sA + buf * a_bytes + (uint32_t)kc * p.lbo_a + pixel * 16) = pack8(f);
+          *reinterpret_cast<uint4*>(sA + ibuf * a_bytes + (uint32_t)kc * p.lbo_a + pixel * 16) = pack8(f);
         }
         fence_proxy_async();
-        mbar_arrive(smem_u32(&full_a[buf]));
-        ++gpass;
+        mbar_arrive(smem_u32(&full_a[ibuf]));
+        if (++ibuf == kABuf) { ibuf = 0; iph ^= 1; }
+        fbuf = ibuf;
         continue;
       }
       // ---- per-tile tables: operand source per window pixel, GroupNorm (mean, rstd) per touched image ----
@@ -258,41 +268,11 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tcgen05_kernel(const Params 
           imgl[j] = s_pimg[pixel];
         }
       }
-      for (int c = 0; c < p.n_pass; ++c, ++gpass) {
-        const int buf = gpass & 1;
-        mbar_wait_relaxed(smem_u32(&empty_a[buf]), ((gpass >> 1) & 1) ^ 1);
-        int cb = c * kCk + kc * 8;        // first (virtual) channel of this thread's k-chunk
-        int sy = 0, sx = 0;
-        if (GEO == GEO_DOWN) {            // virtual channel = sub * C + ci, sub = sy*2 + sx
-          const int sub = cb / p.c.C1;
-          cb -= sub * p.c.C1;
-          sy = sub >> 1;
-          sx = sub & 1;
-        }
-        const bf16* src;
-        int Cs, cofs;
-        if (cb < p.c.C1) { src = src1; Cs = p.c.C1; cofs = cb; }
-        else { src = src2; Cs = p.c.C2; cofs = cb - p.c.C1; }
-        uint4 raw[kMaxItems];
-#pragma unroll
-        for (int j = 0; j < kMaxItems; ++j) {
-          raw[j] = make_uint4(0, 0, 0, 0);
-          if (goff[j] >= 0) {
-            if (GEO == GEO_DOWN) {
-              const int img = goff[j] >> 14, iy = 2 * ((goff[j] >> 7) & 127) - 1 + sy, ix = 2 * (goff[j] & 127) - 1 + sx;
-              if (iy >= 0 && iy < p.H && ix >= 0 && ix < p.W)
-                raw[j] = __ldg(reinterpret_cast<const uint4*>(src + ((long)img * p.HW + iy * p.W + ix) * Cs + cofs));
-            } else {
-              raw[j] = __ldg(reinterpret_cast<const uint4*>(src + (long)goff[j] * Cs + cofs));
-            }
-          }
-        }
-        uint8_t* dstbase = sA + buf * a_bytes + (uint32_t)kc * p.lbo_a;
-        if (GEO != GEO_SAME || p.c.pro == PRO_NONE) {
-#pragma unroll
-          for (int j = 0; j < kMaxItems; ++j)
-            if (goff[j] >= -1) *reinterpret_cast<uint4*>(dstbase + (px0 + (kProdThreads / 4) * j) * 16) = raw[j];   // padding -> zeros
-        } else {
+
+      // finish pass c (in buffer fbuf): prologue in place on this thread's own items, publish to the tensor core
+      auto finish = [&](int c) {
+        if (has_pro) {
+          const int cb = c * kCk + kc * 8;
           float ga[8], be[8], te[8];
           {
             const float4 g0 = *reinterpret_cast<const float4*>(p.c.pgamma + cb), g1 = *reinterpret_cast<const float4*>(p.c.pgamma + cb + 4);
@@ -308,34 +288,84 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tcgen05_kernel(const Params 
             te[0] = t0.x; te[1] = t0.y; te[2] = t0.z; te[3] = t0.w; te[4] = t1.x; te[5] = t1.y; te[6] = t1.z; te[7] = t1.w;
           }
           const int g = cb >> p.cpg_in_shift;
+          uint8_t* base = sA + fbuf * a_bytes + (uint32_t)kc * p.lbo_a;
 #pragma unroll
           for (int j = 0; j < kMaxItems; ++j) {
-            if (goff[j] < -1) continue;
-            uint4 o = make_uint4(0, 0, 0, 0);          // padding stays zero AFTER the transform
-            if (goff[j] >= 0) {
-              const float2 mr = s_gn[imgl[j] * kGroupsMax + g];
-              if ((p.c.pro & PRO_TEMB) && !temb_shared) {
-                const float* tp = temb_base + (long)(img_lo + imgl[j]) * p.c.temb_bstride + cb;
-                const float4 t0 = *reinterpret_cast<const float4*>(tp), t1 = *reinterpret_cast<const float4*>(tp + 4);
-                te[0] = t0.x; te[1] = t0.y; te[2] = t0.z; te[3] = t0.w; te[4] = t1.x; te[5] = t1.y; te[6] = t1.z; te[7] = t1.w;
-              }
-              float v[8];
-              unpack8(raw[j], v);
-              const float sc = mr.y, sh = -mr.x * mr.y;
-#pragma unroll
-              for (int e = 0; e < 8; ++e) {
-                float t = fmaf(v[e], sc, sh);
-                t = fmaf(t, ga[e], be[e]);
-                if (p.c.pro & PRO_SILU) t = silu_fast(t);
-                v[e] = t + te[e];
-              }
-              o = pack8(v);
+            if (goff[j] < 0) continue;                 // padding stays zero AFTER the transform
+            uint4* slot = reinterpret_cast<uint4*>(base + (px0 + (kProdThreads / 4) * j) * 16);
+            const float2 mr = s_gn[imgl[j] * kGroupsMax + g];
+            if ((p.c.pro & PRO_TEMB) && !temb_shared) {
+              const float* tp = temb_base + (long)(img_lo + imgl[j]) * p.c.temb_bstride + cb;
+              const float4 t0 = *reinterpret_cast<const float4*>(tp), t1 = *reinterpret_cast<const float4*>(tp + 4);
+              te[0] = t0.x; te[1] = t0.y; te[2] = t0.z; te[3] = t0.w; te[4] = t1.x; te[5] = t1.y; te[6] = t1.z; te[7] = t1.w;
             }
-            *reinterpret_cast<uint4*>(dstbase + (px0 + (kProdThreads / 4) * j) * 16) = o;
+            float v[8];
+            unpack8(*slot, v);
+            const float sc = mr.y, sh = -mr.x * mr.y;
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              float t = fmaf(v[e], sc, sh);
+              t = fmaf(t, ga[e], be[e]);
+              if (p.c.pro & PRO_SILU) t = silu_fast(t);
+              v[e] = t + te[e];
+            }
+            *slot = pack8(v);
           }
         }
         fence_proxy_async();
-        mbar_arrive(smem_u32(&full_a[buf]));
+        mbar_arrive(smem_u32(&full_a[fbuf]));
+        if (++fbuf == kABuf) fbuf = 0;
+      };
+
+      int inflight = 0;
+      for (int c = 0; c < p.n_pass; ++c) {
+        mbar_wait_relaxed(smem_u32(&empty_a[ibuf]), iph);
+        int cb = c * kCk + kc * 8;        // first (virtual) channel of this thread's k-chunk
+        int sy = 0, sx = 0;
+        if (GEO == GEO_DOWN) {            // virtual channel = sub * C + ci, sub = sy*2 + sx
+          const int sub = cb / p.c.C1;
+          cb -= sub * p.c.C1;
+          sy = sub >> 1;
+          sx = sub & 1;
+        }
+        const bf16* src;
+        int Cs, cofs;
+        if (cb < p.c.C1) { src = src1; Cs = p.c.C1; cofs = cb; }
+        else { src = src2; Cs = p.c.C2; cofs = cb - p.c.C1; }
+        const uint32_t dst0 = sA_u + ibuf * a_bytes + (uint32_t)kc * p.lbo_a + (uint32_t)px0 * 16u;
+#pragma unroll
+        for (int j = 0; j < kMaxItems; ++j) {
+          if (goff[j] < -1) continue;                  // outside the window
+          const uint32_t dst = dst0 + (uint32_t)((kProdThreads / 4) * j) * 16u;
+          const bf16* sp = nullptr;
+          if (goff[j] >= 0) {
+            if (GEO == GEO_DOWN) {
+              const int img = goff[j] >> 14, iy = 2 * ((goff[j] >> 7) & 127) - 1 + sy, ix = 2 * (goff[j] & 127) - 1 + sx;
+              if (iy >= 0 && iy < p.H && ix >= 0 && ix < p.W) sp = src + ((long)img * p.HW + iy * p.W + ix) * Cs + cofs;
+            } else {
+              sp = src + (long)goff[j] * Cs + cofs;
+            }
+          }
+          if (sp) cp_async16(dst, sp);
+          else asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(dst), "r"(0) : "memory");   // padding -> zeros
+        }
+        cp_async_commit();
+        if (++ibuf == kABuf) { ibuf = 0; iph ^= 1; }
+        if (++inflight > kDepth) {
+          cp_async_wait<kDepth>();
+          finish(c - kDepth);
+          --inflight;
+        }
+      }
+      // drain: the last passes of the tile
+      if (kDepth >= 2 && inflight == 2) {
+        cp_async_wait<1>();
+        finish(p.n_pass - 2);
+        --inflight;
+      }
+      if (inflight == 1) {
+        cp_async_wait<0>();
+        finish(p.n_pass - 1);
       }
       if (tid == 0) TRACE(pit, 2);
     }
@@ -540,83 +570,93 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tcgen05_kernel(const Params 
     }
   } else if (warp == kLoaderWarp) {
     // =============================== weight loader ===============================
-    if (lane == 0) {
-      int st = 0, ph = 1;
-      const int per_tile = p.n_pass * p.ntap;
-      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-        const int n_tile = tile % p.n_tiles_n;
-        const uint8_t* wsrc = (const uint8_t*)p.c.w + (size_t)n_tile * per_tile * b_bytes;
-        for (int s = 0; s < per_tile; ++s) {
-          mbar_wait_relaxed(smem_u32(&empty_b[st]), ph);
+    // warp-uniform loop, one elected lane issues: one bulk copy (UBLKCP) of G taps (stage_bytes, contiguous in the blocked
+    // weight image) per stage.  Copies of >= 16 KB are needed to reach the L2 -> shared streaming rate the MMAs consume.
+    const bool leader = elect_one();
+    int st = 0;
+    uint32_t ph = 1;
+    const int per_tile = p.n_pass * p.stages_per_pass;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      const int n_tile = tile % p.n_tiles_n;
+      const uint8_t* wsrc = (const uint8_t*)p.c.w + (size_t)n_tile * per_tile * b_bytes;
+      for (int s = 0; s < per_tile; ++s) {
+        mbar_wait_relaxed(smem_u32(&empty_b[st]), ph);
+        if (leader) {
           mbar_arrive_expect_tx(smem_u32(&full_b[st]), b_bytes);
           bulk_g2s(smem_u32(sB + st * b_bytes), wsrc + (size_t)s * b_bytes, b_bytes, smem_u32(&full_b[st]));
-          if (++st == nst) { st = 0; ph ^= 1; }
         }
+        __syncwarp();
+        if (++st == nst) { st = 0; ph ^= 1; }
       }
     }
   } else {
     // =============================== MMA issuer ===============================
-    // One thread feeds the tensor core; its instruction stream is the critical path, so everything that does not depend on
-    // the stage is hoisted: descriptor high words, LBO fields, operand offsets.
-    if (lane == 0) {
-      const uint32_t idesc = make_idesc(128, p.NT);
-      const uint32_t hi_a = (p.sbo_a >> 4) | (1u << 14), hi_b = (p.sbo_b >> 4) | (1u << 14);
-      const uint32_t lbo_a_f = ((p.lbo_a >> 4) & 0x3FFFu) << 16, lbo_b_f = ((p.lbo_b >> 4) & 0x3FFFu) << 16;
-      const uint32_t a_units0 = (smem_u32(sA) >> 4) + (uint32_t)p.halo_lo;          // 16-byte units
-      const uint32_t a_buf_units = a_bytes >> 4;
-      const uint32_t a_k16 = 2u * (p.lbo_a >> 4);
-      const uint32_t b_units0 = smem_u32(sB) >> 4, b_stage_units = b_bytes >> 4, b_k16 = 2u * (p.lbo_b >> 4);
-      const bool two = p.mt == 2;
-      int st = 0, ph = 0, gpass = 0, it = 0;
-      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
-        const int n_tile = tile % p.n_tiles_n;
-        const int phase = (GEO == GEO_UP) ? n_tile / p.tiles_per_phase : 0;
-        const int* deltas = s_delta + phase * 16;
-        const int as = it & 1;
-        mbar_wait(smem_u32(&acc_empty[as]), ((it >> 1) & 1) ^ 1);      // epilogue has drained this accumulator set
+    // The whole warp runs the loop (waits included) and ONE elected lane issues tcgen05.mma / tcgen05.commit: with a
+    // warp-uniform loop every descriptor word is computed in uniform registers (UIADD3/UMOV feeding UTCHMMA directly).  An
+    // `if (lane == 0)` loop instead makes ptxas wrap every MMA in an R2UR + vote loop (~160 clk per MMA issued, measured),
+    // which alone caps the tensor pipe at ~40 %; see tools/mma_rate2.cu.
+    const bool leader = elect_one();
+    const uint32_t idesc = make_idesc(128, p.NT);
+    const uint32_t hi_a = (p.sbo_a >> 4) | (1u << 14), hi_b = (p.sbo_b >> 4) | (1u << 14);
+    const uint32_t lbo_a_f = ((p.lbo_a >> 4) & 0x3FFFu) << 16, lbo_b_f = ((p.lbo_b >> 4) & 0x3FFFu) << 16;
+    const uint32_t a_units0 = (smem_u32(sA) >> 4) + (uint32_t)p.halo_lo;          // 16-byte units
+    const uint32_t a_buf_units = a_bytes >> 4;
+    const uint32_t a_k16 = 2u * (p.lbo_a >> 4);
+    const uint32_t b_units0 = smem_u32(sB) >> 4, b_stage_units = b_bytes >> 4, b_tap_units = tap_bytes >> 4, b_k16 = 2u * (p.lbo_b >> 4);
+    const bool two = p.mt == 2;
+    const int G = p.G;
+    int st = 0, cbuf = 0, it = 0;
+    uint32_t ph = 0, cph = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+      const int n_tile = tile % p.n_tiles_n;
+      const int phase = (GEO == GEO_UP) ? n_tile / p.tiles_per_phase : 0;
+      const int as = it & 1;
+      mbar_wait(smem_u32(&acc_empty[as]), ((it >> 1) & 1) ^ 1);      // epilogue has drained this accumulator set
+      tc_fence_after();
+      if (leader) TRACE(it, 4);
+      const uint32_t d0 = tmem_base + (uint32_t)(as * p.mt * p.NT), d1 = d0 + (uint32_t)p.NT;
+      for (int c = 0; c < p.n_pass; ++c) {
+        mbar_wait(smem_u32(&full_a[cbuf]), cph);
         tc_fence_after();
-        TRACE(it, 4);
-        const uint32_t d0 = tmem_base + (uint32_t)(as * p.mt * p.NT), d1 = d0 + (uint32_t)p.NT;
-        long long wa = 0, wb = 0;
-        for (int c = 0; c < p.n_pass; ++c, ++gpass) {
-          const int buf = gpass & 1;
-          long long tw = p.trace ? clock64() : 0;
-          mbar_wait(smem_u32(&full_a[buf]), (gpass >> 1) & 1);
-          if (p.trace) wa += clock64() - tw;
+        if (c == 0 && leader) TRACE(it, 5);
+        const uint32_t au = a_units0 + (uint32_t)cbuf * a_buf_units;
+        for (int s = 0; s < p.stages_per_pass; ++s) {
+          const int t0 = s * G;
+          mbar_wait(smem_u32(&full_b[st]), ph);
           tc_fence_after();
-          if (c == 0) TRACE(it, 5);
-          const uint32_t au = a_units0 + (uint32_t)buf * a_buf_units;
-          for (int t = 0; t < p.ntap; ++t) {
-            tw = p.trace ? clock64() : 0;
-            mbar_wait(smem_u32(&full_b[st]), ph);
-            if (p.trace) wb += clock64() - tw;
-            tc_fence_after();
-            const uint32_t a0 = au + (uint32_t)deltas[t];
-            const uint32_t b0 = b_units0 + (uint32_t)st * b_stage_units;
+          const uint32_t bs = b_units0 + (uint32_t)st * b_stage_units;
+          // descriptor words are computed OUTSIDE the elected branch so that they are warp-uniform values (uniform registers)
+          for (int g = 0; g < G; ++g) {
+            const int t = t0 + g;
+            const uint32_t a0 = au + (uint32_t)p.delta[phase * 16 + t];
+            const uint32_t b0 = bs + (uint32_t)g * b_tap_units;
             const uint32_t acc = (c | t) ? 1u : 0u;
-            {
-              const uint64_t bd = ((uint64_t)hi_b << 32) | ((b0 & 0x3FFFu) | lbo_b_f);
-              const uint64_t ad0 = ((uint64_t)hi_a << 32) | ((a0 & 0x3FFFu) | lbo_a_f);
-              const uint64_t ad1 = ((uint64_t)hi_a << 32) | (((a0 + 128u) & 0x3FFFu) | lbo_a_f);
-              umma_bf16(d0, ad0, bd, idesc, acc);
-              if (two) umma_bf16(d1, ad1, bd, idesc, acc);
+            const uint64_t bd0 = ((uint64_t)hi_b << 32) | ((b0 & 0x3FFFu) | lbo_b_f);
+            const uint64_t bd1 = ((uint64_t)hi_b << 32) | (((b0 + b_k16) & 0x3FFFu) | lbo_b_f);
+            const uint64_t ad00 = ((uint64_t)hi_a << 32) | ((a0 & 0x3FFFu) | lbo_a_f);
+            const uint64_t ad01 = ((uint64_t)hi_a << 32) | (((a0 + 128u) & 0x3FFFu) | lbo_a_f);
+            const uint64_t ad10 = ((uint64_t)hi_a << 32) | (((a0 + a_k16) & 0x3FFFu) | lbo_a_f);
+            const uint64_t ad11 = ((uint64_t)hi_a << 32) | (((a0 + a_k16 + 128u) & 0x3FFFu) | lbo_a_f);
+            if (leader) {
+              umma_bf16(d0, ad00, bd0, idesc, acc);
+              if (two) umma_bf16(d1, ad01, bd0, idesc, acc);
+              umma_bf16(d0, ad10, bd1, idesc, 1u);
+              if (two) umma_bf16(d1, ad11, bd1, idesc, 1u);
             }
-            {
-              const uint64_t bd = ((uint64_t)hi_b << 32) | (((b0 + b_k16) & 0x3FFFu) | lbo_b_f);
-              const uint64_t ad0 = ((uint64_t)hi_a << 32) | (((a0 + a_k16) & 0x3FFFu) | lbo_a_f);
-              const uint64_t ad1 = ((uint64_t)hi_a << 32) | (((a0 + a_k16 + 128u) & 0x3FFFu) | lbo_a_f);
-              umma_bf16(d0, ad0, bd, idesc, 1u);
-              if (two) umma_bf16(d1, ad1, bd, idesc, 1u);
-            }
-            umma_commit(smem_u32(&empty_b[st]));     // frees the weight stage once these MMAs retire
-            if (++st == nst) { st = 0; ph ^= 1; }
           }
-          umma_commit(smem_u32(&empty_a[buf]));      // frees the operand buffer
+          if (leader) umma_commit(smem_u32(&empty_b[st]));     // frees the weight stage once these MMAs retire
+          __syncwarp();
+          if (++st == nst) { st = 0; ph ^= 1; }
         }
+        if (leader) umma_commit(smem_u32(&empty_a[cbuf]));      // frees the operand buffer
+        __syncwarp();
+        if (++cbuf == kABuf) { cbuf = 0; cph ^= 1; }
+      }
+      if (leader) {
         umma_commit(smem_u32(&acc_full[as]));        // accumulators of this tile complete -> epilogue
         TRACE(it, 6);
-        if (p.trace && blockIdx.x == (unsigned)p.trace_cta && it < 60) { p.trace[16 * it + 12] = wa; p.trace[16 * it + 13] = wb; }
       }
+      __syncwarp();
     }
   }
 
@@ -629,17 +669,25 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tcgen05_kernel(const Params 
 }
 
 static size_t smem_fixed_bytes(const Params& p) {
-  return (size_t)2 * 4 * p.PA * 16 + (2 * kStagesMax + 8) * 8 + 16 + 64 * 4 + 128 * 4 + (size_t)kNimgMax * kGroupsMax * 8 +
+  return (size_t)kABuf * 4 * p.PA * 16 + (2 * kStagesMax + 2 * kABuf + 4) * 8 + 16 + 128 * 4 + (size_t)kNimgMax * kGroupsMax * 8 +
          (size_t)kSlots * kSegMax * kOgMax * 2 * 4 + kSlots * kSegMax * 4 + 2 * kMcta * 4 + 2 * (size_t)p.P * 4 + 128;
 }
-static size_t smem_bytes(const Params& p) { return smem_fixed_bytes(p) + (size_t)p.nstage * 4 * p.NT * 16; }
-constexpr size_t kSmemLimit = 200 * 1024;
+static size_t smem_bytes(const Params& p) { return smem_fixed_bytes(p) + (size_t)p.nstage * p.stage_bytes; }
+constexpr size_t kSmemLimit = 216 * 1024;
+// taps per weight stage: a whole filter row for 3x3, a tap pair for the 2x2 forms; bulk copies of 16-24 KB stream well
 static bool pick_stages(Params& p) {
-  const size_t fixed = smem_fixed_bytes(p), stage = (size_t)4 * p.NT * 16;
-  if (fixed + 4 * stage > kSmemLimit) return false;
-  int n = (int)((kSmemLimit - fixed) / stage);
-  p.nstage = n > kStagesMax ? kStagesMax : n;
-  return true;
+  const size_t fixed = smem_fixed_bytes(p);
+  for (int G = (p.ntap % 3 == 0 ? 3 : (p.ntap % 2 == 0 ? 2 : 1)); G >= 1; G = (G == 3 ? 1 : G - 1)) {
+    const size_t stage = (size_t)G * 4 * p.NT * 16;
+    if (fixed + 3 * stage > kSmemLimit) continue;
+    int n = (int)((kSmemLimit - fixed) / stage);
+    p.G = G;
+    p.stages_per_pass = p.ntap / G;
+    p.stage_bytes = (uint32_t)stage;
+    p.nstage = n > kStagesMax ? kStagesMax : n;
+    return true;
+  }
+  return false;
 }
 
 static int pick_nt(int cout) { return cout % 128 == 0 ? 128 : (cout % 64 == 0 ? 64 : (cout % 32 == 0 ? 32 : 0)); }
@@ -745,6 +793,8 @@ static bool fill_params(const ConvP& c, int geo, Params& p) {
     if ((p.NT + p.cpg_out - 1) / p.cpg_out > kOgMax) return false;
     if (p.NT < 64) return false;     // each epilogue warp must own whole 16-channel pairs
   }
+  for (int ph = 0; ph < 4; ++ph)
+    for (int t = 0; t < 16; ++t) p.delta[ph * 16 + t] = t < p.ntap ? tap_delta(p, geo, t, ph) : 0;
   return pick_stages(p);
 }
 

@@ -108,6 +108,23 @@ __device__ __forceinline__ void bar_sync_named(int id, int threads) {
 }
 
 
+// one lane of a converged warp (elect.sync): the issuing lane of warp-uniform loops.  Keeping the LOOP warp-uniform and only
+// the tcgen05 / bulk-copy instruction predicated lets ptxas keep descriptors in uniform registers (no R2UR / vote loops).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred P1;\n\telect.sync _|P1, 0xffffffff;\n\tselp.u32 %0, 1, 0, P1;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
+// 16-byte asynchronous global -> shared copy (LDGSTS), L2 only
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
 // ---- TMA tensor copies (cp.async.bulk.tensor -> UTMALDG) ----
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const void* tmap, int c0, int c1, uint32_t bar) {
   asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
