@@ -61,9 +61,6 @@ constexpr int kDepth = 1;              // passes a producer thread keeps in flig
 constexpr int kMaxItems = 7;           // 16-byte operand items per producer thread per pass (P <= 448)
 constexpr int kNimgMax = 20;           // images a 256-position window may touch
 constexpr int kGroupsMax = 32;         // GroupNorm groups of the prologue
-constexpr int kOgMax = 8;              // output-statistics groups per N tile (>= 16 channels each)
-constexpr int kSegMax = 4;             // images a warp's 32 consecutive rows may touch (S >= 16)
-constexpr int kSlots = kMTmax * kEpiWarps;   // statistics slot owners per tile: (mt, epilogue warp)
 
 struct Params {
   ConvP c;
@@ -131,6 +128,74 @@ static int tap_delta(const Params& p, int geo, int t, int phase) {
     return (t - 3) * p.Wv;
   }
 }
+
+// ---- packed fp32x2 arithmetic (FADD2 / FFMA2) ----
+__device__ __forceinline__ unsigned long long pack2(float a, float b) {
+  unsigned long long r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+  return r;
+}
+__device__ __forceinline__ void unpack2(unsigned long long v, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
+__device__ __forceinline__ unsigned long long add2(unsigned long long a, unsigned long long b) {
+  unsigned long long r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ unsigned long long fma2(unsigned long long a, unsigned long long b, unsigned long long c) {
+  unsigned long long r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+
+// Warp reduction of 8 per-row partials (4 group slots x {sum, sum of squares}) over the rows of ONE image and accumulation into
+// the fixed-point statistics: halving butterfly (4 + 2 + 1 + 1 + 1 shuffles); afterwards every lane holds the total of value
+// index lane >> 2, and lanes with (lane & 3) == 0 own one value each: slot = index >> 1, kind = index & 1.  The slots are
+// RIGHT-ALIGNED: slot 3 is group g_last, slot 3 - i is group g_last - i; only the last `nslots` slots are valid.
+__device__ __forceinline__ void reduce8_add(const float* v, int img, stat_t* ostats, int ogroups, int g_last, int nslots, int lane) {
+  float a[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const bool hi = lane & 16;
+    const float send = hi ? v[i] : v[i + 4], keep = hi ? v[i + 4] : v[i];
+    a[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+  }
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const bool hi = lane & 8;
+    const float send = hi ? a[i] : a[i + 2], keep = hi ? a[i + 2] : a[i];
+    a[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+  }
+  {
+    const bool hi = lane & 4;
+    const float send = hi ? a[0] : a[1], keep = hi ? a[1] : a[0];
+    a[0] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+  }
+  a[0] += __shfl_xor_sync(0xffffffffu, a[0], 2);
+  a[0] += __shfl_xor_sync(0xffffffffu, a[0], 1);
+  const int idx = lane >> 2, slot = idx >> 1, kind = idx & 1;
+  if ((lane & 3) == 0 && slot >= 4 - nslots) {
+    stat_t* dst = ostats + ((long)img * ogroups + g_last - 3 + slot) * 2 + kind;
+    const float scale = kind ? kStatScaleSq : kStatScaleSum;
+    atomicAdd(reinterpret_cast<unsigned long long*>(dst), (unsigned long long)__float2ll_rn(a[0] * scale));
+  }
+}
+// rows of a warp are consecutive flat positions: usually one image (fast path), a few at low resolution (one pass per image)
+__device__ __forceinline__ void stats_flush(const float* val, int key, bool valid, stat_t* ostats, int ogroups, int g_last, int nslots,
+                                            int lane) {
+  unsigned todo = __ballot_sync(0xffffffffu, valid);
+  while (todo) {
+    const int leader = __ffs(todo) - 1;
+    const int k = __shfl_sync(0xffffffffu, key, leader);
+    const unsigned mine = __ballot_sync(0xffffffffu, valid && key == k);
+    todo &= ~mine;
+    float m[8];
+    const bool in = valid && key == k;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) m[i] = in ? val[i] : 0.f;
+    reduce8_add(m, k, ostats, ogroups, g_last, nslots, lane);
+  }
+}
+
 // ---------------------------------------------------------------------------------------------------
 // kernel
 // ---------------------------------------------------------------------------------------------------
@@ -156,14 +221,11 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tcgen05_kernel(const Params 
   uint64_t* acc_full = empty_a + kABuf;
   uint64_t* acc_empty = acc_full + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
-  float* s_bias = reinterpret_cast<float*>(tmem_slot + 2);                                  // [128]
-  float2* s_gn = reinterpret_cast<float2*>(s_bias + 128);                                   // [kNimgMax][kGroupsMax] (mean, rstd)
-  float* s_part = reinterpret_cast<float*>(s_gn + kNimgMax * kGroupsMax);                   // [kSlots][kSegMax][kOgMax][2]
-  int* s_partkey = reinterpret_cast<int*>(s_part + kSlots * kSegMax * kOgMax * 2);          // [kSlots][kSegMax] image key or -1
-  int* s_opix = s_partkey + kSlots * kSegMax;                                               // [256] output pixel or -1
-  int* s_oimg = s_opix + kMcta;                                                             // [256] image - img_lo (clamped)
-  int* s_pix = s_oimg + kMcta;                                                              // [P] operand source or -1
+  float2* s_gn = reinterpret_cast<float2*>(tmem_slot + 2);                                  // [kNimgMax][kGroupsMax] (mean, rstd)
+  int* s_pix = reinterpret_cast<int*>(s_gn + kNimgMax * kGroupsMax);                        // [P] operand source or -1
   int* s_pimg = s_pix + p.P;                                                                // [P] image - img_lo
+  // epilogue, private per warp: bf16 output staging [32 rows][ncol] (16-byte chunks XOR-swizzled) + bias [ncol]
+  uint8_t* s_stage = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(s_pimg + p.P) + 127) & ~(uintptr_t)127);
 
   // ---- one-time setup ----
   if (warp == kLoaderWarp) {          // one lane per barrier
@@ -371,202 +433,199 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tcgen05_kernel(const Params 
     }
   } else if (warp < kLoaderWarp) {
     // =============================== epilogue ===============================
+    // Warps are independent: no shared tables and no block barriers.  Each thread decodes its own accumulator rows
+    // (flat position -> output pixel / image), reads 32-column chunks from TMEM, adds bias (+ class embedding, + residual),
+    // stores bf16 and accumulates the GroupNorm statistics of its rows; a warp then reduces 8 partials at a time with a
+    // halving butterfly (9 shuffles) and the owning lanes add them to the (image, group) slots with fixed-point integer
+    // atomics (order independent => deterministic).
     const int ew = warp - kProdWarps;                 // 0..7
-    const int et = tid - kProdThreads;                // 0..255
     const int quarter = ew & 3, half = ew >> 2;       // TMEM lane quarter, column half of the tile
     bf16* out = (bf16*)p.c.out;
     const bf16* res = (const bf16*)p.c.res;
-    // columns owned by this warp: half of the tile (64 / 32); with NT = 32 only the first warp of each lane quarter works
+    // columns owned by this warp: half of the tile; with NT = 32 only the first warp of each lane quarter works
     const bool active = p.NT >= 64 || half == 0;
     const int ncol = p.NT >= 64 ? (p.NT >> 1) : p.NT;
     const int col0 = p.NT >= 64 ? half * ncol : 0;
-    int it = 0, last_ntile = -1;
+    const int sh = p.cpg_out_shift;
+    const bool do_stats = p.c.ostats != nullptr;
+    // staging geometry: row_bytes = ncol * 2 (64 / 128 / 256); lpr lanes per row, rpi rows per store instruction
+    const int row_bytes = ncol * 2, lpr = ncol >> 3, rpi = 32 / lpr;
+    const int swz_shift = row_bytes == 64 ? 1 : 0, swz_mask = row_bytes == 64 ? 3 : 7;
+    uint8_t* my_stage = s_stage + ew * (32 * row_bytes + ncol * 4);
+    float* my_bias = reinterpret_cast<float*>(my_stage + 32 * row_bytes);
+    const int my_swz = (lane >> swz_shift) & swz_mask;
+    int last_ntile = -1;
+    int it = 0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
       const int n_tile = tile % p.n_tiles_n;
       const int m0 = (tile / p.n_tiles_n) * p.mcta;
       const int phase = (GEO == GEO_UP) ? n_tile / p.tiles_per_phase : 0;
       const int n0 = (GEO == GEO_UP ? n_tile % p.tiles_per_phase : n_tile) * p.NT;
-      int f_lo = m0 - p.halo_lo;
-      if (f_lo < 0) f_lo = 0;
-      const int img_lo = f_lo / p.S;
-      // ---- per-tile tables (epilogue owned) ----
-      for (int r = et; r < p.mcta; r += kEpiThreads) {
-        const VPos v = vdecode(m0 + r, p);
-        bool valid = v.img >= 0;
-        int opix = -1;
-        if (valid) {
-          if (GEO == GEO_SAME) {
-            valid = v.row >= p.pad && v.col >= p.pad;
-            opix = v.img * p.HW + (v.row - p.pad) * p.W + (v.col - p.pad);
-          } else if (GEO == GEO_DOWN) {
-            valid = v.row < (p.H >> 1) && v.col < (p.W >> 1);
-            opix = v.img * (p.HW >> 2) + v.row * (p.W >> 1) + v.col;
-          } else if (GEO == GEO_UP) {
-            valid = v.row >= 1 && v.col >= 1;
-            opix = v.img * (p.HW << 2) + (2 * (v.row - 1) + (phase >> 1)) * (2 * p.W) + 2 * (v.col - 1) + (phase & 1);
-          } else {
-            valid = v.row >= 3;
-            opix = v.img * p.HW + (v.row - 3) * p.W + v.col;
+      // ---- this thread's rows ----
+      int opixv[kMTmax], keyv[kMTmax];
+#pragma unroll
+      for (int mt = 0; mt < kMTmax; ++mt) {
+        opixv[mt] = -1;
+        keyv[mt] = -1;
+        if (mt < p.mt) {
+          const VPos v = vdecode(m0 + mt * 128 + quarter * 32 + lane, p);
+          bool valid = v.img >= 0;
+          int opix = -1;
+          if (valid) {
+            if (GEO == GEO_SAME) {
+              valid = v.row >= p.pad && v.col >= p.pad;
+              opix = v.img * p.HW + (v.row - p.pad) * p.W + (v.col - p.pad);
+            } else if (GEO == GEO_DOWN) {
+              valid = v.row < (p.H >> 1) && v.col < (p.W >> 1);
+              opix = v.img * (p.HW >> 2) + v.row * (p.W >> 1) + v.col;
+            } else if (GEO == GEO_UP) {
+              valid = v.row >= 1 && v.col >= 1;
+              opix = v.img * (p.HW << 2) + (2 * (v.row - 1) + (phase >> 1)) * (2 * p.W) + 2 * (v.col - 1) + (phase & 1);
+            } else {
+              valid = v.row >= 3;
+              opix = v.img * p.HW + (v.row - 3) * p.W + v.col;
+            }
           }
+          if (valid) { opixv[mt] = opix; keyv[mt] = v.img; }
         }
-        int il = (v.img >= 0 ? v.img : p.c.B - 1) - img_lo;
-        il = il < 0 ? 0 : (il >= kNimgMax ? kNimgMax - 1 : il);
-        s_opix[r] = valid ? opix : -1;
-        s_oimg[r] = il;
       }
-      if (n_tile != last_ntile) {
-        for (int i = et; i < p.NT; i += kEpiThreads) s_bias[i] = p.c.bias ? p.c.bias[n0 + i] : 0.f;
-        last_ntile = n_tile;
-      }
-      for (int i = et; i < kSlots * kSegMax; i += kEpiThreads) s_partkey[i] = -1;
-      bar_sync_named(1, kEpiThreads);
-      if (et == 0) TRACE(it, 8);
+      if (ew == 0 && lane == 0) TRACE(it, 8);
 
       const int as = it & 1;
       mbar_wait_relaxed(smem_u32(&acc_full[as]), (it >> 1) & 1);
       tc_fence_after();
-      if (et == 0) TRACE(it, 9);
+      if (ew == 0 && lane == 0) TRACE(it, 9);
       const uint32_t tacc = tmem_base + (uint32_t)(as * p.mt * p.NT);
       if (!active) {
         tc_fence_before();
         mbar_arrive(smem_u32(&acc_empty[as]));
+        continue;
       }
+      // bias of this warp's columns -> private shared memory (re-staged only when the N tile changes)
+      if (n_tile != last_ntile) {
+        __syncwarp();
+        for (int i = lane; i < ncol; i += 32) my_bias[i] = p.c.bias ? p.c.bias[n0 + col0 + i] : 0.f;
+        last_ntile = n_tile;
+        __syncwarp();
+      }
+      // software pipeline over 16-column pieces: the TMEM load of piece k+1 is in flight while piece k is processed
+      const int ppm = ncol >> 4;                              // pieces per 128-row accumulator
+      const int npieces = p.mt * ppm;
+      const uint32_t tlane = tacc + ((uint32_t)(quarter * 32) << 16) + (uint32_t)col0;
+      uint32_t rb[2][16];
+      tmem_ld16_nowait(tlane, rb[0]);
+      float val[8];                                           // statistics shift register: 4 group slots x {sum, sumsq}
+#pragma unroll
+      for (int i = 0; i < 8; ++i) val[i] = 0.f;
+      float cs = 0.f, cq = 0.f;                               // current group accumulator (this row)
+      int nslots = 0;
 #pragma unroll 1
-      for (int mt = 0; active && mt < p.mt; ++mt) {
-        const int row = mt * 128 + quarter * 32 + lane;
-        const int opix = s_opix[row];
-        const bool valid = opix >= 0;
-        const long orow = valid ? (long)opix * p.c.Cout + n0 + col0 : 0;
-        const float* cls_row = nullptr;
-        if (GEO == GEO_INIT && p.cls_w && valid)
-          cls_row = p.cls_w + (long)(p.classes ? (int)p.classes[img_lo + s_oimg[row]] : p.pad_class) * p.c.Cout + n0 + col0;
-        // statistics: segmented warp reduction keyed by image (rows of a warp are consecutive flat positions, so the key is
-        // non-decreasing); the last lane of every segment stores the partial into a slot owned by (mt, warp, segment)
-        const int key = s_oimg[row];
-        unsigned segmask = 0;
+      for (int k = 0; k < npieces; k += 2) {
 #pragma unroll
-        for (int i = 0; i < 5; ++i) {
-          const int k2 = __shfl_up_sync(0xffffffffu, key, 1 << i);
-          if (lane >= (1 << i) && k2 == key) segmask |= 1u << i;
-        }
-        const int knext = __shfl_down_sync(0xffffffffu, key, 1);
-        const bool tail = (lane == 31) || (knext != key);
-        const unsigned tails = __ballot_sync(0xffffffffu, tail);
-        int seg = __popc(tails & ((1u << lane) - 1u));
-        seg = seg < kSegMax ? seg : kSegMax - 1;
-        // per-thread partial sums per 16-channel pair (statistics groups have >= 16 channels): independent chains
-        float sa[4], qa[4];
+        for (int u = 0; u < 2; ++u) {                         // static double-buffer index
+          const int kk = k + u;
+          if (kk >= npieces) break;
+          const int mt = kk >= ppm ? 1 : 0, pc = kk - mt * ppm;
+          tmem_ld_wait();
+          if (kk + 1 < npieces) {
+            const int mt1 = (kk + 1) >= ppm ? 1 : 0, pc1 = kk + 1 - mt1 * ppm;
+            tmem_ld16_nowait(tlane + (uint32_t)(mt1 * p.NT + pc1 * 16), rb[u ^ 1]);
+          } else {
+            tc_fence_before();                                // last TMEM read of this tile is complete: hand the accumulators back
+            mbar_arrive(smem_u32(&acc_empty[as]));
+            if (ew == 0 && lane == 0) TRACE(it, 10);
+          }
+          const uint32_t* r = rb[u];
+          const int opix = mt == 0 ? opixv[0] : opixv[kMTmax - 1];
+          const int key = mt == 0 ? keyv[0] : keyv[kMTmax - 1];
+          const bool valid = opix >= 0;
+          const long orow = valid ? (long)opix * p.c.Cout + n0 + col0 + pc * 16 : 0;
+          unsigned long long v2[8];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) sa[i] = qa[i] = 0.f;
+          for (int j = 0; j < 8; ++j) v2[j] = pack2(__uint_as_float(r[2 * j]), __uint_as_float(r[2 * j + 1]));
 #pragma unroll
-        for (int ch = 0; ch < 2; ++ch) {
-          if (ch * 32 < ncol) {
-            uint32_t r[32];
-            tmem_ld32(tacc + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(mt * p.NT + col0 + ch * 32), r);
-            if (mt == p.mt - 1 && (ch + 1) * 32 >= ncol) {     // last TMEM read of this tile: hand the accumulators back
-              tc_fence_before();
-              mbar_arrive(smem_u32(&acc_empty[as]));
-              if (et == 0) TRACE(it, 10);
+          for (int q4 = 0; q4 < 4; ++q4) {
+            const float4 bq = *(reinterpret_cast<const float4*>(my_bias + pc * 16) + q4);     // broadcast LDS.128
+            v2[2 * q4] = add2(v2[2 * q4], pack2(bq.x, bq.y));
+            v2[2 * q4 + 1] = add2(v2[2 * q4 + 1], pack2(bq.z, bq.w));
+          }
+          if (GEO == GEO_INIT && p.cls_w && valid) {
+            const float* cls_row = p.cls_w + (long)(p.classes ? (int)p.classes[key] : p.pad_class) * p.c.Cout + n0 + col0 + pc * 16;
+#pragma unroll
+            for (int q4 = 0; q4 < 4; ++q4) {
+              const float4 bq = __ldg(reinterpret_cast<const float4*>(cls_row) + q4);
+              v2[2 * q4] = add2(v2[2 * q4], pack2(bq.x, bq.y));
+              v2[2 * q4 + 1] = add2(v2[2 * q4 + 1], pack2(bq.z, bq.w));
             }
-            const int nv = ncol < 32 ? ncol : 32;              // valid columns in this chunk (16 when NT = 32)
-            float vv[32];
+          }
+          if (res && valid) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) vv[j] = __uint_as_float(r[j]) + s_bias[col0 + ch * 32 + (j < nv ? j : 0)];
-            if (GEO == GEO_INIT && cls_row) {
+            for (int q = 0; q < 2; ++q) {
+              const uint4 rr = *reinterpret_cast<const uint4*>(res + orow + q * 8);
+              float rf[8];
+              unpack8(rr, rf);
 #pragma unroll
-              for (int j = 0; j < 32; ++j)
-                if (j < nv) vv[j] += __ldg(cls_row + ch * 32 + j);
+              for (int e = 0; e < 4; ++e) v2[q * 4 + e] = add2(v2[q * 4 + e], pack2(rf[2 * e], rf[2 * e + 1]));
             }
-            if (res && valid) {
+          }
+          // bf16 -> this warp's staging tile, row = lane, 16-byte chunk index XOR-swizzled (conflict-free both ways)
 #pragma unroll
-              for (int q = 0; q < 4; ++q) {
-                if (q * 8 < nv) {
-                  const uint4 rr = *reinterpret_cast<const uint4*>(res + orow + ch * 32 + q * 8);
-                  float rf[8];
-                  unpack8(rr, rf);
-#pragma unroll
-                  for (int e = 0; e < 8; ++e) vv[q * 8 + e] += rf[e];
-                }
-              }
+          for (int q = 0; q < 2; ++q) {
+            uint4 o;
+            float a0, a1;
+            unpack2(v2[q * 4 + 0], a0, a1); o.x = pack_bf16x2(a0, a1);
+            unpack2(v2[q * 4 + 1], a0, a1); o.y = pack_bf16x2(a0, a1);
+            unpack2(v2[q * 4 + 2], a0, a1); o.z = pack_bf16x2(a0, a1);
+            unpack2(v2[q * 4 + 3], a0, a1); o.w = pack_bf16x2(a0, a1);
+            *reinterpret_cast<uint4*>(my_stage + lane * row_bytes + (((pc * 2 + q) ^ my_swz) << 4)) = o;
+          }
+          if (pc == ppm - 1) {
+            // the warp's 32 x ncol block is staged: coalesced 16-byte stores, `lpr` consecutive lanes cover one output row
+            __syncwarp();
+#pragma unroll 1
+            for (int i = 0; i < 32; i += rpi) {
+              const int rrow = i + lane / lpr, c = lane % lpr;
+              const int ropix = __shfl_sync(0xffffffffu, opix, rrow);
+              const int rswz = (rrow >> swz_shift) & swz_mask;
+              const uint4 o = *reinterpret_cast<const uint4*>(my_stage + rrow * row_bytes + ((c ^ rswz) << 4));
+              if (ropix >= 0) *reinterpret_cast<uint4*>(out + (long)ropix * p.c.Cout + n0 + col0 + c * 8) = o;
             }
+            __syncwarp();
+          }
+          if (do_stats) {
+            // (sum, sum of squares) of this row's 16 columns: two independent packed chains each
+            unsigned long long s0 = 0ull, q0 = 0ull, s1 = 0ull, q1 = 0ull;
             if (valid) {
 #pragma unroll
-              for (int q = 0; q < 4; ++q)
-                if (q * 8 < nv) *reinterpret_cast<uint4*>(out + orow + ch * 32 + q * 8) = pack8(vv + q * 8);
+              for (int j = 0; j < 4; ++j) {
+                s0 = add2(s0, v2[j]);
+                q0 = fma2(v2[j], v2[j], q0);
+                s1 = add2(s1, v2[4 + j]);
+                q1 = fma2(v2[4 + j], v2[4 + j], q1);
+              }
             }
-            if (p.c.ostats && valid) {
+            float sa0, sb0, qa0, qb0, sa1, sb1, qa1, qb1;
+            unpack2(s0, sa0, sb0); unpack2(q0, qa0, qb0); unpack2(s1, sa1, sb1); unpack2(q1, qa1, qb1);
+            cs += (sa0 + sb0) + (sa1 + sb1);
+            cq += (qa0 + qb0) + (qa1 + qb1);
+            // group bookkeeping (uniform): does the group end with this piece?
+            const int cbase = n0 + col0 + pc * 16;
+            const int g = cbase >> sh;
+            const bool last_of_mt = pc == ppm - 1;
+            if (last_of_mt || ((cbase + 16) >> sh) != g) {
 #pragma unroll
-              for (int j = 0; j < 32; ++j) {
-                if (j < nv) {
-                  sa[ch * 2 + (j >> 4)] += vv[j];
-                  qa[ch * 2 + (j >> 4)] = fmaf(vv[j], vv[j], qa[ch * 2 + (j >> 4)]);
-                }
+              for (int i = 0; i < 6; ++i) val[i] = val[i + 2];
+              val[6] = cs; val[7] = cq;
+              cs = cq = 0.f;
+              if (++nslots == 4 || last_of_mt) {
+                stats_flush(val, key, valid, p.c.ostats, p.c.ogroups, g, nslots, lane);
+                nslots = 0;
               }
             }
           }
         }
-        if (p.c.ostats) {
-          // one segmented scan for all partials (independent shuffle chains), then the segment tails combine the pairs into
-          // groups and store them into the slot owned by (mt, warp, segment): no atomics, fixed order => deterministic
-#pragma unroll
-          for (int i = 0; i < 5; ++i) {
-            const bool take = segmask & (1u << i);
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              const float ta = __shfl_up_sync(0xffffffffu, sa[k], 1 << i), tb = __shfl_up_sync(0xffffffffu, qa[k], 1 << i);
-              if (take) { sa[k] += ta; qa[k] += tb; }
-            }
-          }
-          if (tail) {
-            const int sidx = (mt * kEpiWarps + ew) * kSegMax + seg;
-            float* slot = s_part + sidx * kOgMax * 2;
-            s_partkey[sidx] = key;
-            // group index local to the N tile of the first pair of this warp: (col0 >> 4) pairs in
-            const int sh = p.cpg_out_shift, pair0 = col0 >> 4;
-            if (sh <= 4) {
-#pragma unroll
-              for (int k = 0; k < 4; ++k) { slot[(pair0 + k) * 2] = sa[k]; slot[(pair0 + k) * 2 + 1] = qa[k]; }
-            } else if (sh == 5) {
-#pragma unroll
-              for (int k = 0; k < 2; ++k) { slot[((pair0 >> 1) + k) * 2] = sa[2 * k] + sa[2 * k + 1]; slot[((pair0 >> 1) + k) * 2 + 1] = qa[2 * k] + qa[2 * k + 1]; }
-            } else {
-              // >= 64 channels per group: this warp's (<= 64) columns belong to one group; its two halves are separate slots
-              slot[(pair0 >> (sh - 4)) * 2] = (sa[0] + sa[1]) + (sa[2] + sa[3]);
-              slot[(pair0 >> (sh - 4)) * 2 + 1] = (qa[0] + qa[1]) + (qa[2] + qa[3]);
-            }
-          }
-        }
       }
-      // ---- flush the tile's GroupNorm statistics: fixed-order sum over the slots, then one fixed-point integer atomic per
-      // (image, group) => deterministic ----
-      bar_sync_named(1, kEpiThreads);
-      if (p.c.ostats) {
-        const int sh = p.cpg_out_shift;
-        const int og_tile = (p.NT + (1 << sh) - 1) >> sh;
-        for (int i = et; i < kNimgMax * og_tile; i += kEpiThreads) {
-          const int il = i / og_tile, gl = i - il * og_tile;
-          const int img = img_lo + il;
-          float a = 0.f, b = 0.f;
-          bool any = false;
-          for (int k = 0; k < kSlots * kSegMax; ++k) {
-            if (s_partkey[k] == il) {
-              // a slot only holds the groups its warp's columns cover
-              const int half_k = ((k / kSegMax) % kEpiWarps) >> 2;
-              const int pair0 = (half_k * (p.NT >> 1)) >> 4, pairs = (p.NT >> 1) >> 4;
-              const int g_lo = sh <= 4 ? pair0 : (pair0 >> (sh - 4));
-              const int g_hi = sh <= 4 ? pair0 + (pairs > 0 ? pairs : 1) - 1 : ((pair0 + (pairs > 0 ? pairs : 1) - 1) >> (sh - 4));
-              if (gl >= g_lo && gl <= g_hi) {
-                a += s_part[(k * kOgMax + gl) * 2];
-                b += s_part[(k * kOgMax + gl) * 2 + 1];
-                any = true;
-              }
-            }
-          }
-          if (any && img < p.c.B) stat_add(p.c.ostats + ((long)img * p.c.ogroups + (n0 >> sh) + gl) * 2, a, b);
-        }
-      }
-      bar_sync_named(1, kEpiThreads);       // tables / slots are rewritten by the next tile
-      if (et == 0) TRACE(it, 11);
+      if (ew == 0 && lane == 0) TRACE(it, 11);
     }
   } else if (warp == kLoaderWarp) {
     // =============================== weight loader ===============================
@@ -669,8 +728,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tcgen05_kernel(const Params 
 }
 
 static size_t smem_fixed_bytes(const Params& p) {
-  return (size_t)kABuf * 4 * p.PA * 16 + (2 * kStagesMax + 2 * kABuf + 4) * 8 + 16 + 128 * 4 + (size_t)kNimgMax * kGroupsMax * 8 +
-         (size_t)kSlots * kSegMax * kOgMax * 2 * 4 + kSlots * kSegMax * 4 + 2 * kMcta * 4 + 2 * (size_t)p.P * 4 + 128;
+  const int ncol = p.NT >= 64 ? p.NT / 2 : p.NT;
+  return (size_t)kABuf * 4 * p.PA * 16 + (2 * kStagesMax + 2 * kABuf + 4) * 8 + 16 + (size_t)kNimgMax * kGroupsMax * 8 +
+         2 * (size_t)p.P * 4 + 128 + (size_t)kEpiWarps * (32 * ncol * 2 + ncol * 4) + 128;
 }
 static size_t smem_bytes(const Params& p) { return smem_fixed_bytes(p) + (size_t)p.nstage * p.stage_bytes; }
 constexpr size_t kSmemLimit = 216 * 1024;
@@ -790,7 +850,6 @@ static bool fill_params(const ConvP& c, int geo, Params& p) {
     p.cpg_out = c.Cout / c.ogroups;
     if (p.cpg_out % 16 || (p.cpg_out & (p.cpg_out - 1))) return false;
     while ((1 << p.cpg_out_shift) < p.cpg_out) ++p.cpg_out_shift;
-    if ((p.NT + p.cpg_out - 1) / p.cpg_out > kOgMax) return false;
     if (p.NT < 64) return false;     // each epilogue warp must own whole 16-channel pairs
   }
   for (int ph = 0; ph < 4; ++ph)
