@@ -75,6 +75,7 @@ struct Params {
   int G, stages_per_pass;  // taps per weight stage, ntap / G
   uint32_t stage_bytes;    // G * 4 * NT * 16
   int delta[64];           // [4 phases][16 taps] tap offsets in flat positions (constant bank => uniform registers in the issuer)
+  uint32_t magic_S, magic_W;   // ceil(2^26 / S), ceil(2^24 / Wv): exact small-number division in vdecode_rel
   float inv_cnt_in;
   long long* trace;        // debug timeline (null in production)
   int trace_cta;
@@ -110,6 +111,20 @@ __device__ __forceinline__ VPos vdecode(int f, const Params& p) {
   r.img = (int)img;
   r.row = (int)row;
   r.col = (int)(rem - row * uW);
+  return r;
+}
+// decode f = base_flat + n (0 <= n < 2^12 - ish) given the decoded base (img0, rem0 = base_flat - img0 * S): two multiply-shift
+// divisions, exact for n + rem0 < 8192 and S <= 8192 (n * S < 2^26) and rem < S, Wv <= 128 (rem * Wv < 2^24)
+__device__ __forceinline__ VPos vdecode_rel(int img0, int rem0, int n, const Params& p) {
+  VPos r;
+  const unsigned m = (unsigned)(rem0 + n);
+  const unsigned k = (unsigned)(((unsigned long long)m * p.magic_S) >> 26);
+  const unsigned rem = m - k * (unsigned)p.S;
+  const unsigned row = (unsigned)(((unsigned long long)rem * p.magic_W) >> 24);
+  r.img = img0 + (int)k;
+  r.row = (int)row;
+  r.col = (int)(rem - row * (unsigned)p.Wv);
+  if ((long)r.img * p.S + rem >= p.total_flat) r.img = -1;
   return r;
 }
 // tap offset in flat positions (host: the table is passed in the kernel parameters = constant bank)
@@ -293,8 +308,12 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tcgen05_kernel(const Params 
       }
       // ---- per-tile tables: operand source per window pixel, GroupNorm (mean, rstd) per touched image ----
       bar_sync_named(2, kProdThreads);                 // everyone is done with the previous tile's tables
+      const int pbase = m0 - p.halo_lo > 0 ? m0 - p.halo_lo : 0;            // uniform: decode base of the window
+      const int pimg0 = pbase / p.S, prem0 = pbase - pimg0 * p.S;
       for (int pixel = tid; pixel < p.P; pixel += kProdThreads) {
-        const VPos v = vdecode(m0 - p.halo_lo + pixel, p);
+        VPos v;
+        v.img = -1; v.row = v.col = 0;
+        if (m0 - p.halo_lo + pixel >= 0) v = vdecode_rel(pimg0, prem0, m0 - p.halo_lo + pixel - pbase, p);
         int g = -1, il = 0;
         if (v.img >= 0) {
           if (GEO == GEO_DOWN) {
@@ -451,9 +470,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tcgen05_kernel(const Params 
     // staging geometry: row_bytes = ncol * 2 (64 / 128 / 256); lpr lanes per row, rpi rows per store instruction
     const int row_bytes = ncol * 2, lpr = ncol >> 3, rpi = 32 / lpr;
     const int swz_shift = row_bytes == 64 ? 1 : 0, swz_mask = row_bytes == 64 ? 3 : 7;
-    uint8_t* my_stage = s_stage + ew * (32 * row_bytes + ncol * 4);
-    float* my_bias = reinterpret_cast<float*>(my_stage + 32 * row_bytes);
+    const uint32_t my_stage = smem_u32(s_stage) + (uint32_t)(ew * (32 * row_bytes + ncol * 4));   // shared-space addresses
+    const uint32_t my_bias = my_stage + (uint32_t)(32 * row_bytes);
     const int my_swz = (lane >> swz_shift) & swz_mask;
+    const int lrow = lane / lpr, lcol = lane % lpr;   // this lane's (row within a store instruction, 16-byte chunk)
     int last_ntile = -1;
     int it = 0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
@@ -462,13 +482,14 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tcgen05_kernel(const Params 
       const int phase = (GEO == GEO_UP) ? n_tile / p.tiles_per_phase : 0;
       const int n0 = (GEO == GEO_UP ? n_tile % p.tiles_per_phase : n_tile) * p.NT;
       // ---- this thread's rows ----
+      const int eimg0 = m0 / p.S, erem0 = m0 - eimg0 * p.S;     // uniform
       int opixv[kMTmax], keyv[kMTmax];
 #pragma unroll
       for (int mt = 0; mt < kMTmax; ++mt) {
         opixv[mt] = -1;
         keyv[mt] = -1;
         if (mt < p.mt) {
-          const VPos v = vdecode(m0 + mt * 128 + quarter * 32 + lane, p);
+          const VPos v = vdecode_rel(eimg0, erem0, mt * 128 + quarter * 32 + lane, p);
           bool valid = v.img >= 0;
           int opix = -1;
           if (valid) {
@@ -489,6 +510,13 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tcgen05_kernel(const Params 
           if (valid) { opixv[mt] = opix; keyv[mt] = v.img; }
         }
       }
+      // bias of this warp's columns -> private shared memory (re-staged only when the N tile changes)
+      if (active && n_tile != last_ntile) {
+        __syncwarp();
+        for (int i = lane; i < ncol; i += 32) sts32f(my_bias + 4u * i, p.c.bias ? p.c.bias[n0 + col0 + i] : 0.f);
+        last_ntile = n_tile;
+        __syncwarp();
+      }
       if (ew == 0 && lane == 0) TRACE(it, 8);
 
       const int as = it & 1;
@@ -500,13 +528,6 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tcgen05_kernel(const Params 
         tc_fence_before();
         mbar_arrive(smem_u32(&acc_empty[as]));
         continue;
-      }
-      // bias of this warp's columns -> private shared memory (re-staged only when the N tile changes)
-      if (n_tile != last_ntile) {
-        __syncwarp();
-        for (int i = lane; i < ncol; i += 32) my_bias[i] = p.c.bias ? p.c.bias[n0 + col0 + i] : 0.f;
-        last_ntile = n_tile;
-        __syncwarp();
       }
       // software pipeline over 16-column pieces: the TMEM load of piece k+1 is in flight while piece k is processed
       const int ppm = ncol >> 4;                              // pieces per 128-row accumulator
@@ -526,7 +547,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tcgen05_kernel(const Params 
           const int kk = k + u;
           if (kk >= npieces) break;
           const int mt = kk >= ppm ? 1 : 0, pc = kk - mt * ppm;
+          const bool tr = p.trace && blockIdx.x == (unsigned)p.trace_cta && it == 2 && ew == 0 && lane == 0 && kk < 32;
+          if (tr) p.trace[800 + 3 * kk] = clock64();
           tmem_ld_wait();
+          if (tr) p.trace[801 + 3 * kk] = clock64();
           if (kk + 1 < npieces) {
             const int mt1 = (kk + 1) >= ppm ? 1 : 0, pc1 = kk + 1 - mt1 * ppm;
             tmem_ld16_nowait(tlane + (uint32_t)(mt1 * p.NT + pc1 * 16), rb[u ^ 1]);
@@ -545,9 +569,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tcgen05_kernel(const Params 
           for (int j = 0; j < 8; ++j) v2[j] = pack2(__uint_as_float(r[2 * j]), __uint_as_float(r[2 * j + 1]));
 #pragma unroll
           for (int q4 = 0; q4 < 4; ++q4) {
-            const float4 bq = *(reinterpret_cast<const float4*>(my_bias + pc * 16) + q4);     // broadcast LDS.128
-            v2[2 * q4] = add2(v2[2 * q4], pack2(bq.x, bq.y));
-            v2[2 * q4 + 1] = add2(v2[2 * q4 + 1], pack2(bq.z, bq.w));
+            const uint4 bq = lds128(my_bias + (uint32_t)(pc * 64 + q4 * 16));     // broadcast LDS.128
+            v2[2 * q4] = add2(v2[2 * q4], ((unsigned long long)bq.y << 32) | bq.x);
+            v2[2 * q4 + 1] = add2(v2[2 * q4 + 1], ((unsigned long long)bq.w << 32) | bq.z);
           }
           if (GEO == GEO_INIT && p.cls_w && valid) {
             const float* cls_row = p.cls_w + (long)(p.classes ? (int)p.classes[key] : p.pad_class) * p.c.Cout + n0 + col0 + pc * 16;
@@ -577,18 +601,29 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tcgen05_kernel(const Params 
             unpack2(v2[q * 4 + 1], a0, a1); o.y = pack_bf16x2(a0, a1);
             unpack2(v2[q * 4 + 2], a0, a1); o.z = pack_bf16x2(a0, a1);
             unpack2(v2[q * 4 + 3], a0, a1); o.w = pack_bf16x2(a0, a1);
-            *reinterpret_cast<uint4*>(my_stage + lane * row_bytes + (((pc * 2 + q) ^ my_swz) << 4)) = o;
+            sts128(my_stage + (uint32_t)(lane * row_bytes + (((pc * 2 + q) ^ my_swz) << 4)), o);
           }
           if (pc == ppm - 1) {
             // the warp's 32 x ncol block is staged: coalesced 16-byte stores, `lpr` consecutive lanes cover one output row
             __syncwarp();
+            // batches of 4 store instructions: all row lookups (SHFL) and staging reads (LDS) first, then the predicated
+            // stores -- no branch between them, so the latencies overlap
 #pragma unroll 1
-            for (int i = 0; i < 32; i += rpi) {
-              const int rrow = i + lane / lpr, c = lane % lpr;
-              const int ropix = __shfl_sync(0xffffffffu, opix, rrow);
-              const int rswz = (rrow >> swz_shift) & swz_mask;
-              const uint4 o = *reinterpret_cast<const uint4*>(my_stage + rrow * row_bytes + ((c ^ rswz) << 4));
-              if (ropix >= 0) *reinterpret_cast<uint4*>(out + (long)ropix * p.c.Cout + n0 + col0 + c * 8) = o;
+            for (int i0 = 0; i0 < 32; i0 += 4 * rpi) {
+              int ropix[4];
+              uint4 o[4];
+#pragma unroll
+              for (int ii = 0; ii < 4; ++ii) {
+                const int rrow = (i0 + ii * rpi + lrow) & 31;
+                ropix[ii] = __shfl_sync(0xffffffffu, opix, rrow);
+                const int rswz = (rrow >> swz_shift) & swz_mask;
+                o[ii] = lds128(my_stage + (uint32_t)(rrow * row_bytes + ((lcol ^ rswz) << 4)));
+              }
+#pragma unroll
+              for (int ii = 0; ii < 4; ++ii) {
+                if (i0 + ii * rpi < 32 && ropix[ii] >= 0)
+                  *reinterpret_cast<uint4*>(out + (long)ropix[ii] * p.c.Cout + n0 + col0 + lcol * 8) = o[ii];
+              }
             }
             __syncwarp();
           }
@@ -623,6 +658,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tcgen05_kernel(const Params 
               }
             }
           }
+          if (tr) p.trace[802 + 3 * kk] = clock64();
         }
       }
       if (ew == 0 && lane == 0) TRACE(it, 11);
@@ -852,6 +888,9 @@ static bool fill_params(const ConvP& c, int geo, Params& p) {
     while ((1 << p.cpg_out_shift) < p.cpg_out) ++p.cpg_out_shift;
     if (p.NT < 64) return false;     // each epilogue warp must own whole 16-channel pairs
   }
+  if (p.S > 8192 - 1024 || p.Wv > 128) return false;     // vdecode_rel exactness
+  p.magic_S = (uint32_t)(((1ull << 26) + p.S - 1) / p.S);
+  p.magic_W = (uint32_t)(((1ull << 24) + p.Wv - 1) / p.Wv);
   for (int ph = 0; ph < 4; ++ph)
     for (int t = 0; t < 16; ++t) p.delta[ph * 16 + t] = t < p.ntap ? tap_delta(p, geo, t, ph) : 0;
   return pick_stages(p);
