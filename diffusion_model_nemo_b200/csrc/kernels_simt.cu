@@ -566,6 +566,7 @@ __global__ void __launch_bounds__(256) linattn_kernel(const T* __restrict__ qkv,
 
 int linattn_core(const void* qkv, void* out, int B, int heads, int dh, int N, int act, cudaStream_t st) {
   DMN_REQUIRE(dh == 32 && heads == 4, "linattn_core: heads must be 4 and dim_head 32");
+  if (act == ACT_BF16) return linattn_core_bf16_mma(qkv, out, B, N, st);   // tensor-core kernel (linattn_mma.cu)
   const size_t smem = (size_t)(2 * 32 * 132 + 4 * 32 * 32 + 4 * 128) * sizeof(float);
   static bool attr = false;
   if (!attr) {

@@ -101,6 +101,8 @@ int final_proj(const FinalProjP& p, int act, cudaStream_t s);
 
 int linattn_core(const void* qkv, void* out, int B, int heads, int dh, int N, int act, cudaStream_t s);
 int attn_core(const void* qkv, void* out, int B, int heads, int dh, int N, int act, cudaStream_t s);
+// bf16 tensor-core LinearAttention core (heads = 4, dim_head = 32); linattn_core dispatches to it for ACT_BF16
+int linattn_core_bf16_mma(const void* qkv, void* out, int B, int N, cudaStream_t s);
 
 // time path
 struct TimeP {
