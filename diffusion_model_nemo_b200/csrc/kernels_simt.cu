@@ -259,6 +259,8 @@ int init_conv(const InitConvP& p, int act, cudaStream_t st) {
 template <typename T, int V> struct VecIO;
 template <> struct VecIO<float, 4> {
   static constexpr int N = 4;
+  typedef float4 Raw;
+  static __device__ __forceinline__ void unpack(const Raw& t, float* v) { v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w; }
   static __device__ __forceinline__ void load(const float* p, float* v) {
     const float4 t = *reinterpret_cast<const float4*>(p);
     v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
@@ -267,6 +269,11 @@ template <> struct VecIO<float, 4> {
 };
 template <> struct VecIO<bf16, 4> {
   static constexpr int N = 4;
+  typedef uint2 Raw;
+  static __device__ __forceinline__ void unpack(const Raw& u, float* v) {
+    v[0] = __uint_as_float(u.x << 16); v[1] = __uint_as_float(u.x & 0xffff0000u);
+    v[2] = __uint_as_float(u.y << 16); v[3] = __uint_as_float(u.y & 0xffff0000u);
+  }
   static __device__ __forceinline__ void load(const bf16* p, float* v) {
     const float4 t = load4<bf16>(p);
     v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
@@ -275,12 +282,14 @@ template <> struct VecIO<bf16, 4> {
 };
 template <> struct VecIO<bf16, 8> {
   static constexpr int N = 8;
+  typedef uint4 Raw;
+  static __device__ __forceinline__ void unpack(const Raw& u, float* v) { unpack8(u, v); }
   static __device__ __forceinline__ void load(const bf16* p, float* v) { unpack8(*reinterpret_cast<const uint4*>(p), v); }
   static __device__ __forceinline__ void store(bf16* p, const float* v) { *reinterpret_cast<uint4*>(p) = pack8(v); }
 };
 
 template <typename T, int V>
-__global__ void __launch_bounds__(256) gn_finalize_kernel(const FinalizeP p) {
+__global__ void __launch_bounds__(256, 3) gn_finalize_kernel(const FinalizeP p) {
   __shared__ unsigned long long sm_stats[2 * 64];
   const int b = blockIdx.y;
   const int CV = p.C / V;
@@ -304,36 +313,36 @@ __global__ void __launch_bounds__(256) gn_finalize_kernel(const FinalizeP p) {
   const T* res = p.res ? (const T*)p.res + (long)b * p.HW * p.C : nullptr;
   T* out = (T*)p.out + (long)b * p.HW * p.C;
   const long stride = (long)gridDim.x * blockDim.x;
-  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < items; i += 2 * stride) {
-    const bool two = i + stride < items;
-    float v0[V], v1[V], r0[V], r1[V];
-    VecIO<T, V>::load(raw + i * V, v0);
-    if (two) VecIO<T, V>::load(raw + (i + stride) * V, v1);
+  // 4 independent 16-byte items per thread and iteration (8 loads in flight with the residual): latency is covered by ILP
+  constexpr int U = 4;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < items; i += U * stride) {
+    typedef typename VecIO<T, V>::Raw Raw;
+    Raw vr[U], rr[U];                       // packed: 16 bytes per item until it is processed
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+      if (i + u * stride < items) vr[u] = *reinterpret_cast<const Raw*>(raw + (i + u * stride) * V);
     if (res) {
-      VecIO<T, V>::load(res + i * V, r0);
-      if (two) VecIO<T, V>::load(res + (i + stride) * V, r1);
+#pragma unroll
+      for (int u = 0; u < U; ++u)
+        if (i + u * stride < items) rr[u] = *reinterpret_cast<const Raw*>(res + (i + u * stride) * V);
     }
 #pragma unroll
-    for (int e = 0; e < V; ++e) {
-      float t = fmaf(v0[e], sc[e], sh[e]);
-      if (p.silu) t = silu_f(t);
-      if (res) t += r0[e];
-      v0[e] = t;
-      s += t;
-      ss += t * t;
-    }
-    VecIO<T, V>::store(out + i * V, v0);
-    if (two) {
+    for (int u = 0; u < U; ++u) {
+      if (i + u * stride < items) {
+        float v[V], r[V];
+        VecIO<T, V>::unpack(vr[u], v);
+        if (res) VecIO<T, V>::unpack(rr[u], r);
 #pragma unroll
-      for (int e = 0; e < V; ++e) {
-        float t = fmaf(v1[e], sc[e], sh[e]);
-        if (p.silu) t = silu_f(t);
-        if (res) t += r1[e];
-        v1[e] = t;
-        s += t;
-        ss += t * t;
+        for (int e = 0; e < V; ++e) {
+          float t = fmaf(v[e], sc[e], sh[e]);
+          if (p.silu) t = sizeof(T) == 2 ? silu_fast(t) : silu_f(t);
+          if (res) t += r[e];
+          v[e] = t;
+          s += t;
+          ss += t * t;
+        }
+        VecIO<T, V>::store(out + (i + u * stride) * V, v);
       }
-      VecIO<T, V>::store(out + (i + stride) * V, v1);
     }
   }
   if (p.ostats) {
@@ -364,7 +373,7 @@ int gn_finalize(const FinalizeP& p, int act, cudaStream_t st) {
   DMN_REQUIRE(p.C % p.groups == 0 && (p.C / p.groups) % V == 0, "gn_finalize: channels-per-group must be a multiple of the vector width");
   DMN_REQUIRE(!p.ostats || (p.ogroups <= 64 && p.C % p.ogroups == 0 && (p.C / p.ogroups) % V == 0), "gn_finalize: ogroups");
   const long items = (long)p.HW * (p.C / V);
-  int bpi = (int)((items + 256 * 4 - 1) / (256 * 4));
+  int bpi = (int)((items + 256 * 8 - 1) / (256 * 8));     // ~8 items (2 unrolled iterations) per thread
   if (bpi < 1) bpi = 1;
   if (bpi > 64) bpi = 64;
   dim3 grid(bpi, p.B);
