@@ -7,7 +7,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libdmn_b200.so")
+LIB_PATH = os.environ.get("DMN_LIB_PATH") or os.path.join(_HERE, "libdmn_b200.so")   # override: A/B builds in tools/
 
 ACT_F32, ACT_BF16 = 0, 1
 CONV_SIMT, CONV_TCGEN05 = 0, 1

@@ -32,6 +32,30 @@ int fail(int code, const std::string& msg);
     if (!(cond)) return ::dmn::fail(-1, std::string(msg) + " [" #cond "]");                         \
   } while (0)
 
+// ---- programmatic dependent launch (PDL) ----------------------------------------------------------------
+// Kernels of the forward program are launched with cudaLaunchAttributeProgrammaticStreamSerialization: the next kernel's CTAs
+// may become resident (and run their prologue: barrier init, TMEM allocation, constant-weight prefetch) as soon as this kernel's
+// CTAs have called pdl_trigger() or exited; every such kernel calls pdl_wait() before it touches memory a predecessor wrote.
+// Both instructions are no-ops for a kernel launched without the attribute.  DMN_PDL=1 enables the attribute (default off:
+// measured neutral for the graph-replayed loop, where launch gaps are already ~1 us and persistent CTAs fill every SM).
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+bool pdl_enabled();
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+
 // launch counter (bench.py's gpu_launches is derived from it)
 extern thread_local long g_launches;
 inline void count_launch(int n = 1) { g_launches += n; }

@@ -211,6 +211,36 @@ __device__ __forceinline__ void stats_flush(const float* val, int key, bool vali
   }
 }
 
+// One weight stage (G taps x two k16 steps x 1|2 accumulators) of the MMA issuer.  Descriptor words are computed OUTSIDE the
+// elected branch so that they are warp-uniform values (uniform registers); `didx` indexes the tap-offset table in the constant bank.
+template <int G, bool TWO>
+__device__ __forceinline__ void issue_stage(const Params& p, bool leader, uint32_t d0, uint32_t d1, uint32_t au, uint32_t bs, int didx, int t0,
+                                            uint32_t acc0, uint32_t idesc, uint32_t hi_a, uint32_t hi_b, uint32_t lbo_a_f, uint32_t lbo_b_f,
+                                            uint32_t a_k16, uint32_t b_k16, uint32_t b_tap_units) {
+  uint64_t ad[G][4], bd[G][2];
+#pragma unroll
+  for (int g = 0; g < G; ++g) {
+    const uint32_t a0 = au + (uint32_t)p.delta[didx + g];
+    const uint32_t b0 = bs + (uint32_t)g * b_tap_units;
+    bd[g][0] = ((uint64_t)hi_b << 32) | ((b0 & 0x3FFFu) | lbo_b_f);
+    bd[g][1] = ((uint64_t)hi_b << 32) | (((b0 + b_k16) & 0x3FFFu) | lbo_b_f);
+    ad[g][0] = ((uint64_t)hi_a << 32) | ((a0 & 0x3FFFu) | lbo_a_f);
+    ad[g][1] = ((uint64_t)hi_a << 32) | (((a0 + 128u) & 0x3FFFu) | lbo_a_f);
+    ad[g][2] = ((uint64_t)hi_a << 32) | (((a0 + a_k16) & 0x3FFFu) | lbo_a_f);
+    ad[g][3] = ((uint64_t)hi_a << 32) | (((a0 + a_k16 + 128u) & 0x3FFFu) | lbo_a_f);
+  }
+  if (leader) {
+#pragma unroll
+    for (int g = 0; g < G; ++g) {
+      const uint32_t acc = (acc0 | (uint32_t)(t0 + g)) ? 1u : 0u;
+      umma_bf16(d0, ad[g][0], bd[g][0], idesc, acc);
+      if (TWO) umma_bf16(d1, ad[g][1], bd[g][0], idesc, acc);
+      umma_bf16(d0, ad[g][2], bd[g][1], idesc, 1u);
+      if (TWO) umma_bf16(d1, ad[g][3], bd[g][1], idesc, 1u);
+    }
+  }
+}
+
 // ---------------------------------------------------------------------------------------------------
 // kernel
 // ---------------------------------------------------------------------------------------------------
@@ -254,6 +284,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tcgen05_kernel(const Params 
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_trigger();        // the next kernel may start its prologue; it waits for this grid's completion before reading our output
 
   if (warp < kProdWarps) {
     // =============================== operand producers ===============================
@@ -262,6 +293,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tcgen05_kernel(const Params 
     // thread's own copies, apply the fused prologue in place (GroupNorm-apply, SiLU, time-embedding add), make the writes
     // visible to the tensor core (async proxy) and arrive on the buffer's barrier.  Global latency is thereby covered by
     // kDepth passes in flight without staging the raw data in registers.
+    pdl_wait();                                       // activations / statistics of the previous kernel are complete
     const int kc = tid & 3, px0 = tid >> 2;          // k-chunk, first window pixel of this thread (step 64)
     const bf16* src1 = (const bf16*)p.c.src1;
     const bf16* src2 = (const bf16*)p.c.src2;
@@ -457,6 +489,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tcgen05_kernel(const Params 
     // stores bf16 and accumulates the GroupNorm statistics of its rows; a warp then reduces 8 partials at a time with a
     // halving butterfly (9 shuffles) and the owning lanes add them to the (image, group) slots with fixed-point integer
     // atomics (order independent => deterministic).
+    pdl_wait();                                       // output / residual / statistics buffers are free to touch
     const int ew = warp - kProdWarps;                 // 0..7
     const int quarter = ew & 3, half = ew >> 2;       // TMEM lane quarter, column half of the tile
     bf16* out = (bf16*)p.c.out;
@@ -720,24 +753,32 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tcgen05_kernel(const Params 
           mbar_wait(smem_u32(&full_b[st]), ph);
           tc_fence_after();
           const uint32_t bs = b_units0 + (uint32_t)st * b_stage_units;
-          // descriptor words are computed OUTSIDE the elected branch so that they are warp-uniform values (uniform registers)
-          for (int g = 0; g < G; ++g) {
-            const int t = t0 + g;
-            const uint32_t a0 = au + (uint32_t)p.delta[phase * 16 + t];
-            const uint32_t b0 = bs + (uint32_t)g * b_tap_units;
-            const uint32_t acc = (c | t) ? 1u : 0u;
-            const uint64_t bd0 = ((uint64_t)hi_b << 32) | ((b0 & 0x3FFFu) | lbo_b_f);
-            const uint64_t bd1 = ((uint64_t)hi_b << 32) | (((b0 + b_k16) & 0x3FFFu) | lbo_b_f);
-            const uint64_t ad00 = ((uint64_t)hi_a << 32) | ((a0 & 0x3FFFu) | lbo_a_f);
-            const uint64_t ad01 = ((uint64_t)hi_a << 32) | (((a0 + 128u) & 0x3FFFu) | lbo_a_f);
-            const uint64_t ad10 = ((uint64_t)hi_a << 32) | (((a0 + a_k16) & 0x3FFFu) | lbo_a_f);
-            const uint64_t ad11 = ((uint64_t)hi_a << 32) | (((a0 + a_k16 + 128u) & 0x3FFFu) | lbo_a_f);
-            if (leader) {
-              umma_bf16(d0, ad00, bd0, idesc, acc);
-              if (two) umma_bf16(d1, ad01, bd0, idesc, acc);
-              umma_bf16(d0, ad10, bd1, idesc, 1u);
-              if (two) umma_bf16(d1, ad11, bd1, idesc, 1u);
+          const uint32_t acc0 = c ? 1u : 0u;
+          if (two) {
+            // 256-row tiles: per-tap issue (4 MMAs = 256 clk of tensor work cover the ~20 uniform instructions of the next tap);
+            // batching a whole stage's descriptors first measured slower here (the MMA queue drains during the longer prologue)
+            for (int g = 0; g < G; ++g) {
+              const int t = t0 + g;
+              const uint32_t a0 = au + (uint32_t)p.delta[phase * 16 + t];
+              const uint32_t b0 = bs + (uint32_t)g * b_tap_units;
+              const uint32_t acc = (c | t) ? 1u : 0u;
+              const uint64_t bd0 = ((uint64_t)hi_b << 32) | ((b0 & 0x3FFFu) | lbo_b_f);
+              const uint64_t bd1 = ((uint64_t)hi_b << 32) | (((b0 + b_k16) & 0x3FFFu) | lbo_b_f);
+              const uint64_t ad00 = ((uint64_t)hi_a << 32) | ((a0 & 0x3FFFu) | lbo_a_f);
+              const uint64_t ad01 = ((uint64_t)hi_a << 32) | (((a0 + 128u) & 0x3FFFu) | lbo_a_f);
+              const uint64_t ad10 = ((uint64_t)hi_a << 32) | (((a0 + a_k16) & 0x3FFFu) | lbo_a_f);
+              const uint64_t ad11 = ((uint64_t)hi_a << 32) | (((a0 + a_k16 + 128u) & 0x3FFFu) | lbo_a_f);
+              if (leader) {
+                umma_bf16(d0, ad00, bd0, idesc, acc);
+                umma_bf16(d1, ad01, bd0, idesc, acc);
+                umma_bf16(d0, ad10, bd1, idesc, 1u);
+                umma_bf16(d1, ad11, bd1, idesc, 1u);
+              }
             }
+          } else {
+            if (G == 3) issue_stage<3, false>(p, leader, d0, d1, au, bs, phase * 16 + t0, t0, acc0, idesc, hi_a, hi_b, lbo_a_f, lbo_b_f, a_k16, b_k16, b_tap_units);
+            else if (G == 2) issue_stage<2, false>(p, leader, d0, d1, au, bs, phase * 16 + t0, t0, acc0, idesc, hi_a, hi_b, lbo_a_f, lbo_b_f, a_k16, b_k16, b_tap_units);
+            else issue_stage<1, false>(p, leader, d0, d1, au, bs, phase * 16 + t0, t0, acc0, idesc, hi_a, hi_b, lbo_a_f, lbo_b_f, a_k16, b_k16, b_tap_units);
           }
           if (leader) umma_commit(smem_u32(&empty_b[st]));     // frees the weight stage once these MMAs retire
           __syncwarp();
@@ -917,7 +958,7 @@ static int launch(Params p, cudaStream_t st) {
     attr_set = true;
   }
   const int grid = p.total_tiles < num_sms() ? p.total_tiles : num_sms();
-  conv_tcgen05_kernel<GEO><<<grid, kThreads, smem_bytes(p), st>>>(p);
+  DMN_CUDA_CHECK(launch_pdl(conv_tcgen05_kernel<GEO>, dim3(grid), dim3(kThreads), smem_bytes(p), st, p));
   count_launch();
   DMN_LAUNCH_CHECK("conv_tcgen05");
   return 0;

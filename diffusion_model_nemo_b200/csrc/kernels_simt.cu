@@ -290,6 +290,8 @@ template <> struct VecIO<bf16, 8> {
 
 template <typename T, int V>
 __global__ void __launch_bounds__(256, 3) gn_finalize_kernel(const FinalizeP p) {
+  pdl_trigger();
+  pdl_wait();
   __shared__ unsigned long long sm_stats[2 * 64];
   const int b = blockIdx.y;
   const int CV = p.C / V;
@@ -377,9 +379,9 @@ int gn_finalize(const FinalizeP& p, int act, cudaStream_t st) {
   if (bpi < 1) bpi = 1;
   if (bpi > 64) bpi = 64;
   dim3 grid(bpi, p.B);
-  if (act == ACT_F32) gn_finalize_kernel<float, 4><<<grid, 256, 0, st>>>(p);
-  else if (V == 8) gn_finalize_kernel<bf16, 8><<<grid, 256, 0, st>>>(p);
-  else gn_finalize_kernel<bf16, 4><<<grid, 256, 0, st>>>(p);
+  if (act == ACT_F32) DMN_CUDA_CHECK(launch_pdl(gn_finalize_kernel<float, 4>, grid, dim3(256), 0, st, p));
+  else if (V == 8) DMN_CUDA_CHECK(launch_pdl(gn_finalize_kernel<bf16, 8>, grid, dim3(256), 0, st, p));
+  else DMN_CUDA_CHECK(launch_pdl(gn_finalize_kernel<bf16, 4>, grid, dim3(256), 0, st, p));
   count_launch();
   DMN_LAUNCH_CHECK("gn_finalize");
   return 0;
@@ -392,6 +394,8 @@ int gn_finalize(const FinalizeP& p, int act, cudaStream_t st) {
 // =====================================================================================================
 template <typename T>
 __global__ void __launch_bounds__(128) final_proj_kernel(const FinalProjP p) {
+  pdl_trigger();
+  pdl_wait();
   extern __shared__ float fsm[];
   float* s_sc = fsm;                 // [C] rstd*gamma
   float* s_sh = fsm + p.C;           // [C] beta - mean*rstd*gamma
@@ -435,8 +439,8 @@ int final_proj(const FinalProjP& p, int act, cudaStream_t st) {
   const size_t smem = (size_t)(2 + p.Cout) * p.C * sizeof(float);
   DMN_REQUIRE(smem <= 48 * 1024, "final_proj: channel count too large");
   dim3 grid((unsigned)((p.HW + 127) / 128), (unsigned)p.B);
-  if (act == ACT_F32) final_proj_kernel<float><<<grid, 128, smem, st>>>(p);
-  else final_proj_kernel<bf16><<<grid, 128, smem, st>>>(p);
+  if (act == ACT_F32) DMN_CUDA_CHECK(launch_pdl(final_proj_kernel<float>, grid, dim3(128), smem, st, p));
+  else DMN_CUDA_CHECK(launch_pdl(final_proj_kernel<bf16>, grid, dim3(128), smem, st, p));
   count_launch();
   DMN_LAUNCH_CHECK("final_proj");
   return 0;
@@ -595,6 +599,8 @@ int linattn_core(const void* qkv, void* out, int B, int heads, int dh, int N, in
 // =====================================================================================================
 template <typename T>
 __global__ void attn_kernel(const T* __restrict__ qkv, T* __restrict__ out, int heads, int N) {
+  pdl_trigger();
+  pdl_wait();
   constexpr int D = 32;
   extern __shared__ float kv[];   // k[N][D], v[N][D]
   float* ks = kv;
@@ -640,8 +646,8 @@ int attn_core(const void* qkv, void* out, int B, int heads, int dh, int N, int a
   DMN_REQUIRE(smem <= 48 * 1024, "attn_core: too many tokens for the bottleneck attention kernel");
   int threads = ((N + 31) / 32) * 32;
   if (threads > 256) threads = 256;
-  if (act == ACT_F32) attn_kernel<float><<<B * heads, threads, smem, st>>>((const float*)qkv, (float*)out, heads, N);
-  else attn_kernel<bf16><<<B * heads, threads, smem, st>>>((const bf16*)qkv, (bf16*)out, heads, N);
+  if (act == ACT_F32) DMN_CUDA_CHECK(launch_pdl(attn_kernel<float>, dim3(B * heads), dim3(threads), smem, st, (const float*)qkv, (float*)out, heads, N));
+  else DMN_CUDA_CHECK(launch_pdl(attn_kernel<bf16>, dim3(B * heads), dim3(threads), smem, st, (const bf16*)qkv, (bf16*)out, heads, N));
   count_launch();
   DMN_LAUNCH_CHECK("attn_core");
   return 0;

@@ -60,6 +60,8 @@ __device__ __forceinline__ void st_u32(uint32_t addr, uint32_t v) { asm volatile
 
 __global__ void __launch_bounds__(256, 2) linattn_mma_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out, int N) {
   extern __shared__ __align__(128) uint8_t sm[];
+  pdl_trigger();
+  pdl_wait();
   const uint32_t tiles = smem_u32(sm);
   const uint32_t ctxs = tiles + kTileBytes;
   float* fmax_s = reinterpret_cast<float*>(sm + kTileBytes + kCtxBytes);   // running column max of k
@@ -263,7 +265,7 @@ int linattn_core_bf16_mma(const void* qkv, void* out, int B, int N, cudaStream_t
     DMN_CUDA_CHECK(cudaFuncSetAttribute(la::linattn_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, la::kSmem));
     attr = true;
   }
-  la::linattn_mma_kernel<<<B, 256, la::kSmem, st>>>((const bf16*)qkv, (bf16*)out, N);
+  DMN_CUDA_CHECK(launch_pdl(la::linattn_mma_kernel, dim3(B), dim3(256), la::kSmem, st, (const bf16*)qkv, (bf16*)out, N));
   count_launch();
   DMN_LAUNCH_CHECK("linattn_mma");
   return 0;

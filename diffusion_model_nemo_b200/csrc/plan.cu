@@ -16,6 +16,7 @@
 //   conv 1x1 (to_out)             : + bias (+ statistics of GroupNorm(1) | + residual for the bottleneck Attention)
 //   gn_finalize                   : GroupNorm(1) + residual
 //   concat                        : never materialised (two-source operand load)
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <memory>
@@ -31,6 +32,13 @@ namespace dmn {
 static thread_local std::string g_err;
 thread_local long g_launches = 0;
 void set_error(const std::string& m) { g_err = m; }
+bool pdl_enabled() {
+  static const bool on = [] {
+    const char* e = getenv("DMN_PDL");
+    return e && e[0] == '1';      // opt-in: measured neutral inside the CUDA graph (profiles/README.md)
+  }();
+  return on;
+}
 int fail(int code, const std::string& m) {
   g_err = m;
   return code;

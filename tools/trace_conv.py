@@ -51,3 +51,5 @@ if __name__ == "__main__":
     run(3, 128, 128, 32, 256, False)
     run(3, 256, 256, 16, 256, True)
     run(1, 128, 384, 32, 256, False)
+    run(3, 256, 256, 4, 256, True)
+    run(3, 256, 256, 8, 256, True)
