@@ -31,6 +31,16 @@ IMAGE, BATCH, T = 32, 256, 1000
 FLOPS_PER_SAMPLE_EVAL = 5350096896           # BASELINE.md section 3 (torch FlopCounterMode on the reference U-Net)
 
 
+def ncu_traffic():
+    """DRAM bytes of the dominant kernel's largest launch from the committed ncu capture (profiles/), or None."""
+    p = os.path.join(ROOT, "profiles", "r01_conv_traffic.json")
+    try:
+        d = json.load(open(p))
+        return d["dram_bytes_read"] + d["dram_bytes_write"], d["kernel"]
+    except Exception:
+        return None, None
+
+
 def measured_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -252,8 +262,10 @@ def main():
     gd = groups[dom]
     if gd["flops"] > 0 and dom.startswith("conv"):
         ach = gd["flops"] / (gd["ms"] * 1e-3) / 1e12
+        traffic, traffic_kernel = ncu_traffic()
         roof = {"kernel": dom, "bound": "tensor", "achieved": ach, "peak": sust, "unit": "TFLOP/s", "frac": ach / sust,
-                "peak_source": f"{src} bf16_tflops_sustained (kernel timed inside a long step)", "traffic": None,
+                "peak_source": f"{src} bf16_tflops_sustained (kernel timed inside a long step)", "traffic": traffic,
+                "traffic_of": traffic_kernel,
                 "launches_per_step": gd["launches"], "avg_launch_ms": gd["ms"] / gd["launches"], "share_of_step": gd["ms"] / step_prof_ms}
     else:
         ach = gd["bytes"] / (gd["ms"] * 1e-3) / 1e9

@@ -47,10 +47,10 @@ namespace tc {
 
 enum { GEO_SAME = 0, GEO_DOWN = 1, GEO_UP = 2, GEO_INIT = 3 };
 
-constexpr int kProdWarps = 8, kEpiWarps = 8;
-constexpr int kProdThreads = kProdWarps * 32, kEpiThreads = kEpiWarps * 32;
-constexpr int kLoaderWarp = kProdWarps + kEpiWarps, kMmaWarp = kLoaderWarp + 1;
-constexpr int kThreads = (kMmaWarp + 1) * 32;     // 576
+constexpr int kProdWarps = 8;
+constexpr int kProdThreads = kProdWarps * 32;
+// epilogue warps EW = 8 (3x3 convs: 576 threads, 96 registers) or 16 (1-tap / 4-tap / stem convs, whose main loop is too short to
+// hide an 8-warp epilogue: 832 threads, 72 registers); EW / 4 warps share a TMEM lane quarter and split the tile's columns
 constexpr int kMTmax = 2;              // 128-row accumulators per tile: 2, or 1 when two would leave most SMs idle
 constexpr int kMcta = 128 * kMTmax;    // table sizing
 constexpr int kCk = 32;                // channels per pass (4 k-chunks of 8)
@@ -244,8 +244,9 @@ __device__ __forceinline__ void issue_stage(const Params& p, bool leader, uint32
 // ---------------------------------------------------------------------------------------------------
 // kernel
 // ---------------------------------------------------------------------------------------------------
-template <int GEO>
-__global__ void __launch_bounds__(kThreads, 1) conv_tcgen05_kernel(const Params p) {
+template <int GEO, int EW>
+__global__ void __launch_bounds__((kProdWarps + EW + 2) * 32, 1) conv_tcgen05_kernel(const Params p) {
+  constexpr int kEpiThreads = EW * 32, kLoaderWarp = kProdWarps + EW, kMmaWarp = kLoaderWarp + 1;
   extern __shared__ __align__(128) uint8_t smem[];
   const int tid = threadIdx.x;
   // broadcast => ptxas knows the role branches below are warp-uniform and may use the uniform datapath inside them
@@ -490,14 +491,15 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tcgen05_kernel(const Params 
     // halving butterfly (9 shuffles) and the owning lanes add them to the (image, group) slots with fixed-point integer
     // atomics (order independent => deterministic).
     pdl_wait();                                       // output / residual / statistics buffers are free to touch
-    const int ew = warp - kProdWarps;                 // 0..7
-    const int quarter = ew & 3, half = ew >> 2;       // TMEM lane quarter, column half of the tile
+    const int ew = warp - kProdWarps;                 // 0..EW-1
+    const int quarter = ew & 3, part = ew >> 2;       // TMEM lane quarter, column part of the tile (EW / 4 parts)
     bf16* out = (bf16*)p.c.out;
     const bf16* res = (const bf16*)p.c.res;
-    // columns owned by this warp: half of the tile; with NT = 32 only the first warp of each lane quarter works
-    const bool active = p.NT >= 64 || half == 0;
-    const int ncol = p.NT >= 64 ? (p.NT >> 1) : p.NT;
-    const int col0 = p.NT >= 64 ? half * ncol : 0;
+    // columns owned by this warp: NT / parts, at least 32; surplus warps of a lane quarter stay idle for narrow tiles
+    constexpr int kParts = EW / 4;
+    const int ncol = (p.NT / kParts) >= 32 ? (p.NT / kParts) : 32;
+    const bool active = part * ncol < p.NT;
+    const int col0 = part * ncol;
     const int sh = p.cpg_out_shift;
     const bool do_stats = p.c.ostats != nullptr;
     // staging geometry: row_bytes = ncol * 2 (64 / 128 / 256); lpr lanes per row, rpi rows per store instruction
@@ -804,8 +806,12 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tcgen05_kernel(const Params 
   }
 }
 
+// 16 epilogue warps (832 threads, 72 registers, spills) measured SLOWER than 8 on every 1-tap / 4-tap conv (e.g. to_qkv 0.180 ->
+// 0.215 ms): kept as a template option, not used
+static int epi_warps(const Params& p) { (void)p; return 8; }
 static size_t smem_fixed_bytes(const Params& p) {
-  const int ncol = p.NT >= 64 ? p.NT / 2 : p.NT;
+  const int kEpiWarps = epi_warps(p), parts = kEpiWarps / 4;
+  const int ncol = (p.NT / parts) >= 32 ? (p.NT / parts) : 32;
   return (size_t)kABuf * 4 * p.PA * 16 + (2 * kStagesMax + 2 * kABuf + 4) * 8 + 16 + (size_t)kNimgMax * kGroupsMax * 8 +
          2 * (size_t)p.P * 4 + 128 + (size_t)kEpiWarps * (32 * ncol * 2 + ncol * 4) + 128;
 }
@@ -954,11 +960,15 @@ static int launch(Params p, cudaStream_t st) {
   }
   static bool attr_set = false;
   if (!attr_set) {
-    DMN_CUDA_CHECK(cudaFuncSetAttribute(conv_tcgen05_kernel<GEO>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemLimit));
+    DMN_CUDA_CHECK(cudaFuncSetAttribute(conv_tcgen05_kernel<GEO, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemLimit));
+    DMN_CUDA_CHECK(cudaFuncSetAttribute(conv_tcgen05_kernel<GEO, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemLimit));
     attr_set = true;
   }
   const int grid = p.total_tiles < num_sms() ? p.total_tiles : num_sms();
-  DMN_CUDA_CHECK(launch_pdl(conv_tcgen05_kernel<GEO>, dim3(grid), dim3(kThreads), smem_bytes(p), st, p));
+  if (epi_warps(p) == 8)
+    DMN_CUDA_CHECK(launch_pdl(conv_tcgen05_kernel<GEO, 8>, dim3(grid), dim3((kProdWarps + 8 + 2) * 32), smem_bytes(p), st, p));
+  else
+    DMN_CUDA_CHECK(launch_pdl(conv_tcgen05_kernel<GEO, 16>, dim3(grid), dim3((kProdWarps + 16 + 2) * 32), smem_bytes(p), st, p));
   count_launch();
   DMN_LAUNCH_CHECK("conv_tcgen05");
   return 0;
