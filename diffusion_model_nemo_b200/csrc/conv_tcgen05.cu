@@ -582,10 +582,7 @@ __global__ void __launch_bounds__((kProdWarps + EW + 2) * 32, 1) conv_tcgen05_ke
           const int kk = k + u;
           if (kk >= npieces) break;
           const int mt = kk >= ppm ? 1 : 0, pc = kk - mt * ppm;
-          const bool tr = p.trace && blockIdx.x == (unsigned)p.trace_cta && it == 2 && ew == 0 && lane == 0 && kk < 32;
-          if (tr) p.trace[800 + 3 * kk] = clock64();
           tmem_ld_wait();
-          if (tr) p.trace[801 + 3 * kk] = clock64();
           if (kk + 1 < npieces) {
             const int mt1 = (kk + 1) >= ppm ? 1 : 0, pc1 = kk + 1 - mt1 * ppm;
             tmem_ld16_nowait(tlane + (uint32_t)(mt1 * p.NT + pc1 * 16), rb[u ^ 1]);
@@ -693,7 +690,6 @@ __global__ void __launch_bounds__((kProdWarps + EW + 2) * 32, 1) conv_tcgen05_ke
               }
             }
           }
-          if (tr) p.trace[802 + 3 * kk] = clock64();
         }
       }
       if (ew == 0 && lane == 0) TRACE(it, 11);

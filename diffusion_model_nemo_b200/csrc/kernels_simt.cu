@@ -434,11 +434,85 @@ __global__ void __launch_bounds__(128) final_proj_kernel(const FinalProjP p) {
     if (j < p.Cout) p.out[((long)b * p.Cout + j) * p.HW + pix] = acc[j] + (p.bias ? p.bias[j] : 0.f);
 }
 
+
+// bf16 fast path: the block's 128 pixel rows are first copied (coalesced 16-byte cp.async) into shared memory with padded rows, then
+// one thread per pixel walks its row with conflict-free LDS.128; COUT is a template parameter so the dot products are straight-line.
+template <int COUT>
+__global__ void __launch_bounds__(128) final_proj_bf16_kernel(const FinalProjP p) {
+  pdl_trigger();
+  pdl_wait();
+  extern __shared__ __align__(16) unsigned char fsmb[];
+  const int C = p.C, ld = C * 2 + 16;                       // bytes per staged pixel row
+  float* s_sc = reinterpret_cast<float*>(fsmb);             // [C] rstd*gamma
+  float* s_sh = s_sc + C;                                   // [C] beta - mean*rstd*gamma
+  float* s_w = s_sh + C;                                    // [COUT][C]
+  unsigned char* s_tile = fsmb + (size_t)(2 + COUT) * C * 4;
+  const int b = blockIdx.y, pix0 = blockIdx.x * 128;
+  const int npix = min(128, p.HW - pix0);
+  {
+    const bf16* y = (const bf16*)p.y + ((long)b * p.HW + pix0) * C;
+    const int chunks = C / 8;                               // 16-byte chunks per row
+    const uint32_t tile_u = (uint32_t)__cvta_generic_to_shared(s_tile);
+    for (int i = threadIdx.x; i < npix * chunks; i += 128) {
+      const int r = i / chunks, c16 = i - r * chunks;
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(tile_u + (uint32_t)(r * ld + c16 * 16)), "l"(y + (long)r * C + c16 * 8) : "memory");
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  }
+  const int cpg = C / p.groups;
+  const float inv = 1.f / (float)(p.HW * cpg);
+  for (int c = threadIdx.x; c < C; c += 128) {
+    float mean, rstd;
+    gn_mean_rstd(p.stats + ((long)b * p.groups + c / cpg) * 2, inv, kGnEps, mean, rstd);
+    const float sc = rstd * p.gamma[c];
+    s_sc[c] = sc;
+    s_sh[c] = p.beta[c] - mean * sc;
+  }
+  for (int i = threadIdx.x; i < COUT * C; i += 128) s_w[i] = p.w[i];
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  __syncthreads();
+  if ((int)threadIdx.x >= npix) return;
+  const unsigned char* row = s_tile + (size_t)threadIdx.x * ld;
+  float acc[COUT];
+#pragma unroll
+  for (int j = 0; j < COUT; ++j) acc[j] = 0.f;
+  for (int c = 0; c < C; c += 8) {
+    float v[8];
+    unpack8(*reinterpret_cast<const uint4*>(row + c * 2), v);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const float a = silu_fast(fmaf(v[e], s_sc[c + e], s_sh[c + e]));
+#pragma unroll
+      for (int j = 0; j < COUT; ++j) acc[j] = fmaf(a, s_w[j * C + c + e], acc[j]);
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < COUT; ++j) p.out[((long)b * COUT + j) * p.HW + pix0 + threadIdx.x] = acc[j] + (p.bias ? p.bias[j] : 0.f);
+}
+
 int final_proj(const FinalProjP& p, int act, cudaStream_t st) {
   DMN_REQUIRE(p.Cout <= 8 && p.C % 4 == 0, "final_proj: out_dim > 8 or C % 4 != 0 unsupported");
   const size_t smem = (size_t)(2 + p.Cout) * p.C * sizeof(float);
   DMN_REQUIRE(smem <= 48 * 1024, "final_proj: channel count too large");
   dim3 grid((unsigned)((p.HW + 127) / 128), (unsigned)p.B);
+  if (act == ACT_BF16 && p.C % 8 == 0 && (p.Cout == 3 || p.Cout == 6 || p.Cout == 1)) {
+    const size_t smem2 = (size_t)(2 + p.Cout) * p.C * sizeof(float) + (size_t)128 * (p.C * 2 + 16);
+    if (smem2 <= 200 * 1024) {
+      static bool attr = false;
+      if (!attr) {
+        DMN_CUDA_CHECK(cudaFuncSetAttribute(final_proj_bf16_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        DMN_CUDA_CHECK(cudaFuncSetAttribute(final_proj_bf16_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        DMN_CUDA_CHECK(cudaFuncSetAttribute(final_proj_bf16_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        attr = true;
+      }
+      if (p.Cout == 3) DMN_CUDA_CHECK(launch_pdl(final_proj_bf16_kernel<3>, grid, dim3(128), smem2, st, p));
+      else if (p.Cout == 6) DMN_CUDA_CHECK(launch_pdl(final_proj_bf16_kernel<6>, grid, dim3(128), smem2, st, p));
+      else DMN_CUDA_CHECK(launch_pdl(final_proj_bf16_kernel<1>, grid, dim3(128), smem2, st, p));
+      count_launch();
+      DMN_LAUNCH_CHECK("final_proj");
+      return 0;
+    }
+  }
   if (act == ACT_F32) DMN_CUDA_CHECK(launch_pdl(final_proj_kernel<float>, grid, dim3(128), smem, st, p));
   else DMN_CUDA_CHECK(launch_pdl(final_proj_kernel<bf16>, grid, dim3(128), smem, st, p));
   count_launch();
