@@ -47,10 +47,10 @@ namespace tc {
 
 enum { GEO_SAME = 0, GEO_DOWN = 1, GEO_UP = 2, GEO_INIT = 3 };
 
-constexpr int kProdWarps = 8;
-constexpr int kProdThreads = kProdWarps * 32;
-// epilogue warps EW = 8 (3x3 convs: 576 threads, 96 registers) or 16 (1-tap / 4-tap / stem convs, whose main loop is too short to
-// hide an 8-warp epilogue: 832 threads, 72 registers); EW / 4 warps share a TMEM lane quarter and split the tile's columns
+constexpr int kProdWarps = 8, kEpiWarps = 8;
+constexpr int kProdThreads = kProdWarps * 32, kEpiThreads = kEpiWarps * 32;
+constexpr int kLoaderWarp = kProdWarps + kEpiWarps, kMmaWarp = kLoaderWarp + 1;
+constexpr int kThreads = (kMmaWarp + 1) * 32;     // 576 (16 epilogue warps = 832 threads at 72 registers measured slower)
 constexpr int kMTmax = 2;              // 128-row accumulators per tile: 2, or 1 when two would leave most SMs idle
 constexpr int kMcta = 128 * kMTmax;    // table sizing
 constexpr int kCk = 32;                // channels per pass (4 k-chunks of 8)
@@ -244,9 +244,10 @@ __device__ __forceinline__ void issue_stage(const Params& p, bool leader, uint32
 // ---------------------------------------------------------------------------------------------------
 // kernel
 // ---------------------------------------------------------------------------------------------------
-template <int GEO, int EW>
-__global__ void __launch_bounds__((kProdWarps + EW + 2) * 32, 1) conv_tcgen05_kernel(const Params p) {
-  constexpr int kEpiThreads = EW * 32, kLoaderWarp = kProdWarps + EW, kMmaWarp = kLoaderWarp + 1;
+// NT (the N tile: 32 / 64 / 128 output channels) is a template parameter so that the epilogue's geometry (columns per warp, staging
+// swizzle, store pattern) folds to constants and its loops unroll
+template <int GEO, int NT>
+__global__ void __launch_bounds__(kThreads, 1) conv_tcgen05_kernel(const Params p) {
   extern __shared__ __align__(128) uint8_t smem[];
   const int tid = threadIdx.x;
   // broadcast => ptxas knows the role branches below are warp-uniform and may use the uniform datapath inside them
@@ -255,7 +256,7 @@ __global__ void __launch_bounds__((kProdWarps + EW + 2) * 32, 1) conv_tcgen05_ke
 
   // ---- shared memory carve-up ----
   const uint32_t a_bytes = 4u * p.PA * 16u;           // one A buffer (4 k-chunks)
-  const uint32_t tap_bytes = 4u * p.NT * 16u;         // weights of one tap of one pass
+  const uint32_t tap_bytes = 4u * NT * 16u;           // weights of one tap of one pass
   const uint32_t b_bytes = p.stage_bytes;             // one B stage (G taps)
   uint8_t* sA = smem;
   uint8_t* sB = sA + kABuf * a_bytes;
@@ -491,31 +492,32 @@ __global__ void __launch_bounds__((kProdWarps + EW + 2) * 32, 1) conv_tcgen05_ke
     // halving butterfly (9 shuffles) and the owning lanes add them to the (image, group) slots with fixed-point integer
     // atomics (order independent => deterministic).
     pdl_wait();                                       // output / residual / statistics buffers are free to touch
-    const int ew = warp - kProdWarps;                 // 0..EW-1
-    const int quarter = ew & 3, part = ew >> 2;       // TMEM lane quarter, column part of the tile (EW / 4 parts)
+    const int ew = warp - kProdWarps;                 // 0..7
+    const int quarter = ew & 3, part = ew >> 2;       // TMEM lane quarter, column half of the tile
     bf16* out = (bf16*)p.c.out;
     const bf16* res = (const bf16*)p.c.res;
-    // columns owned by this warp: NT / parts, at least 32; surplus warps of a lane quarter stay idle for narrow tiles
-    constexpr int kParts = EW / 4;
-    const int ncol = (p.NT / kParts) >= 32 ? (p.NT / kParts) : 32;
-    const bool active = part * ncol < p.NT;
-    const int col0 = part * ncol;
+    // columns owned by this warp: half of the tile; with NT = 32 only the first warp of each lane quarter works
+    constexpr int NCOL = NT >= 64 ? NT / 2 : NT;      // 64 | 32 | 32
+    constexpr int PPM = NCOL / 16;                    // 16-column pieces per 128-row accumulator (even)
+    constexpr int ROWB = NCOL * 2, LPR = NCOL / 8, RPI = 32 / LPR;   // staging row bytes, lanes per row, rows per store instruction
+    constexpr int SWS = ROWB == 64 ? 1 : 0, SWM = ROWB == 64 ? 3 : 7;
+    const bool active = NT >= 64 || part == 0;
+    const int col0 = NT >= 64 ? part * NCOL : 0;
     const int sh = p.cpg_out_shift;
     const bool do_stats = p.c.ostats != nullptr;
-    // staging geometry: row_bytes = ncol * 2 (64 / 128 / 256); lpr lanes per row, rpi rows per store instruction
-    const int row_bytes = ncol * 2, lpr = ncol >> 3, rpi = 32 / lpr;
-    const int swz_shift = row_bytes == 64 ? 1 : 0, swz_mask = row_bytes == 64 ? 3 : 7;
-    const uint32_t my_stage = smem_u32(s_stage) + (uint32_t)(ew * (32 * row_bytes + ncol * 4));   // shared-space addresses
-    const uint32_t my_bias = my_stage + (uint32_t)(32 * row_bytes);
-    const int my_swz = (lane >> swz_shift) & swz_mask;
-    const int lrow = lane / lpr, lcol = lane % lpr;   // this lane's (row within a store instruction, 16-byte chunk)
+    const bool has_bias = p.c.bias != nullptr;
+    const uint32_t my_stage = smem_u32(s_stage) + (uint32_t)(ew * (32 * ROWB + NCOL * 4));   // shared-space addresses
+    const uint32_t my_bias = my_stage + (uint32_t)(32 * ROWB);
+    const int my_swz = (lane >> SWS) & SWM;
+    const int lrow = lane / LPR, lcol = lane % LPR;   // this lane's (row within a store instruction, 16-byte chunk)
+    const uint32_t my_wr = my_stage + (uint32_t)(lane * ROWB);   // this lane's staging row
     int last_ntile = -1;
     int it = 0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
       const int n_tile = tile % p.n_tiles_n;
       const int m0 = (tile / p.n_tiles_n) * p.mcta;
       const int phase = (GEO == GEO_UP) ? n_tile / p.tiles_per_phase : 0;
-      const int n0 = (GEO == GEO_UP ? n_tile % p.tiles_per_phase : n_tile) * p.NT;
+      const int n0 = (GEO == GEO_UP ? n_tile % p.tiles_per_phase : n_tile) * NT;
       // ---- this thread's rows ----
       const int eimg0 = m0 / p.S, erem0 = m0 - eimg0 * p.S;     // uniform
       int opixv[kMTmax], keyv[kMTmax];
@@ -546,9 +548,9 @@ __global__ void __launch_bounds__((kProdWarps + EW + 2) * 32, 1) conv_tcgen05_ke
         }
       }
       // bias of this warp's columns -> private shared memory (re-staged only when the N tile changes)
-      if (active && n_tile != last_ntile) {
+      if (has_bias && active && n_tile != last_ntile) {
         __syncwarp();
-        for (int i = lane; i < ncol; i += 32) sts32f(my_bias + 4u * i, p.c.bias ? p.c.bias[n0 + col0 + i] : 0.f);
+        for (int i = lane; i < NCOL; i += 32) sts32f(my_bias + 4u * i, p.c.bias[n0 + col0 + i]);
         last_ntile = n_tile;
         __syncwarp();
       }
@@ -558,16 +560,15 @@ __global__ void __launch_bounds__((kProdWarps + EW + 2) * 32, 1) conv_tcgen05_ke
       mbar_wait_relaxed(smem_u32(&acc_full[as]), (it >> 1) & 1);
       tc_fence_after();
       if (ew == 0 && lane == 0) TRACE(it, 9);
-      const uint32_t tacc = tmem_base + (uint32_t)(as * p.mt * p.NT);
+      const uint32_t tacc = tmem_base + (uint32_t)(as * p.mt * NT);
       if (!active) {
         tc_fence_before();
         mbar_arrive(smem_u32(&acc_empty[as]));
         continue;
       }
-      // software pipeline over 16-column pieces: the TMEM load of piece k+1 is in flight while piece k is processed
-      const int ppm = ncol >> 4;                              // pieces per 128-row accumulator
-      const int npieces = p.mt * ppm;
+      // software pipeline over 16-column pieces: the TMEM load of the next piece is in flight while this one is processed
       const uint32_t tlane = tacc + ((uint32_t)(quarter * 32) << 16) + (uint32_t)col0;
+      bf16* const out_col = out + n0 + col0 + lcol * 8;       // store phase: + row * Cout
       uint32_t rb[2][16];
       tmem_ld16_nowait(tlane, rb[0]);
       float val[8];                                           // statistics shift register: 4 group slots x {sum, sumsq}
@@ -576,34 +577,34 @@ __global__ void __launch_bounds__((kProdWarps + EW + 2) * 32, 1) conv_tcgen05_ke
       float cs = 0.f, cq = 0.f;                               // current group accumulator (this row)
       int nslots = 0;
 #pragma unroll 1
-      for (int k = 0; k < npieces; k += 2) {
+      for (int mt = 0; mt < p.mt; ++mt) {
+        const int opix = mt == 0 ? opixv[0] : opixv[kMTmax - 1];
+        const int key = mt == 0 ? keyv[0] : keyv[kMTmax - 1];
+        const bool valid = opix >= 0;
 #pragma unroll
-        for (int u = 0; u < 2; ++u) {                         // static double-buffer index
-          const int kk = k + u;
-          if (kk >= npieces) break;
-          const int mt = kk >= ppm ? 1 : 0, pc = kk - mt * ppm;
+        for (int pc = 0; pc < PPM; ++pc) {
+          const int u = pc & 1;                               // static double-buffer index (PPM is even)
           tmem_ld_wait();
-          if (kk + 1 < npieces) {
-            const int mt1 = (kk + 1) >= ppm ? 1 : 0, pc1 = kk + 1 - mt1 * ppm;
-            tmem_ld16_nowait(tlane + (uint32_t)(mt1 * p.NT + pc1 * 16), rb[u ^ 1]);
+          if (pc + 1 < PPM) {
+            tmem_ld16_nowait(tlane + (uint32_t)(mt * NT + (pc + 1) * 16), rb[u ^ 1]);
+          } else if (mt + 1 < p.mt) {
+            tmem_ld16_nowait(tlane + (uint32_t)((mt + 1) * NT), rb[u ^ 1]);
           } else {
             tc_fence_before();                                // last TMEM read of this tile is complete: hand the accumulators back
             mbar_arrive(smem_u32(&acc_empty[as]));
             if (ew == 0 && lane == 0) TRACE(it, 10);
           }
           const uint32_t* r = rb[u];
-          const int opix = mt == 0 ? opixv[0] : opixv[kMTmax - 1];
-          const int key = mt == 0 ? keyv[0] : keyv[kMTmax - 1];
-          const bool valid = opix >= 0;
-          const long orow = valid ? (long)opix * p.c.Cout + n0 + col0 + pc * 16 : 0;
           unsigned long long v2[8];
 #pragma unroll
           for (int j = 0; j < 8; ++j) v2[j] = pack2(__uint_as_float(r[2 * j]), __uint_as_float(r[2 * j + 1]));
+          if (has_bias) {
 #pragma unroll
-          for (int q4 = 0; q4 < 4; ++q4) {
-            const uint4 bq = lds128(my_bias + (uint32_t)(pc * 64 + q4 * 16));     // broadcast LDS.128
-            v2[2 * q4] = add2(v2[2 * q4], ((unsigned long long)bq.y << 32) | bq.x);
-            v2[2 * q4 + 1] = add2(v2[2 * q4 + 1], ((unsigned long long)bq.w << 32) | bq.z);
+            for (int q4 = 0; q4 < 4; ++q4) {
+              const uint4 bq = lds128(my_bias + (uint32_t)(pc * 64 + q4 * 16));     // broadcast LDS.128
+              v2[2 * q4] = add2(v2[2 * q4], ((unsigned long long)bq.y << 32) | bq.x);
+              v2[2 * q4 + 1] = add2(v2[2 * q4 + 1], ((unsigned long long)bq.w << 32) | bq.z);
+            }
           }
           if (GEO == GEO_INIT && p.cls_w && valid) {
             const float* cls_row = p.cls_w + (long)(p.classes ? (int)p.classes[key] : p.pad_class) * p.c.Cout + n0 + col0 + pc * 16;
@@ -615,9 +616,10 @@ __global__ void __launch_bounds__((kProdWarps + EW + 2) * 32, 1) conv_tcgen05_ke
             }
           }
           if (res && valid) {
+            const bf16* rrow = res + (long)opix * p.c.Cout + n0 + col0 + pc * 16;
 #pragma unroll
             for (int q = 0; q < 2; ++q) {
-              const uint4 rr = *reinterpret_cast<const uint4*>(res + orow + q * 8);
+              const uint4 rr = *reinterpret_cast<const uint4*>(rrow + q * 8);
               float rf[8];
               unpack8(rr, rf);
 #pragma unroll
@@ -633,31 +635,7 @@ __global__ void __launch_bounds__((kProdWarps + EW + 2) * 32, 1) conv_tcgen05_ke
             unpack2(v2[q * 4 + 1], a0, a1); o.y = pack_bf16x2(a0, a1);
             unpack2(v2[q * 4 + 2], a0, a1); o.z = pack_bf16x2(a0, a1);
             unpack2(v2[q * 4 + 3], a0, a1); o.w = pack_bf16x2(a0, a1);
-            sts128(my_stage + (uint32_t)(lane * row_bytes + (((pc * 2 + q) ^ my_swz) << 4)), o);
-          }
-          if (pc == ppm - 1) {
-            // the warp's 32 x ncol block is staged: coalesced 16-byte stores, `lpr` consecutive lanes cover one output row
-            __syncwarp();
-            // batches of 4 store instructions: all row lookups (SHFL) and staging reads (LDS) first, then the predicated
-            // stores -- no branch between them, so the latencies overlap
-#pragma unroll 1
-            for (int i0 = 0; i0 < 32; i0 += 4 * rpi) {
-              int ropix[4];
-              uint4 o[4];
-#pragma unroll
-              for (int ii = 0; ii < 4; ++ii) {
-                const int rrow = (i0 + ii * rpi + lrow) & 31;
-                ropix[ii] = __shfl_sync(0xffffffffu, opix, rrow);
-                const int rswz = (rrow >> swz_shift) & swz_mask;
-                o[ii] = lds128(my_stage + (uint32_t)(rrow * row_bytes + ((lcol ^ rswz) << 4)));
-              }
-#pragma unroll
-              for (int ii = 0; ii < 4; ++ii) {
-                if (i0 + ii * rpi < 32 && ropix[ii] >= 0)
-                  *reinterpret_cast<uint4*>(out + (long)ropix[ii] * p.c.Cout + n0 + col0 + lcol * 8) = o[ii];
-              }
-            }
-            __syncwarp();
+            sts128(my_wr + (uint32_t)(((pc * 2 + q) ^ my_swz) << 4), o);
           }
           if (do_stats) {
             // (sum, sum of squares) of this row's 16 columns: two independent packed chains each
@@ -678,7 +656,7 @@ __global__ void __launch_bounds__((kProdWarps + EW + 2) * 32, 1) conv_tcgen05_ke
             // group bookkeeping (uniform): does the group end with this piece?
             const int cbase = n0 + col0 + pc * 16;
             const int g = cbase >> sh;
-            const bool last_of_mt = pc == ppm - 1;
+            const bool last_of_mt = pc == PPM - 1;
             if (last_of_mt || ((cbase + 16) >> sh) != g) {
 #pragma unroll
               for (int i = 0; i < 6; ++i) val[i] = val[i + 2];
@@ -691,6 +669,24 @@ __global__ void __launch_bounds__((kProdWarps + EW + 2) * 32, 1) conv_tcgen05_ke
             }
           }
         }
+        // the warp's 32 x NCOL block is staged: coalesced 16-byte stores, LPR consecutive lanes cover one output row.  Batches
+        // of 4 store instructions: all row lookups (SHFL) and staging reads (LDS) first, then the predicated stores
+        __syncwarp();
+#pragma unroll
+        for (int i0 = 0; i0 < 32; i0 += 4 * RPI) {
+          int ropix[4];
+          uint4 o[4];
+#pragma unroll
+          for (int ii = 0; ii < 4; ++ii) {
+            const int rrow = i0 + ii * RPI + lrow;            // < 32 by construction (32 / RPI = LPR is a multiple of 4)
+            ropix[ii] = __shfl_sync(0xffffffffu, opix, rrow);
+            o[ii] = lds128(my_stage + (uint32_t)(rrow * ROWB + ((lcol ^ ((rrow >> SWS) & SWM)) << 4)));
+          }
+#pragma unroll
+          for (int ii = 0; ii < 4; ++ii)
+            if (ropix[ii] >= 0) *reinterpret_cast<uint4*>(out_col + (long)ropix[ii] * p.c.Cout) = o[ii];
+        }
+        __syncwarp();
       }
       if (ew == 0 && lane == 0) TRACE(it, 11);
     }
@@ -722,7 +718,7 @@ __global__ void __launch_bounds__((kProdWarps + EW + 2) * 32, 1) conv_tcgen05_ke
     // `if (lane == 0)` loop instead makes ptxas wrap every MMA in an R2UR + vote loop (~160 clk per MMA issued, measured),
     // which alone caps the tensor pipe at ~40 %; see tools/mma_rate2.cu.
     const bool leader = elect_one();
-    const uint32_t idesc = make_idesc(128, p.NT);
+    const uint32_t idesc = make_idesc(128, NT);
     const uint32_t hi_a = (p.sbo_a >> 4) | (1u << 14), hi_b = (p.sbo_b >> 4) | (1u << 14);
     const uint32_t lbo_a_f = ((p.lbo_a >> 4) & 0x3FFFu) << 16, lbo_b_f = ((p.lbo_b >> 4) & 0x3FFFu) << 16;
     const uint32_t a_units0 = (smem_u32(sA) >> 4) + (uint32_t)p.halo_lo;          // 16-byte units
@@ -740,7 +736,7 @@ __global__ void __launch_bounds__((kProdWarps + EW + 2) * 32, 1) conv_tcgen05_ke
       mbar_wait(smem_u32(&acc_empty[as]), ((it >> 1) & 1) ^ 1);      // epilogue has drained this accumulator set
       tc_fence_after();
       if (leader) TRACE(it, 4);
-      const uint32_t d0 = tmem_base + (uint32_t)(as * p.mt * p.NT), d1 = d0 + (uint32_t)p.NT;
+      const uint32_t d0 = tmem_base + (uint32_t)(as * p.mt * NT), d1 = d0 + (uint32_t)NT;
       for (int c = 0; c < p.n_pass; ++c) {
         mbar_wait(smem_u32(&full_a[cbuf]), cph);
         tc_fence_after();
@@ -802,12 +798,8 @@ __global__ void __launch_bounds__((kProdWarps + EW + 2) * 32, 1) conv_tcgen05_ke
   }
 }
 
-// 16 epilogue warps (832 threads, 72 registers, spills) measured SLOWER than 8 on every 1-tap / 4-tap conv (e.g. to_qkv 0.180 ->
-// 0.215 ms): kept as a template option, not used
-static int epi_warps(const Params& p) { (void)p; return 8; }
 static size_t smem_fixed_bytes(const Params& p) {
-  const int kEpiWarps = epi_warps(p), parts = kEpiWarps / 4;
-  const int ncol = (p.NT / parts) >= 32 ? (p.NT / parts) : 32;
+  const int ncol = p.NT >= 64 ? p.NT / 2 : p.NT;
   return (size_t)kABuf * 4 * p.PA * 16 + (2 * kStagesMax + 2 * kABuf + 4) * 8 + 16 + (size_t)kNimgMax * kGroupsMax * 8 +
          2 * (size_t)p.P * 4 + 128 + (size_t)kEpiWarps * (32 * ncol * 2 + ncol * 4) + 128;
 }
@@ -956,15 +948,15 @@ static int launch(Params p, cudaStream_t st) {
   }
   static bool attr_set = false;
   if (!attr_set) {
-    DMN_CUDA_CHECK(cudaFuncSetAttribute(conv_tcgen05_kernel<GEO, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemLimit));
-    DMN_CUDA_CHECK(cudaFuncSetAttribute(conv_tcgen05_kernel<GEO, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemLimit));
+    DMN_CUDA_CHECK(cudaFuncSetAttribute(conv_tcgen05_kernel<GEO, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemLimit));
+    DMN_CUDA_CHECK(cudaFuncSetAttribute(conv_tcgen05_kernel<GEO, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemLimit));
+    DMN_CUDA_CHECK(cudaFuncSetAttribute(conv_tcgen05_kernel<GEO, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemLimit));
     attr_set = true;
   }
   const int grid = p.total_tiles < num_sms() ? p.total_tiles : num_sms();
-  if (epi_warps(p) == 8)
-    DMN_CUDA_CHECK(launch_pdl(conv_tcgen05_kernel<GEO, 8>, dim3(grid), dim3((kProdWarps + 8 + 2) * 32), smem_bytes(p), st, p));
-  else
-    DMN_CUDA_CHECK(launch_pdl(conv_tcgen05_kernel<GEO, 16>, dim3(grid), dim3((kProdWarps + 16 + 2) * 32), smem_bytes(p), st, p));
+  if (p.NT == 128) DMN_CUDA_CHECK(launch_pdl(conv_tcgen05_kernel<GEO, 128>, dim3(grid), dim3(kThreads), smem_bytes(p), st, p));
+  else if (p.NT == 64) DMN_CUDA_CHECK(launch_pdl(conv_tcgen05_kernel<GEO, 64>, dim3(grid), dim3(kThreads), smem_bytes(p), st, p));
+  else DMN_CUDA_CHECK(launch_pdl(conv_tcgen05_kernel<GEO, 32>, dim3(grid), dim3(kThreads), smem_bytes(p), st, p));
   count_launch();
   DMN_LAUNCH_CHECK("conv_tcgen05");
   return 0;
