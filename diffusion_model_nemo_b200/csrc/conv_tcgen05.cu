@@ -272,7 +272,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tcgen05_kernel(const Params 
   int* s_pix = reinterpret_cast<int*>(s_gn + kNimgMax * kGroupsMax);                        // [P] operand source or -1
   int* s_pimg = s_pix + p.P;                                                                // [P] image - img_lo
   // epilogue, private per warp: bf16 output staging [32 rows][ncol] (16-byte chunks XOR-swizzled) + bias [ncol]
-  uint8_t* s_stage = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(s_pimg + p.P) + 127) & ~(uintptr_t)127);
+  // prologue coefficients per input channel, staged once per CTA: gamma | beta | time embedding (shared-row mode)
+  float* s_coef = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(s_pimg + p.P) + 15) & ~(uintptr_t)15);
+  const int ncoef = (p.c.pro != PRO_NONE) ? p.c.C1 : 0;
+  uint8_t* s_stage = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(s_coef + 3 * ncoef) + 127) & ~(uintptr_t)127);
 
   // ---- one-time setup ----
   if (warp == kLoaderWarp) {          // one lane per barrier
@@ -302,6 +305,14 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tcgen05_kernel(const Params 
     const float* temb_base = nullptr;
     if (GEO == GEO_SAME && (p.c.pro & PRO_TEMB)) temb_base = p.c.temb + (p.c.d_row ? (long)(*p.c.d_row) * p.c.temb_rstride : 0);
     const bool has_pro = GEO == GEO_SAME && p.c.pro != PRO_NONE;
+    const bool temb_shared = (p.c.pro & PRO_TEMB) && p.c.temb_bstride == 0;
+    if (has_pro) {                      // visible to all producers after the first tile's table barrier
+      for (int i = tid; i < ncoef; i += kProdThreads) {
+        s_coef[i] = p.c.pgamma[i];
+        s_coef[ncoef + i] = p.c.pbeta[i];
+        s_coef[2 * ncoef + i] = temb_shared ? temb_base[i] : 0.f;
+      }
+    }
     const uint32_t sA_u = smem_u32(sA);
     int ibuf = 0, fbuf = 0;
     uint32_t iph = 1;                                  // parity of the "buffer is free" wait; flips when the ring wraps
@@ -390,16 +401,11 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tcgen05_kernel(const Params 
           const int cb = c * kCk + kc * 8;
           float ga[8], be[8], te[8];
           {
-            const float4 g0 = *reinterpret_cast<const float4*>(p.c.pgamma + cb), g1 = *reinterpret_cast<const float4*>(p.c.pgamma + cb + 4);
-            const float4 b0 = *reinterpret_cast<const float4*>(p.c.pbeta + cb), b1 = *reinterpret_cast<const float4*>(p.c.pbeta + cb + 4);
+            const float4 g0 = *reinterpret_cast<const float4*>(s_coef + cb), g1 = *reinterpret_cast<const float4*>(s_coef + cb + 4);
+            const float4 b0 = *reinterpret_cast<const float4*>(s_coef + ncoef + cb), b1 = *reinterpret_cast<const float4*>(s_coef + ncoef + cb + 4);
+            const float4 t0 = *reinterpret_cast<const float4*>(s_coef + 2 * ncoef + cb), t1 = *reinterpret_cast<const float4*>(s_coef + 2 * ncoef + cb + 4);
             ga[0] = g0.x; ga[1] = g0.y; ga[2] = g0.z; ga[3] = g0.w; ga[4] = g1.x; ga[5] = g1.y; ga[6] = g1.z; ga[7] = g1.w;
             be[0] = b0.x; be[1] = b0.y; be[2] = b0.z; be[3] = b0.w; be[4] = b1.x; be[5] = b1.y; be[6] = b1.z; be[7] = b1.w;
-          }
-          const bool temb_shared = (p.c.pro & PRO_TEMB) && p.c.temb_bstride == 0;
-#pragma unroll
-          for (int e = 0; e < 8; ++e) te[e] = 0.f;
-          if (temb_shared) {
-            const float4 t0 = *reinterpret_cast<const float4*>(temb_base + cb), t1 = *reinterpret_cast<const float4*>(temb_base + cb + 4);
             te[0] = t0.x; te[1] = t0.y; te[2] = t0.z; te[3] = t0.w; te[4] = t1.x; te[5] = t1.y; te[6] = t1.z; te[7] = t1.w;
           }
           const int g = cb >> p.cpg_in_shift;
@@ -801,7 +807,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tcgen05_kernel(const Params 
 static size_t smem_fixed_bytes(const Params& p) {
   const int ncol = p.NT >= 64 ? p.NT / 2 : p.NT;
   return (size_t)kABuf * 4 * p.PA * 16 + (2 * kStagesMax + 2 * kABuf + 4) * 8 + 16 + (size_t)kNimgMax * kGroupsMax * 8 +
-         2 * (size_t)p.P * 4 + 128 + (size_t)kEpiWarps * (32 * ncol * 2 + ncol * 4) + 128;
+         2 * (size_t)p.P * 4 + 128 + (p.c.pro != PRO_NONE ? 3 * (size_t)p.c.C1 * 4 + 16 : 0) + (size_t)kEpiWarps * (32 * ncol * 2 + ncol * 4) + 128;
 }
 static size_t smem_bytes(const Params& p) { return smem_fixed_bytes(p) + (size_t)p.nstage * p.stage_bytes; }
 constexpr size_t kSmemLimit = 216 * 1024;
