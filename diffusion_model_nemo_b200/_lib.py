@@ -34,7 +34,7 @@ class LoopDesc(C.Structure):
         ("snr", C.c_float), ("denoise", C.c_int32), ("use_graph", C.c_int32), ("corr_kind", C.c_int32),
         ("coef_dev", C.c_void_p), ("coef2_dev", C.c_void_p), ("classes_dev", C.c_void_p), ("noise_dev", C.c_void_p),
         ("rng", Rng), ("state_dev", C.c_void_p), ("aux_dev", C.c_void_p), ("scratch_dev", C.c_void_p),
-        ("scratch_bytes", C.c_size_t), ("traj_dev", C.c_void_p), ("traj_every", C.c_int32), ("reserved2", C.c_int32),
+        ("scratch_bytes", C.c_size_t), ("traj_dev", C.c_void_p), ("traj_every", C.c_int32), ("cfg_scale", C.c_float),
     ]
 
 

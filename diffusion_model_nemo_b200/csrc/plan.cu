@@ -53,6 +53,8 @@ int launch_learned(const float* x, const float* mo, const float* z, float* out, 
 int launch_ddim(const float* x, const float* eps, const float* z, float* out, long n, const float* coef, const int32_t* step_dev,
                 int step, dmn_rng rng, const dmn_rng* rng_dev, cudaStream_t st);
 int launch_traj(const float* x, float* traj, long n, const int32_t* step_dev, int every, int n_steps, cudaStream_t st);
+int launch_cfg_dup(const float* x, float* x2, long n, cudaStream_t st);
+int launch_cfg_combine(const float* mo2, float* mo, long n, float w, cudaStream_t st);
 int launch_langevin(const float* x, const float* mo, const float* z, float* out, float* mean_out, int batch, long chw,
                     float snr, const float* coef, const int32_t* step_dev, int step, int draw, float* scratch, dmn_rng rng,
                     const dmn_rng* rng_dev, cudaStream_t st);
@@ -823,7 +825,16 @@ static int enqueue_step(dmn_plan* p, const dmn_loop_desc* d, int32_t* ctr_dev, b
     if ((rc = launch_affine_noise(d->state_dev, mo, zp, d->state_dev, xmean, n, d->coef_dev, step_dev, s, 7, d->rng, rng_dev, st)))
       return rc;
   } else {
-    if ((rc = run_forward(p, d->state_dev, ctr_dev, d->classes_dev, mo, d->batch, st))) return rc;
+    if (d->cfg_scale != 0.f) {
+      // classifier-free guidance: one U-Net evaluation on the doubled batch [x ; x] (labels ; null class), then the mix
+      float* x2 = lscr + ((2 * d->batch + 16 + 3) & ~3);
+      float* mo2 = x2 + 2 * n;
+      if ((rc = launch_cfg_dup(d->state_dev, x2, n, st))) return rc;
+      if ((rc = run_forward(p, x2, ctr_dev, d->classes_dev, mo2, 2 * d->batch, st))) return rc;
+      if ((rc = launch_cfg_combine(mo2, mo, n_out, d->cfg_scale, st))) return rc;
+    } else if ((rc = run_forward(p, d->state_dev, ctr_dev, d->classes_dev, mo, d->batch, st))) {
+      return rc;
+    }
     if (d->kind == DMN_LOOP_DDPM)
       rc = launch_ddpm(d->state_dev, mo, z0, d->state_dev, n, d->coef_dev, step_dev, s, d->rng, rng_dev, st);
     else if (d->kind == DMN_LOOP_LEARNED)
@@ -842,7 +853,8 @@ static bool same_graph_key(const dmn_loop_desc& a, const dmn_loop_desc& b) {
   const bool traj = a.traj_dev || b.traj_dev;   // only the trajectory kernel bakes n_steps in
   return a.kind == b.kind && (!traj || a.n_steps == b.n_steps) && a.batch == b.batch && a.n_corr == b.n_corr && a.snr == b.snr &&
          a.corr_kind == b.corr_kind && a.coef_dev == b.coef_dev && a.coef2_dev == b.coef2_dev && a.classes_dev == b.classes_dev &&
-         a.state_dev == b.state_dev && a.scratch_dev == b.scratch_dev && a.traj_dev == b.traj_dev && a.traj_every == b.traj_every;
+         a.state_dev == b.state_dev && a.scratch_dev == b.scratch_dev && a.traj_dev == b.traj_dev && a.traj_every == b.traj_every &&
+         a.cfg_scale == b.cfg_scale;
 }
 
 extern "C" {
@@ -864,6 +876,13 @@ int dmn_sample_loop(dmn_plan* p, const dmn_loop_desc* d, void* stream) {
   const long n = (long)d->batch * chw;
   const long n_out = (long)d->batch * c.out_dim * c.image_size * c.image_size;
   DMN_REQUIRE(d->scratch_bytes >= (size_t)(n_out + n + 2 * d->batch + 16) * sizeof(float), "loop scratch too small");
+  if (d->cfg_scale != 0.f) {
+    DMN_REQUIRE(d->kind != DMN_LOOP_PC, "classifier-free guidance is built for the DDPM / learned / DDIM loops");
+    DMN_REQUIRE(c.num_classes >= 0 && d->classes_dev, "classifier-free guidance needs a class-conditional U-Net and 2*batch labels");
+    DMN_REQUIRE(2 * d->batch <= c.max_batch, "classifier-free guidance doubles the batch: plan max_batch too small");
+    DMN_REQUIRE(d->scratch_bytes >= (size_t)(3 * n_out + 3 * n + 2 * d->batch + 36) * sizeof(float), "loop scratch too small for guidance");
+    DMN_REQUIRE(n % 4 == 0 && n_out % 4 == 0, "guidance kernels need 16-byte multiples");
+  }
   cudaStream_t st = (cudaStream_t)stream;
   int32_t* ctr = (int32_t*)(p->wsbase + p->counters.off);
   float* xmean = d->scratch_dev + n_out;
@@ -923,7 +942,7 @@ int dmn_loop_launches_per_step(const dmn_plan* p, const dmn_loop_desc* d) {
   const int per_fwd = (int)p->ops.size() - 1;   // kernels only: the statistics memset is not counted
   int n = 0;
   if (d->kind == DMN_LOOP_PC) n = (d->n_corr + 1) * per_fwd + d->n_corr * (d->corr_kind == 1 ? 1 : 3) + 1;
-  else n = per_fwd + 1;
+  else n = per_fwd + 1 + (d->cfg_scale != 0.f ? 2 : 0);
   if (d->traj_dev && d->traj_every > 0) n += 1;
   return n + 1;   // + advance_counter
 }

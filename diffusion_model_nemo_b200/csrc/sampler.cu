@@ -247,6 +247,23 @@ __global__ void __launch_bounds__(256) traj_kernel(const float* __restrict__ x, 
     dst[i] = reinterpret_cast<const float4*>(x)[i];
 }
 
+// classifier-free guidance helpers (doubled batch): x2 = [x ; x],  eps = eps_u + w (eps_c - eps_u) with mo2 = [eps_c ; eps_u]
+__global__ void __launch_bounds__(256) cfg_dup_kernel(const float* __restrict__ x, float* __restrict__ x2, long n4) {
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long)gridDim.x * blockDim.x) {
+    const float4 v = reinterpret_cast<const float4*>(x)[i];
+    reinterpret_cast<float4*>(x2)[i] = v;
+    reinterpret_cast<float4*>(x2)[n4 + i] = v;
+  }
+}
+__global__ void __launch_bounds__(256) cfg_combine_kernel(const float* __restrict__ mo2, float* __restrict__ mo, long n4, float w) {
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long)gridDim.x * blockDim.x) {
+    const float4 c = reinterpret_cast<const float4*>(mo2)[i], u = reinterpret_cast<const float4*>(mo2)[n4 + i];
+    float4 o;
+    o.x = u.x + w * (c.x - u.x); o.y = u.y + w * (c.y - u.y); o.z = u.z + w * (c.z - u.z); o.w = u.w + w * (c.w - u.w);
+    reinterpret_cast<float4*>(mo)[i] = o;
+  }
+}
+
 static inline unsigned grid_for(long n, int per_block = 256, int cap = 148 * 8) {
   long g = (n + per_block - 1) / per_block;
   if (g < 1) g = 1;
@@ -264,6 +281,18 @@ int launch_set_counter(int32_t* c, int v, dmn_rng rng, cudaStream_t st) {
   set_counter_kernel<<<1, 1, 0, st>>>(c, v, rng);
   count_launch();
   DMN_LAUNCH_CHECK("set_counter");
+  return 0;
+}
+int launch_cfg_dup(const float* x, float* x2, long n, cudaStream_t st) {
+  cfg_dup_kernel<<<grid_for(n / 4), 256, 0, st>>>(x, x2, n / 4);
+  count_launch();
+  DMN_LAUNCH_CHECK("cfg_dup");
+  return 0;
+}
+int launch_cfg_combine(const float* mo2, float* mo, long n, float w, cudaStream_t st) {
+  cfg_combine_kernel<<<grid_for(n / 4), 256, 0, st>>>(mo2, mo, n / 4, w);
+  count_launch();
+  DMN_LAUNCH_CHECK("cfg_combine");
   return 0;
 }
 int launch_traj(const float* x, float* traj, long n, const int32_t* step_dev, int every, int n_steps, cudaStream_t st) {

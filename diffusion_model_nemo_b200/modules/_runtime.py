@@ -64,7 +64,7 @@ def run_native_loop(unet: Unet, *, kind: int, shape: Sequence[int], device, time
                     noise: Optional[torch.Tensor] = None, classes: Optional[torch.Tensor] = None,
                     n_corr: int = 0, corr_kind: int = 0, snr: float = 0.0, denoise: bool = False,
                     seed: Optional[int] = None, traj_every: int = 0, use_graph: bool = True,
-                    init_scale: float = 1.0, n_steps: Optional[int] = None) -> LoopResult:
+                    init_scale: float = 1.0, n_steps: Optional[int] = None, cfg_scale: float = 0.0) -> LoopResult:
     """Run n_steps of (U-Net + update) natively.  noise: [1 + n_steps*draws, B, C, H, W] injected N(0,1) tensors in
     the reference's draw order (element 0 = x_T), or None for in-kernel Philox."""
     lib = L.lib()
@@ -74,7 +74,13 @@ def run_native_loop(unet: Unet, *, kind: int, shape: Sequence[int], device, time
     assert h == w, "square images only"
     n_steps = int(times.shape[0]) if n_steps is None else int(n_steps)
     assert 1 <= n_steps <= times.shape[0]
-    plan = unet.plan(h, b, device, time_rows=int(times.shape[0]))
+    guided = cfg_scale != 0.0
+    if guided:
+        if unet.num_classes is None or classes is None:
+            raise ValueError("classifier-free guidance needs a class-conditional Unet and `classes` labels")
+        if kind == L.LOOP_PC:
+            raise NotImplementedError("classifier-free guidance is built for the DDPM / learned-variance / DDIM loops")
+    plan = unet.plan(h, 2 * b if guided else b, device, time_rows=int(times.shape[0]))
     n = b * c * h * w
     draws = (n_corr + 1) if kind == L.LOOP_PC else 1
     with torch.cuda.device(device):
@@ -87,12 +93,12 @@ def run_native_loop(unet: Unet, *, kind: int, shape: Sequence[int], device, time
         # loop buffers live with the plan so their addresses (baked into the cached CUDA graph) stay stable
         n_out = b * unet.out_dim * h * w
         n_traj = (n_steps // traj_every) if traj_every > 0 else 0
-        bkey = (kind, b, n_steps if n_traj else 0, n_traj, bool(denoise))
+        bkey = (kind, b, n_steps if n_traj else 0, n_traj, bool(denoise), guided)
         bufs = plan.__dict__.setdefault("_loop_bufs", {})
         if bkey not in bufs:
             bufs[bkey] = {
                 "state": torch.empty((b, c, h, w), dtype=torch.float32, device=device),
-                "scratch": torch.empty(n_out + n + 2 * b + 64, dtype=torch.float32, device=device),
+                "scratch": torch.empty((3 if guided else 1) * (n_out + n) + 2 * b + 64, dtype=torch.float32, device=device),
                 "aux": torch.empty((b, c, h, w), dtype=torch.float32, device=device) if (kind == L.LOOP_PC and denoise) else None,
                 "traj": torch.empty((n_traj, b, c, h, w), dtype=torch.float32, device=device) if n_traj > 0 else None,
             }
@@ -114,7 +120,16 @@ def run_native_loop(unet: Unet, *, kind: int, shape: Sequence[int], device, time
             nz = noise[(0 if x_init is not None else 1):]
             noise_dev = nz.to(device, torch.float32).contiguous()
         if classes is not None:
-            classes = classes.to(device, torch.int64).contiguous()
+            classes = classes.to(device, torch.int64).reshape(-1)
+            if guided:     # doubled batch: [labels ; null class] (the padding row of class_embed, reference unet.py:118-120)
+                classes = torch.cat([classes, torch.full_like(classes, unet.num_classes)])
+            # persistent buffer: the cached CUDA graph bakes the pointer in
+            cb = bufs[bkey].get("classes")
+            if cb is None or cb.shape != classes.shape:
+                cb = torch.empty_like(classes)
+                bufs[bkey]["classes"] = cb
+            cb.copy_(classes)
+            classes = cb
         d = L.LoopDesc()
         d.kind, d.n_steps, d.batch, d.n_corr = kind, n_steps, b, n_corr
         d.snr, d.denoise, d.use_graph, d.corr_kind = float(snr), int(denoise), int(use_graph), corr_kind
@@ -129,6 +144,7 @@ def run_native_loop(unet: Unet, *, kind: int, shape: Sequence[int], device, time
         d.scratch_bytes = scratch.numel() * 4
         d.traj_dev = traj.data_ptr() if traj is not None else None
         d.traj_every = traj_every if traj is not None else 0
+        d.cfg_scale = float(cfg_scale)
         L.check(lib.dmn_sample_loop(plan.h, C.byref(d), st), "dmn_sample_loop")
         plan.last_loop_launches = lib.dmn_loop_launches_per_step(plan.h, C.byref(d)) * n_steps
         # keep every buffer alive until the stream has consumed it

@@ -30,6 +30,9 @@ class GaussianDiffusion(AbstractDiffusionProcess):
         self.trajectory_every = 0
         self.seed: Optional[int] = None
         self.use_cuda_graph = True
+        # classifier-free guidance weight w (extension, BASELINE config 5a; the reference only TRAINS with label dropout,
+        # models/conditional_ddpm.py:59-61): eps = eps_u + w (eps_c - eps_u) on a doubled batch per step.  None = off.
+        self.guidance_scale: Optional[float] = None
         self.compute_constants(timesteps)
 
     # ---- tables ------------------------------------------------------------------------------------
@@ -135,9 +138,12 @@ class GaussianDiffusion(AbstractDiffusionProcess):
             coef, times = self._loop_tables(ts, device)
             res = R.run_native_loop(unet, kind=self._loop_kind, shape=shape, device=device, times=times, coef=coef,
                                     x_init=img, noise=noise, classes=classes, seed=self.seed,
-                                    traj_every=self.trajectory_every, use_graph=self.use_cuda_graph)
+                                    traj_every=self.trajectory_every, use_graph=self.use_cuda_graph,
+                                    cfg_scale=float(self.guidance_scale) if (self.guidance_scale is not None and classes is not None) else 0.0)
             return R.to_image_list(res.final, res.traj)
         # foreign model: call it per step, fuse only the update
+        if self.guidance_scale is not None:
+            raise NotImplementedError("guidance_scale needs this package's class-conditional Unet (doubled-batch native loop)")
         b = shape[0]
         seed = self.seed if self.seed is not None else R.draw_seed()
         lib = L.lib()

@@ -186,7 +186,11 @@ typedef struct dmn_loop_desc {
   size_t         scratch_bytes;
   float*         traj_dev;       /* optional [n_traj][batch*C*H*W] trajectory capture, every traj_every steps */
   int32_t        traj_every;
-  int32_t        reserved2;
+  float          cfg_scale;      /* != 0: classifier-free guidance (not in the reference: SURVEY.md section 8 config 5a).  Every step
+                                    evaluates the U-Net on the doubled batch [x ; x] with classes_dev[0..batch) = labels and
+                                    classes_dev[batch..2*batch) = num_classes (the null / padding row, unet.py:118-120) and uses
+                                    eps = eps_u + cfg_scale * (eps_c - eps_u).  Needs max_batch >= 2*batch and scratch for
+                                    3*out_dim*S*S*batch + 3*C*S*S*batch + 2*batch + 16 floats.  DDPM / learned / DDIM loops only. */
 } dmn_loop_desc;
 
 /* Runs the whole loop on `stream`; returns after enqueueing (no host sync unless use_graph needs capture,

@@ -138,3 +138,38 @@ def test_interpolate_runs_from_a_given_state(golden):
         t = torch.full((2,), i, dtype=torch.long)
         img = O.ddpm_step(tb, img, t, O.unet_forward(sd, cfg, img, t.float()), nz[2 + k])
     assert (imgs[-1] - (img + 1) * 0.5).abs().max() <= 2e-4
+
+
+def test_classifier_free_guidance_doubled_batch():
+    """BASELINE config 5a: eps = eps_u + w (eps_c - eps_u) with eps_c / eps_u from ONE U-Net evaluation on the doubled batch.
+    The reference has no guidance at sampling time, so the oracle composes two reference U-Net calls
+    (label k and the null class = num_classes)."""
+    cfg, size, b = CFGS["tiny_cls"]
+    sd = O.random_state_dict(cfg, seed=0)
+    u = make_unet(cfg, sd, dtype="fp32", engine="simt", device=DEV)
+    shape = [b, 3, size, size]
+    labels = torch.tensor([3, 7])
+    w = 2.5
+
+    def guided(x, t):
+        ec = O.unet_forward(sd, cfg, x, t.float(), labels)
+        eu = O.unet_forward(sd, cfg, x, t.float(), torch.full_like(labels, cfg["num_classes"]))
+        return eu + w * (ec - eu)
+
+    ref_final, _ = O.sample_ddpm(guided, shape, O.ddpm_tables(20, "linear"), O.NoiseQueue(5))
+    s = M.GaussianDiffusion(20, "linear", class_conditional=True)
+    s.guidance_scale = w
+    imgs = s.sample(functools.partial(u.forward, classes=labels.to(DEV)), shape, device=DEV, noise=_noise(21, shape))
+    assert (imgs[-1] - (ref_final + 1) * 0.5).abs().max() <= 2e-4
+    # w = 1 reduces to the plain conditional sampler
+    s.guidance_scale = 1.0
+    a = s.sample(functools.partial(u.forward, classes=labels.to(DEV)), shape, device=DEV, noise=_noise(21, shape))[-1]
+    s.guidance_scale = None
+    c = s.sample(functools.partial(u.forward, classes=labels.to(DEV)), shape, device=DEV, noise=_noise(21, shape))[-1]
+    assert (a - c).abs().max() <= 1e-5
+    # throughput mode (graph replay, in-kernel noise) on the tensor-core engine
+    ub = make_unet(cfg, sd, dtype="bf16", engine="tcgen05", device=DEV)
+    s.guidance_scale = w
+    s.seed = 3
+    out = s.sample(functools.partial(ub.forward, classes=labels.to(DEV)), shape, device=DEV)[-1]
+    assert torch.isfinite(out).all()
