@@ -207,7 +207,10 @@ def main():
         torch.cuda.synchronize(dev)
         return e0.elapsed_time(e1), res
 
-    timed(args.warmup)                       # builds the plan, uploads weights, captures the graph, warms clocks
+    _, res_w = timed(args.warmup)            # builds the plan, uploads weights, captures the graph, warms clocks
+    if ws > 1:
+        D.all_gather_samples(res_w.final, total=B * ws)   # warm-up: creates the NCCL communicator outside the timed region
+        torch.cuda.synchronize(dev)
     plan = unet.plan(IMAGE, B, dev)
     clk = ClockSampler(local)
     clk.start()

@@ -15,6 +15,7 @@ from .diffusion_process import (
 from .gaussian_diffusion import GaussianDiffusion
 from .learned_gaussian_diffusion import LearnedGaussianDiffusion
 from .generalized_gaussian_diffusion import GeneralizedGaussianDiffusion
+from .wavegrad_diffusion import WaveGradDiffusion
 from .sde import (
     SDE,
     VPSDE,

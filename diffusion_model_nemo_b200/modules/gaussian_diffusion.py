@@ -125,6 +125,10 @@ class GaussianDiffusion(AbstractDiffusionProcess):
         ti = self._uniform_t(t)
         return self._fused_step(x, model(x, t), torch.tensor([ti], dtype=torch.long), noise=noise)
 
+    def _model_arg(self, ti: int, b: int, device):
+        """Second argument of the denoiser for visited timestep ti (WaveGrad overrides it with the continuous noise level)."""
+        return torch.full((b,), ti, device=device, dtype=torch.long)
+
     def _visit_order(self, start: Optional[int] = None):
         return torch.arange((self.timesteps if start is None else start) - 1, -1, -1, dtype=torch.long)
 
@@ -162,7 +166,7 @@ class GaussianDiffusion(AbstractDiffusionProcess):
                 L.check(lib.dmn_randn(L.ptr(x), x.numel(), rng, -1, st), "dmn_randn")
             keep = []
             for s, ti in enumerate(ts.tolist()):
-                mo = model(x, torch.full((b,), ti, device=device, dtype=torch.long)).float().contiguous()
+                mo = model(x, self._model_arg(ti, b, device)).float().contiguous()
                 z = None if noise is None else noise[k + s].to(device, torch.float32).contiguous()
                 self._launch_step(lib, x, mo, z, x, coef, s, rng, st)
                 if self.trajectory_every and (s + 1) % self.trajectory_every == 0:

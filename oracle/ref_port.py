@@ -301,6 +301,41 @@ def ddim_step(aext, x, t, t_next, eps, z, eta):
     return an.sqrt() * x0 + c1 * z + c2 * eps
 
 
+
+def wavegrad_step(tb, wg, x, t, eps, z, objective="pred_noise"):
+    """WaveGradDiffusion.p_mean_variance + the inherited p_sample, modules/wavegrad_diffusion.py:150-189 and
+    modules/gaussian_diffusion.py:157-167: x0 uses sqrt_alphas_cumprod_m1 = sqrt(1 - acp) * sqrt(1 / acp)."""
+    if objective == "pred_noise":
+        x0 = _ext(tb["sqrt_recip_alphas_cumprod"], t) * x - _ext(wg["sqrt_alphas_cumprod_m1"], t) * eps
+    else:
+        x0 = eps.clone()
+    x0.clamp_(-1.0, 1.0)
+    mean = _ext(tb["posterior_mean_coef1"], t) * x0 + _ext(tb["posterior_mean_coef2"], t) * x
+    logvar = _ext(tb["posterior_log_variance_clipped"], t)
+    mask = (1 - (t == 0).float()).reshape(x.size(0), 1, 1, 1)
+    return mean + mask * torch.exp(0.5 * logvar) * z
+
+
+def sample_wavegrad(model, shape, tb, draw):
+    """The p_sample_loop WaveGradDiffusion inherits (gaussian_diffusion.py:171-189) with its own p_mean_variance: the model is
+    called with the continuous noise level sqrt_alphas_cumprod_prev[t + 1] as a [B,1,1,1] tensor (wavegrad_diffusion.py:169-172)."""
+    wg = wavegrad_tables(tb)
+    T = tb["betas"].shape[0]
+    b = shape[0]
+    img = draw(shape)
+    for i in reversed(range(T)):
+        t = torch.full((b,), i, dtype=torch.long)
+        level = _ext(wg["sqrt_alphas_cumprod_prev"], t + 1)
+        img = wavegrad_step(tb, wg, img, t, model(img, level), draw(shape))
+    return img
+
+
+def wavegrad_toy_model(x, level):
+    """Deterministic stand-in denoiser (x, noise_level[B,1,1,1]) -> eps used by the WaveGrad sampler fixtures: the FiLM U-Net
+    (WaveGradUNet) is outside the built path, the SAMPLER is checked against the executed reference with this callable."""
+    return torch.tanh(0.7 * x) * level + 0.05 * x.flip(-1)
+
+
 def sample_ddpm(model, shape, tb, draw, kind="ddpm", keep_every=0):
     """GaussianDiffusion.p_sample_loop, modules/gaussian_diffusion.py:171-189.
 

@@ -173,3 +173,17 @@ def test_classifier_free_guidance_doubled_batch():
     s.seed = 3
     out = s.sample(functools.partial(ub.forward, classes=labels.to(DEV)), shape, device=DEV)[-1]
     assert torch.isfinite(out).all()
+
+
+def test_wavegrad_sampler_vs_reference_golden(golden):
+    """WaveGradDiffusion (reference modules/wavegrad_diffusion.py): continuous noise level fed to the denoiser, fused update kernel
+    with the sqrt_alphas_cumprod_m1 coefficient; against the fixture written by executing the reference (same injected noise)."""
+    shape = [2, 3, 16, 16]
+    for sched, T in (("linear", 20), ("cosine", 50)):
+        s = M.WaveGradDiffusion(T, sched)
+        imgs = s.sample(O.wavegrad_toy_model, shape, device=DEV, noise=_noise(T + 1, shape))
+        ref = torch.from_numpy(golden["wavegrad"][f"wavegrad/{sched}/{T}/final01"])
+        assert (imgs[-1] - ref).abs().max() <= 2e-4
+    u, cfg, size, b = _unet("tiny")
+    with pytest.raises(NotImplementedError):
+        M.WaveGradDiffusion(20, "linear").sample(u, [b, 1, size, size], device=DEV)

@@ -232,3 +232,22 @@ def test_reference_helper_api_on_cpu():
     m, v, lv = s.q_mean_variance(x0, t)
     assert torch.equal(lv, O._ext(tb["log_one_minus_alphas_cumprod"], t))
     assert s.extract(s.betas, t, x0.shape).shape == (4, 1, 1, 1)
+
+
+def test_wavegrad_tables_and_api(golden):
+    """WaveGradDiffusion drop-in: extra tables bit-exact vs the executed reference, coefficient column swapped, native Unet refused."""
+    import diffusion_model_nemo_b200.modules as M
+
+    s = M.WaveGradDiffusion(1000, "linear")
+    g = golden["tables"]
+    for k in ("sqrt_alphas_cumprod_prev", "sqrt_alphas_cumprod_m1"):
+        assert torch.equal(getattr(s, k), torch.from_numpy(g[f"wavegrad/linear/1000/{k}"])), k
+    ts = torch.tensor([999, 3, 0])
+    rows = s._step_rows(ts)
+    assert torch.equal(rows[1], s.sqrt_alphas_cumprod_m1[ts]) and torch.equal(rows[0], s.sqrt_recip_alphas_cumprod[ts])
+    lv = s._model_arg(5, 4, "cpu")
+    assert lv.shape == (4, 1, 1, 1) and float(lv[0]) == float(s.sqrt_alphas_cumprod_prev[6])
+    x0 = torch.randn(2, 3, 8, 8)
+    noise = torch.randn_like(x0)
+    lvl = torch.full((2, 1, 1, 1), 0.8)
+    assert torch.allclose(s.q_sample(x0, lvl, noise), 0.8 * x0 + (1 - 0.64) ** 0.5 * noise, atol=1e-5)

@@ -121,3 +121,13 @@ def test_teacher_forced_step_fixture(golden):
     assert (eps - ref).abs().max() <= 2e-5 * ref.abs().max()
     xn = O.ddpm_step(tb, x, t, eps, O.NoiseQueue(9)(x.shape))
     assert (xn - torch.from_numpy(golden["step"][f"cfg2/t{ti}/x_next"])).abs().max() < 2e-5
+
+
+def test_wavegrad_sampler_oracle_vs_executed_reference(golden):
+    """WaveGradDiffusion (reference modules/wavegrad_diffusion.py) with the stand-in denoiser: the oracle loop reproduces the
+    fixture written by executing the reference (tests/golden/make_golden_wavegrad.py)."""
+    shape = [2, 3, 16, 16]
+    for sched, T in (("linear", 20), ("cosine", 50)):
+        mine = O.sample_wavegrad(O.wavegrad_toy_model, shape, O.ddpm_tables(T, sched), O.NoiseQueue(5))
+        ref01 = torch.from_numpy(golden["wavegrad"][f"wavegrad/{sched}/{T}/final01"])
+        assert ((mine + 1) * 0.5 - ref01).abs().max() <= 2e-5
