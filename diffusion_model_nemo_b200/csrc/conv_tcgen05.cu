@@ -68,6 +68,7 @@ struct Params {
   int S, Wv, pad, halo_lo, P, PA, mt, mcta;
   int H, W, HW;            // input image
   int ksize, ntap, NT, n_pass, tiles_per_phase, n_tiles_n, m_tiles, total_tiles;
+  int n_big_tiles, big_rows, halo_hi;   // tiles [0, n_big_tiles) have 256 rows, the rest 128 rows starting at flat position big_rows
   long total_flat;
   uint32_t lbo_a, sbo_a, lbo_b, sbo_b;   // bytes
   uint32_t tmem_cols;
@@ -112,6 +113,25 @@ __device__ __forceinline__ VPos vdecode(int f, const Params& p) {
   r.row = (int)row;
   r.col = (int)(rem - row * uW);
   return r;
+}
+// tile index -> (first flat position, 128-row accumulators, N tile).  Mixed tiling: whole rounds of 256-row tiles, then the
+// remainder of the flat range in 128-row tiles so that the last round costs half (wave quantisation of one CTA per SM).
+struct TileGeom {
+  int m0, mt, n_tile;
+};
+__device__ __forceinline__ TileGeom tile_geom(int tile, const Params& p) {
+  TileGeom g;
+  if (tile < p.n_big_tiles) {
+    g.m0 = (tile / p.n_tiles_n) * 256;
+    g.mt = 2;
+    g.n_tile = tile % p.n_tiles_n;
+  } else {
+    const int k = tile - p.n_big_tiles;
+    g.m0 = p.big_rows + (k / p.n_tiles_n) * 128;
+    g.mt = 1;
+    g.n_tile = k % p.n_tiles_n;
+  }
+  return g;
 }
 // decode f = base_flat + n (0 <= n < 2^12 - ish) given the decoded base (img0, rem0 = base_flat - img0 * S): two multiply-shift
 // divisions, exact for n + rem0 < 8192 and S <= 8192 (n * S < 2^26) and rem < S, Wv <= 128 (rem * Wv < 2^24)
@@ -319,7 +339,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tcgen05_kernel(const Params 
     int pit = 0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++pit) {
       if (tid == 0) TRACE(pit, 0);
-      const int m0 = (tile / p.n_tiles_n) * p.mcta;
+      const TileGeom tg = tile_geom(tile, p);
+      const int m0 = tg.m0;
+      const int Pt = tg.mt * 128 + p.halo_lo + p.halo_hi;       // window of THIS tile
       int f_lo = m0 - p.halo_lo;
       if (f_lo < 0) f_lo = 0;
       const int img_lo = f_lo / p.S;
@@ -328,7 +350,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tcgen05_kernel(const Params 
         const float* x = (const float*)p.c.src1;
         const int Cin = p.c.C1;
         mbar_wait_relaxed(smem_u32(&empty_a[ibuf]), iph);
-        for (int pixel = px0; pixel < p.P; pixel += kProdThreads / 4) {
+        for (int pixel = px0; pixel < Pt; pixel += kProdThreads / 4) {
           const VPos v = vdecode(m0 - p.halo_lo + pixel, p);
           float f[8];
 #pragma unroll
@@ -355,7 +377,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tcgen05_kernel(const Params 
       bar_sync_named(2, kProdThreads);                 // everyone is done with the previous tile's tables
       const int pbase = m0 - p.halo_lo > 0 ? m0 - p.halo_lo : 0;            // uniform: decode base of the window
       const int pimg0 = pbase / p.S, prem0 = pbase - pimg0 * p.S;
-      for (int pixel = tid; pixel < p.P; pixel += kProdThreads) {
+      for (int pixel = tid; pixel < Pt; pixel += kProdThreads) {
         VPos v;
         v.img = -1; v.row = v.col = 0;
         if (m0 - p.halo_lo + pixel >= 0) v = vdecode_rel(pimg0, prem0, m0 - p.halo_lo + pixel - pbase, p);
@@ -389,7 +411,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tcgen05_kernel(const Params 
         const int pixel = px0 + (kProdThreads / 4) * j;
         goff[j] = -2;
         imgl[j] = 0;
-        if (pixel < p.P) {
+        if (pixel < Pt) {
           goff[j] = s_pix[pixel];
           imgl[j] = s_pimg[pixel];
         }
@@ -520,8 +542,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tcgen05_kernel(const Params 
     int last_ntile = -1;
     int it = 0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
-      const int n_tile = tile % p.n_tiles_n;
-      const int m0 = (tile / p.n_tiles_n) * p.mcta;
+      const TileGeom tg = tile_geom(tile, p);
+      const int n_tile = tg.n_tile, m0 = tg.m0, tmt = tg.mt;
       const int phase = (GEO == GEO_UP) ? n_tile / p.tiles_per_phase : 0;
       const int n0 = (GEO == GEO_UP ? n_tile % p.tiles_per_phase : n_tile) * NT;
       // ---- this thread's rows ----
@@ -531,7 +553,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tcgen05_kernel(const Params 
       for (int mt = 0; mt < kMTmax; ++mt) {
         opixv[mt] = -1;
         keyv[mt] = -1;
-        if (mt < p.mt) {
+        if (mt < tmt) {
           const VPos v = vdecode_rel(eimg0, erem0, mt * 128 + quarter * 32 + lane, p);
           bool valid = v.img >= 0;
           int opix = -1;
@@ -566,7 +588,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tcgen05_kernel(const Params 
       mbar_wait_relaxed(smem_u32(&acc_full[as]), (it >> 1) & 1);
       tc_fence_after();
       if (ew == 0 && lane == 0) TRACE(it, 9);
-      const uint32_t tacc = tmem_base + (uint32_t)(as * p.mt * NT);
+      const uint32_t tacc = tmem_base + (uint32_t)(as * 2 * NT);
       if (!active) {
         tc_fence_before();
         mbar_arrive(smem_u32(&acc_empty[as]));
@@ -583,7 +605,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tcgen05_kernel(const Params 
       float cs = 0.f, cq = 0.f;                               // current group accumulator (this row)
       int nslots = 0;
 #pragma unroll 1
-      for (int mt = 0; mt < p.mt; ++mt) {
+      for (int mt = 0; mt < tmt; ++mt) {
         const int opix = mt == 0 ? opixv[0] : opixv[kMTmax - 1];
         const int key = mt == 0 ? keyv[0] : keyv[kMTmax - 1];
         const bool valid = opix >= 0;
@@ -593,7 +615,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tcgen05_kernel(const Params 
           tmem_ld_wait();
           if (pc + 1 < PPM) {
             tmem_ld16_nowait(tlane + (uint32_t)(mt * NT + (pc + 1) * 16), rb[u ^ 1]);
-          } else if (mt + 1 < p.mt) {
+          } else if (mt + 1 < tmt) {
             tmem_ld16_nowait(tlane + (uint32_t)((mt + 1) * NT), rb[u ^ 1]);
           } else {
             tc_fence_before();                                // last TMEM read of this tile is complete: hand the accumulators back
@@ -705,7 +727,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tcgen05_kernel(const Params 
     uint32_t ph = 1;
     const int per_tile = p.n_pass * p.stages_per_pass;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-      const int n_tile = tile % p.n_tiles_n;
+      const int n_tile = tile_geom(tile, p).n_tile;
       const uint8_t* wsrc = (const uint8_t*)p.c.w + (size_t)n_tile * per_tile * b_bytes;
       for (int s = 0; s < per_tile; ++s) {
         mbar_wait_relaxed(smem_u32(&empty_b[st]), ph);
@@ -731,18 +753,19 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tcgen05_kernel(const Params 
     const uint32_t a_buf_units = a_bytes >> 4;
     const uint32_t a_k16 = 2u * (p.lbo_a >> 4);
     const uint32_t b_units0 = smem_u32(sB) >> 4, b_stage_units = b_bytes >> 4, b_tap_units = tap_bytes >> 4, b_k16 = 2u * (p.lbo_b >> 4);
-    const bool two = p.mt == 2;
     const int G = p.G;
     int st = 0, cbuf = 0, it = 0;
     uint32_t ph = 0, cph = 0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
-      const int n_tile = tile % p.n_tiles_n;
+      const TileGeom tg = tile_geom(tile, p);
+      const int n_tile = tg.n_tile;
+      const bool two = tg.mt == 2;
       const int phase = (GEO == GEO_UP) ? n_tile / p.tiles_per_phase : 0;
       const int as = it & 1;
       mbar_wait(smem_u32(&acc_empty[as]), ((it >> 1) & 1) ^ 1);      // epilogue has drained this accumulator set
       tc_fence_after();
       if (leader) TRACE(it, 4);
-      const uint32_t d0 = tmem_base + (uint32_t)(as * p.mt * NT), d1 = d0 + (uint32_t)NT;
+      const uint32_t d0 = tmem_base + (uint32_t)(as * 2 * NT), d1 = d0 + (uint32_t)NT;
       for (int c = 0; c < p.n_pass; ++c) {
         mbar_wait(smem_u32(&full_a[cbuf]), cph);
         tc_fence_after();
@@ -896,8 +919,34 @@ static bool fill_params(const ConvP& c, int geo, Params& p) {
     p.mt = tiles2 >= num_sms() ? 2 : 1;
     p.mcta = 128 * p.mt;
   }
-  p.m_tiles = (int)((p.total_flat + p.mcta - 1) / p.mcta);
-  p.total_tiles = p.m_tiles * p.n_tiles_n;
+  p.halo_hi = halo_hi;
+  {
+    // mixed tiling: whole rounds of 256-row tiles, the remainder in 128-row tiles (the last round then costs half)
+    const long nsm = num_sms();
+    const long m2 = (p.total_flat + 255) / 256, t2 = m2 * p.n_tiles_n;
+    if (p.mt == 2) {
+      long big_m = m2;
+      if (t2 % nsm != 0) big_m = (t2 / nsm) * nsm / p.n_tiles_n;       // m-tiles inside the whole rounds
+      long rem = p.total_flat - big_m * 256;
+      long small_m = rem > 0 ? (rem + 127) / 128 : 0;
+      // a 128-row tile costs ~0.6 of a 256-row tile (it streams the same weights): mix only when the estimate is lower
+      const double cost_uniform = (double)((t2 + nsm - 1) / nsm);
+      const double cost_mixed = (double)(t2 / nsm) + 0.6 * (double)((small_m * p.n_tiles_n + nsm - 1) / nsm);
+      if (cost_mixed >= cost_uniform - 0.05) {
+        big_m = m2;
+        rem = 0;
+        small_m = 0;
+      }
+      p.n_big_tiles = (int)(big_m * p.n_tiles_n);
+      p.big_rows = (int)(big_m * 256);
+      p.total_tiles = p.n_big_tiles + (int)(small_m * p.n_tiles_n);
+    } else {
+      p.n_big_tiles = 0;
+      p.big_rows = 0;
+      p.total_tiles = (int)((p.total_flat + 127) / 128) * p.n_tiles_n;
+    }
+    p.m_tiles = p.total_tiles / p.n_tiles_n;
+  }
   p.P = p.mcta + p.halo_lo + halo_hi;
   p.PA = p.P;
   while (p.PA % 8 != 2) ++p.PA;
@@ -908,7 +957,7 @@ static bool fill_params(const ConvP& c, int geo, Params& p) {
   p.lbo_b = (uint32_t)p.NT * 16u;
   p.sbo_b = 128u;
   p.tmem_cols = 32;
-  while (p.tmem_cols < (uint32_t)(2 * p.mt * p.NT)) p.tmem_cols <<= 1;    // double-buffered accumulators, power of two
+  while (p.tmem_cols < (uint32_t)(2 * 2 * p.NT)) p.tmem_cols <<= 1;    // double-buffered pairs of accumulators, power of two
   p.cpg_in = 1;
   p.cpg_in_shift = p.cpg_out_shift = 0;
   p.inv_cnt_in = 0.f;
