@@ -534,7 +534,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tcgen05_kernel(const Params 
     const int sh = p.cpg_out_shift;
     const bool do_stats = p.c.ostats != nullptr;
     const bool has_bias = p.c.bias != nullptr;
-    const uint32_t my_stage = smem_u32(s_stage) + (uint32_t)(ew * (32 * ROWB + NCOL * 4));   // shared-space addresses
+    const bool has_fold = p.c.fold_s1 != nullptr;     // GroupNorm(1) of the input folded into an epilogue affine (to_qkv)
+    const uint32_t my_stage = smem_u32(s_stage) + (uint32_t)(ew * (32 * ROWB + NCOL * 8));   // shared-space addresses
     const uint32_t my_bias = my_stage + (uint32_t)(32 * ROWB);
     const int my_swz = (lane >> SWS) & SWM;
     const int lrow = lane / LPR, lcol = lane % LPR;   // this lane's (row within a store instruction, 16-byte chunk)
@@ -576,9 +577,16 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tcgen05_kernel(const Params 
         }
       }
       // bias of this warp's columns -> private shared memory (re-staged only when the N tile changes)
-      if (has_bias && active && n_tile != last_ntile) {
+      if ((has_bias || has_fold) && active && n_tile != last_ntile) {
         __syncwarp();
-        for (int i = lane; i < NCOL; i += 32) sts32f(my_bias + 4u * i, p.c.bias[n0 + col0 + i]);
+        if (has_fold) {
+          for (int i = lane; i < NCOL; i += 32) {
+            sts32f(my_bias + 4u * i, p.c.fold_s1[n0 + col0 + i]);
+            sts32f(my_bias + 4u * (NCOL + i), p.c.fold_s2[n0 + col0 + i]);
+          }
+        } else {
+          for (int i = lane; i < NCOL; i += 32) sts32f(my_bias + 4u * i, p.c.bias[n0 + col0 + i]);
+        }
         last_ntile = n_tile;
         __syncwarp();
       }
@@ -609,6 +617,13 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tcgen05_kernel(const Params 
         const int opix = mt == 0 ? opixv[0] : opixv[kMTmax - 1];
         const int key = mt == 0 ? keyv[0] : keyv[kMTmax - 1];
         const bool valid = opix >= 0;
+        unsigned long long fa2 = 0ull, fc2 = 0ull;            // fold: (rstd, rstd), (-mean*rstd, -mean*rstd) of this row's image
+        if (has_fold && valid) {
+          float mean, rstd;
+          gn_mean_rstd(p.c.pstats + (long)key * 2, p.inv_cnt_in, kGnEps, mean, rstd);
+          fa2 = pack2(rstd, rstd);
+          fc2 = pack2(-mean * rstd, -mean * rstd);
+        }
 #pragma unroll
         for (int pc = 0; pc < PPM; ++pc) {
           const int u = pc & 1;                               // static double-buffer index (PPM is even)
@@ -626,7 +641,15 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tcgen05_kernel(const Params 
           unsigned long long v2[8];
 #pragma unroll
           for (int j = 0; j < 8; ++j) v2[j] = pack2(__uint_as_float(r[2 * j]), __uint_as_float(r[2 * j + 1]));
-          if (has_bias) {
+          if (has_fold) {
+#pragma unroll
+            for (int q4 = 0; q4 < 4; ++q4) {
+              const uint4 s1 = lds128(my_bias + (uint32_t)(pc * 64 + q4 * 16));
+              const uint4 s2 = lds128(my_bias + (uint32_t)(NCOL * 4 + pc * 64 + q4 * 16));
+              v2[2 * q4] = fma2(v2[2 * q4], fa2, fma2(fc2, ((unsigned long long)s1.y << 32) | s1.x, ((unsigned long long)s2.y << 32) | s2.x));
+              v2[2 * q4 + 1] = fma2(v2[2 * q4 + 1], fa2, fma2(fc2, ((unsigned long long)s1.w << 32) | s1.z, ((unsigned long long)s2.w << 32) | s2.z));
+            }
+          } else if (has_bias) {
 #pragma unroll
             for (int q4 = 0; q4 < 4; ++q4) {
               const uint4 bq = lds128(my_bias + (uint32_t)(pc * 64 + q4 * 16));     // broadcast LDS.128
@@ -830,7 +853,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tcgen05_kernel(const Params 
 static size_t smem_fixed_bytes(const Params& p) {
   const int ncol = p.NT >= 64 ? p.NT / 2 : p.NT;
   return (size_t)kABuf * 4 * p.PA * 16 + (2 * kStagesMax + 2 * kABuf + 4) * 8 + 16 + (size_t)kNimgMax * kGroupsMax * 8 +
-         2 * (size_t)p.P * 4 + 128 + (p.c.pro != PRO_NONE ? 3 * (size_t)p.c.C1 * 4 + 16 : 0) + (size_t)kEpiWarps * (32 * ncol * 2 + ncol * 4) + 128;
+         2 * (size_t)p.P * 4 + 128 + (p.c.pro != PRO_NONE ? 3 * (size_t)p.c.C1 * 4 + 16 : 0) + (size_t)kEpiWarps * (32 * ncol * 2 + ncol * 8) + 128;
 }
 static size_t smem_bytes(const Params& p) { return smem_fixed_bytes(p) + (size_t)p.nstage * p.stage_bytes; }
 constexpr size_t kSmemLimit = 216 * 1024;
@@ -961,6 +984,10 @@ static bool fill_params(const ConvP& c, int geo, Params& p) {
   p.cpg_in = 1;
   p.cpg_in_shift = p.cpg_out_shift = 0;
   p.inv_cnt_in = 0.f;
+  if (c.fold_s1) {
+    if (geo != GEO_SAME || c.ksize != 1 || c.pro != PRO_NONE || !c.fold_s2 || !c.pstats || c.pgroups != 1 || c.C2 != 0) return false;
+    p.inv_cnt_in = 1.f / (float)(p.HW * c.C1);
+  }
   if (c.pro & PRO_GN) {
     if (geo != GEO_SAME || c.C2 != 0 || c.pgroups <= 0 || c.pgroups > kGroupsMax || c.C1 % c.pgroups) return false;
     p.cpg_in = c.C1 / c.pgroups;

@@ -35,6 +35,11 @@ struct ConvP {
   const float* temb = nullptr;     // effective row = temb + (d_row ? *d_row * temb_rstride : 0) + b * temb_bstride
   long temb_bstride = 0, temb_rstride = 0;
   const int* d_row = nullptr;
+  // GroupNorm(1) of the INPUT folded through a 1x1 conv (to_qkv): with W' = W * diag(gamma) packed as the weights,
+  //   out[n] = rstd_b * (W' x)[n] - mean_b * rstd_b * s1[n] + s2[n],  s1[n] = sum_c W'[n][c],  s2[n] = sum_c W[n][c] * beta[c]
+  // so the operand is loaded raw (no prologue) and the normalisation is an affine in the epilogue.  Uses pstats (pgroups == 1).
+  const float* fold_s1 = nullptr;
+  const float* fold_s2 = nullptr;
   // epilogue
   void* out = nullptr;             // raw conv output (+bias, +res)
   const void* res = nullptr;       // optional residual added to the output (same layout as out)

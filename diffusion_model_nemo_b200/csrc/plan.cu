@@ -81,6 +81,9 @@ struct Param {
   int mode = 0, ksize = 0, cin = 0, cout = 0;   // PK_CONV
   int col = 0;           // PK_BLOCK_MLP_*: column offset
   bool loaded = false;
+  bool keep_host = false;          // parameters of a folded to_qkv: host copy kept until all three (weight, gamma, beta) arrived
+  int fold_op = -1;                // op index of that conv
+  std::vector<float> host;
   int64_t numel() const {
     int64_t n = 1;
     for (auto s : shape) n *= s;
@@ -108,6 +111,10 @@ struct Op {
   int ogroups = 0;
   int temb_col = -1;
   bool tc = false;                  // tcgen05 engine for this conv
+  // to_qkv with the PreNorm GroupNorm(1) folded into weights + epilogue affine (ops.h: ConvP::fold_s1)
+  bool fold = false;
+  int fold_gamma = -1, fold_beta = -1;
+  size_t fold_off = 0;              // s1 | s2, 2 * Cout floats in the weight arena
   // finalize / final proj
   int groups = 0, gamma = -1, beta = -1, silu = 0, C = 0, HW = 0;
   Buf raw, stats;
@@ -284,7 +291,23 @@ struct Builder {
     const int hidden = 128;
     int nw = add_param(p + ".fn.norm.weight", {C}, PK_RAW);
     int nb = add_param(p + ".fn.norm.bias", {C}, PK_RAW);
-    conv(p + ".fn.fn.to_qkv", CONV_SAME, 1, x, C, Buf(), 0, 3 * hidden, H, qkv, false, 0, PRO_GN, 1, xstats, nw, nb);
+    if (P.engine == DMN_CONV_TCGEN05 && want_tc(CONV_SAME, 1, C, 0, 3 * hidden, H, 0, 0, 0)) {
+      // tensor-core engine: GroupNorm(1) folded through the 1x1 conv (raw operand load, affine in the epilogue)
+      const int ci = conv(p + ".fn.fn.to_qkv", CONV_SAME, 1, x, C, Buf(), 0, 3 * hidden, H, qkv, false, 0);
+      Op& o = P.ops[ci];
+      o.fold = true;
+      o.pstats = xstats;
+      o.pgroups = 1;
+      o.fold_gamma = nw;
+      o.fold_beta = nb;
+      o.fold_off = walloc((size_t)2 * 3 * hidden * sizeof(float));
+      for (int pi : {o.w, nw, nb}) {
+        P.params[pi].keep_host = true;
+        P.params[pi].fold_op = ci;
+      }
+    } else {
+      conv(p + ".fn.fn.to_qkv", CONV_SAME, 1, x, C, Buf(), 0, 3 * hidden, H, qkv, false, 0, PRO_GN, 1, xstats, nw, nb);
+    }
     Op a;
     a.kind = linear ? OP_LINATTN : OP_ATTN;
     a.name = p + ".core";
@@ -504,6 +527,12 @@ static int run_forward(dmn_plan* P, const float* x_dev, const int32_t* row_dev, 
           if (row_dev) { q.d_row = row_dev; q.temb_rstride = P->sumC; q.temb_bstride = 0; }
           else { q.d_row = nullptr; q.temb_rstride = 0; q.temb_bstride = P->sumC; }
         }
+        if (o.fold) {
+          q.pro = PRO_NONE;
+          q.pgroups = 1;
+          q.fold_s1 = (const float*)(P->wbase + o.fold_off);
+          q.fold_s2 = q.fold_s1 + o.Cout;
+        }
         q.out = B(o.out); q.res = B(o.res);
         q.ostats = (stat_t*)B(o.ostats); q.ogroups = o.ogroups;
         rc = o.tc ? conv_tcgen05(q, st) : conv_simt(q, P->act, st);
@@ -673,7 +702,7 @@ int dmn_plan_load_param(dmn_plan* p, const char* name, const float* host, int64_
         conv_simt_pack_weights(q.mode, q.ksize, q.cin, q.cout, host, tmp.data(), rb);
         DMN_CUDA_CHECK(cudaMemcpyAsync(p->wbase + q.off, tmp.data(), numel * sizeof(float), cudaMemcpyHostToDevice, st));
       }
-      if (q.has_tc) {
+      if (q.has_tc && q.fold_op < 0) {
         const size_t nb = conv_tcgen05_weight_bytes(q.mode, q.ksize, q.cin, q.cout);
         std::vector<char> img(nb);
         conv_tcgen05_pack_weights(q.mode, q.ksize, q.cin, q.cout, host, img.data());
@@ -685,6 +714,32 @@ int dmn_plan_load_param(dmn_plan* p, const char* name, const float* host, int64_
   }
   DMN_CUDA_CHECK(cudaStreamSynchronize(st));   // staging buffers are stack-scoped
   q.loaded = true;
+  if (q.keep_host) {
+    q.host.assign(host, host + numel);
+    // folded to_qkv: pack once weight, gamma and beta are all here (any arrival order; re-packed on every reload)
+    const Op& o = p->ops[q.fold_op];
+    const Param &pw = p->params[o.w], &pg = p->params[o.fold_gamma], &pb = p->params[o.fold_beta];
+    if (!pw.host.empty() && !pg.host.empty() && !pb.host.empty()) {
+      const int cin = pw.cin, cout = pw.cout;
+      std::vector<float> wf((size_t)cout * cin), s12((size_t)2 * cout);
+      for (int n = 0; n < cout; ++n) {
+        double s1 = 0.0, s2 = 0.0;
+        for (int c = 0; c < cin; ++c) {
+          const float wg = pw.host[(size_t)n * cin + c] * pg.host[c];
+          wf[(size_t)n * cin + c] = wg;
+          s1 += (double)__bfloat162float(__float2bfloat16_rn(wg));     // the value the tensor core multiplies with
+          s2 += (double)pw.host[(size_t)n * cin + c] * (double)pb.host[c];
+        }
+        s12[n] = (float)s1;
+        s12[cout + n] = (float)s2;
+      }
+      std::vector<char> img(conv_tcgen05_weight_bytes(pw.mode, pw.ksize, cin, cout));
+      conv_tcgen05_pack_weights(pw.mode, pw.ksize, cin, cout, wf.data(), img.data());
+      DMN_CUDA_CHECK(cudaMemcpyAsync(p->wbase + pw.off2, img.data(), img.size(), cudaMemcpyHostToDevice, st));
+      DMN_CUDA_CHECK(cudaMemcpyAsync(p->wbase + o.fold_off, s12.data(), s12.size() * sizeof(float), cudaMemcpyHostToDevice, st));
+      DMN_CUDA_CHECK(cudaStreamSynchronize(st));
+    }
+  }
   return 0;
 }
 
