@@ -20,7 +20,7 @@ class UnetCfg(C.Structure):
         ("dim", C.c_int32), ("n_mults", C.c_int32), ("dim_mults", C.c_int32 * 8), ("channels", C.c_int32),
         ("out_dim", C.c_int32), ("groups", C.c_int32), ("with_time_emb", C.c_int32), ("num_classes", C.c_int32),
         ("image_size", C.c_int32), ("max_batch", C.c_int32), ("act_dtype", C.c_int32), ("conv_engine", C.c_int32),
-        ("max_time_rows", C.c_int32), ("reserved", C.c_int32 * 3),
+        ("max_time_rows", C.c_int32), ("film", C.c_int32), ("reserved", C.c_int32 * 2),
     ]
 
 
@@ -65,6 +65,7 @@ SYMBOLS = {
     "dmn_plan_load_param": (_I, [_P, C.c_char_p, _P, _L, _P]),
     "dmn_plan_load_freqs": (_I, [_P, _P, _I, _P]),
     "dmn_plan_ready": (_I, [_P]),
+    "dmn_plan_film_layout": (_I, [_P, _P, _I]),
     "dmn_time_table": (_I, [_P, _P, _I, _I, _P]),
     "dmn_unet_forward": (_I, [_P, _P, _P, _P, _P, _I, _P]),
     "dmn_plan_launches_per_forward": (_I, [_P]),

@@ -266,7 +266,9 @@ __device__ __forceinline__ void issue_stage(const Params& p, bool leader, uint32
 // ---------------------------------------------------------------------------------------------------
 // NT (the N tile: 32 / 64 / 128 output channels) is a template parameter so that the epilogue's geometry (columns per warp, staging
 // swizzle, store pattern) folds to constants and its loops unroll
-template <int GEO, int NT>
+// FILM selects the FiLM signal prologue (LeakyReLU(0.2) + positional encoding, no GroupNorm; parts/film.py:22,58) at compile time so
+// that the GroupNorm + SiLU prologue of the ResnetBlocks keeps its code unchanged
+template <int GEO, int NT, bool FILM = false>
 __global__ void __launch_bounds__(kThreads, 1) conv_tcgen05_kernel(const Params p) {
   extern __shared__ __align__(128) uint8_t smem[];
   const int tid = threadIdx.x;
@@ -328,8 +330,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tcgen05_kernel(const Params 
     const bool temb_shared = (p.c.pro & PRO_TEMB) && p.c.temb_bstride == 0;
     if (has_pro) {                      // visible to all producers after the first tile's table barrier
       for (int i = tid; i < ncoef; i += kProdThreads) {
-        s_coef[i] = p.c.pgamma[i];
-        s_coef[ncoef + i] = p.c.pbeta[i];
+        s_coef[i] = FILM ? 1.f : p.c.pgamma[i];
+        s_coef[ncoef + i] = FILM ? 0.f : p.c.pbeta[i];
         s_coef[2 * ncoef + i] = temb_shared ? temb_base[i] : 0.f;
       }
     }
@@ -436,7 +438,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tcgen05_kernel(const Params 
           for (int j = 0; j < kMaxItems; ++j) {
             if (goff[j] < 0) continue;                 // padding stays zero AFTER the transform
             uint4* slot = reinterpret_cast<uint4*>(base + (px0 + (kProdThreads / 4) * j) * 16);
-            const float2 mr = s_gn[imgl[j] * kGroupsMax + g];
+            const float2 mr = FILM ? make_float2(0.f, 1.f) : s_gn[imgl[j] * kGroupsMax + g];
             if ((p.c.pro & PRO_TEMB) && !temb_shared) {
               const float* tp = temb_base + (long)(img_lo + imgl[j]) * p.c.temb_bstride + cb;
               const float4 t0 = *reinterpret_cast<const float4*>(tp), t1 = *reinterpret_cast<const float4*>(tp + 4);
@@ -447,10 +449,14 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tcgen05_kernel(const Params 
             const float sc = mr.y, sh = -mr.x * mr.y;
 #pragma unroll
             for (int e = 0; e < 8; ++e) {
-              float t = fmaf(v[e], sc, sh);
-              t = fmaf(t, ga[e], be[e]);
-              if (p.c.pro & PRO_SILU) t = silu_fast(t);
-              v[e] = t + te[e];
+              if (FILM) {
+                v[e] = fmaxf(v[e], 0.2f * v[e]) + te[e];
+              } else {
+                float t = fmaf(v[e], sc, sh);
+                t = fmaf(t, ga[e], be[e]);
+                if (p.c.pro & PRO_SILU) t = silu_fast(t);
+                v[e] = t + te[e];
+              }
             }
             *slot = pack8(v);
           }
@@ -995,7 +1001,8 @@ static bool fill_params(const ConvP& c, int geo, Params& p) {
     while ((1 << p.cpg_in_shift) < p.cpg_in) ++p.cpg_in_shift;
     p.inv_cnt_in = 1.f / (float)(p.HW * p.cpg_in);
   } else if (c.pro != PRO_NONE) {
-    return false;   // SiLU / temb only come together with the GroupNorm apply
+    // without the GroupNorm apply only the FiLM signal prologue exists: LeakyReLU (+ per-sample / per-step encoding)
+    if (geo != GEO_SAME || c.C2 != 0 || !(c.pro & PRO_LRELU) || (c.pro & ~(PRO_LRELU | PRO_TEMB))) return false;
   }
   p.cpg_out = 1;
   if (c.ogroups > 0) {
@@ -1033,10 +1040,19 @@ static int launch(Params p, cudaStream_t st) {
     DMN_CUDA_CHECK(cudaFuncSetAttribute(conv_tcgen05_kernel<GEO, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemLimit));
     DMN_CUDA_CHECK(cudaFuncSetAttribute(conv_tcgen05_kernel<GEO, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemLimit));
     DMN_CUDA_CHECK(cudaFuncSetAttribute(conv_tcgen05_kernel<GEO, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemLimit));
+    if (GEO == GEO_SAME) {
+      DMN_CUDA_CHECK(cudaFuncSetAttribute(conv_tcgen05_kernel<GEO_SAME, 32, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemLimit));
+      DMN_CUDA_CHECK(cudaFuncSetAttribute(conv_tcgen05_kernel<GEO_SAME, 64, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemLimit));
+      DMN_CUDA_CHECK(cudaFuncSetAttribute(conv_tcgen05_kernel<GEO_SAME, 128, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemLimit));
+    }
     attr_set = true;
   }
   const int grid = p.total_tiles < num_sms() ? p.total_tiles : num_sms();
-  if (p.NT == 128) DMN_CUDA_CHECK(launch_pdl(conv_tcgen05_kernel<GEO, 128>, dim3(grid), dim3(kThreads), smem_bytes(p), st, p));
+  if (GEO == GEO_SAME && (p.c.pro & PRO_LRELU)) {
+    if (p.NT == 128) DMN_CUDA_CHECK(launch_pdl(conv_tcgen05_kernel<GEO_SAME, 128, true>, dim3(grid), dim3(kThreads), smem_bytes(p), st, p));
+    else if (p.NT == 64) DMN_CUDA_CHECK(launch_pdl(conv_tcgen05_kernel<GEO_SAME, 64, true>, dim3(grid), dim3(kThreads), smem_bytes(p), st, p));
+    else DMN_CUDA_CHECK(launch_pdl(conv_tcgen05_kernel<GEO_SAME, 32, true>, dim3(grid), dim3(kThreads), smem_bytes(p), st, p));
+  } else if (p.NT == 128) DMN_CUDA_CHECK(launch_pdl(conv_tcgen05_kernel<GEO, 128>, dim3(grid), dim3(kThreads), smem_bytes(p), st, p));
   else if (p.NT == 64) DMN_CUDA_CHECK(launch_pdl(conv_tcgen05_kernel<GEO, 64>, dim3(grid), dim3(kThreads), smem_bytes(p), st, p));
   else DMN_CUDA_CHECK(launch_pdl(conv_tcgen05_kernel<GEO, 32>, dim3(grid), dim3(kThreads), smem_bytes(p), st, p));
   count_launch();

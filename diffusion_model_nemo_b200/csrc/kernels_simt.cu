@@ -101,6 +101,10 @@ __global__ void __launch_bounds__(256) conv_simt_kernel(const ConvP p) {
         if (p.pro & PRO_SILU) {
           v.x = silu_f(v.x); v.y = silu_f(v.y); v.z = silu_f(v.z); v.w = silu_f(v.w);
         }
+        if (p.pro & PRO_LRELU) {      // LeakyReLU(0.2), parts/film.py:22
+          v.x = v.x > 0.f ? v.x : 0.2f * v.x; v.y = v.y > 0.f ? v.y : 0.2f * v.y;
+          v.z = v.z > 0.f ? v.z : 0.2f * v.z; v.w = v.w > 0.f ? v.w : 0.2f * v.w;
+        }
         if (p.pro & PRO_TEMB) {
           const float4 te = *reinterpret_cast<const float4*>(temb_row + c);
           v.x += te.x; v.y += te.y; v.z += te.z; v.w += te.w;
@@ -782,6 +786,49 @@ int time_table(const TimeP& p, cudaStream_t st) {
   rows_linear_kernel<<<g2, 256, td * sizeof(float), st>>>(e0, td, td, p.wct, p.bc, p.sumC, p.table, p.sumC, 0);
   count_launch();
   DMN_LAUNCH_CHECK("block_mlps");
+  return 0;
+}
+
+// =====================================================================================================
+// FiLM (WaveGradUNet): positional encoding of the noise level, and the modulation x * scale + shift
+// =====================================================================================================
+// table[r][c] = sin | cos ((5000 * level[r]) * freq[c]) in fp32 with the reference's multiplication order (parts/film.py:21-24)
+__global__ void film_pe_kernel(const float* __restrict__ levels, const float* __restrict__ freq, const float* __restrict__ is_cos,
+                               float* __restrict__ table, int rows, int sumC) {
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long)rows * sumC) return;
+  const int r = (int)(i / sumC), c = (int)(i - (long)r * sumC);
+  const float a = __fmul_rn(__fmul_rn(5000.0f, levels[r]), freq[c]);
+  table[i] = is_cos[c] != 0.f ? cosf(a) : sinf(a);
+}
+int film_pe_table(const float* levels, const float* freq, const float* is_cos, float* table, int rows, int sumC, cudaStream_t st) {
+  DMN_REQUIRE(rows > 0 && sumC > 0, "film_pe_table: bad shape");
+  const long n = (long)rows * sumC;
+  film_pe_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(levels, freq, is_cos, table, rows, sumC);
+  count_launch();
+  DMN_LAUNCH_CHECK("film_pe_table");
+  return 0;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) film_modulate_kernel(const T* __restrict__ x, const T* __restrict__ scale, const T* __restrict__ shift,
+                                                            T* __restrict__ out, long n4) {
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long)gridDim.x * blockDim.x) {
+    const float4 a = load4<T>(x + 4 * i), s = load4<T>(scale + 4 * i), t = load4<T>(shift + 4 * i);
+    // reference order: x * scale + shift with a rounding after the product (two torch ops)
+    store4<T>(out + 4 * i, make_float4(__fadd_rn(__fmul_rn(a.x, s.x), t.x), __fadd_rn(__fmul_rn(a.y, s.y), t.y),
+                                       __fadd_rn(__fmul_rn(a.z, s.z), t.z), __fadd_rn(__fmul_rn(a.w, s.w), t.w)));
+  }
+}
+int film_modulate(const void* x, const void* scale, const void* shift, void* out, long n, int act, cudaStream_t st) {
+  DMN_REQUIRE(n > 0 && n % 4 == 0, "film_modulate: element count must be a multiple of 4");
+  const long n4 = n / 4;
+  long blocks = (n4 + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  if (act == ACT_F32) film_modulate_kernel<float><<<(unsigned)blocks, 256, 0, st>>>((const float*)x, (const float*)scale, (const float*)shift, (float*)out, n4);
+  else film_modulate_kernel<bf16><<<(unsigned)blocks, 256, 0, st>>>((const bf16*)x, (const bf16*)scale, (const bf16*)shift, (bf16*)out, n4);
+  count_launch();
+  DMN_LAUNCH_CHECK("film_modulate");
   return 0;
 }
 

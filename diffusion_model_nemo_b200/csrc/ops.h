@@ -13,7 +13,7 @@ typedef long long stat_t;   // fixed-point GroupNorm statistics (common.cuh)
 
 enum { ACT_F32 = 0, ACT_BF16 = 1 };
 enum { CONV_SAME = 0, CONV_DOWN = 1, CONV_UP = 2 };
-enum { PRO_NONE = 0, PRO_GN = 1, PRO_SILU = 2, PRO_TEMB = 4 };
+enum { PRO_NONE = 0, PRO_GN = 1, PRO_SILU = 2, PRO_TEMB = 4, PRO_LRELU = 8 };   // PRO_LRELU: LeakyReLU(0.2), FiLM signal path (no GroupNorm)
 
 // One convolution (+ fused prologue on its input, + fused epilogue on its output).
 struct ConvP {
@@ -124,6 +124,13 @@ struct TimeP {
   int rows = 0, dim = 0, sumC = 0;
 };
 int time_table(const TimeP& p, cudaStream_t s);
+
+// FiLM positional encoding of a continuous noise level (parts/film.py:17-26): table[r][c] = sin | cos (5000 * level[r] * freq[c]);
+// is_cos[c] selects the half.  freq / is_cos are per table column (all FiLM layers side by side).
+int film_pe_table(const float* levels, const float* freq, const float* is_cos, float* table, int rows, int sumC, cudaStream_t s);
+
+// FiLM apply: out = x * scale + shift (elementwise, NHWC activations; out may alias x)   (modules/unet.py:259,262)
+int film_modulate(const void* x, const void* scale, const void* shift, void* out, long n, int act, cudaStream_t s);
 
 // layout conversion at the public ABI boundary
 int nchw_to_nhwc(const float* in, void* out, int B, int C, int HW, int act, cudaStream_t s);

@@ -91,7 +91,7 @@ struct Param {
   }
 };
 
-enum OpKind { OP_MEMSET, OP_INIT, OP_CONV, OP_FINALIZE, OP_LINATTN, OP_ATTN, OP_FINALPROJ };
+enum OpKind { OP_MEMSET, OP_INIT, OP_CONV, OP_FINALIZE, OP_LINATTN, OP_ATTN, OP_FINALPROJ, OP_MODULATE };
 
 // Buffers are addressed as (region id, so pointers can be resolved after bind)
 struct Buf {
@@ -140,6 +140,8 @@ struct dmn_plan {
   int sumC = 0;
   size_t off_freqs = 0, off_wct = 0, off_bc = 0;
   bool freqs_loaded = false;
+  // FiLM (WaveGradUNet): channels of every evaluated FiLM layer, in table-column order
+  std::vector<int> film_channels;
   Buf time_tmp, time_table;
   // statistics arena
   size_t stats_off = 0, stats_bytes = 0;
@@ -286,6 +288,26 @@ struct Builder {
     P.ops.push_back(f);
   }
 
+  // FeatureWiseLinearModulation (parts/film.py:29-61): signal conv3x3 -> [LeakyReLU(0.2) + positional encoding of the noise level,
+  // fused into the operand load of the next two convs] -> scale conv3x3, shift conv3x3
+  void film(int idx, Buf x, int C, int H, Buf tmp, Buf scale, Buf shift) {
+    const std::string p = "films." + std::to_string(idx);
+    const int col = P.sumC;
+    P.sumC += C;
+    P.film_channels.push_back(C);
+    conv(p + ".signal_conv.0", CONV_SAME, 3, x, C, Buf(), 0, C, H, tmp, true, 0);
+    conv(p + ".scale_conv", CONV_SAME, 3, tmp, C, Buf(), 0, C, H, scale, true, 0, PRO_LRELU | PRO_TEMB, 0, Buf(), -1, -1, col);
+    conv(p + ".shift_conv", CONV_SAME, 3, tmp, C, Buf(), 0, C, H, shift, true, 0, PRO_LRELU | PRO_TEMB, 0, Buf(), -1, -1, col);
+  }
+  // x = x * scale + shift   (modules/unet.py:259,262)
+  void modulate(const std::string& name, Buf x, Buf scale, Buf shift, int C, int H) {
+    Op m;
+    m.kind = OP_MODULATE;
+    m.name = name;
+    m.src1 = x; m.src2 = scale; m.res = shift; m.out = x; m.C = C; m.HW = H * H;
+    P.ops.push_back(m);
+  }
+
   // Residual(PreNorm(dim, LinearAttention | Attention))   (utils.py:68-93, parts/mha.py)
   void attn_block(const std::string& p, bool linear, Buf x, Buf xstats, int C, int H, Buf qkv, Buf att, Buf oraw, Buf out) {
     const int hidden = 128;
@@ -364,6 +386,19 @@ struct Builder {
     Buf QKV = actbuf(maxqkv), ATT = actbuf(maxatt);
     std::vector<Buf> skip(n);
     for (int i = 0; i < n; ++i) skip[i] = actbuf((size_t)Hs[i] * Hs[i] * dims[i + 1]);
+    // WaveGradUNet (unet.py:204-266): FiLM 0 on the stem output, FiLM i+1 on the output of down level i; the last level's FiLM is
+    // computed and discarded by the reference (unet.py:247), so it is not evaluated here.  (scale, shift) live until the up path.
+    const bool film_on = c.film != 0;
+    if (film_on && c.num_classes >= 0)
+      return fail(DMN_ENOTSUP, "WaveGradUNet with num_classes is not built (FiLM 0 reads the stem output before the class embedding)");
+    if (film_on && c.with_time_emb) return fail(DMN_EINVAL, "film requires with_time_emb = 0 (unet.py:195)");
+    std::vector<Buf> fscale(n), fshift(n);
+    if (film_on)
+      for (int i = 0; i < n; ++i) {
+        const size_t per = (size_t)Hs[i == 0 ? 0 : i - 1] * Hs[i == 0 ? 0 : i - 1] * dims[i];
+        fscale[i] = actbuf(per);
+        fshift[i] = actbuf(per);
+      }
 
     // parameters that are not attached to a conv op
     {
@@ -395,6 +430,7 @@ struct Builder {
 
     int cur = 0;   // index of the X buffer holding the current activation
     Buf x = X[0];
+    if (film_on) film(0, x, dim, S, H1, fscale[0], fshift[0]);
     for (int i = 0; i < n; ++i) {
       const int ci = dims[i], co = dims[i + 1], Hh = Hs[i];
       const std::string p = "downs." + std::to_string(i);
@@ -404,6 +440,7 @@ struct Builder {
       Buf st;
       resblock(p + ".1", o1, co, Buf(), 0, co, Hh, H1, H2, R, o2, true, 1, &st);
       attn_block(p + ".2", true, o2, st, co, Hh, QKV, ATT, O, skip[i]);
+      if (film_on && i < n - 1) film(i + 1, skip[i], co, Hh, H1, fscale[i + 1], fshift[i + 1]);
       if (i < n - 1) {
         Buf o3 = X[cur % 3];
         conv(p + ".3", CONV_DOWN, 4, skip[i], co, Buf(), 0, co, Hh, o3, true, 0);
@@ -442,7 +479,9 @@ struct Builder {
       x = o4;
       cur = (cur + 1) % 3;
       Hu *= 2;
+      if (film_on) modulate(p + ".film", x, fscale[lvl], fshift[lvl], ci, Hu);    // statistics of down level lvl-1: dims[lvl] channels at Hs[lvl-1]
     }
+    if (film_on) modulate("film0", x, fscale[0], fshift[0], dim, S);
     if (Hu != S) return fail(DMN_EINVAL, "internal: resolution bookkeeping");
     // final_conv = ResnetBlock(dim, dim) without time embedding, GroupNorm, SiLU, Conv1x1
     {
@@ -462,6 +501,10 @@ struct Builder {
     if (P.stats_bytes > stats_reserve) return fail(DMN_EINVAL, "internal: statistics arena overflow");
 
     // time path storage
+    if (film_on) {
+      P.off_freqs = walloc((size_t)2 * P.sumC * sizeof(float));     // freq | is_cos per table column
+      P.time_table = wsalloc((size_t)c.max_time_rows * P.sumC * sizeof(float));
+    }
     if (c.with_time_emb) {
       P.off_freqs = walloc((size_t)(dim / 2) * sizeof(float));
       P.off_wct = walloc((size_t)4 * dim * P.sumC * sizeof(float));
@@ -553,6 +596,9 @@ static int run_forward(dmn_plan* P, const float* x_dev, const int32_t* row_dev, 
       case OP_ATTN:
         rc = attn_core(B(o.src1), B(o.out), batch, o.heads, o.dh, o.N, P->act, st);
         break;
+      case OP_MODULATE:
+        rc = film_modulate(B(o.src1), B(o.src2), B(o.res), B(o.out), (long)batch * o.HW * o.C, P->act, st);
+        break;
       case OP_FINALPROJ: {
         FinalProjP q;
         q.y = B(o.src1); q.stats = (const stat_t*)B(o.stats); q.groups = o.groups;
@@ -578,7 +624,8 @@ static int check_ready(const dmn_plan* p) {
   if (!p->wbase || !p->wsbase) return fail(DMN_ESTATE, "plan is not bound to device memory (dmn_plan_bind)");
   for (const auto& q : p->params)
     if (!q.loaded) return fail(DMN_ESTATE, "parameter not loaded: " + q.name);
-  if (p->cfg.with_time_emb && !p->freqs_loaded) return fail(DMN_ESTATE, "sinusoid frequencies not loaded (dmn_plan_load_freqs)");
+  if ((p->cfg.with_time_emb || p->cfg.film) && !p->freqs_loaded)
+    return fail(DMN_ESTATE, "sinusoid / FiLM frequencies not loaded (dmn_plan_load_freqs)");
   return 0;
 }
 
@@ -600,7 +647,8 @@ int dmn_plan_create(const dmn_unet_cfg* cfg, dmn_plan** out) {
   DMN_REQUIRE(cfg->act_dtype == DMN_ACT_F32 || cfg->act_dtype == DMN_ACT_BF16, "act_dtype");
   DMN_REQUIRE(cfg->conv_engine == DMN_CONV_SIMT || (cfg->conv_engine == DMN_CONV_TCGEN05 && cfg->act_dtype == DMN_ACT_BF16),
               "tcgen05 engine requires bf16 activations");
-  DMN_REQUIRE(cfg->with_time_emb == 1, "with_time_emb=False (WaveGradUNet) is not built yet");
+  DMN_REQUIRE(cfg->with_time_emb == 0 || cfg->with_time_emb == 1, "with_time_emb must be 0 or 1");
+  DMN_REQUIRE(cfg->film == 0 || cfg->film == 1, "film must be 0 or 1");
   for (int i = 0; i < cfg->n_mults; ++i) DMN_REQUIRE(cfg->dim_mults[i] >= 1, "dim_mults must be positive");
   std::unique_ptr<dmn_plan> p(new dmn_plan());
   p->cfg = *cfg;
@@ -746,7 +794,17 @@ int dmn_plan_load_param(dmn_plan* p, const char* name, const float* host, int64_
 int dmn_plan_load_freqs(dmn_plan* p, const float* host_freqs, int n, void* stream) {
   if (!p || !host_freqs) return fail(DMN_EINVAL, "null argument");
   if (!p->wbase) return fail(DMN_ESTATE, "bind the plan before loading parameters");
-  DMN_REQUIRE(n == p->cfg.dim / 2, "expected dim/2 frequencies");
+  if (p->cfg.film) {
+    // one frequency per table column (every FiLM layer's [exponents | exponents], parts/film.py:20-24); the sin / cos half mask is built here
+    DMN_REQUIRE(n == p->sumC, "expected one frequency per FiLM table column (dmn_plan_film_layout)");
+    std::vector<float> is_cos;
+    for (int ch : p->film_channels)
+      for (int k = 0; k < ch; ++k) is_cos.push_back(k >= ch / 2 ? 1.f : 0.f);
+    DMN_CUDA_CHECK(cudaMemcpyAsync(p->wbase + p->off_freqs + (size_t)n * sizeof(float), is_cos.data(), n * sizeof(float),
+                                   cudaMemcpyHostToDevice, (cudaStream_t)stream));
+  } else {
+    DMN_REQUIRE(n == p->cfg.dim / 2, "expected dim/2 frequencies");
+  }
   DMN_CUDA_CHECK(cudaMemcpyAsync(p->wbase + p->off_freqs, host_freqs, n * sizeof(float), cudaMemcpyHostToDevice, (cudaStream_t)stream));
   DMN_CUDA_CHECK(cudaStreamSynchronize((cudaStream_t)stream));
   p->freqs_loaded = true;
@@ -755,10 +813,23 @@ int dmn_plan_load_freqs(dmn_plan* p, const float* host_freqs, int n, void* strea
 
 int dmn_plan_ready(const dmn_plan* p) { return check_ready(p) == 0 ? 1 : 0; }
 
+int dmn_plan_film_layout(const dmn_plan* p, int32_t* channels_out, int cap) {
+  if (!p) return 0;
+  const int n = (int)p->film_channels.size();
+  for (int i = 0; i < n && i < cap && channels_out; ++i) channels_out[i] = p->film_channels[i];
+  return n;
+}
+
 int dmn_time_table(dmn_plan* p, const float* times_dev, int row0, int rows, void* stream) {
   int rc = check_ready(p);
   if (rc) return rc;
   DMN_REQUIRE(times_dev && row0 >= 0 && rows > 0 && row0 + rows <= p->cfg.max_time_rows, "time table rows out of range");
+  if (p->cfg.film) {
+    const float* fr = (const float*)(p->wbase + p->off_freqs);
+    return film_pe_table(times_dev, fr, fr + p->sumC, (float*)(p->wsbase + p->time_table.off) + (size_t)row0 * p->sumC, rows, p->sumC,
+                         (cudaStream_t)stream);
+  }
+  if (!p->cfg.with_time_emb) return 0;     // nothing depends on time (unet.py:68-69)
   const int dim = p->cfg.dim;
   TimeP t;
   t.times = times_dev;
@@ -810,6 +881,7 @@ int dmn_plan_op_info(const dmn_plan* p, int i, char* name_out, int name_cap, int
       break;
     }
     case OP_FINALIZE: by = esz * (double)o.HW * o.C * 3.0; break;
+    case OP_MODULATE: by = esz * (double)o.HW * o.C * 4.0; break;
     case OP_LINATTN: fl = 2.0 * 2.0 * o.heads * o.dh * o.dh * o.N; by = esz * (double)o.N * o.heads * o.dh * 4.0; break;
     case OP_ATTN: fl = 2.0 * 2.0 * o.heads * o.dh * (double)o.N * o.N; by = esz * (double)o.N * o.heads * o.dh * 4.0; break;
     case OP_FINALPROJ: fl = 2.0 * o.HW * o.C * o.Cout; by = esz * (double)o.HW * o.C + 4.0 * o.HW * o.Cout; break;

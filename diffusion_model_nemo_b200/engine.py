@@ -11,6 +11,19 @@ import torch
 from . import _lib as L
 
 
+def film_freqs(channels) -> torch.Tensor:
+    """Per-column frequencies of the FiLM positional encodings: for every FiLM layer (C channels) its
+    [exponents | exponents] with exponents = 1e-4 ** (arange(C/2) / (C/2)), built with the reference's own torch CPU ops
+    (reference parts/film.py:19-21)."""
+    cols = []
+    for c in channels:
+        half = c // 2
+        e = torch.arange(half, dtype=torch.float32) / float(half)
+        e = 1e-4 ** e
+        cols += [e, e]
+    return torch.cat(cols).float().contiguous()
+
+
 def sinusoid_freqs(dim: int) -> torch.Tensor:
     """Frequencies of SinusoidalPositionEmbeddings, built with the reference's own torch CPU ops
     (reference parts/positional_encoding.py:13-15) so the device table starts from bit-identical values."""
@@ -23,7 +36,7 @@ class UnetPlan:
     """One (config, image_size, max_batch, dtype, engine) instance of the native U-Net."""
 
     def __init__(self, *, dim, dim_mults, channels, out_dim, groups, num_classes, image_size, max_batch,
-                 act_dtype, conv_engine, max_time_rows, device):
+                 act_dtype, conv_engine, max_time_rows, device, with_time_emb=True, film=False):
         self.lib = L.lib()
         self.device = torch.device(device)
         if self.device.type != "cuda":
@@ -34,7 +47,8 @@ class UnetPlan:
         for i, m in enumerate(dim_mults):
             cfg.dim_mults[i] = int(m)
         cfg.channels, cfg.out_dim, cfg.groups = channels, out_dim, groups
-        cfg.with_time_emb = 1
+        cfg.with_time_emb = 1 if with_time_emb else 0
+        cfg.film = 1 if film else 0
         cfg.num_classes = -1 if num_classes is None else int(num_classes)
         cfg.image_size, cfg.max_batch = image_size, max_batch
         cfg.act_dtype, cfg.conv_engine = act_dtype, conv_engine
@@ -76,8 +90,16 @@ class UnetPlan:
                     raise KeyError(f"missing parameter {name}")
                 t = sd[name].detach().to("cpu", torch.float32).contiguous()
                 L.check(self.lib.dmn_plan_load_param(self.h, name.encode(), L.ptr(t), t.numel(), st), f"load {name}")
-            f = sinusoid_freqs(self.dim)
-            L.check(self.lib.dmn_plan_load_freqs(self.h, L.ptr(f), f.numel(), st), "load freqs")
+            if self.cfg.film:
+                ch = (C.c_int32 * 16)()
+                n = self.lib.dmn_plan_film_layout(self.h, ch, 16)
+                f = film_freqs([ch[i] for i in range(n)])
+            elif self.cfg.with_time_emb:
+                f = sinusoid_freqs(self.dim)
+            else:
+                f = None
+            if f is not None:
+                L.check(self.lib.dmn_plan_load_freqs(self.h, L.ptr(f), f.numel(), st), "load freqs")
         self._loaded_version = version
         self.time_rows_key = None
 

@@ -1,6 +1,6 @@
 """Same export surface as the reference's `diffusion_model_nemo.modules` for the sampling hot path, so a Hydra
 `_target_: diffusion_model_nemo.modules.X` becomes `_target_: diffusion_model_nemo_b200.modules.X`."""
-from .unet import Unet
+from .unet import Unet, WaveGradUNet
 from .diffusion_process import (
     linear_beta_schedule,
     quadratic_beta_schedule,

@@ -90,8 +90,6 @@ class Unet(nn.Module):
             raise ValueError("Valid ordering for block are : ['conv_bn_act', 'bn_act_conv']")
         if resnet_block_order != "bn_act_conv":
             raise NotImplementedError("resnet_block_order='conv_bn_act' drops the final GroupNorm/SiLU; not built")
-        if not with_time_emb:
-            raise NotImplementedError("with_time_emb=False (WaveGradUNet) is not built yet")
         if dim_mults is None:
             dim_mults = (1, 2, 4, 8)
         self.channels, self.learned_variance, self.dim = channels, learned_variance, dim
@@ -107,8 +105,13 @@ class Unet(nn.Module):
         dims = [dim, *[dim * m for m in self.dim_mults]]
         in_out = list(zip(dims[:-1], dims[1:]))
         self.dim_list, self.in_out_list = dims, in_out
-        time_dim = dim * 4
-        self.time_mlp = nn.Sequential(_Holder(), nn.Linear(dim, time_dim), nn.GELU(), nn.Linear(time_dim, time_dim))
+        self.with_time_emb = bool(with_time_emb)
+        if with_time_emb:
+            time_dim = dim * 4
+            self.time_mlp = nn.Sequential(_Holder(), nn.Linear(dim, time_dim), nn.GELU(), nn.Linear(time_dim, time_dim))
+        else:                       # reference unet.py:67-69
+            time_dim = None
+            self.time_mlp = None
         g = resnet_block_groups
         self.downs, self.ups = nn.ModuleList([]), nn.ModuleList([])
         n = len(in_out)
@@ -133,6 +136,7 @@ class Unet(nn.Module):
                                         nn.Conv2d(dim, self.out_dim, kernel_size=1))
         if num_classes is not None:
             self.class_embed = nn.Embedding(num_classes + 1, embedding_dim=dim, padding_idx=num_classes)
+        self._film = False
         self.requires_grad_(False)
         self._plans = {}
 
@@ -161,7 +165,8 @@ class Unet(nn.Module):
             rows = max(time_rows, batch, 0 if p is None else p.max_time_rows)
             p = UnetPlan(dim=self.dim, dim_mults=self.dim_mults, channels=self.channels, out_dim=self.out_dim,
                          groups=self.groups, num_classes=self.num_classes, image_size=image_size, max_batch=mb,
-                         act_dtype=act, conv_engine=eng, max_time_rows=rows, device=device)
+                         act_dtype=act, conv_engine=eng, max_time_rows=rows, device=device,
+                         with_time_emb=self.with_time_emb, film=self._film)
             self._plans[key] = p
         ver = self._params_version()
         if p._loaded_version != ver:
@@ -178,3 +183,63 @@ class Unet(nn.Module):
         assert time.shape[0] == x.shape[0], "time must have one entry per sample"
         p = self.plan(x.shape[-1], x.shape[0], x.device)
         return p.forward(x.float().contiguous(), time, classes)
+
+
+def _film(c):
+    # reference parts/film.py:29-54 (signal conv3x3 + LeakyReLU, scale / shift conv3x3)
+    m = _Holder()
+    m.signal_conv = nn.Sequential(nn.Conv2d(c, c, kernel_size=3, stride=1, padding=1), nn.LeakyReLU(0.2))
+    m.positional_encoding = _Holder()
+    m.scale_conv = nn.Conv2d(c, c, kernel_size=3, stride=1, padding=1)
+    m.shift_conv = nn.Conv2d(c, c, kernel_size=3, stride=1, padding=1)
+    return m
+
+
+class WaveGradUNet(Unet):
+    """Drop-in for the reference `WaveGradUNet` (modules/unet.py:171-266): the U-Net without time embedding whose up path is
+    modulated by FeatureWiseLinearModulation statistics (parts/film.py) computed on the way down from a CONTINUOUS noise level.
+    `forward(x, noise_level, classes=None)`, noise_level float [B,1,1,1] (or [B]).  Same parameter names / shapes as the
+    reference, including the three FiLM layers the reference constructs but never evaluates and the bottleneck FiLM whose
+    output it discards (unet.py:204-210,247): they are held for state_dict compatibility and skipped by the engine."""
+
+    def __init__(
+        self,
+        input_dim: None,
+        dim: int,
+        out_dim: Optional[int] = None,
+        dim_mults: Optional[List[int]] = None,
+        channels: int = 3,
+        with_time_emb: bool = None,  # ignored, as in the reference
+        resnet_block_groups: int = 8,
+        use_convnext: bool = True,
+        convnext_mult: int = 2,
+        resnet_block_order: str = "bn_act_conv",
+        dropout: Optional[float] = None,
+        learned_variance: bool = False,
+        num_classes: Optional[int] = None,
+        compute_dtype: str = "bf16",
+        conv_engine: str = "tcgen05",
+    ):
+        super().__init__(input_dim=input_dim, dim=dim, out_dim=out_dim, dim_mults=dim_mults, channels=channels,
+                         with_time_emb=False, resnet_block_groups=resnet_block_groups, use_convnext=use_convnext,
+                         convnext_mult=convnext_mult, resnet_block_order=resnet_block_order, dropout=dropout,
+                         learned_variance=learned_variance, num_classes=num_classes, compute_dtype=compute_dtype,
+                         conv_engine=conv_engine)
+        if num_classes is not None:
+            raise NotImplementedError("WaveGradUNet with num_classes is not built (FiLM 0 reads the stem before the class embedding)")
+        films = [_film(dim)]
+        films.extend(_film(co) for (_, co) in self.in_out_list)
+        films.extend(_film(co) for (_, co) in reversed(self.in_out_list[1:]))
+        self.films = nn.ModuleList(films)
+        self._film = True
+        self.requires_grad_(False)
+
+    def forward(self, x, noise_level, classes=None):
+        """eps = WaveGradUNet.forward(x, noise_level, classes) (reference modules/unet.py:212-266)."""
+        if x.device.type != "cuda":
+            raise L.DmnError("diffusion_model_nemo_b200.WaveGradUNet runs on CUDA only: there is no CPU fallback")
+        assert x.dim() == 4 and x.shape[1] == self.channels and x.shape[2] == x.shape[3], f"bad input shape {tuple(x.shape)}"
+        level = noise_level.reshape(-1)
+        assert level.shape[0] == x.shape[0], "noise_level must have one entry per sample"
+        p = self.plan(x.shape[-1], x.shape[0], x.device)
+        return p.forward(x.float().contiguous(), level, classes)

@@ -8,8 +8,9 @@ wavegrad_diffusion.py:219-226).  Differences from DDPM on the hot path:
   * x0 = sqrt_recip_alphas_cumprod * x - sqrt_alphas_cumprod_m1 * eps with sqrt_alphas_cumprod_m1 = sqrt(1 - acp) * sqrt(1 / acp)
     (:106,150-158) -- same value as DDPM's sqrt(1/acp - 1) in exact arithmetic, different fp32 rounding, so the table is built
     with the reference's op order and fed to the SAME fused update kernel (dmn_ddpm_step) as a coefficient column.
-The denoiser is any callable (x, noise_level) -> eps.  The reference's FiLM U-Net (WaveGradUNet, modules/unet.py:171-266) is not
-part of the native engine: pass the stock torch module or any other callable; the update stays fused.
+The denoiser is this package's WaveGradUNet (reference modules/unet.py:171-266) -- then the whole loop runs natively: the FiLM
+positional encodings of all T noise levels are tabulated once, and ONE CUDA graph (U-Net + fused update) is replayed T times --
+or any other callable (x, noise_level) -> eps, which is called per step while the update stays the fused kernel.
 """
 import copy
 from typing import Optional
@@ -20,6 +21,7 @@ import torch.nn.functional as F
 
 from . import _runtime as R
 from .gaussian_diffusion import GaussianDiffusion
+from .unet import WaveGradUNet
 
 
 class WaveGradDiffusion(GaussianDiffusion):
@@ -83,6 +85,17 @@ class WaveGradDiffusion(GaussianDiffusion):
         rows[1] = self.sqrt_alphas_cumprod_m1[ts]
         return rows
 
+    def _loop_tables(self, ts: torch.Tensor, device):
+        """Coefficient rows + the denoiser's per-step argument: the continuous noise level sqrt_alphas_cumprod_prev[t + 1]
+        (reference wavegrad_diffusion.py:169-172) instead of the integer timestep."""
+        coef, _ = super()._loop_tables(ts, device)
+        key = ("levels", str(device), tuple(ts[:: max(1, len(ts) // 5)].tolist()), len(ts))
+        lv = self._coef_cache.get(key)
+        if lv is None:
+            lv = self.sqrt_alphas_cumprod_prev[ts + 1].to(torch.float32).to(device)
+            self._coef_cache[key] = lv
+        return coef, lv
+
     def _model_arg(self, ti: int, b: int, device):
         lv = self.sqrt_alphas_cumprod_prev[ti + 1]
         return torch.full((b, 1, 1, 1), float(lv), dtype=torch.float32, device=device)
@@ -95,7 +108,7 @@ class WaveGradDiffusion(GaussianDiffusion):
     @torch.no_grad()
     def p_sample_loop(self, model, shape, device=None, use_tqdm=True, noise=None, img=None, start: Optional[int] = None):
         unet, _ = R.resolve_model(model)
-        if unet is not None:
+        if unet is not None and not isinstance(unet, WaveGradUNet):
             raise NotImplementedError("WaveGradDiffusion drives a (x, noise_level) denoiser; the native Unet takes timesteps. "
-                                      "Pass the FiLM WaveGradUNet (torch) or another callable: the update stays the fused kernel")
+                                      "Pass this package's WaveGradUNet (native loop) or any other (x, noise_level) callable")
         return super().p_sample_loop(model, shape, device=device, use_tqdm=use_tqdm, noise=noise, img=img, start=start)

@@ -48,7 +48,8 @@ int dmn_abi_version(void);
  * U-Net plan.  Replaces Unet.__init__ / Unet.forward (modules/unet.py:14-168) and everything below it:
  * ResnetBlock/Block (parts/convnext.py:8-86), LinearAttention/Attention (parts/mha.py:8-59),
  * SinusoidalPositionEmbeddings (parts/positional_encoding.py:6-18), Residual/PreNorm/Upsample/Downsample
- * (utils.py:68-93).  use_convnext=True is DMN_ENOTSUP (no shipped config uses it).
+ * (utils.py:68-93), and WaveGradUNet.forward + FeatureWiseLinearModulation / PositionalEncoding (unet.py:171-266,
+ * parts/film.py:11-61) when cfg.film = 1.  use_convnext=True is DMN_ENOTSUP (no shipped config uses it).
  * ---------------------------------------------------------------------------------------------------- */
 typedef struct dmn_plan dmn_plan;
 
@@ -66,7 +67,9 @@ typedef struct dmn_unet_cfg {
   int32_t act_dtype;       /* DMN_ACT_*                          */
   int32_t conv_engine;     /* DMN_CONV_*                         */
   int32_t max_time_rows;   /* rows of the time-embedding table (>= max_batch and >= loop steps) */
-  int32_t reserved[3];
+  int32_t film;            /* 1 = WaveGradUNet (unet.py:171-266): requires with_time_emb = 0; FeatureWiseLinearModulation
+                              layers films.0 .. films.{n_mults-1} (parts/film.py:29-61) driven by a continuous noise level */
+  int32_t reserved[2];
 } dmn_unet_cfg;
 
 int    dmn_plan_create(const dmn_unet_cfg* cfg, dmn_plan** out);
@@ -85,10 +88,17 @@ int dmn_plan_load_param(dmn_plan* p, const char* name, const float* host_data, i
  * (positional_encoding.py:13-15) so the table is bit-exact. */
 int dmn_plan_load_freqs(dmn_plan* p, const float* host_freqs, int n, void* stream);
 int dmn_plan_ready(const dmn_plan* p);                 /* 1 when every parameter has been loaded */
+/* film plans: channels of every evaluated FiLM layer in table-column order (returns the count).  dmn_plan_load_freqs then takes
+ * sum(channels) values: for each layer its [exponents | exponents], exponents = 1e-4 ** (arange(C/2) / (C/2)) computed by the
+ * host with the reference's torch ops (PositionalEncoding.forward, parts/film.py:19-21). */
+int dmn_plan_film_layout(const dmn_plan* p, int32_t* channels_out, int cap);
 
 /* time_mlp + the 16 per-block `mlp` projections for `rows` time values -> table rows [row0, row0+rows).
  * Replaces Unet.time_mlp (unet.py:61-66) and ResnetBlock.mlp (convnext.py:68-72,81-83). */
 int dmn_time_table(dmn_plan* p, const float* times_dev, int row0, int rows, void* stream);
+/* film plans: `times_dev` holds continuous noise levels and the table rows are the FiLM positional encodings
+ * sin | cos (5000 * level * exponents) of every FiLM layer (parts/film.py:17-26); dmn_unet_forward then evaluates
+ * WaveGradUNet.forward(x, noise_level) (unet.py:212-266).  Plans with neither time embedding nor FiLM ignore the call. */
 
 /* eps = Unet.forward(x, time, classes)  (unet.py:131-168).
  *   x_dev    fp32 NCHW [batch, channels, S, S]         out_dev  fp32 NCHW [batch, out_dim, S, S]
@@ -102,7 +112,7 @@ int dmn_plan_launches_per_forward(const dmn_plan* p);
 
 /* Measurement aids for bench.py's roofline (no reference counterpart).
  * dmn_plan_num_ops / dmn_plan_op_info: static description of launch i of the forward program -- name, kind
- *   (0 memset, 1 init_conv, 2 conv, 3 gn_finalize, 4 linattn, 5 attn, 6 final_proj), engine (0 CUDA cores, 1 tcgen05),
+ *   (0 memset, 1 init_conv, 2 conv, 3 gn_finalize, 4 linattn, 5 attn, 6 final_proj, 7 film_modulate), engine (0 CUDA cores, 1 tcgen05),
  *   algorithmic FLOPs (2*MAC) and algorithmic bytes (operands read once + result written once) PER SAMPLE.
  * dmn_plan_profile_forward: one forward with a CUDA event pair around every launch on `stream`; writes per-launch
  *   milliseconds to ms_out[0..num_ops) and synchronises the stream (not graph-capturable). */

@@ -254,6 +254,76 @@ def make_model(sd, cfg) -> Callable:
 
 
 # ----------------------------------------------------------------------------------------------
+# WaveGradUNet: the U-Net without time embedding + feature-wise linear modulation (FiLM) driven by a
+# continuous noise level (reference modules/unet.py:171-266, parts/film.py:11-61)
+# ----------------------------------------------------------------------------------------------
+FILM_LINEAR_SCALE = 5000
+
+
+def film_positional_encoding(noise_level: Tensor, n_channels: int) -> Tensor:
+    """PositionalEncoding.forward, parts/film.py:17-26: noise_level [B,1,1,1] -> [B,C,1,1]."""
+    if noise_level.dim() > 1:
+        noise_level = noise_level.squeeze(-1)
+    half = n_channels // 2
+    e = torch.arange(half, dtype=torch.float32).to(noise_level) / float(half)
+    e = 1e-4 ** e
+    e = FILM_LINEAR_SCALE * noise_level.unsqueeze(1) * e.unsqueeze(0)
+    out = torch.cat([e.sin(), e.cos()], dim=-1)
+    return out.transpose(1, 3)
+
+
+def film_fwd(sd, p, x, noise_level):
+    """FeatureWiseLinearModulation.forward, parts/film.py:56-60 -> (scale, shift)."""
+    o = F.leaky_relu(F.conv2d(x, sd[p + ".signal_conv.0.weight"], sd[p + ".signal_conv.0.bias"], padding=1), 0.2)
+    o = o + film_positional_encoding(noise_level, x.shape[1])
+    scale = F.conv2d(o, sd[p + ".scale_conv.weight"], sd[p + ".scale_conv.bias"], padding=1)
+    shift = F.conv2d(o, sd[p + ".shift_conv.weight"], sd[p + ".shift_conv.bias"], padding=1)
+    return scale, shift
+
+
+def wavegrad_unet_forward(sd: Dict[str, Tensor], cfg: dict, x: Tensor, noise_level: Tensor, classes: Optional[Tensor] = None) -> Tensor:
+    """WaveGradUNet.forward, modules/unet.py:212-266 (use_convnext=False).  noise_level: [B,1,1,1] float."""
+    dim, mults, groups = cfg["dim"], list(cfg["dim_mults"]), cfg.get("groups", 8)
+    n_res = len(mults)
+    x = F.conv2d(x, sd["init_conv.weight"], sd["init_conv.bias"], padding=3)
+    stats = [film_fwd(sd, "films.0", x, noise_level)]
+    if cfg.get("num_classes") is not None:
+        if classes is None:
+            classes = torch.ones(x.size(0), dtype=torch.long) * cfg["num_classes"]
+        x = x + sd["class_embed.weight"][classes].view(x.size(0), x.size(1), 1, 1)
+    h = []
+    for i in range(n_res):
+        x = resnet_block_fwd(sd, f"downs.{i}.0", x, None, groups)
+        x = resnet_block_fwd(sd, f"downs.{i}.1", x, None, groups)
+        x = residual_prenorm_fwd(sd, f"downs.{i}.2", x, linear_attention_fwd)
+        h.append(x)
+        stats.append(film_fwd(sd, f"films.{i + 1}", x, noise_level))
+        if i < n_res - 1:
+            x = F.conv2d(x, sd[f"downs.{i}.3.weight"], sd[f"downs.{i}.3.bias"], stride=2, padding=1)
+    x = resnet_block_fwd(sd, "mid_block1", x, None, groups)
+    x = residual_prenorm_fwd(sd, "mid_attn", x, attention_fwd)
+    x = resnet_block_fwd(sd, "mid_block2", x, None, groups)
+    stats.pop()                                    # the bottleneck level's FiLM is computed and discarded (unet.py:247)
+    for i in range(n_res - 1):
+        scale, shift = stats.pop()
+        x = torch.cat((x, h.pop()), dim=1)
+        x = resnet_block_fwd(sd, f"ups.{i}.0", x, None, groups)
+        x = resnet_block_fwd(sd, f"ups.{i}.1", x, None, groups)
+        x = residual_prenorm_fwd(sd, f"ups.{i}.2", x, linear_attention_fwd)
+        x = F.conv_transpose2d(x, sd[f"ups.{i}.3.weight"], sd[f"ups.{i}.3.bias"], stride=2, padding=1)
+        x = x * scale + shift
+    scale, shift = stats.pop()
+    x = scale * x + shift
+    x = resnet_block_fwd(sd, "final_conv.0", x, None, groups)
+    x = F.silu(_gn(x, sd, "final_conv.1", groups))
+    return F.conv2d(x, sd["final_conv.3.weight"], sd["final_conv.3.bias"])
+
+
+def make_wavegrad_model(sd, cfg) -> Callable:
+    return lambda x, level, classes=None: wavegrad_unet_forward(sd, cfg, x, level, classes)
+
+
+# ----------------------------------------------------------------------------------------------
 # sampler updates
 # ----------------------------------------------------------------------------------------------
 
@@ -498,7 +568,7 @@ def unet_param_shapes(cfg: dict) -> Dict[str, Sequence[int]]:
     dim, mults, ch = cfg["dim"], list(cfg["dim_mults"]), cfg.get("channels", 3)
     dims = [dim] + [dim * m for m in mults]
     in_out = list(zip(dims[:-1], dims[1:]))
-    td = dim * 4 if cfg.get("with_time_emb", True) else None
+    td = dim * 4 if cfg.get("with_time_emb", True) and not cfg.get("film") else None
     shapes = {"init_conv.weight": (dim, ch, 7, 7), "init_conv.bias": (dim,)}
     if td:
         shapes.update({"time_mlp.1.weight": (td, dim), "time_mlp.1.bias": (td,),
@@ -556,6 +626,13 @@ def unet_param_shapes(cfg: dict) -> Dict[str, Sequence[int]]:
     shapes["final_conv.3.bias"] = (out_dim,)
     if cfg.get("num_classes") is not None:
         shapes["class_embed.weight"] = (cfg["num_classes"] + 1, dim)
+    if cfg.get("film"):
+        # WaveGradUNet.films (unet.py:204-210): [dim] + out channels of every level + out channels of reversed(in_out[1:])
+        chans = [dim] + [co for _, co in in_out] + [co for _, co in reversed(in_out[1:])]
+        for i, c in enumerate(chans):
+            for conv in ("signal_conv.0", "scale_conv", "shift_conv"):
+                shapes[f"films.{i}.{conv}.weight"] = (c, c, 3, 3)
+                shapes[f"films.{i}.{conv}.bias"] = (c,)
     return shapes
 
 

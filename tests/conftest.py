@@ -27,7 +27,7 @@ def pytest_collection_modifyitems(config, items):
 @pytest.fixture(scope="session")
 def golden():
     out = {}
-    for name in ("tables", "unet", "samplers", "step", "wavegrad"):
+    for name in ("tables", "unet", "samplers", "step", "wavegrad", "wavegrad_unet"):
         out[name] = dict(np.load(os.path.join(GOLDEN, name + ".npz")))
     return out
 
@@ -53,6 +53,32 @@ CFGS = {
     "tiny_g4": (dict(dim=32, dim_mults=[1, 2], channels=3, groups=4), 16, 2),
     "tiny_cls": (dict(dim=32, dim_mults=[1, 2], channels=3, groups=8, num_classes=10), 16, 2),
 }
+
+
+WG_CFGS = {
+    # WaveGradUNet fixtures (tests/golden/make_golden_wavegrad_unet.py): name -> (cfg, image size, batch)
+    "wg_tiny": (dict(dim=32, dim_mults=[1, 2], channels=3, groups=8, film=True), 16, 2),
+    "wg_cfg": (dict(dim=128, dim_mults=[1, 2, 2, 2], channels=3, groups=8, film=True), 32, 1),
+}
+
+
+def wg_inputs(name):
+    """The seeded input of the WaveGradUNet fixture (x is regenerated, the noise level is stored)."""
+    cfg, size, b = WG_CFGS[name]
+    g = torch.Generator().manual_seed(11)
+    return torch.randn(b, cfg["channels"], size, size, generator=g)
+
+
+def make_wavegrad_unet(cfg, sd=None, dtype="fp32", engine="simt", device=None):
+    import diffusion_model_nemo_b200.modules as M
+
+    u = M.WaveGradUNet(None, dim=cfg["dim"], dim_mults=cfg["dim_mults"], channels=cfg["channels"], use_convnext=False,
+                       resnet_block_groups=cfg["groups"], compute_dtype=dtype, conv_engine=engine)
+    if sd is not None:
+        u.load_state_dict(sd, strict=True)
+    if device is not None:
+        u = u.to(device)
+    return u
 
 
 def make_unet(cfg, sd=None, dtype="fp32", engine="simt", device=None):
