@@ -88,8 +88,42 @@ struct Params {
 
 // debug timeline (DMN_TC_TRACE=1): CTA `trace_cta` records clock64 per role and tile: slot = 16*tile_iter + k
 //   k: 0 producer tile start, 1 producer tables done, 2 producer last pass filled, 4 MMA got accumulators, 5 MMA first operand,
-//      6 MMA tile issued, 8 epilogue tables done, 9 epilogue accumulators ready, 10 epilogue TMEM drained, 11 epilogue tile done
+//      6 MMA tile issued, 8 epilogue tables done, 9 epilogue accumulators ready, 10 epilogue TMEM drained, 11 epilogue tile done,
+//      12 / 13 clocks the MMA issuer waited for operands / weights, 14 / 15 clocks producer thread 0 waited for a free operand
+//      buffer / for its own cp.async copies
 __device__ long long g_trace[1024];
+#ifndef DMN_TC_TRACE_PRODUCER
+#define DMN_TC_TRACE_PRODUCER 0     // 1: also account the producers' wait clocks (slots 14 / 15); costs registers in the hot role
+#endif
+constexpr bool kTraceProducer = DMN_TC_TRACE_PRODUCER != 0;
+#ifndef DMN_EXP_ZFILL
+#define DMN_EXP_ZFILL 1
+#endif
+#ifndef DMN_EXP_MMATRACE
+#define DMN_EXP_MMATRACE 0          // 1: account the MMA issuer's wait clocks (slots 12 / 13); measured -1.3 % on the whole step
+#endif
+// contention experiments (tools/trace_conv.py with a variant build; results are garbage, only the timeline is meaningful)
+#ifndef DMN_EXP_NO_FENCE
+#define DMN_EXP_NO_FENCE 0          // MMA issuer: no tcgen05.fence::after_thread_sync after the operand / weight barrier waits
+#endif
+#ifndef DMN_EXP_NO_LEAN
+#define DMN_EXP_NO_LEAN 0           // 1: the generic (looped) MMA issue path for every geometry
+#endif
+#ifndef DMN_EXP_LEAN_MIN_PASS
+#define DMN_EXP_LEAN_MIN_PASS 8
+#endif
+#ifndef DMN_EXP_ACC_RELAXED
+#define DMN_EXP_ACC_RELAXED 0       // 1: the MMA issuer backs off while it waits for the epilogue to drain an accumulator set
+#endif
+#ifndef DMN_EXP_NO_EPI
+#define DMN_EXP_NO_EPI 0            // epilogue: TMEM reads only (no staging, no global stores, no statistics)
+#endif
+#ifndef DMN_EXP_NO_LOAD
+#define DMN_EXP_NO_LOAD 0           // producers: no operand copies
+#endif
+#ifndef DMN_EXP_NO_WEIGHTS
+#define DMN_EXP_NO_WEIGHTS 0        // weight loader: barrier arrivals without the bulk copies
+#endif
 #define TRACE(it, k)                                                                                       \
   do {                                                                                                     \
     if (p.trace && blockIdx.x == (unsigned)p.trace_cta && (it) < 60) p.trace[16 * (it) + (k)] = clock64(); \
@@ -258,6 +292,46 @@ __device__ __forceinline__ void issue_stage(const Params& p, bool leader, uint32
       umma_bf16(d0, ad[g][2], bd[g][1], idesc, 1u);
       if (TWO) umma_bf16(d1, ad[g][3], bd[g][1], idesc, 1u);
     }
+  }
+}
+
+// Lean issue path.  The issuing thread runs in near lock-step with the tensor pipe: what it executes between the last MMA of one
+// tap and the first MMA of the next is hidden only while that last MMA (64 clk at N = 128) is still streaming its operands
+// (tools/mma_rate2.cu: one extra mbarrier probe or an R2UR per tap costs its full latency).  So the per-tap preparation is cut
+// to a handful of uniform adds: the tap offsets live in registers (loaded once), tap / stage indices are compile-time constants
+// (fully unrolled pass), and the descriptor low words (start address | LBO field) are formed by plain additions -- shared memory
+// is < 256 KB, so (address >> 4) never carries into the LBO field and no masking is needed.
+template <bool TWO>
+__device__ __forceinline__ void issue_tap(bool leader, uint32_t d0, uint32_t d1, uint32_t a_lo, uint32_t b_lo, uint32_t hi_a, uint32_t hi_b,
+                                          uint32_t a_k16, uint32_t b_k16, uint32_t idesc, uint32_t acc) {
+  const uint64_t bd0 = ((uint64_t)hi_b << 32) | b_lo, bd1 = ((uint64_t)hi_b << 32) | (b_lo + b_k16);
+  const uint64_t ad00 = ((uint64_t)hi_a << 32) | a_lo, ad10 = ((uint64_t)hi_a << 32) | (a_lo + a_k16);
+  const uint64_t ad01 = ((uint64_t)hi_a << 32) | (a_lo + 128u), ad11 = ((uint64_t)hi_a << 32) | (a_lo + a_k16 + 128u);
+  if (leader) {
+    umma_bf16(d0, ad00, bd0, idesc, acc);
+    if (TWO) umma_bf16(d1, ad01, bd0, idesc, acc);
+    umma_bf16(d0, ad10, bd1, idesc, 1u);
+    if (TWO) umma_bf16(d1, ad11, bd1, idesc, 1u);
+  }
+}
+// One 32-channel pass = NTAP taps in stages of GG taps, fully unrolled.  `st` / `ph` walk the weight ring.
+template <int NTAP, int GG, bool TWO>
+__device__ __forceinline__ void issue_pass(bool leader, uint32_t d0, uint32_t d1, uint32_t au_lo, const int (&dl)[NTAP], uint32_t b_lo0,
+                                           uint32_t b_stage_units, uint32_t b_tap_units, uint32_t hi_a, uint32_t hi_b, uint32_t a_k16,
+                                           uint32_t b_k16, uint32_t idesc, uint32_t acc_first, uint64_t* full_b, uint64_t* empty_b, int nst,
+                                           int& st, uint32_t& ph) {
+#pragma unroll
+  for (int s = 0; s < NTAP / GG; ++s) {
+    mbar_wait(smem_u32(&full_b[st]), ph);
+    tc_fence_after();
+    const uint32_t b_lo = b_lo0 + (uint32_t)st * b_stage_units;
+#pragma unroll
+    for (int g = 0; g < GG; ++g)
+      issue_tap<TWO>(leader, d0, d1, au_lo + (uint32_t)dl[s * GG + g], b_lo + (uint32_t)g * b_tap_units, hi_a, hi_b, a_k16, b_k16, idesc,
+                     (s | g) ? 1u : acc_first);
+    if (leader) umma_commit(smem_u32(&empty_b[st]));     // frees the weight stage once these MMAs retire
+    __syncwarp();
+    if (++st == nst) { st = 0; ph ^= 1; }
   }
 }
 
@@ -434,6 +508,15 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tcgen05_kernel(const Params 
           }
           const int g = cb >> p.cpg_in_shift;
           uint8_t* base = sA + fbuf * a_bytes + (uint32_t)kc * p.lbo_a;
+          // packed fp32x2 arithmetic (FFMA2 / FADD2).  hx = t / 2 with t = GroupNorm affine: the halving is folded into gamma / beta
+          // (exact: a power of two), SiLU(t) = hx * tanh(hx) + hx is one MUFU per element
+          unsigned long long gah2[4], beh2[4], te2[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            gah2[e] = pack2(0.5f * ga[2 * e], 0.5f * ga[2 * e + 1]);
+            beh2[e] = pack2(0.5f * be[2 * e], 0.5f * be[2 * e + 1]);
+            te2[e] = pack2(te[2 * e], te[2 * e + 1]);
+          }
 #pragma unroll
           for (int j = 0; j < kMaxItems; ++j) {
             if (goff[j] < 0) continue;                 // padding stays zero AFTER the transform
@@ -442,20 +525,35 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tcgen05_kernel(const Params 
             if ((p.c.pro & PRO_TEMB) && !temb_shared) {
               const float* tp = temb_base + (long)(img_lo + imgl[j]) * p.c.temb_bstride + cb;
               const float4 t0 = *reinterpret_cast<const float4*>(tp), t1 = *reinterpret_cast<const float4*>(tp + 4);
-              te[0] = t0.x; te[1] = t0.y; te[2] = t0.z; te[3] = t0.w; te[4] = t1.x; te[5] = t1.y; te[6] = t1.z; te[7] = t1.w;
+              te2[0] = pack2(t0.x, t0.y); te2[1] = pack2(t0.z, t0.w); te2[2] = pack2(t1.x, t1.y); te2[3] = pack2(t1.z, t1.w);
             }
             float v[8];
             unpack8(*slot, v);
-            const float sc = mr.y, sh = -mr.x * mr.y;
+            if (FILM) {                                 // LeakyReLU(0.2) + positional encoding (parts/film.py:22,58)
 #pragma unroll
-            for (int e = 0; e < 8; ++e) {
-              if (FILM) {
-                v[e] = fmaxf(v[e], 0.2f * v[e]) + te[e];
-              } else {
-                float t = fmaf(v[e], sc, sh);
-                t = fmaf(t, ga[e], be[e]);
-                if (p.c.pro & PRO_SILU) t = silu_fast(t);
-                v[e] = t + te[e];
+              for (int e = 0; e < 4; ++e) {
+                const unsigned long long y2 = add2(pack2(fmaxf(v[2 * e], 0.2f * v[2 * e]), fmaxf(v[2 * e + 1], 0.2f * v[2 * e + 1])), te2[e]);
+                unpack2(y2, v[2 * e], v[2 * e + 1]);
+              }
+            } else {
+              const float sc = mr.y, sh = -mr.x * mr.y;
+              const unsigned long long sc2 = pack2(sc, sc), sh2 = pack2(sh, sh);
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                unsigned long long x2 = fma2(pack2(v[2 * e], v[2 * e + 1]), sc2, sh2);
+                x2 = fma2(x2, gah2[e], beh2[e]);                       // hx
+                unsigned long long y2;
+                if (p.c.pro & PRO_SILU) {
+                  float h0, h1, t0, t1;
+                  unpack2(x2, h0, h1);
+                  asm("tanh.approx.f32 %0, %1;" : "=f"(t0) : "f"(h0));
+                  asm("tanh.approx.f32 %0, %1;" : "=f"(t1) : "f"(h1));
+                  y2 = fma2(x2, pack2(t0, t1), x2);
+                } else {
+                  y2 = add2(x2, x2);
+                }
+                y2 = add2(y2, te2[e]);
+                unpack2(y2, v[2 * e], v[2 * e + 1]);
               }
             }
             *slot = pack8(v);
@@ -467,8 +565,12 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tcgen05_kernel(const Params 
       };
 
       int inflight = 0;
+      const bool ptracing = kTraceProducer && p.trace && tid == 0 && blockIdx.x == (unsigned)p.trace_cta && pit < 60;
+      long long wait_e = 0, wait_g = 0;
       for (int c = 0; c < p.n_pass; ++c) {
+        long long w0 = ptracing ? clock64() : 0;
         mbar_wait_relaxed(smem_u32(&empty_a[ibuf]), iph);
+        if (ptracing) wait_e += clock64() - w0;
         int cb = c * kCk + kc * 8;        // first (virtual) channel of this thread's k-chunk
         int sy = 0, sx = 0;
         if (GEO == GEO_DOWN) {            // virtual channel = sub * C + ci, sub = sy*2 + sx
@@ -482,30 +584,46 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tcgen05_kernel(const Params 
         if (cb < p.c.C1) { src = src1; Cs = p.c.C1; cofs = cb; }
         else { src = src2; Cs = p.c.C2; cofs = cb - p.c.C1; }
         const uint32_t dst0 = sA_u + ibuf * a_bytes + (uint32_t)kc * p.lbo_a + (uint32_t)px0 * 16u;
+        if (GEO == GEO_DOWN || !DMN_EXP_ZFILL) {
 #pragma unroll
-        for (int j = 0; j < kMaxItems; ++j) {
-          if (goff[j] < -1) continue;                  // outside the window
-          const uint32_t dst = dst0 + (uint32_t)((kProdThreads / 4) * j) * 16u;
-          const bf16* sp = nullptr;
-          if (goff[j] >= 0) {
-            if (GEO == GEO_DOWN) {
-              const int img = goff[j] >> 14, iy = 2 * ((goff[j] >> 7) & 127) - 1 + sy, ix = 2 * (goff[j] & 127) - 1 + sx;
-              if (iy >= 0 && iy < p.H && ix >= 0 && ix < p.W) sp = src + ((long)img * p.HW + iy * p.W + ix) * Cs + cofs;
-            } else {
-              sp = src + (long)goff[j] * Cs + cofs;
+          for (int j = 0; j < kMaxItems; ++j) {
+            if (goff[j] < -1) continue;                  // outside the window
+            const uint32_t dst = dst0 + (uint32_t)((kProdThreads / 4) * j) * 16u;
+            const bf16* sp = nullptr;
+            if (goff[j] >= 0) {
+              if (GEO == GEO_DOWN) {
+                const int img = goff[j] >> 14, iy = 2 * ((goff[j] >> 7) & 127) - 1 + sy, ix = 2 * (goff[j] & 127) - 1 + sx;
+                if (iy >= 0 && iy < p.H && ix >= 0 && ix < p.W) sp = src + ((long)img * p.HW + iy * p.W + ix) * Cs + cofs;
+              } else {
+                sp = src + (long)goff[j] * Cs + cofs;
+              }
             }
+            if (sp) cp_async16(dst, sp);
+            else asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(dst), "r"(0) : "memory");   // padding -> zeros
           }
-          if (sp) cp_async16(dst, sp);
-          else asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(dst), "r"(0) : "memory");   // padding -> zeros
+        } else {
+          // straight-line issue: one predicated LDGSTS per item; padding positions copy 0 bytes and zero-fill the 16 (src-size
+          // operand), items outside the window are predicated off.  32-bit byte offsets (the host checks the tensor is < 4 GB)
+          const uint8_t* sbase = reinterpret_cast<const uint8_t*>(src + cofs);
+          const uint32_t row_bytes = (uint32_t)Cs * 2u;
+#pragma unroll
+          for (int j = 0; j < kMaxItems; ++j) {
+            const bool ok = goff[j] >= 0;
+            const uint8_t* sp = sbase + (size_t)((uint32_t)(ok ? goff[j] : 0) * row_bytes);
+            cp_async16_zfill_pred(dst0 + (uint32_t)((kProdThreads / 4) * j) * 16u, sp, ok ? 16u : 0u, !DMN_EXP_NO_LOAD && goff[j] >= -1);
+          }
         }
         cp_async_commit();
         if (++ibuf == kABuf) { ibuf = 0; iph ^= 1; }
         if (++inflight > kDepth) {
+          w0 = ptracing ? clock64() : 0;
           cp_async_wait<kDepth>();
+          if (ptracing) wait_g += clock64() - w0;
           finish(c - kDepth);
           --inflight;
         }
       }
+      if (ptracing) { p.trace[16 * pit + 14] = wait_e; p.trace[16 * pit + 15] = wait_g; }
       // drain: the last passes of the tile
       if (kDepth >= 2 && inflight == 2) {
         cp_async_wait<1>();
@@ -692,9 +810,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tcgen05_kernel(const Params 
             unpack2(v2[q * 4 + 1], a0, a1); o.y = pack_bf16x2(a0, a1);
             unpack2(v2[q * 4 + 2], a0, a1); o.z = pack_bf16x2(a0, a1);
             unpack2(v2[q * 4 + 3], a0, a1); o.w = pack_bf16x2(a0, a1);
-            sts128(my_wr + (uint32_t)(((pc * 2 + q) ^ my_swz) << 4), o);
+            if (!DMN_EXP_NO_EPI) sts128(my_wr + (uint32_t)(((pc * 2 + q) ^ my_swz) << 4), o);
+            else if (o.x == 0x12345678u && o.w == 0x9abcdef0u) sts128(my_wr, o);     // keep the values alive
           }
-          if (do_stats) {
+          if (do_stats && !DMN_EXP_NO_EPI) {
             // (sum, sum of squares) of this row's 16 columns: two independent packed chains each
             unsigned long long s0 = 0ull, q0 = 0ull, s1 = 0ull, q1 = 0ull;
             if (valid) {
@@ -729,6 +848,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tcgen05_kernel(const Params 
         // the warp's 32 x NCOL block is staged: coalesced 16-byte stores, LPR consecutive lanes cover one output row.  Batches
         // of 4 store instructions: all row lookups (SHFL) and staging reads (LDS) first, then the predicated stores
         __syncwarp();
+        if (DMN_EXP_NO_EPI) continue;
 #pragma unroll
         for (int i0 = 0; i0 < 32; i0 += 4 * RPI) {
           int ropix[4];
@@ -761,8 +881,12 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tcgen05_kernel(const Params 
       for (int s = 0; s < per_tile; ++s) {
         mbar_wait_relaxed(smem_u32(&empty_b[st]), ph);
         if (leader) {
-          mbar_arrive_expect_tx(smem_u32(&full_b[st]), b_bytes);
-          bulk_g2s(smem_u32(sB + st * b_bytes), wsrc + (size_t)s * b_bytes, b_bytes, smem_u32(&full_b[st]));
+          if (DMN_EXP_NO_WEIGHTS) {
+            mbar_arrive(smem_u32(&full_b[st]));
+          } else {
+            mbar_arrive_expect_tx(smem_u32(&full_b[st]), b_bytes);
+            bulk_g2s(smem_u32(sB + st * b_bytes), wsrc + (size_t)s * b_bytes, b_bytes, smem_u32(&full_b[st]));
+          }
         }
         __syncwarp();
         if (++st == nst) { st = 0; ph ^= 1; }
@@ -785,25 +909,54 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tcgen05_kernel(const Params 
     const int G = p.G;
     int st = 0, cbuf = 0, it = 0;
     uint32_t ph = 0, cph = 0;
+    // lean, fully unrolled issue paths: 3x3 (9 taps in stages of 3) and the 2x2 forms (4 taps in stages of 2)
+    // measured rule: with fewer than DMN_EXP_LEAN_MIN_PASS passes per tile the tile is epilogue-bound and the faster main loop
+    // only adds contention (level-0 convs 0.078 -> 0.084 ms), so those keep the looped path
+    const bool lean9 = !DMN_EXP_NO_LEAN && GEO == GEO_SAME && p.ntap == 9 && G == 3 && p.n_pass >= DMN_EXP_LEAN_MIN_PASS;
+    const bool lean4 = !DMN_EXP_NO_LEAN && (GEO == GEO_DOWN || GEO == GEO_UP) && p.ntap == 4 && G == 2 && p.n_pass >= DMN_EXP_LEAN_MIN_PASS;
+    const uint32_t b_lo0 = b_units0 | lbo_b_f;
+    int dl9[9];
+#pragma unroll
+    for (int t = 0; t < 9; ++t) dl9[t] = GEO == GEO_SAME ? p.delta[t] : 0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
       const TileGeom tg = tile_geom(tile, p);
       const int n_tile = tg.n_tile;
       const bool two = tg.mt == 2;
       const int phase = (GEO == GEO_UP) ? n_tile / p.tiles_per_phase : 0;
       const int as = it & 1;
-      mbar_wait(smem_u32(&acc_empty[as]), ((it >> 1) & 1) ^ 1);      // epilogue has drained this accumulator set
+      if (DMN_EXP_ACC_RELAXED) mbar_wait_relaxed(smem_u32(&acc_empty[as]), ((it >> 1) & 1) ^ 1);
+      else mbar_wait(smem_u32(&acc_empty[as]), ((it >> 1) & 1) ^ 1);      // epilogue has drained this accumulator set
       tc_fence_after();
       if (leader) TRACE(it, 4);
       const uint32_t d0 = tmem_base + (uint32_t)(as * 2 * NT), d1 = d0 + (uint32_t)NT;
+      const bool tracing = DMN_EXP_MMATRACE && p.trace && blockIdx.x == (unsigned)p.trace_cta && it < 60;
+      long long wait_a = 0, wait_b = 0;
       for (int c = 0; c < p.n_pass; ++c) {
+        long long w0 = tracing ? clock64() : 0;
         mbar_wait(smem_u32(&full_a[cbuf]), cph);
-        tc_fence_after();
+        if (tracing) wait_a += clock64() - w0;
+        if (!DMN_EXP_NO_FENCE) tc_fence_after();
         if (c == 0 && leader) TRACE(it, 5);
         const uint32_t au = a_units0 + (uint32_t)cbuf * a_buf_units;
+        if (lean9 || lean4) {
+          const uint32_t au_lo = au | lbo_a_f, acc0 = c ? 1u : 0u;
+          if (lean9) {
+            if (two) issue_pass<9, 3, true>(leader, d0, d1, au_lo, dl9, b_lo0, b_stage_units, b_tap_units, hi_a, hi_b, a_k16, b_k16, idesc, acc0, full_b, empty_b, nst, st, ph);
+            else issue_pass<9, 3, false>(leader, d0, d1, au_lo, dl9, b_lo0, b_stage_units, b_tap_units, hi_a, hi_b, a_k16, b_k16, idesc, acc0, full_b, empty_b, nst, st, ph);
+          } else {
+            int dl4[4];
+#pragma unroll
+            for (int t = 0; t < 4; ++t) dl4[t] = p.delta[phase * 16 + t];
+            if (two) issue_pass<4, 2, true>(leader, d0, d1, au_lo, dl4, b_lo0, b_stage_units, b_tap_units, hi_a, hi_b, a_k16, b_k16, idesc, acc0, full_b, empty_b, nst, st, ph);
+            else issue_pass<4, 2, false>(leader, d0, d1, au_lo, dl4, b_lo0, b_stage_units, b_tap_units, hi_a, hi_b, a_k16, b_k16, idesc, acc0, full_b, empty_b, nst, st, ph);
+          }
+        } else
         for (int s = 0; s < p.stages_per_pass; ++s) {
           const int t0 = s * G;
+          w0 = tracing ? clock64() : 0;
           mbar_wait(smem_u32(&full_b[st]), ph);
-          tc_fence_after();
+          if (tracing) wait_b += clock64() - w0;
+          if (!DMN_EXP_NO_FENCE) tc_fence_after();
           const uint32_t bs = b_units0 + (uint32_t)st * b_stage_units;
           const uint32_t acc0 = c ? 1u : 0u;
           if (two) {
@@ -843,6 +996,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tcgen05_kernel(const Params 
       if (leader) {
         umma_commit(smem_u32(&acc_full[as]));        // accumulators of this tile complete -> epilogue
         TRACE(it, 6);
+        if (tracing) { p.trace[16 * it + 12] = wait_a; p.trace[16 * it + 13] = wait_b; }
       }
       __syncwarp();
     }
@@ -942,6 +1096,7 @@ static bool fill_params(const ConvP& c, int geo, Params& p) {
   }
   p.total_flat = (long)c.B * p.S;
   if (p.total_flat + 4096 >= (1L << 30) || (long)c.B * 4 * p.HW >= (1L << 30)) return false;   // 32-bit index arithmetic
+  if (geo != GEO_INIT && (long)c.B * p.HW * (c.C1 > c.C2 ? c.C1 : c.C2) * 2 >= (1L << 32)) return false;   // 32-bit operand byte offsets
   {
     // two accumulators (256 rows) per tile halve the weight traffic per FLOP; with few tiles one accumulator keeps more SMs busy
     const long tiles2 = (p.total_flat + 255) / 256 * p.n_tiles_n;

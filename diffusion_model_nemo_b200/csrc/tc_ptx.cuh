@@ -123,6 +123,13 @@ __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
 __device__ __forceinline__ void cp_async16_zfill(uint32_t dst, const void* src, uint32_t bytes) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(bytes) : "memory");
 }
+// predicated zero-fill copy: nothing happens when `pred` is false (no branch: the predicate guards the single instruction)
+__device__ __forceinline__ void cp_async16_zfill_pred(uint32_t dst, const void* src, uint32_t bytes, bool pred) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %3, 0;\n\t@p cp.async.cg.shared.global [%0], [%1], 16, %2;\n\t}" ::"r"(dst),
+      "l"(src), "r"(bytes), "r"((uint32_t)pred)
+      : "memory");
+}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() {

@@ -2,7 +2,7 @@
 //   nacc      accumulators the issuer alternates between (dependent-accumulate chains)
 //   N         MMA N (128 / 256), M = 128, K = 16 (bf16)
 //   commit    tcgen05.commit every `commit` MMAs (0 = only at the end)
-//   twait     one mbarrier.try_wait (already complete) every `twait` MMAs (0 = none)
+//   twait     1: one mbarrier.try_wait (already complete) + tcgen05.fence::after_thread_sync per tap; 2: the wait without the fence
 //   stw       8 disturber warps stream st.shared.v4 (stw stores per thread per loop iteration; 0 = idle)
 //   bulk      a loader thread keeps `bulk` 4 KB cp.async.bulk global->shared copies in flight (0 = none)
 // nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o tools/mma_rate2 tools/mma_rate2.cu
@@ -76,8 +76,14 @@ __global__ void __launch_bounds__(384, 1) k(Cfg c, const uint8_t* gsrc, long lon
     const uint32_t k16A = 2 * (lboA >> 4), k16B = 2 * (lboB >> 4);
     const int ntap = c.nmma / (2 * c.nacc);
     uint32_t st = 0;
+    bool pre_ok = false;
+    if (c.twait == 3) pre_ok = try_wait(smem_u32(&bar_free), 1);
     for (int t = 0; t < ntap; ++t) {
-      if (c.twait) { while (!try_wait(smem_u32(&bar_free), 1)) {} asm volatile("tcgen05.fence::after_thread_sync;"); }
+      if (c.twait == 3) {
+        // software-pipelined wait: the barrier of tap t was probed BEFORE the MMAs of tap t-1 were issued
+        if (!pre_ok) while (!try_wait(smem_u32(&bar_free), 1)) {}
+        pre_ok = try_wait(smem_u32(&bar_free), 1);      // probe for tap t+1; consumed one iteration later
+      } else if (c.twait) { while (!try_wait(smem_u32(&bar_free), 1)) {} if (c.twait == 1) asm volatile("tcgen05.fence::after_thread_sync;"); }
       const uint32_t loA = loA0 + (uint32_t)((t * 35) & 63);
       const uint32_t loB = loB0 + st * 512u;
       const uint32_t acc = t ? 1u : 0u;
@@ -150,7 +156,7 @@ int main() {
   cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 192 * 1024);
   const int nm = 1024;
   const Cfg cfgs[] = {
-      {2, 128, 0, 0, 0, 0, nm}, {2, 128, 1, 0, 0, 0, nm}, {2, 128, 1, 1, 0, 0, nm}, {1, 256, 0, 0, 0, 0, nm}, {1, 256, 1, 1, 0, 0, nm},
+      {2, 128, 0, 0, 0, 0, nm}, {2, 128, 1, 0, 0, 0, nm}, {2, 128, 1, 1, 0, 0, nm}, {2, 128, 1, 2, 0, 0, nm}, {2, 128, 1, 2, 16, 8, nm}, {2, 128, 1, 3, 0, 0, nm}, {2, 128, 1, 3, 16, 8, nm}, {1, 256, 1, 3, 16, 8, nm}, {1, 128, 1, 1, 0, 0, nm}, {1, 128, 1, 3, 0, 0, nm}, {1, 256, 0, 0, 0, 0, nm}, {1, 256, 1, 1, 0, 0, nm},
       {2, 256, 1, 1, 0, 0, nm}, {2, 128, 1, 1, 4, 0, nm}, {2, 128, 1, 1, 16, 0, nm}, {2, 128, 1, 1, 0, 8, nm}, {2, 128, 1, 1, 16, 8, nm},
       {1, 256, 1, 1, 4, 0, nm}, {1, 256, 1, 1, 16, 0, nm}, {1, 256, 1, 1, 16, 8, nm}, {2, 256, 1, 1, 16, 8, nm},
   };

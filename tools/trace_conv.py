@@ -32,24 +32,36 @@ def run(k, cin, cout, h, b, gn, mode=0):
     buf = (C.c_longlong * 1024)()
     lib.dmn_debug_conv_trace(buf, 1024)
     t = list(buf)
-    t0 = min(v for v in t if v)
+    t0 = min(v for v in t if v > 10 ** 7)
     rel = lambda v: (v - t0) if v else None
+    per = [(t[16 * i + 6] - t[16 * i + 5]) for i in range(1, 10) if t[16 * i + 6] and t[16 * i + 16 + 6]]
+    if per:
+        print(f"   MMA main loop per tile (steady state): {sum(per) / len(per):.0f} clk")
     print(f"== k{k} mode{mode} {cin}->{cout} @{h}x{h} B={b} gn={gn}")
     for it in range(10):
         row = t[16 * it:16 * it + 16]
         if not any(row):
             break
         print(f"   tile {it}: prod start {rel(row[0])} tables {rel(row[1])} filled {rel(row[2])} | mma acc {rel(row[4])} firstA {rel(row[5])} "
-              f"issued {rel(row[6])} (waitA {row[12]} waitB {row[13]}) | epi tables {rel(row[8])} ready {rel(row[9])} drained {rel(row[10])} done {rel(row[11])}")
+              f"issued {rel(row[6])} (waitA {row[12]} waitB {row[13]}; prod waitEmpty {row[14]} waitCp {row[15]}) | epi tables {rel(row[8])} ready {rel(row[9])} drained {rel(row[10])} done {rel(row[11])}")
     pcs = t[800:800 + 96]
     if any(pcs):
         print("   epilogue pieces of tile 2 (warp 8): (wait, work) clk:", " ".join(
             f"({pcs[3*k+1]-pcs[3*k]},{pcs[3*k+2]-pcs[3*k+1]})" for k in range(32) if pcs[3 * k]))
 
 
+if __name__ == "__main__" and os.environ.get("TRACE_QUICK"):
+    run(3, 128, 128, 32, 256, False)
+    run(3, 256, 256, 16, 256, False)
+    run(3, 128, 128, 32, 256, True)
+    sys.exit(0)
 if __name__ == "__main__":
     run(3, 128, 128, 32, 256, False)
+    run(3, 128, 128, 32, 256, True)
+    run(3, 256, 256, 16, 256, False)
     run(3, 256, 256, 16, 256, True)
     run(1, 128, 384, 32, 256, False)
+    run(3, 256, 256, 4, 256, False)
     run(3, 256, 256, 4, 256, True)
+    run(3, 256, 256, 8, 256, False)
     run(3, 256, 256, 8, 256, True)
