@@ -342,7 +342,8 @@ __device__ __forceinline__ void issue_pass(bool leader, uint32_t d0, uint32_t d1
 // swizzle, store pattern) folds to constants and its loops unroll
 // FILM selects the FiLM signal prologue (LeakyReLU(0.2) + positional encoding, no GroupNorm; parts/film.py:22,58) at compile time so
 // that the GroupNorm + SiLU prologue of the ResnetBlocks keeps its code unchanged
-template <int GEO, int NT, bool FILM = false>
+// LEAN selects the unrolled MMA issue path (a separate instantiation, so that the looped path keeps its own code generation)
+template <int GEO, int NT, bool FILM = false, bool LEAN = false>
 __global__ void __launch_bounds__(kThreads, 1) conv_tcgen05_kernel(const Params p) {
   extern __shared__ __align__(128) uint8_t smem[];
   const int tid = threadIdx.x;
@@ -584,7 +585,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tcgen05_kernel(const Params 
         if (cb < p.c.C1) { src = src1; Cs = p.c.C1; cofs = cb; }
         else { src = src2; Cs = p.c.C2; cofs = cb - p.c.C1; }
         const uint32_t dst0 = sA_u + ibuf * a_bytes + (uint32_t)kc * p.lbo_a + (uint32_t)px0 * 16u;
-        if (GEO == GEO_DOWN || !DMN_EXP_ZFILL) {
+        // measured: the predicated zero-fill form wins when the fused prologue follows (-0.003 ms on the level-0 GroupNorm convs)
+        // and loses for plain copies (+0.004 ms), so plain operands keep the branchy issue
+        if (GEO == GEO_DOWN || !DMN_EXP_ZFILL || !has_pro) {
 #pragma unroll
           for (int j = 0; j < kMaxItems; ++j) {
             if (goff[j] < -1) continue;                  // outside the window
@@ -910,14 +913,12 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tcgen05_kernel(const Params 
     int st = 0, cbuf = 0, it = 0;
     uint32_t ph = 0, cph = 0;
     // lean, fully unrolled issue paths: 3x3 (9 taps in stages of 3) and the 2x2 forms (4 taps in stages of 2)
-    // measured rule: with fewer than DMN_EXP_LEAN_MIN_PASS passes per tile the tile is epilogue-bound and the faster main loop
-    // only adds contention (level-0 convs 0.078 -> 0.084 ms), so those keep the looped path
-    const bool lean9 = !DMN_EXP_NO_LEAN && GEO == GEO_SAME && p.ntap == 9 && G == 3 && p.n_pass >= DMN_EXP_LEAN_MIN_PASS;
-    const bool lean4 = !DMN_EXP_NO_LEAN && (GEO == GEO_DOWN || GEO == GEO_UP) && p.ntap == 4 && G == 2 && p.n_pass >= DMN_EXP_LEAN_MIN_PASS;
+    constexpr bool lean9 = LEAN && GEO == GEO_SAME;                     // the host launches LEAN only for 9 taps in stages of 3 ...
+    constexpr bool lean4 = LEAN && (GEO == GEO_DOWN || GEO == GEO_UP);  // ... or 4 taps in stages of 2 (lean_ok below)
     const uint32_t b_lo0 = b_units0 | lbo_b_f;
     int dl9[9];
 #pragma unroll
-    for (int t = 0; t < 9; ++t) dl9[t] = GEO == GEO_SAME ? p.delta[t] : 0;
+    for (int t = 0; t < 9; ++t) dl9[t] = lean9 ? p.delta[t] : 0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
       const TileGeom tg = tile_geom(tile, p);
       const int n_tile = tg.n_tile;
@@ -938,9 +939,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tcgen05_kernel(const Params 
         if (!DMN_EXP_NO_FENCE) tc_fence_after();
         if (c == 0 && leader) TRACE(it, 5);
         const uint32_t au = a_units0 + (uint32_t)cbuf * a_buf_units;
-        if (lean9 || lean4) {
+        if constexpr (lean9 || lean4) {
           const uint32_t au_lo = au | lbo_a_f, acc0 = c ? 1u : 0u;
-          if (lean9) {
+          if constexpr (lean9) {
             if (two) issue_pass<9, 3, true>(leader, d0, d1, au_lo, dl9, b_lo0, b_stage_units, b_tap_units, hi_a, hi_b, a_k16, b_k16, idesc, acc0, full_b, empty_b, nst, st, ph);
             else issue_pass<9, 3, false>(leader, d0, d1, au_lo, dl9, b_lo0, b_stage_units, b_tap_units, hi_a, hi_b, a_k16, b_k16, idesc, acc0, full_b, empty_b, nst, st, ph);
           } else {
@@ -1203,6 +1204,22 @@ static int launch(Params p, cudaStream_t st) {
     attr_set = true;
   }
   const int grid = p.total_tiles < num_sms() ? p.total_tiles : num_sms();
+  // measured rule for the lean issue path: with fewer than DMN_EXP_LEAN_MIN_PASS passes per tile the tile is epilogue-bound and the
+  // faster main loop only adds contention (level-0 convs 0.078 -> 0.084 ms), so those keep the looped path
+  const bool lean_ok = !DMN_EXP_NO_LEAN && p.NT == 128 && !(p.c.pro & PRO_LRELU) && p.n_pass >= DMN_EXP_LEAN_MIN_PASS &&
+                       ((GEO == GEO_SAME && p.ntap == 9 && p.G == 3) || ((GEO == GEO_DOWN || GEO == GEO_UP) && p.ntap == 4 && p.G == 2));
+  if (GEO != GEO_INIT && lean_ok) {
+    constexpr int G2 = GEO == GEO_INIT ? GEO_SAME : GEO;
+    static bool lean_attr = false;
+    if (!lean_attr) {
+      DMN_CUDA_CHECK(cudaFuncSetAttribute(conv_tcgen05_kernel<G2, 128, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemLimit));
+      lean_attr = true;
+    }
+    DMN_CUDA_CHECK(launch_pdl(conv_tcgen05_kernel<G2, 128, false, true>, dim3(grid), dim3(kThreads), smem_bytes(p), st, p));
+    count_launch();
+    DMN_LAUNCH_CHECK("conv_tcgen05");
+    return 0;
+  }
   if (GEO == GEO_SAME && (p.c.pro & PRO_LRELU)) {
     if (p.NT == 128) DMN_CUDA_CHECK(launch_pdl(conv_tcgen05_kernel<GEO_SAME, 128, true>, dim3(grid), dim3(kThreads), smem_bytes(p), st, p));
     else if (p.NT == 64) DMN_CUDA_CHECK(launch_pdl(conv_tcgen05_kernel<GEO_SAME, 64, true>, dim3(grid), dim3(kThreads), smem_bytes(p), st, p));
