@@ -22,6 +22,31 @@ def needs_rebuild() -> bool:
     return any(os.path.getmtime(d) > t for d in deps if os.path.exists(d))
 
 
+def build_variant(path: str, extra_flags) -> str:
+    """Build a differently-configured copy of the library (e.g. -DDMN_TC_TRACE_BUILD=1 for tools/trace_conv.py, the DMN_EXP_*
+    experiment switches) at `path`; select it with DMN_LIB_PATH.  Objects go to a scratch directory, the in-tree build is untouched."""
+    import tempfile
+
+    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+    with tempfile.TemporaryDirectory() as tmp:
+        procs, objs = [], []
+        for src in SOURCES:
+            obj = os.path.join(tmp, src.replace(".cu", ".o"))
+            objs.append(obj)
+            cmd = [nvcc, *[f for f in NVCC_FLAGS if f not in ("-Xptxas", "-v")], *extra_flags, "-c", os.path.join(CSRC, src), "-o", obj]
+            procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+        for src, p in procs:
+            out, _ = p.communicate()
+            if p.returncode != 0:
+                sys.stderr.write(out)
+                raise RuntimeError(f"nvcc failed on {src}")
+        out = subprocess.run([nvcc, "-shared", "-o", path, *objs, "-lcudart"], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+        if out.returncode != 0:
+            sys.stderr.write(out.stdout)
+            raise RuntimeError("link failed")
+    return path
+
+
 def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not needs_rebuild():
         return LIB
@@ -53,4 +78,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    if "--variant" in sys.argv:       # python -m diffusion_model_nemo_b200._build --variant tools/libdmn_x.so -DDMN_EXP_NO_LEAN=1 ...
+        i = sys.argv.index("--variant")
+        print(build_variant(sys.argv[i + 1], sys.argv[i + 2:]))
+    else:
+        print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

@@ -36,6 +36,7 @@
 // work for 3x3: 6 % at 32x32, 11 % at 16x16, 21 % at 8x8, 36 % at 4x4).
 #include <cstdlib>
 #include <cstring>
+#include <type_traits>
 #include <vector>
 
 #include "common.cuh"
@@ -116,9 +117,9 @@ constexpr bool kTraceProducer = DMN_TC_TRACE_PRODUCER != 0;
 #define DMN_EXP_ACC_RELAXED 0       // 1: the MMA issuer backs off while it waits for the epilogue to drain an accumulator set
 #endif
 #ifndef DMN_EXP_BRANCHY_PRO
-#define DMN_EXP_BRANCHY_PRO 1       // 1: skip padding / out-of-window items of the prologue transform with a branch per item
-                                    // (0 = branch-free with a predicated store: measured 3 % slower on the whole step, the 7 item slots
-                                    //  of a thread are then always transformed although only ~5 are inside the window)
+#define DMN_EXP_BRANCHY_PRO 1       // 0: the in-window item slots of the prologue transform without per-item branches (interleaved chains);
+                                    // measured SLOWER on every conv of the step, including those without a prologue (+0.002..0.004 ms each):
+                                    // the three extra unrolled copies grow the kernel, and the engine is sensitive to code size
 #endif
 #ifndef DMN_EXP_NO_EPI
 #define DMN_EXP_NO_EPI 0            // epilogue: TMEM reads only (no staging, no global stores, no statistics)
@@ -129,9 +130,12 @@ constexpr bool kTraceProducer = DMN_TC_TRACE_PRODUCER != 0;
 #ifndef DMN_EXP_NO_WEIGHTS
 #define DMN_EXP_NO_WEIGHTS 0        // weight loader: barrier arrivals without the bulk copies
 #endif
-#define TRACE(it, k)                                                                                       \
-  do {                                                                                                     \
-    if (p.trace && blockIdx.x == (unsigned)p.trace_cta && (it) < 60) p.trace[16 * (it) + (k)] = clock64(); \
+#ifndef DMN_TC_TRACE_BUILD
+#define DMN_TC_TRACE_BUILD 0        // 1: compile the role timeline in (tools/trace_conv.py builds such a library); costs 1.5 % of the step
+#endif
+#define TRACE(it, k)                                                                                                             \
+  do {                                                                                                                           \
+    if (DMN_TC_TRACE_BUILD && p.trace && blockIdx.x == (unsigned)p.trace_cta && (it) < 60) p.trace[16 * (it) + (k)] = clock64(); \
   } while (0)
 
 // flat virtual position -> (image, virtual row, virtual col); img < 0 when out of range.  32-bit arithmetic only
@@ -348,7 +352,9 @@ __device__ __forceinline__ void issue_pass(bool leader, uint32_t d0, uint32_t d1
 // FILM selects the FiLM signal prologue (LeakyReLU(0.2) + positional encoding, no GroupNorm; parts/film.py:22,58) at compile time so
 // that the GroupNorm + SiLU prologue of the ResnetBlocks keeps its code unchanged
 // LEAN selects the unrolled MMA issue path (a separate instantiation, so that the looped path keeps its own code generation)
-template <int GEO, int NT, bool FILM = false, bool LEAN = false>
+// EXTRA keeps the rarely used epilogue terms (residual add, folded-GroupNorm affine); the hot instantiations drop them: the engine is
+// measurably sensitive to the size of the code in its inner loops (compiling the debug timeline out alone gave +1.5 %)
+template <int GEO, int NT, bool FILM = false, bool LEAN = false, bool EXTRA = true>
 __global__ void __launch_bounds__(kThreads, 1) conv_tcgen05_kernel(const Params p) {
   extern __shared__ __align__(128) uint8_t smem[];
   const int tid = threadIdx.x;
@@ -486,6 +492,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tcgen05_kernel(const Params 
       }
       bar_sync_named(2, kProdThreads);
       if (tid == 0) TRACE(pit, 1);
+      const int nfull = Pt / (kProdThreads / 4);      // item slots that are inside the window for EVERY thread (uniform)
       int goff[kMaxItems];      // SAME/UP: img*HW + pix (or -1 = padding); DOWN: packed (img, u, v) (or -1); -2 = outside the window
       int imgl[kMaxItems];
 #pragma unroll
@@ -523,10 +530,12 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tcgen05_kernel(const Params 
             beh2[e] = pack2(0.5f * be[2 * e], 0.5f * be[2 * e + 1]);
             te2[e] = pack2(te[2 * e], te[2 * e + 1]);
           }
-#pragma unroll
-          for (int j = 0; j < kMaxItems; ++j) {
-            // padding stays zero AFTER the transform, items outside the window are never written
-            if (DMN_EXP_BRANCHY_PRO && goff[j] < 0) continue;
+          // one item = one independent chain (LDS -> FFMA2 -> MUFU -> FFMA2 -> STS).  The first `nfull` item slots of a thread are
+          // always inside the window, so they are transformed WITHOUT a per-item branch (one basic block: the scheduler interleaves
+          // their chains; only the store is predicated, padding stays zero AFTER the transform); the tail slots keep the branch so
+          // that slots outside the window cost nothing
+          auto do_item = [&](int j, bool check) {
+            if (check && goff[j] < 0) return;
             uint4* slot = reinterpret_cast<uint4*>(base + (px0 + (kProdThreads / 4) * j) * 16);
             const float2 mr = FILM ? make_float2(0.f, 1.f) : s_gn[imgl[j] * kGroupsMax + g];
             if ((p.c.pro & PRO_TEMB) && !temb_shared) {
@@ -564,6 +573,18 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tcgen05_kernel(const Params 
               }
             }
             if (goff[j] >= 0) *slot = pack8(v);
+          };
+          auto run = [&](auto nf_tag) {
+            constexpr int NF = decltype(nf_tag)::value;
+#pragma unroll
+            for (int j = 0; j < kMaxItems; ++j) do_item(j, j >= NF);
+          };
+          switch (DMN_EXP_BRANCHY_PRO ? 0 : nfull) {
+            // the window sizes of the U-Net's 3x3 convs: 256-row tiles at 32x32 (5 full slots), at 16x16 / 8x8 (4), 128-row tiles (2)
+            case 7: case 6: case 5: run(std::integral_constant<int, 5>()); break;
+            case 4: run(std::integral_constant<int, 4>()); break;
+            case 3: case 2: run(std::integral_constant<int, 2>()); break;
+            default: run(std::integral_constant<int, 0>()); break;
           }
         }
         fence_proxy_async();
@@ -656,7 +677,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tcgen05_kernel(const Params 
     const int ew = warp - kProdWarps;                 // 0..7
     const int quarter = ew & 3, part = ew >> 2;       // TMEM lane quarter, column half of the tile
     bf16* out = (bf16*)p.c.out;
-    const bf16* res = (const bf16*)p.c.res;
+    constexpr bool kExtra = EXTRA && GEO == GEO_SAME;      // fill_params rejects residual / fold for the other geometries
+    const bf16* res = kExtra ? (const bf16*)p.c.res : nullptr;
     // columns owned by this warp: half of the tile; with NT = 32 only the first warp of each lane quarter works
     constexpr int NCOL = NT >= 64 ? NT / 2 : NT;      // 64 | 32 | 32
     constexpr int PPM = NCOL / 16;                    // 16-column pieces per 128-row accumulator (even)
@@ -667,7 +689,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tcgen05_kernel(const Params 
     const int sh = p.cpg_out_shift;
     const bool do_stats = p.c.ostats != nullptr;
     const bool has_bias = p.c.bias != nullptr;
-    const bool has_fold = p.c.fold_s1 != nullptr;     // GroupNorm(1) of the input folded into an epilogue affine (to_qkv)
+    const bool has_fold = kExtra && p.c.fold_s1 != nullptr;     // GroupNorm(1) of the input folded into an epilogue affine (to_qkv)
     const uint32_t my_stage = smem_u32(s_stage) + (uint32_t)(ew * (32 * ROWB + NCOL * 8));   // shared-space addresses
     const uint32_t my_bias = my_stage + (uint32_t)(32 * ROWB);
     const int my_swz = (lane >> SWS) & SWM;
@@ -1214,14 +1236,18 @@ static int launch(Params p, cudaStream_t st) {
   // faster main loop only adds contention (level-0 convs 0.078 -> 0.084 ms), so those keep the looped path
   const bool lean_ok = !DMN_EXP_NO_LEAN && p.NT == 128 && !(p.c.pro & PRO_LRELU) && p.n_pass >= DMN_EXP_LEAN_MIN_PASS &&
                        ((GEO == GEO_SAME && p.ntap == 9 && p.G == 3) || ((GEO == GEO_DOWN || GEO == GEO_UP) && p.ntap == 4 && p.G == 2));
-  if (GEO != GEO_INIT && lean_ok) {
+  const bool extra = p.c.res != nullptr || p.c.fold_s1 != nullptr;
+  if (GEO != GEO_INIT && p.NT == 128 && !(p.c.pro & PRO_LRELU) && !extra) {
+    // the hot instantiations: no residual / fold terms in the epilogue, lean or looped issue
     constexpr int G2 = GEO == GEO_INIT ? GEO_SAME : GEO;
-    static bool lean_attr = false;
-    if (!lean_attr) {
-      DMN_CUDA_CHECK(cudaFuncSetAttribute(conv_tcgen05_kernel<G2, 128, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemLimit));
-      lean_attr = true;
+    static bool hot_attr = false;
+    if (!hot_attr) {
+      DMN_CUDA_CHECK(cudaFuncSetAttribute(conv_tcgen05_kernel<G2, 128, false, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemLimit));
+      DMN_CUDA_CHECK(cudaFuncSetAttribute(conv_tcgen05_kernel<G2, 128, false, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemLimit));
+      hot_attr = true;
     }
-    DMN_CUDA_CHECK(launch_pdl(conv_tcgen05_kernel<G2, 128, false, true>, dim3(grid), dim3(kThreads), smem_bytes(p), st, p));
+    if (lean_ok) DMN_CUDA_CHECK(launch_pdl(conv_tcgen05_kernel<G2, 128, false, true, false>, dim3(grid), dim3(kThreads), smem_bytes(p), st, p));
+    else DMN_CUDA_CHECK(launch_pdl(conv_tcgen05_kernel<G2, 128, false, false, false>, dim3(grid), dim3(kThreads), smem_bytes(p), st, p));
     count_launch();
     DMN_LAUNCH_CHECK("conv_tcgen05");
     return 0;

@@ -559,6 +559,77 @@ def sample_pc(model, shape, sde: SDESpec, draw, predictor="reverse_diffusion", c
 
 
 # ----------------------------------------------------------------------------------------------
+# bits-per-dimension evaluation: models/abstract_diffusion_model.py:137-197,
+# loss/variational_bound_loss.py:31-52, utils.py:24-56
+# ----------------------------------------------------------------------------------------------
+def normal_kl(mean1, logvar1, mean2, logvar2):
+    """utils.normal_kl, utils.py:28-34."""
+    return 0.5 * (-1.0 + logvar2 - logvar1 + torch.exp(logvar1 - logvar2) + ((mean1 - mean2) ** 2) * torch.exp(-logvar2))
+
+
+def _approx_std_normal_cdf(x):
+    return 0.5 * (1.0 + torch.tanh(math.sqrt(2.0 / math.pi) * (x + 0.044715 * (x ** 3))))
+
+
+def _log(t, eps=1e-12):
+    return torch.log(t.clamp(min=eps))
+
+
+def discretized_gaussian_log_likelihood(x, means, log_scales, thres=0.999):
+    """utils.discretized_gaussian_log_likelihood, utils.py:41-56."""
+    centered = x - means
+    inv_stdv = torch.exp(-log_scales)
+    cdf_plus = _approx_std_normal_cdf(inv_stdv * (centered + 1.0 / 255.0))
+    cdf_min = _approx_std_normal_cdf(inv_stdv * (centered - 1.0 / 255.0))
+    return torch.where(x < -thres, _log(cdf_plus), torch.where(x > thres, _log(1.0 - cdf_min), _log(cdf_plus - cdf_min)))
+
+
+def _mean_flat(x):
+    return x.mean(dim=tuple(range(1, x.dim())))
+
+
+def bits_per_dimension(model, x_start: Tensor, tb: Dict[str, Tensor], draw, learned: bool = False, objective: str = "pred_noise"):
+    """AbstractDiffusionModel.calculate_bits_per_dimension, models/abstract_diffusion_model.py:137-197, with the sampler's
+    q_sample / q_posterior / p_mean_variance restated inline.  draw(shape) supplies the q_sample noise of every timestep
+    (one draw per step, t = T-1 .. 0).  Returns {'total_bpd' [B], 'terms_bpd' [B,T], 'prior_bpd' [B]}."""
+    T = tb["betas"].shape[0]
+    b = x_start.shape[0]
+    terms = torch.zeros(b, T)
+    ln2 = math.log(2.0)
+    for ti in range(T - 1, -1, -1):
+        t = torch.full((b,), ti, dtype=torch.long)
+        z = draw(tuple(x_start.shape))
+        x_t = _ext(tb["sqrt_alphas_cumprod"], t) * x_start + _ext(tb["sqrt_one_minus_alphas_cumprod"], t) * z
+        c1, c2 = _ext(tb["posterior_mean_coef1"], t), _ext(tb["posterior_mean_coef2"], t)
+        true_mean = c1 * x_start + c2 * x_t
+        true_logvar = _ext(tb["posterior_log_variance_clipped"], t)
+        out = model(x_t, t)
+        if learned:
+            out, v = out.chunk(2, dim=1)
+            frac = (v + 1) * 0.5
+            model_logvar = frac * _ext(torch.log(tb["betas"]), t) + (1 - frac) * true_logvar
+        else:
+            model_logvar = true_logvar
+        if objective == "pred_noise":
+            x0 = _ext(tb["sqrt_recip_alphas_cumprod"], t) * x_t - _ext(tb["sqrt_recipm1_alphas_cumprod"], t) * out
+        else:
+            x0 = out
+        x0 = x0.clamp(-1.0, 1.0)
+        model_mean = c1 * x0 + c2 * x_t
+        if model_logvar.shape != model_mean.shape:
+            model_logvar = model_logvar.expand(-1, *model_mean.shape[1:])
+        kl = _mean_flat(normal_kl(true_mean, true_logvar, model_mean, model_logvar)) * (1.0 / ln2)
+        nll = _mean_flat(-discretized_gaussian_log_likelihood(x_start, model_mean, 0.5 * model_logvar)) * (1.0 / ln2)
+        terms[:, ti] = torch.where(t == 0, nll, kl)
+    t_prior = torch.full((b,), T - 1, dtype=torch.long)
+    qt_mean = x_start * _ext(tb["sqrt_alphas_cumprod"], t_prior)
+    qt_logvar = _ext(tb["log_one_minus_alphas_cumprod"], t_prior)
+    zero = torch.tensor(0.0)
+    prior = _mean_flat(normal_kl(qt_mean, qt_logvar, zero, zero)) / ln2
+    return {"total_bpd": terms.sum(dim=1) + prior, "terms_bpd": terms, "prior_bpd": prior}
+
+
+# ----------------------------------------------------------------------------------------------
 # helpers shared by tests / bench
 # ----------------------------------------------------------------------------------------------
 

@@ -8,6 +8,13 @@ import sys
 os.environ["DMN_TC_TRACE"] = "1"
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
+# the production library compiles the timeline out (it costs 1.5 % of the step): use / build the trace variant
+if "DMN_LIB_PATH" not in os.environ:
+    _trace_lib = os.path.join(ROOT, "tools", "libdmn_trace.so")
+    if not os.path.exists(_trace_lib):
+        from diffusion_model_nemo_b200 import _build
+        _build.build_variant(_trace_lib, ["-DDMN_TC_TRACE_BUILD=1", "-DDMN_EXP_MMATRACE=1"])
+    os.environ["DMN_LIB_PATH"] = _trace_lib
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 import torch
 from diffusion_model_nemo_b200 import _lib as L
