@@ -354,7 +354,8 @@ __device__ __forceinline__ void issue_pass(bool leader, uint32_t d0, uint32_t d1
 // LEAN selects the unrolled MMA issue path (a separate instantiation, so that the looped path keeps its own code generation)
 // EXTRA keeps the rarely used epilogue terms (residual add, folded-GroupNorm affine); the hot instantiations drop them: the engine is
 // measurably sensitive to the size of the code in its inner loops (compiling the debug timeline out alone gave +1.5 %)
-template <int GEO, int NT, bool FILM = false, bool LEAN = false, bool EXTRA = true>
+// PRO: 0 = no fused prologue compiled in, 1 = the prologue is always on (GroupNorm convs), 2 = decided at run time (generic instantiations)
+template <int GEO, int NT, bool FILM = false, bool LEAN = false, bool EXTRA = true, int PRO = 2>
 __global__ void __launch_bounds__(kThreads, 1) conv_tcgen05_kernel(const Params p) {
   extern __shared__ __align__(128) uint8_t smem[];
   const int tid = threadIdx.x;
@@ -412,7 +413,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tcgen05_kernel(const Params 
     const bf16* src2 = (const bf16*)p.c.src2;
     const float* temb_base = nullptr;
     if (GEO == GEO_SAME && (p.c.pro & PRO_TEMB)) temb_base = p.c.temb + (p.c.d_row ? (long)(*p.c.d_row) * p.c.temb_rstride : 0);
-    const bool has_pro = GEO == GEO_SAME && p.c.pro != PRO_NONE;
+    const bool has_pro = PRO == 2 ? (GEO == GEO_SAME && p.c.pro != PRO_NONE) : (PRO == 1 && GEO == GEO_SAME);
     const bool temb_shared = (p.c.pro & PRO_TEMB) && p.c.temb_bstride == 0;
     if (has_pro) {                      // visible to all producers after the first tile's table barrier
       for (int i = tid; i < ncoef; i += kProdThreads) {
@@ -687,7 +688,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tcgen05_kernel(const Params 
     const bool active = NT >= 64 || part == 0;
     const int col0 = NT >= 64 ? part * NCOL : 0;
     const int sh = p.cpg_out_shift;
-    const bool do_stats = p.c.ostats != nullptr;
+    const bool do_stats = GEO == GEO_SAME && p.c.ostats != nullptr;     // fill_params rejects output statistics for the other geometries
     const bool has_bias = p.c.bias != nullptr;
     const bool has_fold = kExtra && p.c.fold_s1 != nullptr;     // GroupNorm(1) of the input folded into an epilogue affine (to_qkv)
     const uint32_t my_stage = smem_u32(s_stage) + (uint32_t)(ew * (32 * ROWB + NCOL * 8));   // shared-space addresses
@@ -1242,12 +1243,19 @@ static int launch(Params p, cudaStream_t st) {
     constexpr int G2 = GEO == GEO_INIT ? GEO_SAME : GEO;
     static bool hot_attr = false;
     if (!hot_attr) {
-      DMN_CUDA_CHECK(cudaFuncSetAttribute(conv_tcgen05_kernel<G2, 128, false, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemLimit));
-      DMN_CUDA_CHECK(cudaFuncSetAttribute(conv_tcgen05_kernel<G2, 128, false, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemLimit));
+      DMN_CUDA_CHECK(cudaFuncSetAttribute(conv_tcgen05_kernel<G2, 128, false, true, false, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemLimit));
+      DMN_CUDA_CHECK(cudaFuncSetAttribute(conv_tcgen05_kernel<G2, 128, false, false, false, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemLimit));
+      if (G2 == GEO_SAME) {
+        DMN_CUDA_CHECK(cudaFuncSetAttribute(conv_tcgen05_kernel<GEO_SAME, 128, false, true, false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemLimit));
+        DMN_CUDA_CHECK(cudaFuncSetAttribute(conv_tcgen05_kernel<GEO_SAME, 128, false, false, false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemLimit));
+      }
       hot_attr = true;
     }
-    if (lean_ok) DMN_CUDA_CHECK(launch_pdl(conv_tcgen05_kernel<G2, 128, false, true, false>, dim3(grid), dim3(kThreads), smem_bytes(p), st, p));
-    else DMN_CUDA_CHECK(launch_pdl(conv_tcgen05_kernel<G2, 128, false, false, false>, dim3(grid), dim3(kThreads), smem_bytes(p), st, p));
+    const bool pro = G2 == GEO_SAME && p.c.pro != PRO_NONE;
+    if (pro && lean_ok) DMN_CUDA_CHECK(launch_pdl(conv_tcgen05_kernel<GEO_SAME, 128, false, true, false, 1>, dim3(grid), dim3(kThreads), smem_bytes(p), st, p));
+    else if (pro) DMN_CUDA_CHECK(launch_pdl(conv_tcgen05_kernel<GEO_SAME, 128, false, false, false, 1>, dim3(grid), dim3(kThreads), smem_bytes(p), st, p));
+    else if (lean_ok) DMN_CUDA_CHECK(launch_pdl(conv_tcgen05_kernel<G2, 128, false, true, false, 0>, dim3(grid), dim3(kThreads), smem_bytes(p), st, p));
+    else DMN_CUDA_CHECK(launch_pdl(conv_tcgen05_kernel<G2, 128, false, false, false, 0>, dim3(grid), dim3(kThreads), smem_bytes(p), st, p));
     count_launch();
     DMN_LAUNCH_CHECK("conv_tcgen05");
     return 0;
