@@ -11,7 +11,7 @@ LIB_PATH = os.environ.get("DMN_LIB_PATH") or os.path.join(_HERE, "libdmn_b200.so
 
 ACT_F32, ACT_BF16 = 0, 1
 CONV_SIMT, CONV_TCGEN05 = 0, 1
-LOOP_DDPM, LOOP_LEARNED, LOOP_DDIM, LOOP_PC = 0, 1, 2, 3
+LOOP_DDPM, LOOP_LEARNED, LOOP_DDIM, LOOP_PC, LOOP_BPD = 0, 1, 2, 3, 4
 COEF_STRIDE = 8
 
 
@@ -78,6 +78,8 @@ SYMBOLS = {
     "dmn_ddim_step": (_I, [_P, _P, _P, _P, _L, _P, _P, _I, Rng, _P]),
     "dmn_affine_noise_step": (_I, [_P, _P, _P, _P, _P, _L, _P, _P, _I, Rng, _P]),
     "dmn_langevin_step": (_I, [_P, _P, _P, _P, _P, _I, _L, _F, _P, _P, _I, _P, Rng, _P]),
+    "dmn_bpd_qsample": (_I, [_P, _P, _P, _L, _P, _P, _I, Rng, _P]),
+    "dmn_bpd_term": (_I, [_P, _P, _P, _P, _I, _L, _I, _I, _I, _P, _P, _P, _I, _P]),
     "dmn_unnormalize": (_I, [_P, _P, _L, _P]),
     "dmn_randn": (_I, [_P, _L, Rng, _I, _P]),
     "dmn_axpby": (_I, [_P, _P, _F, _F, _P, _L, _P]),

@@ -53,6 +53,10 @@ int launch_learned(const float* x, const float* mo, const float* z, float* out, 
 int launch_ddim(const float* x, const float* eps, const float* z, float* out, long n, const float* coef, const int32_t* step_dev,
                 int step, dmn_rng rng, const dmn_rng* rng_dev, cudaStream_t st);
 int launch_traj(const float* x, float* traj, long n, const int32_t* step_dev, int every, int n_steps, cudaStream_t st);
+int launch_bpd_qsample(const float* x0, const float* z, float* xt, long n, const float* coef, const int32_t* step_dev, int step, dmn_rng rng,
+                       const dmn_rng* rng_dev, cudaStream_t st);
+int launch_bpd_term(const float* x0, const float* xt, const float* mo, float* terms, int batch, long chw, int learned, int n_cols, int mode,
+                    const float* coef, const float* coef2, const int32_t* step_dev, int step, cudaStream_t st);
 int launch_cfg_dup(const float* x, float* x2, long n, cudaStream_t st);
 int launch_cfg_combine(const float* mo2, float* mo, long n, float w, cudaStream_t st);
 int launch_langevin(const float* x, const float* mo, const float* z, float* out, float* mean_out, int batch, long chw,
@@ -936,6 +940,16 @@ static int enqueue_step(dmn_plan* p, const dmn_loop_desc* d, int32_t* ctr_dev, b
   const int32_t* step_dev = use_ctr ? ctr_dev : nullptr;
   const dmn_rng* rng_dev = z0 ? nullptr : reinterpret_cast<const dmn_rng*>(ctr_dev + 4);
   int rc;
+  if (d->kind == DMN_LOOP_BPD) {
+    // bits-per-dimension term of one timestep: x_t ~ q(x_t | x_0), U-Net on x_t, fused KL / decoder-NLL reduction into terms[b][t]
+    float* xt = xmean;
+    if ((rc = launch_bpd_qsample(d->state_dev, z0, xt, n, d->coef_dev, step_dev, s, d->rng, rng_dev, st))) return rc;
+    if ((rc = run_forward(p, xt, ctr_dev, d->classes_dev, mo, d->batch, st))) return rc;
+    if ((rc = launch_bpd_term(d->state_dev, xt, mo, d->aux_dev, d->batch, chw, c.out_dim == 2 * c.channels ? 1 : 0, d->n_steps, 0,
+                              d->coef_dev, d->coef2_dev, step_dev, s, st)))
+      return rc;
+    return launch_advance_counter(ctr_dev, st);
+  }
   if (d->kind == DMN_LOOP_PC) {
     for (int k = 0; k < d->n_corr; ++k) {
       if ((rc = run_forward(p, d->state_dev, ctr_dev, d->classes_dev, mo, d->batch, st))) return rc;
@@ -981,7 +995,7 @@ static bool same_graph_key(const dmn_loop_desc& a, const dmn_loop_desc& b) {
   return a.kind == b.kind && (!traj || a.n_steps == b.n_steps) && a.batch == b.batch && a.n_corr == b.n_corr && a.snr == b.snr &&
          a.corr_kind == b.corr_kind && a.coef_dev == b.coef_dev && a.coef2_dev == b.coef2_dev && a.classes_dev == b.classes_dev &&
          a.state_dev == b.state_dev && a.scratch_dev == b.scratch_dev && a.traj_dev == b.traj_dev && a.traj_every == b.traj_every &&
-         a.cfg_scale == b.cfg_scale;
+         a.cfg_scale == b.cfg_scale && (a.kind != DMN_LOOP_BPD || (a.aux_dev == b.aux_dev && a.n_steps == b.n_steps));
 }
 
 extern "C" {
@@ -991,13 +1005,16 @@ int dmn_sample_loop(dmn_plan* p, const dmn_loop_desc* d, void* stream) {
   if (rc) return rc;
   if (!d) return fail(DMN_EINVAL, "null descriptor");
   const dmn_unet_cfg& c = p->cfg;
-  DMN_REQUIRE(d->kind >= DMN_LOOP_DDPM && d->kind <= DMN_LOOP_PC, "unknown loop kind");
+  DMN_REQUIRE(d->kind >= DMN_LOOP_DDPM && d->kind <= DMN_LOOP_BPD, "unknown loop kind");
+  DMN_REQUIRE(d->kind != DMN_LOOP_BPD || (d->aux_dev && d->coef2_dev && d->cfg_scale == 0.f && !d->traj_dev),
+              "BPD loop needs the terms buffer (aux_dev) and the second coefficient table; no guidance / trajectory");
   DMN_REQUIRE(d->batch >= 1 && d->batch <= c.max_batch, "batch exceeds the plan's max_batch");
   DMN_REQUIRE(d->n_steps >= 1 && d->n_steps <= c.max_time_rows, "n_steps exceeds the plan's time table");
   DMN_REQUIRE(d->state_dev && d->scratch_dev && d->coef_dev, "null device pointer in loop descriptor");
   DMN_REQUIRE(d->kind != DMN_LOOP_PC || d->n_corr == 0 || d->coef2_dev, "PC loop needs corrector coefficients");
   DMN_REQUIRE(d->n_corr >= 0 && d->n_corr <= 6, "n_corr out of range (0..6)");
   if (d->kind == DMN_LOOP_LEARNED) DMN_REQUIRE(c.out_dim == 2 * c.channels, "learned-variance loop needs a U-Net with 2*channels outputs");
+  else if (d->kind == DMN_LOOP_BPD) DMN_REQUIRE(c.out_dim == c.channels || c.out_dim == 2 * c.channels, "BPD: out_dim must be C or 2C");
   else DMN_REQUIRE(c.out_dim == c.channels, "U-Net out_dim must equal channels for this sampler");
   const long chw = (long)c.channels * c.image_size * c.image_size;
   const long n = (long)d->batch * chw;
@@ -1068,6 +1085,7 @@ int dmn_loop_launches_per_step(const dmn_plan* p, const dmn_loop_desc* d) {
   if (!p || !d) return 0;
   const int per_fwd = (int)p->ops.size() - 1;   // kernels only: the statistics memset is not counted
   int n = 0;
+  if (d->kind == DMN_LOOP_BPD) return per_fwd + 3;
   if (d->kind == DMN_LOOP_PC) n = (d->n_corr + 1) * per_fwd + d->n_corr * (d->corr_kind == 1 ? 1 : 3) + 1;
   else n = per_fwd + 1 + (d->cfg_scale != 0.f ? 2 : 0);
   if (d->traj_dev && d->traj_every > 0) n += 1;

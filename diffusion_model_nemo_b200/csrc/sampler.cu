@@ -264,6 +264,93 @@ __global__ void __launch_bounds__(256) cfg_combine_kernel(const float* __restric
   }
 }
 
+// ---- bits-per-dimension evaluation (models/abstract_diffusion_model.py:137-197) ------------------------------------------
+// q_sample (gaussian_diffusion.py:104-116): x_t = sqrt_ac[t] * x0 + sqrt_1m_ac[t] * z.  coef row columns 6 / 7.
+__global__ void __launch_bounds__(256) bpd_qsample_kernel(const float* __restrict__ x0, const float* __restrict__ z, float* __restrict__ xt,
+                                                          long n4, const float* __restrict__ coef, const int32_t* step_dev, int step,
+                                                          dmn_rng rng_v, const dmn_rng* rng_dev) {
+  const dmn_rng rng = pick_rng(rng_v, rng_dev);
+  const float* c = coef_row(coef, step_dev, step);
+  const float a = c[6], b = c[7];
+  const uint32_t sw = step_word(step_dev, step, 0);
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long)gridDim.x * blockDim.x) {
+    const float4 xv = reinterpret_cast<const float4*>(x0)[i];
+    const float4 zv = z ? reinterpret_cast<const float4*>(z)[i] : Philox::normal4(rng.seed, rng.stream_id, sw, (uint64_t)i);
+    reinterpret_cast<float4*>(xt)[i] = make_float4(a * xv.x + b * zv.x, a * xv.y + b * zv.y, a * xv.z + b * zv.z, a * xv.w + b * zv.w);
+  }
+}
+
+__device__ __forceinline__ float approx_std_normal_cdf(float x) {      // utils.py:37-38
+  return 0.5f * (1.0f + tanhf(0.7978845608028654f * (x + 0.044715f * (x * x * x))));
+}
+// One variational-bound term per sample (loss/variational_bound_loss.py:31-52 on top of q_posterior / p_mean_variance,
+// gaussian_diffusion.py:91-101,125-154; learned variance: learned_gaussian_diffusion.py:27-53):
+//   t > 0 : mean_chw KL( q(x_{t-1} | x_t, x_0) || p(x_{t-1} | x_t) ) / ln 2        t == 0 : mean_chw decoder NLL / ln 2
+// One block per sample, fixed reduction order (deterministic).  coef row = {sqrt_recip_ac, sqrt_recipm1_ac, post_coef1, post_coef2,
+// post_logvar_clipped, pred_x0 flag, sqrt_ac, sqrt_1m_ac}; coef2 row = {log beta_t (learned max log variance), t, is_t0}.
+// mode 1 = prior term: mean_chw KL( q(x_T | x_0) || N(0, 1) ) / ln 2 with coef2 row = {log(1 - ac_T)}, coef column 6 = sqrt_ac_T.
+__global__ void __launch_bounds__(256) bpd_term_kernel(const float* __restrict__ x0, const float* __restrict__ xt, const float* __restrict__ mo,
+                                                       float* __restrict__ terms, long chw, int learned, int n_cols, int mode,
+                                                       const float* __restrict__ coef, const float* __restrict__ coef2,
+                                                       const int32_t* step_dev, int step) {
+  const int b = blockIdx.x;
+  const float* c = coef_row(coef, step_dev, step);
+  const float* c2 = coef2 + (long)(step_dev ? *step_dev : step) * DMN_COEF_STRIDE;
+  const float c0 = c[0], c1 = c[1], p1 = c[2], p2 = c[3], lv_true = c[4];
+  const bool pred_x0 = c[5] != 0.f;
+  const float max_log = c2[0];
+  const int col = (int)c2[1];
+  const bool t0 = c2[2] != 0.f;
+  const float* xs = x0 + (long)b * chw;
+  float acc = 0.f;
+  if (mode == 1) {
+    const float a = c[6], lv1 = c2[0];
+    for (long i = threadIdx.x; i < chw; i += blockDim.x) {
+      const float m1 = xs[i] * a;
+      acc += 0.5f * (-1.0f + 0.0f - lv1 + expf(lv1 - 0.0f) + (m1 * m1) * expf(-0.0f));
+    }
+  } else {
+    const float* xts = xt + (long)b * chw;
+    const float* eps = mo + (long)b * chw * (learned ? 2 : 1);
+    for (long i = threadIdx.x; i < chw; i += blockDim.x) {
+      const float xv = xs[i], xtv = xts[i], ev = eps[i];
+      float lv = lv_true;
+      if (learned) {
+        const float frac = (eps[chw + i] + 1.0f) * 0.5f;
+        lv = frac * max_log + (1.0f - frac) * lv_true;
+      }
+      float x0p = pred_x0 ? ev : (c0 * xtv - c1 * ev);
+      x0p = clamp1(x0p);
+      const float mm = p1 * x0p + p2 * xtv;      // model mean
+      const float tm = p1 * xv + p2 * xtv;       // true posterior mean
+      float v;
+      if (!t0) {
+        const float d = tm - mm;
+        v = 0.5f * (-1.0f + lv - lv_true + expf(lv_true - lv) + (d * d) * expf(-lv));      // utils.normal_kl
+      } else {                                                                                // utils.discretized_gaussian_log_likelihood
+        const float centered = xv - mm, inv_stdv = expf(-0.5f * lv);
+        const float cdf_plus = approx_std_normal_cdf(inv_stdv * (centered + 1.0f / 255.0f));
+        const float cdf_min = approx_std_normal_cdf(inv_stdv * (centered - 1.0f / 255.0f));
+        const float lp = xv < -0.999f ? logf(fmaxf(cdf_plus, 1e-12f))
+                                      : (xv > 0.999f ? logf(fmaxf(1.0f - cdf_min, 1e-12f)) : logf(fmaxf(cdf_plus - cdf_min, 1e-12f)));
+        v = -lp;
+      }
+      acc += v;
+    }
+  }
+  __shared__ float red[8];
+  acc = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int w = 0; w < 8; ++w) t += red[w];
+    const float val = t / (float)chw * 1.4426950408889634f;       // mean over C*H*W, in bits
+    if (mode == 1) terms[b] = val;
+    else terms[(long)b * n_cols + col] = val;
+  }
+}
+
 static inline unsigned grid_for(long n, int per_block = 256, int cap = 148 * 8) {
   long g = (n + per_block - 1) / per_block;
   if (g < 1) g = 1;
@@ -350,6 +437,22 @@ int launch_learned(const float* x, const float* mo, const float* z, float* out, 
   DMN_LAUNCH_CHECK("learned_step");
   return 0;
 }
+int launch_bpd_qsample(const float* x0, const float* z, float* xt, long n, const float* coef, const int32_t* step_dev, int step,
+                       dmn_rng rng, const dmn_rng* rng_dev, cudaStream_t st) {
+  DMN_REQUIRE(n % 4 == 0 && n > 0, "bpd_qsample: element count must be a positive multiple of 4");
+  bpd_qsample_kernel<<<grid_for(n / 4), 256, 0, st>>>(x0, z, xt, n / 4, coef, step_dev, step, rng, rng_dev);
+  count_launch();
+  DMN_LAUNCH_CHECK("bpd_qsample");
+  return 0;
+}
+int launch_bpd_term(const float* x0, const float* xt, const float* mo, float* terms, int batch, long chw, int learned, int n_cols,
+                    int mode, const float* coef, const float* coef2, const int32_t* step_dev, int step, cudaStream_t st) {
+  DMN_REQUIRE(batch > 0 && chw > 0 && coef && coef2 && terms && x0, "bpd_term: bad arguments");
+  bpd_term_kernel<<<batch, 256, 0, st>>>(x0, xt, mo, terms, chw, learned, n_cols, mode, coef, coef2, step_dev, step);
+  count_launch();
+  DMN_LAUNCH_CHECK("bpd_term");
+  return 0;
+}
 int launch_ddim(const float* x, const float* eps, const float* z, float* out, long n, const float* coef, const int32_t* step_dev,
                 int step, dmn_rng rng, const dmn_rng* rng_dev, cudaStream_t st) {
   DMN_REQUIRE(n % 4 == 0 && n > 0, "ddim_step: element count must be a positive multiple of 4");
@@ -391,6 +494,16 @@ int dmn_langevin_step(const float* x, const float* model_out, const float* z_dev
                       dmn_rng rng, void* stream) {
   return launch_langevin(x, model_out, z_dev, x_out, x_mean_out, batch, chw, snr, coef_dev, step_dev, step, 0, scratch_dev, rng,
                          nullptr, (cudaStream_t)stream);
+}
+
+int dmn_bpd_qsample(const float* x0, const float* z_dev, float* x_t, int64_t n, const float* coef_dev, const int32_t* step_dev, int step,
+                    dmn_rng rng, void* stream) {
+  return launch_bpd_qsample(x0, z_dev, x_t, n, coef_dev, step_dev, step, rng, nullptr, (cudaStream_t)stream);
+}
+int dmn_bpd_term(const float* x0, const float* x_t, const float* model_out, float* terms, int batch, int64_t chw, int learned, int n_cols,
+                 int mode, const float* coef_dev, const float* coef2_dev, const int32_t* step_dev, int step, void* stream) {
+  return launch_bpd_term(x0, x_t, model_out, terms, batch, chw, learned, n_cols, mode, coef_dev, coef2_dev, step_dev, step,
+                         (cudaStream_t)stream);
 }
 
 int dmn_unnormalize(const float* x, float* out, int64_t n, void* stream) {

@@ -93,13 +93,14 @@ def run_native_loop(unet: Unet, *, kind: int, shape: Sequence[int], device, time
         # loop buffers live with the plan so their addresses (baked into the cached CUDA graph) stay stable
         n_out = b * unet.out_dim * h * w
         n_traj = (n_steps // traj_every) if traj_every > 0 else 0
-        bkey = (kind, b, n_steps if n_traj else 0, n_traj, bool(denoise), guided)
+        bkey = (kind, b, n_steps if (n_traj or kind == L.LOOP_BPD) else 0, n_traj, bool(denoise), guided)
         bufs = plan.__dict__.setdefault("_loop_bufs", {})
         if bkey not in bufs:
             bufs[bkey] = {
                 "state": torch.empty((b, c, h, w), dtype=torch.float32, device=device),
                 "scratch": torch.empty((3 if guided else 1) * (n_out + n) + 2 * b + 64, dtype=torch.float32, device=device),
-                "aux": torch.empty((b, c, h, w), dtype=torch.float32, device=device) if (kind == L.LOOP_PC and denoise) else None,
+                "aux": (torch.empty((b, c, h, w), dtype=torch.float32, device=device) if (kind == L.LOOP_PC and denoise) else
+                        torch.zeros((b, n_steps), dtype=torch.float32, device=device) if kind == L.LOOP_BPD else None),
                 "traj": torch.empty((n_traj, b, c, h, w), dtype=torch.float32, device=device) if n_traj > 0 else None,
             }
         state, scratch, aux, traj = (bufs[bkey][k] for k in ("state", "scratch", "aux", "traj"))

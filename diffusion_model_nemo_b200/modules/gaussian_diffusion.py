@@ -174,6 +174,59 @@ class GaussianDiffusion(AbstractDiffusionProcess):
             traj = torch.stack(keep) if keep else None
         return R.to_image_list(x, traj)
 
+    # ---- bits-per-dimension evaluation ------------------------------------------------------------
+    @torch.no_grad()
+    def calculate_bits_per_dimension(self, x_start, diffusion_model_fn, max_batch_size: int = 32, noise=None):
+        """Drop-in for AbstractDiffusionModel.calculate_bits_per_dimension (reference models/abstract_diffusion_model.py:137-197;
+        there a method of the model shell that only touches `self.sampler`, here a method of the sampler).  For every t = T-1..0:
+        x_t = q_sample(x_0, t), one U-Net evaluation, and the variational-bound term (KL of the two posteriors, decoder NLL at t = 0) of
+        every sample, plus the prior term.  With this package's Unet the T steps are ONE replayed CUDA graph (q_sample kernel, U-Net,
+        fused term reduction); any other callable is evaluated per step and only the two kernels are native.
+        `noise` ([T, *x.shape], optional) injects the q_sample draws in the reference's order.  Returns the reference's dict:
+        {'total_bpd' [B], 'terms_bpd' [B, T], 'prior_bpd' [B]} on x_start's device."""
+        device = x_start.device
+        R.require_cuda(device)
+        lib = L.lib()
+        b = x_start.shape[0]
+        if max_batch_size > 0:
+            b = min(max_batch_size, b)
+        x0 = x_start[:b].float().contiguous()
+        T = self.timesteps
+        ts = torch.arange(T - 1, -1, -1, dtype=torch.long)
+        flag = torch.full((T,), 1.0 if self.objective == "pred_x0" else 0.0)
+        coef = R.coef_rows([self.sqrt_recip_alphas_cumprod[ts], self.sqrt_recipm1_alphas_cumprod[ts], self.posterior_mean_coef1[ts],
+                            self.posterior_mean_coef2[ts], self.posterior_log_variance_clipped[ts], flag, self.sqrt_alphas_cumprod[ts],
+                            self.sqrt_one_minus_alphas_cumprod[ts]], device)
+        coef2 = R.coef_rows([torch.log(self.betas)[ts], ts.float(), (ts == 0).float()], device)
+        chw = x0[0].numel()
+        unet, classes = R.resolve_model(diffusion_model_fn)
+        if unet is not None:
+            res = R.run_native_loop(unet, kind=L.LOOP_BPD, shape=list(x0.shape), device=device, times=ts.float().to(device), coef=coef,
+                                    coef2=coef2, x_init=x0, noise=noise, classes=classes, seed=self.seed, use_graph=self.use_cuda_graph)
+            terms = res.aux
+        else:
+            terms = torch.zeros((b, T), dtype=torch.float32, device=device)
+            xt = torch.empty_like(x0)
+            rng = L.Rng(self.seed if self.seed is not None else R.draw_seed(), R.rank_stream_id())
+            with torch.cuda.device(device):
+                st = L.stream_ptr(device)
+                for s, ti in enumerate(ts.tolist()):
+                    z = None if noise is None else noise[s].to(device, torch.float32).contiguous()
+                    L.check(lib.dmn_bpd_qsample(L.ptr(x0), L.ptr(z), L.ptr(xt), x0.numel(), L.ptr(coef), None, s, rng, st), "dmn_bpd_qsample")
+                    mo = diffusion_model_fn(xt, torch.full((b,), ti, device=device, dtype=torch.long)).float().contiguous()
+                    learned = int(mo.shape[1] == 2 * x0.shape[1])
+                    L.check(lib.dmn_bpd_term(L.ptr(x0), L.ptr(xt), L.ptr(mo), L.ptr(terms), b, chw, learned, T, 0, L.ptr(coef), L.ptr(coef2),
+                                             None, s, st), "dmn_bpd_term")
+        # prior: KL( q(x_T | x_0) || N(0, I) )  (abstract_diffusion_model.py:180-184)
+        prior = torch.empty((b,), dtype=torch.float32, device=device)
+        pc = R.coef_rows([torch.zeros(1)] * 6 + [self.sqrt_alphas_cumprod[T - 1:T]], device)
+        pc2 = R.coef_rows([self.log_one_minus_alphas_cumprod[T - 1:T]], device)
+        with torch.cuda.device(device):
+            L.check(lib.dmn_bpd_term(L.ptr(x0), None, None, L.ptr(prior), b, chw, 0, 1, 1, L.ptr(pc), L.ptr(pc2), None, 0,
+                                     L.stream_ptr(device)), "dmn_bpd_term(prior)")
+            torch.cuda.current_stream(device).synchronize()
+        return {"total_bpd": terms.sum(dim=1) + prior, "terms_bpd": terms, "prior_bpd": prior}
+
     @torch.no_grad()
     def sample(self, model, shape, device=None, noise=None):
         """Returns a list of CPU tensors in [0,1] whose LAST element is the final sample (reference contract,

@@ -158,6 +158,21 @@ int dmn_affine_noise_step(const float* x, const float* model_out, const float* z
 int dmn_langevin_step(const float* x, const float* model_out, const float* z_dev, float* x_out, float* x_mean_out,
                       int batch, int64_t chw, float snr, const float* coef_dev, const int32_t* step_dev, int step,
                       float* scratch_dev, dmn_rng rng, void* stream);
+/* Bits-per-dimension evaluation pieces (models/abstract_diffusion_model.py:137-197).
+ * dmn_bpd_qsample: x_t = sqrt_ac[t] * x_0 + sqrt_1m_ac[t] * z  (GaussianDiffusion.q_sample, gaussian_diffusion.py:104-116); coef row
+ *   columns 6 / 7; z_dev == NULL draws z in-kernel.
+ * dmn_bpd_term: one block per sample reduces, in a fixed order, mean_chw of KL(q(x_{t-1}|x_t,x_0) || p(x_{t-1}|x_t)) (t > 0) or of the
+ *   discretised-Gaussian decoder NLL (t == 0), in bits (VariationalBoundLoss.compute_variation_loss_terms,
+ *   loss/variational_bound_loss.py:31-52; utils.normal_kl / discretized_gaussian_log_likelihood, utils.py:28-56), with the posterior of
+ *   q_posterior / p_mean_variance (gaussian_diffusion.py:91-101,125-154) or the learned variance interpolation
+ *   (learned_gaussian_diffusion.py:27-53; model_out is [batch, 2C, H, W] when `learned`).  Writes terms[b * n_cols + col].
+ *   coef row  = {sqrt_recip_ac, sqrt_recipm1_ac, post_coef1, post_coef2, post_logvar_clipped, pred_x0 ? 1 : 0, sqrt_ac, sqrt_1m_ac}
+ *   coef2 row = {log beta_t, col (= t), t == 0 ? 1 : 0}
+ *   mode 1 = prior term mean_chw KL(q(x_T|x_0) || N(0,1)) / ln 2 -> terms[b]; coef column 6 = sqrt_ac[T-1], coef2 row = {log(1 - ac[T-1])}. */
+int dmn_bpd_qsample(const float* x0, const float* z_dev, float* x_t, int64_t n, const float* coef_dev, const int32_t* step_dev, int step,
+                    dmn_rng rng, void* stream);
+int dmn_bpd_term(const float* x0, const float* x_t, const float* model_out, float* terms, int batch, int64_t chw, int learned, int n_cols,
+                 int mode, const float* coef_dev, const float* coef2_dev, const int32_t* step_dev, int step, void* stream);
 /* x0 -> [0,1] image: (x + 1) * 0.5  (gaussian_diffusion.py:187) */
 int dmn_unnormalize(const float* x, float* out, int64_t n, void* stream);
 /* standard normal fill (the x_T draw, gaussian_diffusion.py:177) with the same Philox stream layout (step = -1). */
@@ -175,6 +190,10 @@ int dmn_axpby(const float* x, const float* y, float a, float b, float* out, int6
 #define DMN_LOOP_LEARNED  1
 #define DMN_LOOP_DDIM     2
 #define DMN_LOOP_PC       3   /* [langevin corrector x n_corr] + affine-noise predictor */
+#define DMN_LOOP_BPD      4   /* bits-per-dimension evaluation: per step q_sample(x_0) -> U-Net -> one variational-bound term per sample
+                                 (AbstractDiffusionModel.calculate_bits_per_dimension, models/abstract_diffusion_model.py:137-197).
+                                 state_dev = x_0 (read only), aux_dev = terms [batch][n_steps] (column = coef2 row[1]),
+                                 coef_dev / coef2_dev rows as documented at dmn_bpd_term; noise_dev injects the q_sample draws */
 
 typedef struct dmn_loop_desc {
   int32_t kind;            /* DMN_LOOP_* */

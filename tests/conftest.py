@@ -27,7 +27,7 @@ def pytest_collection_modifyitems(config, items):
 @pytest.fixture(scope="session")
 def golden():
     out = {}
-    for name in ("tables", "unet", "samplers", "step", "wavegrad", "wavegrad_unet"):
+    for name in ("tables", "unet", "samplers", "step", "wavegrad", "wavegrad_unet", "bpd"):
         out[name] = dict(np.load(os.path.join(GOLDEN, name + ".npz")))
     return out
 
