@@ -438,20 +438,31 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tcgen05_kernel(const Params 
         // one pass: virtual channel vc = kx*Cin + ch  (7*Cin <= 32); source is the fp32 NCHW sampler state
         const float* x = (const float*)p.c.src1;
         const int Cin = p.c.C1;
+        // this thread's 8 virtual channels (fixed k-chunk): source offset and kx shift, decoded once per tile instead of per element
+        int koff[8], kxs[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const int vc = kc * 8 + e;
+          const int kx = vc / Cin, ch = vc - kx * Cin;
+          kxs[e] = kx < 7 ? kx - 3 : (1 << 20);            // unused virtual channels never pass the range check below
+          koff[e] = ch * p.HW + kx - 3;
+        }
+        const int ibase = m0 - p.halo_lo > 0 ? m0 - p.halo_lo : 0;
+        const int iimg0 = ibase / p.S, irem0 = ibase - iimg0 * p.S;
         mbar_wait_relaxed(smem_u32(&empty_a[ibuf]), iph);
         for (int pixel = px0; pixel < Pt; pixel += kProdThreads / 4) {
-          const VPos v = vdecode(m0 - p.halo_lo + pixel, p);
+          VPos v;
+          v.img = -1; v.row = v.col = 0;
+          if (m0 - p.halo_lo + pixel >= 0) v = vdecode_rel(iimg0, irem0, m0 - p.halo_lo + pixel - ibase, p);
           float f[8];
 #pragma unroll
           for (int e = 0; e < 8; ++e) f[e] = 0.f;
           if (v.img >= 0 && v.row >= 3) {              // rows 0..2 of every block are the shared zero rows
-            const int iy = v.row - 3;
+            const float* xp = x + ((long)v.img * Cin * p.HW + (v.row - 3) * p.W + v.col);
 #pragma unroll
             for (int e = 0; e < 8; ++e) {
-              const int vc = kc * 8 + e;
-              const int kx = vc / Cin, ch = vc - kx * Cin;
-              const int ix = v.col + kx - 3;
-              if (kx < 7 && ix >= 0 && ix < p.W) f[e] = __ldg(x + (((long)v.img * Cin + ch) * p.H + iy) * p.W + ix);
+              const unsigned ix = (unsigned)(v.col + kxs[e]);
+              if (ix < (unsigned)p.W) f[e] = __ldg(xp + koff[e]);
             }
           }
           *reinterpret_cast<uint4*>(sA + ibuf * a_bytes + (uint32_t)kc * p.lbo_a + pixel * 16) = pack8(f);
