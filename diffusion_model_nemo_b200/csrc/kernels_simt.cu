@@ -832,6 +832,30 @@ int film_modulate(const void* x, const void* scale, const void* shift, void* out
   return 0;
 }
 
+template <typename T>
+__global__ void __launch_bounds__(256) class_embed_add_kernel(T* __restrict__ x, const float* __restrict__ cls_w, const int64_t* __restrict__ classes,
+                                                              int pad_class, long per_sample4, int C, long n4) {
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long)gridDim.x * blockDim.x) {
+    const int b = (int)(i / per_sample4);
+    const int c = (int)((i * 4) % C);
+    const float* row = cls_w + (long)(classes ? (int)classes[b] : pad_class) * C + c;
+    float4 v = load4<T>(x + 4 * i);
+    v.x += row[0]; v.y += row[1]; v.z += row[2]; v.w += row[3];
+    store4<T>(x + 4 * i, v);
+  }
+}
+int class_embed_add(void* x, const float* cls_w, const int64_t* classes, int pad_class, int B, int HW, int C, int act, cudaStream_t st) {
+  DMN_REQUIRE(C % 4 == 0 && cls_w, "class_embed_add: channels must be a multiple of 4");
+  const long n4 = (long)B * HW * C / 4, per4 = (long)HW * C / 4;
+  long blocks = (n4 + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  if (act == ACT_F32) class_embed_add_kernel<float><<<(unsigned)blocks, 256, 0, st>>>((float*)x, cls_w, classes, pad_class, per4, C, n4);
+  else class_embed_add_kernel<bf16><<<(unsigned)blocks, 256, 0, st>>>((bf16*)x, cls_w, classes, pad_class, per4, C, n4);
+  count_launch();
+  DMN_LAUNCH_CHECK("class_embed_add");
+  return 0;
+}
+
 // =====================================================================================================
 // layout conversion (public-ABI boundary only; not on the loop's hot path)
 // =====================================================================================================

@@ -131,6 +131,8 @@ int film_pe_table(const float* levels, const float* freq, const float* is_cos, f
 
 // FiLM apply: out = x * scale + shift (elementwise, NHWC activations; out may alias x)   (modules/unet.py:259,262)
 int film_modulate(const void* x, const void* scale, const void* shift, void* out, long n, int act, cudaStream_t s);
+// x[b][pix][c] += class_embed[classes[b] or pad_class][c], in place (WaveGradUNet adds the class embedding after FiLM 0, unet.py:219-226)
+int class_embed_add(void* x, const float* cls_w, const int64_t* classes, int pad_class, int B, int HW, int C, int act, cudaStream_t s);
 
 // layout conversion at the public ABI boundary
 int nchw_to_nhwc(const float* in, void* out, int B, int C, int HW, int act, cudaStream_t s);

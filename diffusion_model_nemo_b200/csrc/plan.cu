@@ -95,7 +95,7 @@ struct Param {
   }
 };
 
-enum OpKind { OP_MEMSET, OP_INIT, OP_CONV, OP_FINALIZE, OP_LINATTN, OP_ATTN, OP_FINALPROJ, OP_MODULATE };
+enum OpKind { OP_MEMSET, OP_INIT, OP_CONV, OP_FINALIZE, OP_LINATTN, OP_ATTN, OP_FINALPROJ, OP_MODULATE, OP_CLASSADD };
 
 // Buffers are addressed as (region id, so pointers can be resolved after bind)
 struct Buf {
@@ -393,8 +393,6 @@ struct Builder {
     // WaveGradUNet (unet.py:204-266): FiLM 0 on the stem output, FiLM i+1 on the output of down level i; the last level's FiLM is
     // computed and discarded by the reference (unet.py:247), so it is not evaluated here.  (scale, shift) live until the up path.
     const bool film_on = c.film != 0;
-    if (film_on && c.num_classes >= 0)
-      return fail(DMN_ENOTSUP, "WaveGradUNet with num_classes is not built (FiLM 0 reads the stem output before the class embedding)");
     if (film_on && c.with_time_emb) return fail(DMN_EINVAL, "film requires with_time_emb = 0 (unet.py:195)");
     std::vector<Buf> fscale(n), fshift(n);
     if (film_on)
@@ -434,7 +432,17 @@ struct Builder {
 
     int cur = 0;   // index of the X buffer holding the current activation
     Buf x = X[0];
-    if (film_on) film(0, x, dim, S, H1, fscale[0], fshift[0]);
+    if (film_on) {
+      film(0, x, dim, S, H1, fscale[0], fshift[0]);
+      if (c.num_classes >= 0) {
+        // WaveGradUNet adds the class embedding AFTER FiLM 0 has read the stem output (unet.py:214-226), so the stem runs without it
+        Op a;
+        a.kind = OP_CLASSADD;
+        a.name = "class_embed.add";
+        a.src1 = x; a.out = x; a.C = dim; a.HW = S * S;
+        P.ops.push_back(a);
+      }
+    }
     for (int i = 0; i < n; ++i) {
       const int ci = dims[i], co = dims[i + 1], Hh = Hs[i];
       const std::string p = "downs." + std::to_string(i);
@@ -544,7 +552,7 @@ static int run_forward(dmn_plan* P, const float* x_dev, const int32_t* row_dev, 
         q.x = x_dev;
         q.w = W(P->pidx["init_conv.weight"]);
         q.bias = W(P->pidx["init_conv.bias"]);
-        if (c.num_classes >= 0) {
+        if (c.num_classes >= 0 && !c.film) {
           q.cls_w = W(P->pidx["class_embed.weight"]);
           q.classes = classes_dev;
           q.pad_class = c.num_classes;
@@ -599,6 +607,9 @@ static int run_forward(dmn_plan* P, const float* x_dev, const int32_t* row_dev, 
         break;
       case OP_ATTN:
         rc = attn_core(B(o.src1), B(o.out), batch, o.heads, o.dh, o.N, P->act, st);
+        break;
+      case OP_CLASSADD:
+        rc = class_embed_add(B(o.src1), W(P->pidx["class_embed.weight"]), classes_dev, c.num_classes, batch, o.HW, o.C, P->act, st);
         break;
       case OP_MODULATE:
         rc = film_modulate(B(o.src1), B(o.src2), B(o.res), B(o.out), (long)batch * o.HW * o.C, P->act, st);
@@ -886,6 +897,7 @@ int dmn_plan_op_info(const dmn_plan* p, int i, char* name_out, int name_cap, int
     }
     case OP_FINALIZE: by = esz * (double)o.HW * o.C * 3.0; break;
     case OP_MODULATE: by = esz * (double)o.HW * o.C * 4.0; break;
+    case OP_CLASSADD: by = esz * (double)o.HW * o.C * 2.0; break;
     case OP_LINATTN: fl = 2.0 * 2.0 * o.heads * o.dh * o.dh * o.N; by = esz * (double)o.N * o.heads * o.dh * 4.0; break;
     case OP_ATTN: fl = 2.0 * 2.0 * o.heads * o.dh * (double)o.N * o.N; by = esz * (double)o.N * o.heads * o.dh * 4.0; break;
     case OP_FINALPROJ: fl = 2.0 * o.HW * o.C * o.Cout; by = esz * (double)o.HW * o.C + 4.0 * o.HW * o.Cout; break;

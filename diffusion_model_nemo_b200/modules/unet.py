@@ -225,8 +225,6 @@ class WaveGradUNet(Unet):
                          convnext_mult=convnext_mult, resnet_block_order=resnet_block_order, dropout=dropout,
                          learned_variance=learned_variance, num_classes=num_classes, compute_dtype=compute_dtype,
                          conv_engine=conv_engine)
-        if num_classes is not None:
-            raise NotImplementedError("WaveGradUNet with num_classes is not built (FiLM 0 reads the stem before the class embedding)")
         films = [_film(dim)]
         films.extend(_film(co) for (_, co) in self.in_out_list)
         films.extend(_film(co) for (_, co) in reversed(self.in_out_list[1:]))

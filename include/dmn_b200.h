@@ -112,7 +112,7 @@ int dmn_plan_launches_per_forward(const dmn_plan* p);
 
 /* Measurement aids for bench.py's roofline (no reference counterpart).
  * dmn_plan_num_ops / dmn_plan_op_info: static description of launch i of the forward program -- name, kind
- *   (0 memset, 1 init_conv, 2 conv, 3 gn_finalize, 4 linattn, 5 attn, 6 final_proj, 7 film_modulate), engine (0 CUDA cores, 1 tcgen05),
+ *   (0 memset, 1 init_conv, 2 conv, 3 gn_finalize, 4 linattn, 5 attn, 6 final_proj, 7 film_modulate, 8 class_embed_add), engine (0 CUDA cores, 1 tcgen05),
  *   algorithmic FLOPs (2*MAC) and algorithmic bytes (operands read once + result written once) PER SAMPLE.
  * dmn_plan_profile_forward: one forward with a CUDA event pair around every launch on `stream`; writes per-launch
  *   milliseconds to ms_out[0..num_ops) and synchronises the stream (not graph-capturable). */

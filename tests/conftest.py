@@ -59,6 +59,7 @@ WG_CFGS = {
     # WaveGradUNet fixtures (tests/golden/make_golden_wavegrad_unet.py): name -> (cfg, image size, batch)
     "wg_tiny": (dict(dim=32, dim_mults=[1, 2], channels=3, groups=8, film=True), 16, 2),
     "wg_cfg": (dict(dim=128, dim_mults=[1, 2, 2, 2], channels=3, groups=8, film=True), 32, 1),
+    "wg_cls": (dict(dim=32, dim_mults=[1, 2], channels=3, groups=8, film=True, num_classes=10), 16, 2),
 }
 
 
@@ -73,7 +74,7 @@ def make_wavegrad_unet(cfg, sd=None, dtype="fp32", engine="simt", device=None):
     import diffusion_model_nemo_b200.modules as M
 
     u = M.WaveGradUNet(None, dim=cfg["dim"], dim_mults=cfg["dim_mults"], channels=cfg["channels"], use_convnext=False,
-                       resnet_block_groups=cfg["groups"], compute_dtype=dtype, conv_engine=engine)
+                       resnet_block_groups=cfg["groups"], num_classes=cfg.get("num_classes"), compute_dtype=dtype, conv_engine=engine)
     if sd is not None:
         u.load_state_dict(sd, strict=True)
     if device is not None:

@@ -18,7 +18,8 @@ def test_oracle_matches_reference_golden(golden, name):
     sd = O.random_state_dict(cfg, seed=0)
     x = wg_inputs(name)
     level = torch.from_numpy(golden["wavegrad_unet"][f"{name}/level"])
-    y = O.wavegrad_unet_forward(sd, cfg, x, level)
+    cls = torch.tensor([3, 10][:b]) if cfg.get("num_classes") is not None else None
+    y = O.wavegrad_unet_forward(sd, cfg, x, level, cls)
     ref = torch.from_numpy(golden["wavegrad_unet"][f"{name}/eps"])
     assert rel_l2(y, ref) <= 1e-6
 
@@ -42,6 +43,9 @@ def test_dropin_parameter_tree_matches_reference_names():
     assert not any(k.startswith("time_mlp") or ".mlp." in k for k in got)
     # 1 + n_levels + (n_levels - 1) FiLM layers, as the reference constructs them (unet.py:204-210)
     assert len(u.films) == 1 + 2 + 1
+    cfg_c, _, _ = WG_CFGS["wg_cls"]
+    got_c = {k: tuple(v.shape) for k, v in make_wavegrad_unet(cfg_c).state_dict().items()}
+    assert got_c == {k: tuple(v) for k, v in O.unet_param_shapes(cfg_c).items()} and "class_embed.weight" in got_c
 
 
 def test_dropin_rejects_cpu_and_convnext():
@@ -74,10 +78,15 @@ def test_native_wavegrad_unet_vs_reference_golden(golden, name, dtype, engine):
     u = make_wavegrad_unet(cfg, sd, dtype=dtype, engine=engine, device=DEV)
     x = wg_inputs(name).to(DEV)
     level = torch.from_numpy(golden["wavegrad_unet"][f"{name}/level"]).to(DEV)
-    y = u(x, level)
+    cls = torch.tensor([3, 10][:b], device=DEV) if cfg.get("num_classes") is not None else None
+    y = u(x, level, cls)
     ref = torch.from_numpy(golden["wavegrad_unet"][f"{name}/eps"])
     assert y.shape == ref.shape and torch.isfinite(y).all()
     assert rel_l2(y.cpu(), ref) <= TOL[dtype], (name, dtype, engine)
+    if cls is not None:       # classes=None: the padding row for every sample; the embedding is added AFTER FiLM 0 read the stem
+        ref_none = torch.from_numpy(golden["wavegrad_unet"][f"{name}/eps_noclass"])
+        assert rel_l2(u(x, level).cpu(), ref_none) <= TOL[dtype]
+        assert rel_l2(ref, ref_none) > 1e-3
     if name == "wg_cfg" and engine == "tcgen05":
         ops = u.plan(size, b, DEV).op_table()
         film_convs = [o for o in ops if o[0].startswith("films.")]
