@@ -121,6 +121,9 @@ constexpr bool kTraceProducer = DMN_TC_TRACE_PRODUCER != 0;
                                     // measured SLOWER on every conv of the step, including those without a prologue (+0.002..0.004 ms each):
                                     // the three extra unrolled copies grow the kernel, and the engine is sensitive to code size
 #endif
+#ifndef DMN_EXP_NO_ONETAP
+#define DMN_EXP_NO_ONETAP 0
+#endif
 #ifndef DMN_EXP_NO_EPI
 #define DMN_EXP_NO_EPI 0            // epilogue: TMEM reads only (no staging, no global stores, no statistics)
 #endif
@@ -354,7 +357,9 @@ __device__ __forceinline__ void issue_pass(bool leader, uint32_t d0, uint32_t d1
 // LEAN selects the unrolled MMA issue path (a separate instantiation, so that the looped path keeps its own code generation)
 // EXTRA keeps the rarely used epilogue terms (residual add, folded-GroupNorm affine); the hot instantiations drop them: the engine is
 // measurably sensitive to the size of the code in its inner loops (compiling the debug timeline out alone gave +1.5 %)
-// PRO: 0 = no fused prologue compiled in, 1 = the prologue is always on (GroupNorm convs), 2 = decided at run time (generic instantiations)
+// PRO: 0 = no fused prologue compiled in, 1 = the prologue is always on (GroupNorm convs), 2 = decided at run time (generic instantiations),
+//      3 = 1x1 convolution without prologue: no halo and no padding, so the operand source of window pixel i is simply flat position
+//          m0 + i and the per-tile tables (two producer barriers, a decode per pixel) are skipped
 template <int GEO, int NT, bool FILM = false, bool LEAN = false, bool EXTRA = true, int PRO = 2>
 __global__ void __launch_bounds__(kThreads, 1) conv_tcgen05_kernel(const Params p) {
   extern __shared__ __align__(128) uint8_t smem[];
@@ -414,6 +419,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tcgen05_kernel(const Params 
     const float* temb_base = nullptr;
     if (GEO == GEO_SAME && (p.c.pro & PRO_TEMB)) temb_base = p.c.temb + (p.c.d_row ? (long)(*p.c.d_row) * p.c.temb_rstride : 0);
     const bool has_pro = PRO == 2 ? (GEO == GEO_SAME && p.c.pro != PRO_NONE) : (PRO == 1 && GEO == GEO_SAME);
+    constexpr bool kOneTap = PRO == 3 && GEO == GEO_SAME;
     const bool temb_shared = (p.c.pro & PRO_TEMB) && p.c.temb_bstride == 0;
     if (has_pro) {                      // visible to all producers after the first tile's table barrier
       for (int i = tid; i < ncoef; i += kProdThreads) {
@@ -473,6 +479,17 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tcgen05_kernel(const Params 
         fbuf = ibuf;
         continue;
       }
+      int goff[kMaxItems];      // SAME/UP: img*HW + pix (or -1 = padding); DOWN: packed (img, u, v) (or -1); -2 = outside the window
+      int imgl[kMaxItems];
+      const int nfull = Pt / (kProdThreads / 4);      // item slots that are inside the window for EVERY thread (uniform)
+      if constexpr (kOneTap) {
+#pragma unroll
+        for (int j = 0; j < kMaxItems; ++j) {
+          const int pixel = px0 + (kProdThreads / 4) * j;
+          imgl[j] = 0;
+          goff[j] = (pixel < Pt && m0 + pixel < (int)p.total_flat) ? m0 + pixel : -2;
+        }
+      } else {
       // ---- per-tile tables: operand source per window pixel, GroupNorm (mean, rstd) per touched image ----
       bar_sync_named(2, kProdThreads);                 // everyone is done with the previous tile's tables
       const int pbase = m0 - p.halo_lo > 0 ? m0 - p.halo_lo : 0;            // uniform: decode base of the window
@@ -504,9 +521,6 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tcgen05_kernel(const Params 
       }
       bar_sync_named(2, kProdThreads);
       if (tid == 0) TRACE(pit, 1);
-      const int nfull = Pt / (kProdThreads / 4);      // item slots that are inside the window for EVERY thread (uniform)
-      int goff[kMaxItems];      // SAME/UP: img*HW + pix (or -1 = padding); DOWN: packed (img, u, v) (or -1); -2 = outside the window
-      int imgl[kMaxItems];
 #pragma unroll
       for (int j = 0; j < kMaxItems; ++j) {
         const int pixel = px0 + (kProdThreads / 4) * j;
@@ -516,6 +530,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tcgen05_kernel(const Params 
           goff[j] = s_pix[pixel];
           imgl[j] = s_pimg[pixel];
         }
+      }
       }
 
       // finish pass c (in buffer fbuf): prologue in place on this thread's own items, publish to the tensor core
@@ -1249,6 +1264,21 @@ static int launch(Params p, cudaStream_t st) {
   const bool lean_ok = !DMN_EXP_NO_LEAN && p.NT == 128 && !(p.c.pro & PRO_LRELU) && p.n_pass >= DMN_EXP_LEAN_MIN_PASS &&
                        ((GEO == GEO_SAME && p.ntap == 9 && p.G == 3) || ((GEO == GEO_DOWN || GEO == GEO_UP) && p.ntap == 4 && p.G == 2));
   const bool extra = p.c.res != nullptr || p.c.fold_s1 != nullptr;
+  if (GEO == GEO_SAME && p.NT == 128 && p.ntap == 1 && p.c.pro == PRO_NONE && !DMN_EXP_NO_ONETAP) {
+    // 1x1 convolutions (to_qkv with the folded GroupNorm, to_out, res_conv): table-free producers
+    constexpr int G2 = GEO_SAME;
+    static bool one_attr = false;
+    if (!one_attr) {
+      DMN_CUDA_CHECK(cudaFuncSetAttribute(conv_tcgen05_kernel<G2, 128, false, false, true, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemLimit));
+      DMN_CUDA_CHECK(cudaFuncSetAttribute(conv_tcgen05_kernel<G2, 128, false, false, false, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemLimit));
+      one_attr = true;
+    }
+    if (extra) DMN_CUDA_CHECK(launch_pdl(conv_tcgen05_kernel<G2, 128, false, false, true, 3>, dim3(grid), dim3(kThreads), smem_bytes(p), st, p));
+    else DMN_CUDA_CHECK(launch_pdl(conv_tcgen05_kernel<G2, 128, false, false, false, 3>, dim3(grid), dim3(kThreads), smem_bytes(p), st, p));
+    count_launch();
+    DMN_LAUNCH_CHECK("conv_tcgen05");
+    return 0;
+  }
   if (GEO != GEO_INIT && p.NT == 128 && !(p.c.pro & PRO_LRELU) && !extra) {
     // the hot instantiations: no residual / fold terms in the epilogue, lean or looped issue
     constexpr int G2 = GEO == GEO_INIT ? GEO_SAME : GEO;
