@@ -43,6 +43,10 @@
 #include "ops.h"
 #include "tc_ptx.cuh"
 
+#ifndef DMN_EXP_ONE_ABUF
+#define DMN_EXP_ONE_ABUF 5
+#endif
+
 namespace dmn {
 namespace tc {
 
@@ -51,12 +55,16 @@ enum { GEO_SAME = 0, GEO_DOWN = 1, GEO_UP = 2, GEO_INIT = 3 };
 constexpr int kProdWarps = 8, kEpiWarps = 8;
 constexpr int kProdThreads = kProdWarps * 32, kEpiThreads = kEpiWarps * 32;
 constexpr int kLoaderWarp = kProdWarps + kEpiWarps, kMmaWarp = kLoaderWarp + 1;
-constexpr int kThreads = (kMmaWarp + 1) * 32;     // 576 (16 epilogue warps = 832 threads at 72 registers measured slower)
+constexpr int kThreads = (kMmaWarp + 1) * 32;     // 576
+constexpr int kThreads16 = (kProdWarps + 16 + 2) * 32;   // 832: the 16-epilogue-warp instantiations (template parameter EW)
 constexpr int kMTmax = 2;              // 128-row accumulators per tile: 2, or 1 when two would leave most SMs idle
 constexpr int kMcta = 128 * kMTmax;    // table sizing
 constexpr int kCk = 32;                // channels per pass (4 k-chunks of 8)
 constexpr int kStagesMax = 8;          // weight-ring depth (chosen per launch to fit shared memory); one stage = G taps
 constexpr int kABuf = 3;               // operand (A) buffers: the producers run up to kABuf passes ahead of the MMA issuer
+constexpr int kABufMax = 6;            // barrier-array spacing / host sizing; the 1x1 instantiations use kABufOne buffers
+constexpr int kABufOne = DMN_EXP_ONE_ABUF, kDepthOne = kABufOne - 2;   // 1x1 convs: MMA work per pass is tiny, the producers are
+                                       // bound by the global-load latency of the passes they keep in flight
 constexpr int kDepth = 1;              // passes a producer thread keeps in flight (cp.async groups) before it finishes the oldest;
                                        // kABuf >= kDepth + 2, else finishing pass c would wait for the MMAs of pass c-1
 constexpr int kMaxItems = 7;           // 16-byte operand items per producer thread per pass (P <= 448)
@@ -69,6 +77,7 @@ struct Params {
   int S, Wv, pad, halo_lo, P, PA, mt, mcta;
   int H, W, HW;            // input image
   int ksize, ntap, NT, n_pass, tiles_per_phase, n_tiles_n, m_tiles, total_tiles;
+  int abuf;                // operand buffers of the instantiation that will be launched (kABuf, or kABufOne for the 1x1 form)
   int n_big_tiles, big_rows, halo_hi;   // tiles [0, n_big_tiles) have 256 rows, the rest 128 rows starting at flat position big_rows
   long total_flat;
   uint32_t lbo_a, sbo_a, lbo_b, sbo_b;   // bytes
@@ -123,6 +132,9 @@ constexpr bool kTraceProducer = DMN_TC_TRACE_PRODUCER != 0;
 #endif
 #ifndef DMN_EXP_NO_ONETAP
 #define DMN_EXP_NO_ONETAP 0
+#endif
+#ifndef DMN_EXP_EW16
+#define DMN_EXP_EW16 1              // 0: never use the 16-epilogue-warp instantiations
 #endif
 #ifndef DMN_EXP_NO_EPI
 #define DMN_EXP_NO_EPI 0            // epilogue: TMEM reads only (no staging, no global stores, no statistics)
@@ -360,8 +372,15 @@ __device__ __forceinline__ void issue_pass(bool leader, uint32_t d0, uint32_t d1
 // PRO: 0 = no fused prologue compiled in, 1 = the prologue is always on (GroupNorm convs), 2 = decided at run time (generic instantiations),
 //      3 = 1x1 convolution without prologue: no halo and no padding, so the operand source of window pixel i is simply flat position
 //          m0 + i and the per-tile tables (two producer barriers, a decode per pixel) are skipped
-template <int GEO, int NT, bool FILM = false, bool LEAN = false, bool EXTRA = true, int PRO = 2>
-__global__ void __launch_bounds__(kThreads, 1) conv_tcgen05_kernel(const Params p) {
+// EW: epilogue warps, 8 or 16.  The 16-warp form (832 threads, 72 registers per thread at launch) is for the epilogue-bound tiles
+//     whose producers only issue copies: the producer warps hand registers back (setmaxnreg.dec 40) and the epilogue warps take
+//     them (setmaxnreg.inc 88), so twice as many epilogue chains are in flight at the register budget the epilogue code needs.
+template <int GEO, int NT, bool FILM = false, bool LEAN = false, bool EXTRA = true, int PRO = 2, int EW = kEpiWarps>
+__global__ void __launch_bounds__((kProdWarps + EW + 2) * 32, 1) conv_tcgen05_kernel(const Params p) {
+  constexpr int kLoaderW = kProdWarps + EW, kMmaW = kLoaderW + 1, kEpiT = EW * 32;
+  constexpr int AB = (PRO == 3 && GEO == GEO_SAME) ? kABufOne : kABuf, DEPTH = (PRO == 3 && GEO == GEO_SAME) ? kDepthOne : kDepth;
+  static_assert(AB <= kABufMax && DEPTH >= 1 && DEPTH <= 3 && AB >= DEPTH + 2, "operand ring geometry");
+  static_assert(EW == 8 || (EW == 16 && NT == 128 && (PRO == 0 || PRO == 3)), "16 epilogue warps: 128-column tiles without prologue");
   extern __shared__ __align__(128) uint8_t smem[];
   const int tid = threadIdx.x;
   // broadcast => ptxas knows the role branches below are warp-uniform and may use the uniform datapath inside them
@@ -373,13 +392,13 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tcgen05_kernel(const Params 
   const uint32_t tap_bytes = 4u * NT * 16u;           // weights of one tap of one pass
   const uint32_t b_bytes = p.stage_bytes;             // one B stage (G taps)
   uint8_t* sA = smem;
-  uint8_t* sB = sA + kABuf * a_bytes;
+  uint8_t* sB = sA + AB * a_bytes;
   uint64_t* bars = reinterpret_cast<uint64_t*>(sB + nst * b_bytes);
   uint64_t* full_b = bars;
   uint64_t* empty_b = bars + kStagesMax;
   uint64_t* full_a = bars + 2 * kStagesMax;
-  uint64_t* empty_a = full_a + kABuf;
-  uint64_t* acc_full = empty_a + kABuf;
+  uint64_t* empty_a = full_a + kABufMax;
+  uint64_t* acc_full = empty_a + kABufMax;
   uint64_t* acc_empty = acc_full + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
   float2* s_gn = reinterpret_cast<float2*>(tmem_slot + 2);                                  // [kNimgMax][kGroupsMax] (mean, rstd)
@@ -392,13 +411,13 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tcgen05_kernel(const Params 
   uint8_t* s_stage = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(s_coef + 3 * ncoef) + 127) & ~(uintptr_t)127);
 
   // ---- one-time setup ----
-  if (warp == kLoaderWarp) {          // one lane per barrier
+  if (warp == kLoaderW) {          // one lane per barrier
     if (lane < nst) { mbar_init(smem_u32(&full_b[lane]), 1); mbar_init(smem_u32(&empty_b[lane]), 1); }
-    if (lane >= 16 && lane < 16 + kABuf) { mbar_init(smem_u32(&full_a[lane - 16]), kProdThreads); mbar_init(smem_u32(&empty_a[lane - 16]), 1); }
-    if (lane >= 24 && lane < 26) { mbar_init(smem_u32(&acc_full[lane - 24]), 1); mbar_init(smem_u32(&acc_empty[lane - 24]), kEpiThreads); }
+    if (lane >= 16 && lane < 16 + AB) { mbar_init(smem_u32(&full_a[lane - 16]), kProdThreads); mbar_init(smem_u32(&empty_a[lane - 16]), 1); }
+    if (lane >= 24 && lane < 26) { mbar_init(smem_u32(&acc_full[lane - 24]), 1); mbar_init(smem_u32(&acc_empty[lane - 24]), kEpiT); }
     fence_barrier_init();
   }
-  if (warp == kMmaWarp) tmem_alloc(smem_u32(tmem_slot), p.tmem_cols);
+  if (warp == kMmaW) tmem_alloc(smem_u32(tmem_slot), p.tmem_cols);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -407,6 +426,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tcgen05_kernel(const Params 
 
   if (warp < kProdWarps) {
     // =============================== operand producers ===============================
+    if (EW == 16) asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
     // Each thread owns up to kMaxItems 16-byte items (pixel, k-chunk) of every pass.  A pass is ISSUED as cp.async (LDGSTS)
     // copies straight into the operand buffer (padding is stored as zeros), and FINISHED kDepth passes later: wait for the
     // thread's own copies, apply the fused prologue in place (GroupNorm-apply, SiLU, time-embedding add), make the writes
@@ -475,7 +495,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tcgen05_kernel(const Params 
         }
         fence_proxy_async();
         mbar_arrive(smem_u32(&full_a[ibuf]));
-        if (++ibuf == kABuf) { ibuf = 0; iph ^= 1; }
+        if (++ibuf == AB) { ibuf = 0; iph ^= 1; }
         fbuf = ibuf;
         continue;
       }
@@ -616,7 +636,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tcgen05_kernel(const Params 
         }
         fence_proxy_async();
         mbar_arrive(smem_u32(&full_a[fbuf]));
-        if (++fbuf == kABuf) fbuf = 0;
+        if (++fbuf == AB) fbuf = 0;
       };
 
       int inflight = 0;
@@ -671,18 +691,23 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tcgen05_kernel(const Params 
           }
         }
         cp_async_commit();
-        if (++ibuf == kABuf) { ibuf = 0; iph ^= 1; }
-        if (++inflight > kDepth) {
+        if (++ibuf == AB) { ibuf = 0; iph ^= 1; }
+        if (++inflight > DEPTH) {
           w0 = ptracing ? clock64() : 0;
-          cp_async_wait<kDepth>();
+          cp_async_wait<DEPTH>();
           if (ptracing) wait_g += clock64() - w0;
-          finish(c - kDepth);
+          finish(c - DEPTH);
           --inflight;
         }
       }
       if (ptracing) { p.trace[16 * pit + 14] = wait_e; p.trace[16 * pit + 15] = wait_g; }
       // drain: the last passes of the tile
-      if (kDepth >= 2 && inflight == 2) {
+      if (DEPTH >= 3 && inflight == 3) {
+        cp_async_wait<2>();
+        finish(p.n_pass - 3);
+        --inflight;
+      }
+      if (DEPTH >= 2 && inflight == 2) {
         cp_async_wait<1>();
         finish(p.n_pass - 2);
         --inflight;
@@ -693,21 +718,24 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tcgen05_kernel(const Params 
       }
       if (tid == 0) TRACE(pit, 2);
     }
-  } else if (warp < kLoaderWarp) {
+  } else if (warp < kLoaderW) {
     // =============================== epilogue ===============================
+    // register pool of the CTA: the 8 producer warps release 8 x 32 x (72 - 40) = 8192 registers, exactly what 16 epilogue warps need to
+    // grow from 72 to 88 (setmaxnreg only moves registers inside the CTA's launch allocation; asking for 96 here deadlocks)
+    if (EW == 16) asm volatile("setmaxnreg.inc.sync.aligned.u32 88;");
     // Warps are independent: no shared tables and no block barriers.  Each thread decodes its own accumulator rows
     // (flat position -> output pixel / image), reads 32-column chunks from TMEM, adds bias (+ class embedding, + residual),
     // stores bf16 and accumulates the GroupNorm statistics of its rows; a warp then reduces 8 partials at a time with a
     // halving butterfly (9 shuffles) and the owning lanes add them to the (image, group) slots with fixed-point integer
     // atomics (order independent => deterministic).
     pdl_wait();                                       // output / residual / statistics buffers are free to touch
-    const int ew = warp - kProdWarps;                 // 0..7
-    const int quarter = ew & 3, part = ew >> 2;       // TMEM lane quarter, column half of the tile
+    const int ew = warp - kProdWarps;                 // 0 .. EW-1
+    const int quarter = ew & 3, part = ew >> 2;       // TMEM lane quarter, column part (half / quarter) of the tile
     bf16* out = (bf16*)p.c.out;
     constexpr bool kExtra = EXTRA && GEO == GEO_SAME;      // fill_params rejects residual / fold for the other geometries
     const bf16* res = kExtra ? (const bf16*)p.c.res : nullptr;
     // columns owned by this warp: half of the tile; with NT = 32 only the first warp of each lane quarter works
-    constexpr int NCOL = NT >= 64 ? NT / 2 : NT;      // 64 | 32 | 32
+    constexpr int NCOL = NT >= 64 ? NT / (EW / 4) : NT;      // 64 | 32 | 32 (8 warps), 32 (16 warps)
     constexpr int PPM = NCOL / 16;                    // 16-column pieces per 128-row accumulator (even)
     constexpr int ROWB = NCOL * 2, LPR = NCOL / 8, RPI = 32 / LPR;   // staging row bytes, lanes per row, rows per store instruction
     constexpr int SWS = ROWB == 64 ? 1 : 0, SWM = ROWB == 64 ? 3 : 7;
@@ -718,11 +746,30 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tcgen05_kernel(const Params 
     const bool has_bias = p.c.bias != nullptr;
     const bool has_fold = kExtra && p.c.fold_s1 != nullptr;     // GroupNorm(1) of the input folded into an epilogue affine (to_qkv)
     const uint32_t my_stage = smem_u32(s_stage) + (uint32_t)(ew * (32 * ROWB + NCOL * 8));   // shared-space addresses
-    const uint32_t my_bias = my_stage + (uint32_t)(32 * ROWB);
+    // bias (or the folded-GroupNorm vectors s1 | s2) of ALL output channels and, for the fold, (rstd, -mean * rstd) of every image are
+    // staged ONCE per CTA: with several N tiles per M tile the N tile changes on every tile of a CTA, and re-staging from global
+    // memory (plus a double-precision mean / rstd per accumulator row) was 30 % of the to_qkv epilogue
+    float* s_ball = reinterpret_cast<float*>(s_stage + EW * (32 * ROWB + NCOL * 8));
+    float2* s_rst = reinterpret_cast<float2*>(s_ball + 2 * p.c.Cout);
+    {
+      const int et = tid - kProdThreads;
+      if (has_bias || has_fold)
+        for (int i = et; i < p.c.Cout; i += kEpiT) {
+          s_ball[i] = has_fold ? p.c.fold_s1[i] : p.c.bias[i];
+          s_ball[p.c.Cout + i] = has_fold ? p.c.fold_s2[i] : 0.f;
+        }
+      if (has_fold)
+        for (int i = et; i < p.c.B; i += kEpiT) {
+          float mean, rstd;
+          gn_mean_rstd(p.c.pstats + (long)i * 2, p.inv_cnt_in, kGnEps, mean, rstd);
+          s_rst[i] = make_float2(rstd, -mean * rstd);
+        }
+      bar_sync_named(3, kEpiT);
+    }
+    const uint32_t s_ball_u = smem_u32(s_ball);
     const int my_swz = (lane >> SWS) & SWM;
     const int lrow = lane / LPR, lcol = lane % LPR;   // this lane's (row within a store instruction, 16-byte chunk)
     const uint32_t my_wr = my_stage + (uint32_t)(lane * ROWB);   // this lane's staging row
-    int last_ntile = -1;
     int it = 0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
       const TileGeom tg = tile_geom(tile, p);
@@ -758,20 +805,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tcgen05_kernel(const Params 
           if (valid) { opixv[mt] = opix; keyv[mt] = v.img; }
         }
       }
-      // bias of this warp's columns -> private shared memory (re-staged only when the N tile changes)
-      if ((has_bias || has_fold) && active && n_tile != last_ntile) {
-        __syncwarp();
-        if (has_fold) {
-          for (int i = lane; i < NCOL; i += 32) {
-            sts32f(my_bias + 4u * i, p.c.fold_s1[n0 + col0 + i]);
-            sts32f(my_bias + 4u * (NCOL + i), p.c.fold_s2[n0 + col0 + i]);
-          }
-        } else {
-          for (int i = lane; i < NCOL; i += 32) sts32f(my_bias + 4u * i, p.c.bias[n0 + col0 + i]);
-        }
-        last_ntile = n_tile;
-        __syncwarp();
-      }
+      const uint32_t my_bias = s_ball_u + 4u * (uint32_t)(n0 + col0);      // this warp's columns of the staged vectors
       if (ew == 0 && lane == 0) TRACE(it, 8);
 
       const int as = it & 1;
@@ -801,10 +835,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tcgen05_kernel(const Params 
         const bool valid = opix >= 0;
         unsigned long long fa2 = 0ull, fc2 = 0ull;            // fold: (rstd, rstd), (-mean*rstd, -mean*rstd) of this row's image
         if (has_fold && valid) {
-          float mean, rstd;
-          gn_mean_rstd(p.c.pstats + (long)key * 2, p.inv_cnt_in, kGnEps, mean, rstd);
-          fa2 = pack2(rstd, rstd);
-          fc2 = pack2(-mean * rstd, -mean * rstd);
+          const float2 rs = s_rst[key];
+          fa2 = pack2(rs.x, rs.x);
+          fc2 = pack2(rs.y, rs.y);
         }
 #pragma unroll
         for (int pc = 0; pc < PPM; ++pc) {
@@ -827,7 +860,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tcgen05_kernel(const Params 
 #pragma unroll
             for (int q4 = 0; q4 < 4; ++q4) {
               const uint4 s1 = lds128(my_bias + (uint32_t)(pc * 64 + q4 * 16));
-              const uint4 s2 = lds128(my_bias + (uint32_t)(NCOL * 4 + pc * 64 + q4 * 16));
+              const uint4 s2 = lds128(my_bias + (uint32_t)(p.c.Cout * 4 + pc * 64 + q4 * 16));
               v2[2 * q4] = fma2(v2[2 * q4], fa2, fma2(fc2, ((unsigned long long)s1.y << 32) | s1.x, ((unsigned long long)s2.y << 32) | s2.x));
               v2[2 * q4 + 1] = fma2(v2[2 * q4 + 1], fa2, fma2(fc2, ((unsigned long long)s1.w << 32) | s1.z, ((unsigned long long)s2.w << 32) | s2.z));
             }
@@ -925,7 +958,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tcgen05_kernel(const Params 
       }
       if (ew == 0 && lane == 0) TRACE(it, 11);
     }
-  } else if (warp == kLoaderWarp) {
+  } else if (warp == kLoaderW) {
     // =============================== weight loader ===============================
     // warp-uniform loop, one elected lane issues: one bulk copy (UBLKCP) of G taps (stage_bytes, contiguous in the blocked
     // weight image) per stage.  Copies of >= 16 KB are needed to reach the L2 -> shared streaming rate the MMAs consume.
@@ -1047,7 +1080,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tcgen05_kernel(const Params 
         }
         if (leader) umma_commit(smem_u32(&empty_a[cbuf]));      // frees the operand buffer
         __syncwarp();
-        if (++cbuf == kABuf) { cbuf = 0; cph ^= 1; }
+        if (++cbuf == AB) { cbuf = 0; cph ^= 1; }
       }
       if (leader) {
         umma_commit(smem_u32(&acc_full[as]));        // accumulators of this tile complete -> epilogue
@@ -1060,7 +1093,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tcgen05_kernel(const Params 
 
   tc_fence_before();
   __syncthreads();
-  if (warp == kMmaWarp) {
+  if (warp == kMmaW) {
     tc_fence_after();
     tmem_dealloc(tmem_base, p.tmem_cols);
   }
@@ -1068,8 +1101,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tcgen05_kernel(const Params 
 
 static size_t smem_fixed_bytes(const Params& p) {
   const int ncol = p.NT >= 64 ? p.NT / 2 : p.NT;
-  return (size_t)kABuf * 4 * p.PA * 16 + (2 * kStagesMax + 2 * kABuf + 4) * 8 + 16 + (size_t)kNimgMax * kGroupsMax * 8 +
-         2 * (size_t)p.P * 4 + 128 + (p.c.pro != PRO_NONE ? 3 * (size_t)p.c.C1 * 4 + 16 : 0) + (size_t)kEpiWarps * (32 * ncol * 2 + ncol * 8) + 128;
+  return (size_t)p.abuf * 4 * p.PA * 16 + (2 * kStagesMax + 2 * kABufMax + 4) * 8 + 16 + (size_t)kNimgMax * kGroupsMax * 8 +
+         2 * (size_t)p.P * 4 + 128 + (p.c.pro != PRO_NONE ? 3 * (size_t)p.c.C1 * 4 + 16 : 0) + (size_t)kEpiWarps * (32 * ncol * 2 + ncol * 8) + 128 +
+         2 * (size_t)p.c.Cout * 4 + (p.c.fold_s1 ? (size_t)p.c.B * 8 : 0) + 32;
 }
 static size_t smem_bytes(const Params& p) { return smem_fixed_bytes(p) + (size_t)p.nstage * p.stage_bytes; }
 constexpr size_t kSmemLimit = 216 * 1024;
@@ -1201,6 +1235,7 @@ static bool fill_params(const ConvP& c, int geo, Params& p) {
   p.cpg_in = 1;
   p.cpg_in_shift = p.cpg_out_shift = 0;
   p.inv_cnt_in = 0.f;
+  if (c.Cout > 2048 || (c.fold_s1 && c.B > 4096)) return false;      // per-CTA staging of the bias / fold vectors and image statistics
   if (c.fold_s1) {
     if (geo != GEO_SAME || c.ksize != 1 || c.pro != PRO_NONE || !c.fold_s2 || !c.pstats || c.pgroups != 1 || c.C2 != 0) return false;
     p.inv_cnt_in = 1.f / (float)(p.HW * c.C1);
@@ -1228,6 +1263,7 @@ static bool fill_params(const ConvP& c, int geo, Params& p) {
   p.magic_W = (uint32_t)(((1ull << 24) + p.Wv - 1) / p.Wv);
   for (int ph = 0; ph < 4; ++ph)
     for (int t = 0; t < 16; ++t) p.delta[ph * 16 + t] = t < p.ntap ? tap_delta(p, geo, t, ph) : 0;
+  p.abuf = (geo == GEO_SAME && p.NT == 128 && p.ntap == 1 && c.pro == PRO_NONE && !DMN_EXP_NO_ONETAP) ? kABufOne : kABuf;
   return pick_stages(p);
 }
 
@@ -1273,7 +1309,16 @@ static int launch(Params p, cudaStream_t st) {
       DMN_CUDA_CHECK(cudaFuncSetAttribute(conv_tcgen05_kernel<G2, 128, false, false, false, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemLimit));
       one_attr = true;
     }
-    if (extra) DMN_CUDA_CHECK(launch_pdl(conv_tcgen05_kernel<G2, 128, false, false, true, 3>, dim3(grid), dim3(kThreads), smem_bytes(p), st, p));
+    if (DMN_EXP_EW16) {
+      static bool a16 = false;
+      if (!a16) {
+        DMN_CUDA_CHECK(cudaFuncSetAttribute(conv_tcgen05_kernel<G2, 128, false, false, true, 3, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemLimit));
+        DMN_CUDA_CHECK(cudaFuncSetAttribute(conv_tcgen05_kernel<G2, 128, false, false, false, 3, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemLimit));
+        a16 = true;
+      }
+      if (extra) DMN_CUDA_CHECK(launch_pdl(conv_tcgen05_kernel<G2, 128, false, false, true, 3, 16>, dim3(grid), dim3(kThreads16), smem_bytes(p), st, p));
+      else DMN_CUDA_CHECK(launch_pdl(conv_tcgen05_kernel<G2, 128, false, false, false, 3, 16>, dim3(grid), dim3(kThreads16), smem_bytes(p), st, p));
+    } else if (extra) DMN_CUDA_CHECK(launch_pdl(conv_tcgen05_kernel<G2, 128, false, false, true, 3>, dim3(grid), dim3(kThreads), smem_bytes(p), st, p));
     else DMN_CUDA_CHECK(launch_pdl(conv_tcgen05_kernel<G2, 128, false, false, false, 3>, dim3(grid), dim3(kThreads), smem_bytes(p), st, p));
     count_launch();
     DMN_LAUNCH_CHECK("conv_tcgen05");
@@ -1296,7 +1341,15 @@ static int launch(Params p, cudaStream_t st) {
     if (pro && lean_ok) DMN_CUDA_CHECK(launch_pdl(conv_tcgen05_kernel<GEO_SAME, 128, false, true, false, 1>, dim3(grid), dim3(kThreads), smem_bytes(p), st, p));
     else if (pro) DMN_CUDA_CHECK(launch_pdl(conv_tcgen05_kernel<GEO_SAME, 128, false, false, false, 1>, dim3(grid), dim3(kThreads), smem_bytes(p), st, p));
     else if (lean_ok) DMN_CUDA_CHECK(launch_pdl(conv_tcgen05_kernel<G2, 128, false, true, false, 0>, dim3(grid), dim3(kThreads), smem_bytes(p), st, p));
-    else DMN_CUDA_CHECK(launch_pdl(conv_tcgen05_kernel<G2, 128, false, false, false, 0>, dim3(grid), dim3(kThreads), smem_bytes(p), st, p));
+    else if (DMN_EXP_EW16 && G2 == GEO_SAME) {
+      // epilogue-bound plain 3x3 tiles (fewer than 8 passes): 16 epilogue warps
+      static bool b16 = false;
+      if (!b16) {
+        DMN_CUDA_CHECK(cudaFuncSetAttribute(conv_tcgen05_kernel<GEO_SAME, 128, false, false, false, 0, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemLimit));
+        b16 = true;
+      }
+      DMN_CUDA_CHECK(launch_pdl(conv_tcgen05_kernel<GEO_SAME, 128, false, false, false, 0, 16>, dim3(grid), dim3(kThreads16), smem_bytes(p), st, p));
+    } else DMN_CUDA_CHECK(launch_pdl(conv_tcgen05_kernel<G2, 128, false, false, false, 0>, dim3(grid), dim3(kThreads), smem_bytes(p), st, p));
     count_launch();
     DMN_LAUNCH_CHECK("conv_tcgen05");
     return 0;
