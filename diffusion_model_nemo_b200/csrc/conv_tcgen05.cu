@@ -43,6 +43,12 @@
 #include "ops.h"
 #include "tc_ptx.cuh"
 
+#ifndef DMN_EXP_PRO_ABUF
+#define DMN_EXP_PRO_ABUF 3
+#endif
+#ifndef DMN_EXP_SMEM_KB
+#define DMN_EXP_SMEM_KB 226
+#endif
 #ifndef DMN_EXP_ONE_ABUF
 #define DMN_EXP_ONE_ABUF 5
 #endif
@@ -63,6 +69,8 @@ constexpr int kCk = 32;                // channels per pass (4 k-chunks of 8)
 constexpr int kStagesMax = 8;          // weight-ring depth (chosen per launch to fit shared memory); one stage = G taps
 constexpr int kABuf = 3;               // operand (A) buffers: the producers run up to kABuf passes ahead of the MMA issuer
 constexpr int kABufMax = 6;            // barrier-array spacing / host sizing; the 1x1 instantiations use kABufOne buffers
+constexpr int kABufPro = DMN_EXP_PRO_ABUF;   // GroupNorm-prologue instantiations (PRO = 1): ncu shows 13 % of producer time waiting for the copies
+                                       // of the pass issued one iteration earlier; a deeper ring hides it at the price of shared memory
 constexpr int kABufOne = DMN_EXP_ONE_ABUF, kDepthOne = kABufOne - 2;   // 1x1 convs: MMA work per pass is tiny, the producers are
                                        // bound by the global-load latency of the passes they keep in flight
 constexpr int kDepth = 1;              // passes a producer thread keeps in flight (cp.async groups) before it finishes the oldest;
@@ -132,6 +140,9 @@ constexpr bool kTraceProducer = DMN_TC_TRACE_PRODUCER != 0;
 #endif
 #ifndef DMN_EXP_NO_ONETAP
 #define DMN_EXP_NO_ONETAP 0
+#endif
+#ifndef DMN_EXP_EW16_LEAN
+#define DMN_EXP_EW16_LEAN 1
 #endif
 #ifndef DMN_EXP_EW16
 #define DMN_EXP_EW16 1              // 0: never use the 16-epilogue-warp instantiations
@@ -378,9 +389,11 @@ __device__ __forceinline__ void issue_pass(bool leader, uint32_t d0, uint32_t d1
 template <int GEO, int NT, bool FILM = false, bool LEAN = false, bool EXTRA = true, int PRO = 2, int EW = kEpiWarps>
 __global__ void __launch_bounds__((kProdWarps + EW + 2) * 32, 1) conv_tcgen05_kernel(const Params p) {
   constexpr int kLoaderW = kProdWarps + EW, kMmaW = kLoaderW + 1, kEpiT = EW * 32;
-  constexpr int AB = (PRO == 3 && GEO == GEO_SAME) ? kABufOne : kABuf, DEPTH = (PRO == 3 && GEO == GEO_SAME) ? kDepthOne : kDepth;
+  constexpr int AB = (PRO == 3 && GEO == GEO_SAME) ? kABufOne : ((PRO == 1 && GEO == GEO_SAME) ? kABufPro : kABuf);
+  constexpr int DEPTH = (PRO == 3 && GEO == GEO_SAME) ? kDepthOne : ((PRO == 1 && GEO == GEO_SAME) ? kABufPro - 2 : kDepth);
   static_assert(AB <= kABufMax && DEPTH >= 1 && DEPTH <= 3 && AB >= DEPTH + 2, "operand ring geometry");
   static_assert(EW == 8 || (EW == 16 && NT == 128 && (PRO == 0 || PRO == 3)), "16 epilogue warps: 128-column tiles without prologue");
+  static_assert(!(LEAN && PRO == 3), "the lean issue path is for 9- and 4-tap convolutions");
   extern __shared__ __align__(128) uint8_t smem[];
   const int tid = threadIdx.x;
   // broadcast => ptxas knows the role branches below are warp-uniform and may use the uniform datapath inside them
@@ -1106,7 +1119,7 @@ static size_t smem_fixed_bytes(const Params& p) {
          2 * (size_t)p.c.Cout * 4 + (p.c.fold_s1 ? (size_t)p.c.B * 8 : 0) + 32;
 }
 static size_t smem_bytes(const Params& p) { return smem_fixed_bytes(p) + (size_t)p.nstage * p.stage_bytes; }
-constexpr size_t kSmemLimit = 216 * 1024;
+constexpr size_t kSmemLimit = (size_t)DMN_EXP_SMEM_KB * 1024;     // a CTA may opt in to 227 KB
 // taps per weight stage: a whole filter row for 3x3, a tap pair for the 2x2 forms; bulk copies of 16-24 KB stream well
 static bool pick_stages(Params& p) {
   const size_t fixed = smem_fixed_bytes(p);
@@ -1264,6 +1277,8 @@ static bool fill_params(const ConvP& c, int geo, Params& p) {
   for (int ph = 0; ph < 4; ++ph)
     for (int t = 0; t < 16; ++t) p.delta[ph * 16 + t] = t < p.ntap ? tap_delta(p, geo, t, ph) : 0;
   p.abuf = (geo == GEO_SAME && p.NT == 128 && p.ntap == 1 && c.pro == PRO_NONE && !DMN_EXP_NO_ONETAP) ? kABufOne : kABuf;
+  // the GroupNorm-prologue instantiation (PRO = 1) is launched for 128-column tiles without residual / fold / FiLM (launch<>)
+  if (geo == GEO_SAME && p.NT == 128 && c.pro != PRO_NONE && !(c.pro & PRO_LRELU) && !c.res && !c.fold_s1) p.abuf = kABufPro;
   return pick_stages(p);
 }
 
@@ -1342,13 +1357,18 @@ static int launch(Params p, cudaStream_t st) {
     else if (pro) DMN_CUDA_CHECK(launch_pdl(conv_tcgen05_kernel<GEO_SAME, 128, false, false, false, 1>, dim3(grid), dim3(kThreads), smem_bytes(p), st, p));
     else if (lean_ok) DMN_CUDA_CHECK(launch_pdl(conv_tcgen05_kernel<G2, 128, false, true, false, 0>, dim3(grid), dim3(kThreads), smem_bytes(p), st, p));
     else if (DMN_EXP_EW16 && G2 == GEO_SAME) {
-      // epilogue-bound plain 3x3 tiles (fewer than 8 passes): 16 epilogue warps
+      // epilogue-bound plain 3x3 tiles (fewer than 8 passes): 16 epilogue warps; ncu then shows the epilogue waiting for the
+      // accumulators 24 % of the time, so these tiles take the lean issue path as well (DMN_EXP_EW16_LEAN)
       static bool b16 = false;
       if (!b16) {
         DMN_CUDA_CHECK(cudaFuncSetAttribute(conv_tcgen05_kernel<GEO_SAME, 128, false, false, false, 0, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemLimit));
+        DMN_CUDA_CHECK(cudaFuncSetAttribute(conv_tcgen05_kernel<GEO_SAME, 128, false, true, false, 0, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemLimit));
         b16 = true;
       }
-      DMN_CUDA_CHECK(launch_pdl(conv_tcgen05_kernel<GEO_SAME, 128, false, false, false, 0, 16>, dim3(grid), dim3(kThreads16), smem_bytes(p), st, p));
+      if (DMN_EXP_EW16_LEAN && p.ntap == 9 && p.G == 3)
+        DMN_CUDA_CHECK(launch_pdl(conv_tcgen05_kernel<GEO_SAME, 128, false, true, false, 0, 16>, dim3(grid), dim3(kThreads16), smem_bytes(p), st, p));
+      else
+        DMN_CUDA_CHECK(launch_pdl(conv_tcgen05_kernel<GEO_SAME, 128, false, false, false, 0, 16>, dim3(grid), dim3(kThreads16), smem_bytes(p), st, p));
     } else DMN_CUDA_CHECK(launch_pdl(conv_tcgen05_kernel<G2, 128, false, false, false, 0>, dim3(grid), dim3(kThreads), smem_bytes(p), st, p));
     count_launch();
     DMN_LAUNCH_CHECK("conv_tcgen05");
