@@ -43,8 +43,11 @@
 #include "ops.h"
 #include "tc_ptx.cuh"
 
+#ifndef DMN_EXP_PRO_DEPTH
+#define DMN_EXP_PRO_DEPTH 2
+#endif
 #ifndef DMN_EXP_PRO_ABUF
-#define DMN_EXP_PRO_ABUF 3
+#define DMN_EXP_PRO_ABUF 5
 #endif
 #ifndef DMN_EXP_SMEM_KB
 #define DMN_EXP_SMEM_KB 226
@@ -390,7 +393,7 @@ template <int GEO, int NT, bool FILM = false, bool LEAN = false, bool EXTRA = tr
 __global__ void __launch_bounds__((kProdWarps + EW + 2) * 32, 1) conv_tcgen05_kernel(const Params p) {
   constexpr int kLoaderW = kProdWarps + EW, kMmaW = kLoaderW + 1, kEpiT = EW * 32;
   constexpr int AB = (PRO == 3 && GEO == GEO_SAME) ? kABufOne : ((PRO == 1 && GEO == GEO_SAME) ? kABufPro : kABuf);
-  constexpr int DEPTH = (PRO == 3 && GEO == GEO_SAME) ? kDepthOne : ((PRO == 1 && GEO == GEO_SAME) ? kABufPro - 2 : kDepth);
+  constexpr int DEPTH = (PRO == 3 && GEO == GEO_SAME) ? kDepthOne : ((PRO == 1 && GEO == GEO_SAME) ? DMN_EXP_PRO_DEPTH : kDepth);
   static_assert(AB <= kABufMax && DEPTH >= 1 && DEPTH <= 3 && AB >= DEPTH + 2, "operand ring geometry");
   static_assert(EW == 8 || (EW == 16 && NT == 128 && (PRO == 0 || PRO == 3)), "16 epilogue warps: 128-column tiles without prologue");
   static_assert(!(LEAN && PRO == 3), "the lean issue path is for 9- and 4-tap convolutions");
