@@ -292,6 +292,16 @@ template <> struct VecIO<bf16, 8> {
   static __device__ __forceinline__ void store(bf16* p, const float* v) { *reinterpret_cast<uint4*>(p) = pack8(v); }
 };
 
+// raw conv output and residual are dead (raw) or cold (residual) after this kernel while the result is read by the very next kernel:
+// streaming loads (evict-first) keep the 126 MB L2 for the output.  DMN_EXP_FIN_STREAM=0 restores plain loads.
+#ifndef DMN_EXP_FIN_STREAM
+#define DMN_EXP_FIN_STREAM 1
+#endif
+#if DMN_EXP_FIN_STREAM
+#define DMN_FIN_LD(ptr) __ldcs(ptr)
+#else
+#define DMN_FIN_LD(ptr) (*(ptr))
+#endif
 template <typename T, int V>
 __global__ void __launch_bounds__(256, 3) gn_finalize_kernel(const FinalizeP p) {
   pdl_trigger();
@@ -326,11 +336,11 @@ __global__ void __launch_bounds__(256, 3) gn_finalize_kernel(const FinalizeP p) 
     Raw vr[U], rr[U];                       // packed: 16 bytes per item until it is processed
 #pragma unroll
     for (int u = 0; u < U; ++u)
-      if (i + u * stride < items) vr[u] = *reinterpret_cast<const Raw*>(raw + (i + u * stride) * V);
+      if (i + u * stride < items) vr[u] = DMN_FIN_LD(reinterpret_cast<const Raw*>(raw + (i + u * stride) * V));
     if (res) {
 #pragma unroll
       for (int u = 0; u < U; ++u)
-        if (i + u * stride < items) rr[u] = *reinterpret_cast<const Raw*>(res + (i + u * stride) * V);
+        if (i + u * stride < items) rr[u] = DMN_FIN_LD(reinterpret_cast<const Raw*>(res + (i + u * stride) * V));
     }
 #pragma unroll
     for (int u = 0; u < U; ++u) {
