@@ -248,7 +248,7 @@ def main():
     groups = {}
     for (name, kind, eng, fl, by), ms in zip(ops, acc):
         key = {0: "memset", 1: "init_conv", 2: "conv_tcgen05" if eng else "conv_simt", 3: "gn_finalize", 4: "linattn_core",
-               5: "attn_core", 6: "final_proj"}[kind]
+               5: "attn_core", 6: "final_proj", 7: "film_modulate", 8: "class_embed_add"}.get(kind, "other")
         g = groups.setdefault(key, {"ms": 0.0, "flops": 0.0, "bytes": 0.0, "launches": 0})
         g["ms"] += ms
         g["flops"] += fl * B
