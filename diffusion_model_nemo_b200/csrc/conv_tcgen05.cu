@@ -150,6 +150,10 @@ constexpr bool kTraceProducer = DMN_TC_TRACE_PRODUCER != 0;
 #ifndef DMN_EXP_EW16
 #define DMN_EXP_EW16 1              // 0: never use the 16-epilogue-warp instantiations
 #endif
+#ifndef DMN_EXP_FENCE_MODE
+#define DMN_EXP_FENCE_MODE 0        // 0: every producer thread fences (generic -> async proxy) before it arrives on the operand barrier;
+                                    // 1: no fence at all (timing probe only, NOT correct); 2: the MMA warp fences after it has acquired the barrier
+#endif
 #ifndef DMN_EXP_NO_EPI
 #define DMN_EXP_NO_EPI 0            // epilogue: TMEM reads only (no staging, no global stores, no statistics)
 #endif
@@ -509,7 +513,7 @@ __global__ void __launch_bounds__((kProdWarps + EW + 2) * 32, 1) conv_tcgen05_ke
           }
           *reinterpret_cast<uint4*>(sA + ibuf * a_bytes + (uint32_t)kc * p.lbo_a + pixel * 16) = pack8(f);
         }
-        fence_proxy_async();
+        if (DMN_EXP_FENCE_MODE == 0) fence_proxy_async();
         mbar_arrive(smem_u32(&full_a[ibuf]));
         if (++ibuf == AB) { ibuf = 0; iph ^= 1; }
         fbuf = ibuf;
@@ -650,7 +654,7 @@ __global__ void __launch_bounds__((kProdWarps + EW + 2) * 32, 1) conv_tcgen05_ke
             default: run(std::integral_constant<int, 0>()); break;
           }
         }
-        fence_proxy_async();
+        if (DMN_EXP_FENCE_MODE == 0) fence_proxy_async();
         mbar_arrive(smem_u32(&full_a[fbuf]));
         if (++fbuf == AB) fbuf = 0;
       };
@@ -1040,6 +1044,7 @@ __global__ void __launch_bounds__((kProdWarps + EW + 2) * 32, 1) conv_tcgen05_ke
         long long w0 = tracing ? clock64() : 0;
         mbar_wait(smem_u32(&full_a[cbuf]), cph);
         if (tracing) wait_a += clock64() - w0;
+        if (DMN_EXP_FENCE_MODE == 2) fence_proxy_async();     // consumer-side generic -> async proxy fence (see DMN_EXP_FENCE_MODE)
         if (!DMN_EXP_NO_FENCE) tc_fence_after();
         if (c == 0 && leader) TRACE(it, 5);
         const uint32_t au = a_units0 + (uint32_t)cbuf * a_buf_units;
