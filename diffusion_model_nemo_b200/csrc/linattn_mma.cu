@@ -103,13 +103,16 @@ __global__ void __launch_bounds__(256, 2) linattn_mma_kernel(const bf16* __restr
     else cp_async_wait<0>();
     __syncthreads();
     const int nvalid = min(TN, N - tile * TN);
-    // tile column max (this thread: channel c, rows [32*half, 32*half + 32))
+    // tile column max (this thread: channel c, rows [32*half, 32*half + 32)); the 32 values stay in registers for the exp pass
+    float kv[32];
     {
       float m = -INFINITY;
       const uint32_t a0 = tb + (uint32_t)(half * 32 * KV_LD + c * 2);
-#pragma unroll 8
-      for (int r = 0; r < 32; ++r)
-        if (half * 32 + r < nvalid) m = fmaxf(m, ld_bf16(a0 + (uint32_t)(r * KV_LD)));
+#pragma unroll
+      for (int r = 0; r < 32; ++r) {
+        kv[r] = ld_bf16(a0 + (uint32_t)(r * KV_LD));
+        if (half * 32 + r < nvalid) m = fmaxf(m, kv[r]);
+      }
       red_s[half * 128 + c] = m;
     }
     __syncthreads();
@@ -124,12 +127,12 @@ __global__ void __launch_bounds__(256, 2) linattn_mma_kernel(const bf16* __restr
       const float mn = fmax_s[c];
       ksum *= fac_s[c];
       const uint32_t a0 = tb + (uint32_t)(half * 32 * KV_LD + c * 2);
-#pragma unroll 8
+#pragma unroll
       for (int r = 0; r < 32; ++r) {
         const uint32_t a = a0 + (uint32_t)(r * KV_LD);
         bf16 pv = __float2bfloat16_rn(0.f);
         if (half * 32 + r < nvalid) {
-          pv = __float2bfloat16_rn(__expf(ld_bf16(a) - mn));
+          pv = __float2bfloat16_rn(__expf(kv[r] - mn));
           ksum += __bfloat162float(pv);
         }
         st_bf16(a, pv);
