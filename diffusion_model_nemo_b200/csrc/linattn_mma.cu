@@ -35,7 +35,7 @@ constexpr int Q_LD = 272;     // bytes per token row of a q tile: 128 channels x
 constexpr int CTX_LD = 80;    // bytes per d row of the bf16 context: 32 e x 2 B + 16 B pad
 constexpr int kTileBytes = 2 * TN * KV_LD;                         // double buffer (the q tiles reuse it)
 constexpr int kCtxBytes = 4 * 32 * CTX_LD;
-constexpr int kSmem = kTileBytes + kCtxBytes + 128 * 4 * 6;        // + fmax, fac, red[2], ksum[2]
+constexpr int kSmem = kTileBytes + kCtxBytes + 128 * 4 * 10;       // + fmax, fac, red[4], ksum[4]
 
 __device__ __forceinline__ void ldsm_x4(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
   asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];" : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
@@ -66,8 +66,8 @@ __global__ void __launch_bounds__(256, 2) linattn_mma_kernel(const bf16* __restr
   const uint32_t ctxs = tiles + kTileBytes;
   float* fmax_s = reinterpret_cast<float*>(sm + kTileBytes + kCtxBytes);   // running column max of k
   float* fac_s = fmax_s + 128;                                              // exp(old max - new max) of this tile
-  float* red_s = fac_s + 128;                                               // [2][128] per-half tile max
-  float* ksum_s = red_s + 256;                                              // [2][128] per-half column sums
+  float* red_s = fac_s + 128;                                               // [4][128] per-quarter tile max
+  float* ksum_s = red_s + 512;                                              // [4][128] per-quarter column sums
   const int b = blockIdx.x, t = threadIdx.x, w = t >> 5, lane = t & 31;
   const bf16* base = qkv + (long)b * N * 384;
   const int ntiles = (N + TN - 1) / TN;
@@ -87,8 +87,9 @@ __global__ void __launch_bounds__(256, 2) linattn_mma_kernel(const bf16* __restr
     cp_async_commit();
   };
   if (t < 128) fmax_s[t] = -INFINITY;
-  const int c = t & 127, half = t >> 7;      // column-softmax role: channel, token half of the tile
-  float ksum = 0.f;
+  // column-softmax role: a PAIR of adjacent channels (one 32-bit word per row) and a quarter of the tile's tokens
+  const int c2 = (t & 63) * 2, qtr = t >> 6;
+  float ksum0 = 0.f, ksum1 = 0.f;
   float acc[4][4];
 #pragma unroll
   for (int i = 0; i < 4; ++i)
@@ -103,39 +104,46 @@ __global__ void __launch_bounds__(256, 2) linattn_mma_kernel(const bf16* __restr
     else cp_async_wait<0>();
     __syncthreads();
     const int nvalid = min(TN, N - tile * TN);
-    // tile column max (this thread: channel c, rows [32*half, 32*half + 32)); the 32 values stay in registers for the exp pass
-    float kv[32];
+    // tile column max (this thread: channels c2, c2 + 1, rows [16*qtr, 16*qtr + 16)); the values stay in registers for the exp pass
+    uint32_t kw[16];
     {
-      float m = -INFINITY;
-      const uint32_t a0 = tb + (uint32_t)(half * 32 * KV_LD + c * 2);
+      float m0 = -INFINITY, m1 = -INFINITY;
+      const uint32_t a0 = tb + (uint32_t)(qtr * 16 * KV_LD + c2 * 2);
 #pragma unroll
-      for (int r = 0; r < 32; ++r) {
-        kv[r] = ld_bf16(a0 + (uint32_t)(r * KV_LD));
-        if (half * 32 + r < nvalid) m = fmaxf(m, kv[r]);
+      for (int r = 0; r < 16; ++r) {
+        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(kw[r]) : "r"(a0 + (uint32_t)(r * KV_LD)));
+        if (qtr * 16 + r < nvalid) {
+          m0 = fmaxf(m0, __uint_as_float(kw[r] << 16));
+          m1 = fmaxf(m1, __uint_as_float(kw[r] & 0xffff0000u));
+        }
       }
-      red_s[half * 128 + c] = m;
+      red_s[qtr * 128 + c2] = m0;
+      red_s[qtr * 128 + c2 + 1] = m1;
     }
     __syncthreads();
     if (t < 128) {
-      const float mo = fmax_s[t], mn = fmaxf(mo, fmaxf(red_s[t], red_s[128 + t]));
+      const float mo = fmax_s[t], mn = fmaxf(fmaxf(mo, fmaxf(red_s[t], red_s[128 + t])), fmaxf(red_s[256 + t], red_s[384 + t]));
       fac_s[t] = __expf(mo - mn);            // first tile: exp(-inf) = 0
       fmax_s[t] = mn;
     }
     __syncthreads();
     // P = exp(k - max) in place (bf16); column sums of the ROUNDED values so numerator and denominator agree
     {
-      const float mn = fmax_s[c];
-      ksum *= fac_s[c];
-      const uint32_t a0 = tb + (uint32_t)(half * 32 * KV_LD + c * 2);
+      const float mn0 = fmax_s[c2], mn1 = fmax_s[c2 + 1];
+      ksum0 *= fac_s[c2];
+      ksum1 *= fac_s[c2 + 1];
+      const uint32_t a0 = tb + (uint32_t)(qtr * 16 * KV_LD + c2 * 2);
 #pragma unroll
-      for (int r = 0; r < 32; ++r) {
-        const uint32_t a = a0 + (uint32_t)(r * KV_LD);
-        bf16 pv = __float2bfloat16_rn(0.f);
-        if (half * 32 + r < nvalid) {
-          pv = __float2bfloat16_rn(__expf(kv[r] - mn));
-          ksum += __bfloat162float(pv);
+      for (int r = 0; r < 16; ++r) {
+        uint32_t pw = 0u;
+        if (qtr * 16 + r < nvalid) {
+          const bf16 p0 = __float2bfloat16_rn(__expf(__uint_as_float(kw[r] << 16) - mn0));
+          const bf16 p1 = __float2bfloat16_rn(__expf(__uint_as_float(kw[r] & 0xffff0000u) - mn1));
+          ksum0 += __bfloat162float(p0);
+          ksum1 += __bfloat162float(p1);
+          pw = (uint32_t)(*reinterpret_cast<const unsigned short*>(&p0)) | ((uint32_t)(*reinterpret_cast<const unsigned short*>(&p1)) << 16);
         }
-        st_bf16(a, pv);
+        st_u32(a0 + (uint32_t)(r * KV_LD), pw);
       }
     }
     __syncthreads();
@@ -161,11 +169,13 @@ __global__ void __launch_bounds__(256, 2) linattn_mma_kernel(const bf16* __restr
     }
     __syncthreads();      // the next iteration's prefetch overwrites the buffer read here one tile later
   }
-  ksum_s[half * 128 + c] = ksum;
+  ksum_s[qtr * 128 + c2] = ksum0;
+  ksum_s[qtr * 128 + c2 + 1] = ksum1;
   __syncthreads();
   {
-    const float i0 = 1.f / (ksum_s[h * 32 + dh + g] + ksum_s[128 + h * 32 + dh + g]);
-    const float i1 = 1.f / (ksum_s[h * 32 + dh + g + 8] + ksum_s[128 + h * 32 + dh + g + 8]);
+    const int ch0 = h * 32 + dh + g, ch1 = ch0 + 8;
+    const float i0 = 1.f / ((ksum_s[ch0] + ksum_s[128 + ch0]) + (ksum_s[256 + ch0] + ksum_s[384 + ch0]));
+    const float i1 = 1.f / ((ksum_s[ch1] + ksum_s[128 + ch1]) + (ksum_s[256 + ch1] + ksum_s[384 + ch1]));
 #pragma unroll
     for (int nt = 0; nt < 4; ++nt) {
       const uint32_t a = ctxs + (uint32_t)((h * 32 + dh + g) * CTX_LD + (nt * 8 + 2 * tq) * 2);
