@@ -251,3 +251,37 @@ def test_wavegrad_tables_and_api(golden):
     noise = torch.randn_like(x0)
     lvl = torch.full((2, 1, 1, 1), 0.8)
     assert torch.allclose(s.q_sample(x0, lvl, noise), 0.8 * x0 + (1 - 0.64) ** 0.5 * noise, atol=1e-5)
+
+
+def test_film_frequency_table_matches_reference_positional_encoding():
+    """engine.film_freqs builds the per-column exponents of the FiLM positional encoding with the reference's own torch ops
+    (parts/film.py:19-21): 5000 * level * freq must reproduce the oracle's sin / cos arguments bit for bit."""
+    import torch
+    from diffusion_model_nemo_b200.engine import film_freqs
+    from oracle import ref_port as O
+
+    chans = [32, 64, 128]
+    f = film_freqs(chans)
+    assert f.shape == (sum(chans),)
+    level = torch.tensor([0.37]).view(1, 1, 1, 1)
+    col = 0
+    for c in chans:
+        pe = O.film_positional_encoding(level, c).flatten()
+        arg = (5000 * level.view(1) * f[col:col + c])                      # same left-to-right product as the reference
+        want = torch.cat([arg[:c // 2].sin(), arg[c // 2:].cos()])
+        assert torch.equal(pe, want), c
+        assert torch.equal(f[col:col + c // 2], f[col + c // 2:col + c])     # [exponents | exponents]
+        col += c
+
+
+def test_bpd_prior_term_is_schedule_only():
+    """The prior term of the bits-per-dimension evaluation depends on x_0 and the schedule alone (abstract_diffusion_model.py:180-184)."""
+    import torch
+    from oracle import ref_port as O
+
+    tb = O.ddpm_tables(50, "linear")
+    x0 = torch.rand(3, 1, 8, 8) * 2 - 1
+    a = O.bits_per_dimension(lambda x, t: torch.zeros_like(x), x0, tb, O.NoiseQueue(1))
+    b = O.bits_per_dimension(lambda x, t: torch.ones_like(x), x0, tb, O.NoiseQueue(2))
+    assert torch.equal(a["prior_bpd"], b["prior_bpd"]) and (a["prior_bpd"] > 0).all()
+    assert a["terms_bpd"].shape == (3, 50) and not torch.equal(a["terms_bpd"], b["terms_bpd"])
