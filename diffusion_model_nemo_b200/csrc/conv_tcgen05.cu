@@ -24,13 +24,19 @@
 // [n_tile][pass][tap][kchunk][n] 16-byte items and streamed with 1-D bulk async copies (cp.async.bulk -> UBLKCP, the TMA
 // engine's non-tensor mode) through an mbarrier ring.
 //
-// PERSISTENT, warp-specialised CTA (one per SM, 576 threads), tiles assigned round-robin:
+// PERSISTENT, warp-specialised CTA (one per SM, 576 threads; 832 in the 16-epilogue-warp instantiations), tiles assigned round-robin:
 //   warps 0-7   operand producers (global -> prologue transform -> shared), run ahead across tiles (2 operand buffers)
 //   warps 8-15  epilogue (TMEM -> registers -> +bias, +residual, GroupNorm statistics, bf16 -> global); two warps per TMEM
 //               lane quarter, each taking half of the tile's columns
 //   warp 16     weight loader (one lane), warp 17 TMEM allocator + single-thread MMA issuer
 // The accumulators are double buffered in TMEM (2 x mt x NT <= 512 columns), so the epilogue of tile i overlaps the main
 // loop of tile i+1 and the per-CTA setup is paid once per launch.
+//
+// The kernel is a template over <geometry, N tile, FiLM prologue, lean issue, rare epilogue terms, prologue mode, epilogue warps>:
+// the engine is sensitive to the amount of code around its inner loops, so every launch picks the smallest instantiation that
+// covers it (launch<>() below).  Compile-time switches DMN_EXP_* keep the measured alternatives buildable
+// (python -m diffusion_model_nemo_b200._build --variant <lib.so> -DDMN_EXP_...=1; select with DMN_LIB_PATH); profiles/README.md
+// records what each of them measured.
 //
 // Garbage rows: flat positions that fall on a pad column/row are computed and discarded (1 - HW/S of the MMA
 // work for 3x3: 6 % at 32x32, 11 % at 16x16, 21 % at 8x8, 36 % at 4x4).
