@@ -82,3 +82,39 @@ def test_argument_validation_is_loud():
     L.check(lib.dmn_plan_create(C.byref(good), C.byref(h)))
     assert lib.dmn_unet_forward(h, None, None, None, None, 1, None) == -4
     lib.dmn_plan_destroy(h)
+
+
+@pytest.mark.parametrize("mode", [(L.ACT_F32, L.CONV_SIMT), (L.ACT_BF16, L.CONV_TCGEN05)])
+def test_film_plan_parameter_table_and_layout(mode):
+    """WaveGradUNet plans (cfg.film = 1): the engine's parameter table is the subset of the reference state_dict it evaluates -- no
+    time MLP, FiLM layers 0 .. n_levels-1 (the bottleneck FiLM is discarded by the reference and the last n_levels-1 are never called,
+    unet.py:204-210,247) -- and dmn_plan_film_layout reports their channels in table-column order."""
+    from conftest import WG_CFGS
+
+    cfg, size, b = WG_CFGS["wg_cfg"]
+    lib = L.lib()
+    c = _cfg(cfg, size, b, *mode)
+    c.with_time_emb, c.film = 0, 1
+    h = C.c_void_p()
+    L.check(lib.dmn_plan_create(C.byref(c), C.byref(h)))
+    try:
+        names = {lib.dmn_plan_param_name(h, i).decode() for i in range(lib.dmn_plan_num_params(h))}
+        ref = set(O.unet_param_shapes(cfg))
+        assert names <= ref and not any(n.startswith("time_mlp") or ".mlp." in n for n in names)
+        films = sorted({int(n.split(".")[1]) for n in names if n.startswith("films.")})
+        assert films == [0, 1, 2, 3]
+        assert (ref - names) == {n for n in ref if n.startswith("films.") and int(n.split(".")[1]) >= 4}
+        ch = (C.c_int32 * 16)()
+        n = lib.dmn_plan_film_layout(h, ch, 16)
+        assert [ch[i] for i in range(n)] == [128, 128, 256, 256]
+        kinds = []
+        for i in range(lib.dmn_plan_num_ops(h)):
+            k, e, fl, by = C.c_int32(), C.c_int32(), C.c_double(), C.c_double()
+            L.check(lib.dmn_plan_op_info(h, i, None, 0, C.byref(k), C.byref(e), C.byref(fl), C.byref(by)))
+            kinds.append(k.value)
+        assert kinds.count(7) == 4                                   # one modulation per evaluated FiLM layer
+    finally:
+        lib.dmn_plan_destroy(h)
+    # a FiLM plan must not carry a time embedding (unet.py:195)
+    c.with_time_emb = 1
+    assert lib.dmn_plan_create(C.byref(c), C.byref(h)) == -1
