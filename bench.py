@@ -56,11 +56,15 @@ class ClockSampler:
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, gpu_index):
-        self.gpu, self.rows, self.proc = gpu_index, [], None
+        self.gpu, self.rows, self.proc, self.t_begin = gpu_index, [], None, 0.0
+
+    def mark_begin(self):
+        """Samples that arrive from now on (until stop()) belong to the timed region."""
+        self.t_begin = time.perf_counter()
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200",
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50",
                                           "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.th = threading.Thread(target=self._read, daemon=True)
             self.th.start()
@@ -69,15 +73,17 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.perf_counter(), [c.strip() for c in line.split(",")]))
 
     def stop(self):
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.25)
+        t_end = time.perf_counter() + 0.06      # one more sampling period: a sample taken at the end of the region is still in flight
+        time.sleep(0.12)
         self.proc.terminate()
         sm, mx, reasons = [], [], set()
-        for r in self.rows:
+        rows = [r for (ts, r) in self.rows if self.t_begin <= ts <= t_end] or [r for (_, r) in self.rows[-3:]]
+        for r in rows:
             try:
                 sm.append(float(r[1]))
                 mx.append(float(r[2]))
@@ -91,7 +97,7 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
-def cpu_baseline(sample_batch=8, steps=3, warm=1):
+def cpu_baseline(sample_batch=32, steps=6, warm=1):
     """The CPU oracle port (oracle/ref_port.py == the reference's torch CPU arithmetic) on the host cores, bounded sample."""
     from oracle import ref_port as O
 
@@ -116,10 +122,27 @@ def cpu_baseline(sample_batch=8, steps=3, warm=1):
             "ms_per_step": s_per_step * 1e3}
 
 
+def _load_executed_reference():
+    """The UNMODIFIED reference package from baseline/_ref (pip --target install of /root/reference, git-ignored, shipped to the GPU
+    box) behind the import shim of tests/_shim (nemo / pytorch_lightning / omegaconf / hydra are absent offline).  None if not shipped."""
+    ref_dir = os.path.join(ROOT, "baseline", "_ref")
+    if not os.path.isdir(os.path.join(ref_dir, "diffusion_model_nemo")):
+        return None
+    sys.path.insert(0, os.path.join(ROOT, "tests", "_shim"))
+    sys.path.insert(1, ref_dir)
+    try:
+        import diffusion_model_nemo.modules as RM
+        return RM
+    except Exception as e:        # pragma: no cover
+        sys.stderr.write(f"executed reference unavailable ({e}); timing the oracle port instead\n")
+        return None
+
+
 def run_reference(args):
-    """`--impl reference`: the reference's own CPU arithmetic on the host cores.  The reference is pure PyTorch with no
-    build of its own, so the arm times the oracle port (== the same aten CPU ops in the same order)
-    on a bounded sample: each step is one reverse-diffusion step (U-Net + posterior update) at batch 8."""
+    """`--impl reference`: the reference's own CPU sampling path on the host cores, all threads.  When baseline/_ref is present the
+    EXECUTED reference runs (its Unet + GaussianDiffusion.p_sample with the per-step `extract` gathers and the per-step `.cpu()` of
+    p_sample_loop, modules/gaussian_diffusion.py:157-189), else the pinned oracle port (the same aten calls).  Bounded sample: each
+    step is one reverse-diffusion step at batch 32 of the benchmark workload."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
@@ -127,32 +150,97 @@ def run_reference(args):
 
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    sb = 8
+    sb = 32
     sd = O.random_state_dict(CFG2, seed=0)
-    tb = O.ddpm_tables(T, "linear")
+    RM = _load_executed_reference()
     q = O.NoiseQueue(0)
     x = q([sb, 3, IMAGE, IMAGE])
     dt, budget0 = [], time.perf_counter()
-    with torch.no_grad():
-        for i in range(args.warmup + args.steps):
-            t = torch.full((sb,), T - 1 - (i % T), dtype=torch.long)
-            t0 = time.perf_counter()
-            eps = O.unet_forward(sd, CFG2, x, t.float())
-            x = O.ddpm_step(tb, x, t, eps, q(x.shape))
-            if i >= args.warmup:
-                dt.append(time.perf_counter() - t0)
-            if time.perf_counter() - budget0 > 150 and len(dt) >= 3:
-                break
+    if RM is not None:
+        kind = "reference"
+        unet = RM.Unet(input_dim=None, dim=CFG2["dim"], dim_mults=CFG2["dim_mults"], channels=3, use_convnext=False,
+                       resnet_block_groups=CFG2["groups"], dropout=0.0).eval()
+        unet.load_state_dict(sd, strict=True)
+        sampler = RM.GaussianDiffusion(timesteps=T, schedule_name="linear")
+        imgs = []
+        with torch.inference_mode():
+            for i in range(args.warmup + args.steps):
+                t = torch.full((sb,), T - 1 - (i % T), dtype=torch.long)
+                t0 = time.perf_counter()
+                x = sampler.p_sample(unet, x, t)                # reference gaussian_diffusion.py:157-167 (own randn_like)
+                imgs = [(x.cpu() + 1) * 0.5]                     # :187 keeps every step; keeping one bounds the memory
+                if i >= args.warmup:
+                    dt.append(time.perf_counter() - t0)
+                if time.perf_counter() - budget0 > 150 and len(dt) >= 3:
+                    break
+    else:
+        kind = "port"
+        tb = O.ddpm_tables(T, "linear")
+        with torch.no_grad():
+            for i in range(args.warmup + args.steps):
+                t = torch.full((sb,), T - 1 - (i % T), dtype=torch.long)
+                t0 = time.perf_counter()
+                eps = O.unet_forward(sd, CFG2, x, t.float())
+                x = O.ddpm_step(tb, x, t, eps, q(x.shape))
+                if i >= args.warmup:
+                    dt.append(time.perf_counter() - t0)
+                if time.perf_counter() - budget0 > 150 and len(dt) >= 3:
+                    break
     ms = 1e3 * sum(dt) / len(dt)
     val = sb / (ms * 1e-3 * T)
     line = {"impl": "reference", "metric": "ddpm_samples_per_sec_32x32_unet_1000_steps", "value": val, "unit": "samples/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "configs[1]: DDPM 3x32x32 U-Net dim128 mults(1,2,2,2) groups8, T=1000; CPU arm: batch 8 per step"},
-            "cpu_baseline": {"value": val, "unit": "samples/s", "cores": cores, "kind": "port",
-                             "sample": f"{len(dt)} timed reverse steps at batch {sb} on {cores} host threads, extrapolated to T={T}"},
+            "config": {"workload": f"configs[1]: DDPM 3x32x32 U-Net dim128 mults(1,2,2,2) groups8, T=1000; CPU arm: batch {sb} per step"},
+            "cpu_baseline": {"value": val, "unit": "samples/s", "cores": cores, "kind": kind,
+                             "sample": f"{len(dt)} timed reverse steps at batch {sb} on {cores} host threads ("
+                                       + ("executed reference from baseline/_ref: Unet + GaussianDiffusion.p_sample + per-step .cpu()"
+                                          if kind == "reference" else "oracle port, same aten ops") + f"), extrapolated to T={T}"},
             "e2e": {"value": val, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
+
+
+def library_bar(dev, batch, steps=5, warm=2):
+    """the reference U-Net's aten program under torch eager ON THE B200 (bf16, channels_last, cuDNN /
+    cuBLAS), same batch, ms per evaluation.  A reported on-box bar for the hand-written engine; not a product path."""
+    from oracle import ref_port as O
+
+    try:
+        sd = {k: v.to(dev, torch.bfloat16) for k, v in O.random_state_dict(CFG2, seed=0).items()}
+        for k, v in sd.items():
+            if v.dim() == 4:
+                sd[k] = v.contiguous(memory_format=torch.channels_last)
+        x = torch.randn(batch, 3, IMAGE, IMAGE, device=dev, dtype=torch.bfloat16).contiguous(memory_format=torch.channels_last)
+        t = torch.full((batch,), 500.0, device=dev)
+        orig = O.sinusoidal_embedding
+
+        def emb(time, dim):          # the port builds the frequency vector on the CPU; keep it on the device and in the activation dtype
+            import math
+            half = dim // 2
+            e = torch.exp(torch.arange(half, device=time.device) * -(math.log(10000) / (half - 1)))
+            e = time[:, None].float() * e[None, :]
+            return torch.cat((e.sin(), e.cos()), dim=-1).to(torch.bfloat16)
+
+        O.sinusoidal_embedding = emb
+        try:
+            with torch.no_grad():
+                for _ in range(warm):
+                    O.unet_forward(sd, CFG2, x, t)
+                torch.cuda.synchronize(dev)
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                for _ in range(steps):
+                    O.unet_forward(sd, CFG2, x, t)
+                e1.record()
+                torch.cuda.synchronize(dev)
+        finally:
+            O.sinusoidal_embedding = orig
+        ms = e0.elapsed_time(e1) / steps
+        return {"ms_per_unet_eval": ms, "samples_per_s_equiv": batch / (ms * 1e-3 * T), "batch": batch,
+                "what": "reference U-Net aten program (oracle port) under torch eager on this GPU: bf16, channels_last, cuDNN/cuBLAS; "
+                        "U-Net evaluation only (no sampler update)"}
+    except Exception as e:       # pragma: no cover
+        return {"error": str(e)[:200]}
 
 
 def main():
@@ -166,6 +254,7 @@ def main():
     ap.add_argument("--dtype", default="bf16")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-library-bar", action="store_true")
     ap.add_argument("--dump-ops", default="", help="write the per-launch table of one step (name, ms, TFLOP/s, GB/s) to this file")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -207,26 +296,36 @@ def main():
         torch.cuda.synchronize(dev)
         return e0.elapsed_time(e1), res
 
+    clk = ClockSampler(local)                # started before the warm-up: nvidia-smi takes a while to deliver its first sample
+    clk.start()
     _, res_w = timed(args.warmup)            # builds the plan, uploads weights, captures the graph, warms clocks
     if ws > 1:
         D.all_gather_samples(res_w.final, total=B * ws)   # warm-up: creates the NCCL communicator outside the timed region
         torch.cuda.synchronize(dev)
     plan = unet.plan(IMAGE, B, dev)
-    clk = ClockSampler(local)
-    clk.start()
+    clk.mark_begin()
     ms_total, res = timed(args.steps)
     clocks = clk.stop()
     # the single collective of the job: all-gather of the final samples (timed once, amortised over T steps)
     ag_ms = 0.0
+    gather_check = None
     if ws > 1:
         torch.cuda.synchronize(dev)
         dist.barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        D.all_gather_samples(res.final, total=B * ws)
+        full = D.all_gather_samples(res.final, total=B * ws)
         e1.record()
         torch.cuda.synchronize(dev)
         ag_ms = e0.elapsed_time(e1)
+        # content check of the one collective: slice r of the gathered batch is rank r's local final, and the shards differ
+        ok = torch.equal(full[rank * B:(rank + 1) * B], res.final)
+        if rank > 0:
+            ok = ok and not torch.equal(full[:B], res.final)
+        okt = torch.tensor([1 if ok else 0], device=dev)
+        dist.all_reduce(okt, op=dist.ReduceOp.MIN)
+        gather_check = bool(okt.item())
+        assert gather_check, "all-gather content check failed"
     ms_step = ms_total / args.steps + ag_ms / T
     if ws > 1:
         tmax = torch.tensor([ms_step], device=dev)
@@ -294,6 +393,8 @@ def main():
         t0 = time.perf_counter()
         imgs = s2.p_sample_loop(unet, shape, device=dev, img=x_host.to(dev, non_blocking=True))
         final_host = imgs[-1]
+        if ws > 1:                                # the job's one collective belongs to the end-to-end time
+            D.all_gather_samples(final_host.to(dev, non_blocking=True), total=B * ws)
         torch.cuda.synchronize(dev)
         el = time.perf_counter() - t0
         if ws > 1:
@@ -304,12 +405,16 @@ def main():
         e2e = {"value": ws * B / el * (e2e_T / T), "unit": "samples/s", "h2d_bytes_per_step": nbytes / e2e_T,
                "d2h_bytes_per_step": nbytes / e2e_T, "loop_steps": e2e_T, "wall_s": el,
                "note": "one GaussianDiffusion.p_sample_loop(unet, shape, img=pinned x_T) call incl. H2D of x_T and D2H of the images"
+                       + (" and the NCCL all-gather of the final samples" if ws > 1 else "")
                        + ("" if e2e_T == T else f"; T shortened to {e2e_T} steps to bound the run, value scaled to T={T}")}
 
     cpu = None
+    lib_bar = None
     if rank == 0 and ws == 1 and not args.no_cpu_baseline:
         cpu = cpu_baseline()
         cpu.pop("ms_per_step", None)
+    if rank == 0 and ws == 1 and not args.no_library_bar:
+        lib_bar = library_bar(dev, B)
 
     loop_launches = getattr(plan, "last_loop_launches", 0)
     if rank == 0:
@@ -322,7 +427,8 @@ def main():
                        "noise": "in-kernel Philox4x32-10, stream per rank", "l2": "per-step working set > 126 MB L2; no explicit flush",
                        "parallelism": f"batch-sharded x{ws}, one all-gather of final samples"},
             "unet_tflops": unet_tflops, "unet_frac_of_bf16_sustained": unet_tflops / sust, "unet_frac_of_bf16_burst": unet_tflops / burst,
-            "roofline": roof, "kernel_breakdown": breakdown, "allgather_ms": ag_ms,
+            "roofline": roof, "kernel_breakdown": breakdown, "allgather_ms": ag_ms, "gather_check": gather_check,
+            "library_bar": lib_bar,
             "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(loop_launches), "clocks": clocks,
         }
         print(json.dumps(line), flush=True)

@@ -20,7 +20,7 @@ class UnetCfg(C.Structure):
         ("dim", C.c_int32), ("n_mults", C.c_int32), ("dim_mults", C.c_int32 * 8), ("channels", C.c_int32),
         ("out_dim", C.c_int32), ("groups", C.c_int32), ("with_time_emb", C.c_int32), ("num_classes", C.c_int32),
         ("image_size", C.c_int32), ("max_batch", C.c_int32), ("act_dtype", C.c_int32), ("conv_engine", C.c_int32),
-        ("max_time_rows", C.c_int32), ("film", C.c_int32), ("reserved", C.c_int32 * 2),
+        ("max_time_rows", C.c_int32), ("film", C.c_int32), ("plain_tail", C.c_int32), ("reserved", C.c_int32 * 1),
     ]
 
 
@@ -35,6 +35,7 @@ class LoopDesc(C.Structure):
         ("coef_dev", C.c_void_p), ("coef2_dev", C.c_void_p), ("classes_dev", C.c_void_p), ("noise_dev", C.c_void_p),
         ("rng", Rng), ("state_dev", C.c_void_p), ("aux_dev", C.c_void_p), ("scratch_dev", C.c_void_p),
         ("scratch_bytes", C.c_size_t), ("traj_dev", C.c_void_p), ("traj_every", C.c_int32), ("cfg_scale", C.c_float),
+        ("cfg_on", C.c_int32), ("state_elems", C.c_int64),
     ]
 
 

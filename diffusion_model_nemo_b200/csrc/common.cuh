@@ -56,6 +56,31 @@ inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, s
   return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
 }
 
+// One-time per-DEVICE setup (cudaFuncSetAttribute is a per-device property; a process-wide flag would leave a second GPU of the
+// same process without the > 48 KB shared-memory opt-in).  A race between two host threads only repeats the idempotent setup.
+struct DeviceOnce {
+  bool done[64] = {};
+  bool first() {
+    int d = 0;
+    cudaGetDevice(&d);
+    if (d < 0 || d >= 64) return true;
+    if (done[d]) return false;
+    done[d] = true;
+    return true;
+  }
+};
+inline int current_device_sms() {
+  static int n[64] = {};
+  int d = 0;
+  cudaGetDevice(&d);
+  if (d < 0 || d >= 64) d = 0;
+  if (!n[d]) {
+    cudaDeviceGetAttribute(&n[d], cudaDevAttrMultiProcessorCount, d);
+    if (n[d] <= 0) n[d] = 148;
+  }
+  return n[d];
+}
+
 // launch counter (bench.py's gpu_launches is derived from it)
 extern thread_local long g_launches;
 inline void count_launch(int n = 1) { g_launches += n; }

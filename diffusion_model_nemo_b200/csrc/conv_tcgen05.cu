@@ -1152,16 +1152,7 @@ static bool pick_stages(Params& p) {
 
 static int pick_nt(int cout) { return cout % 128 == 0 ? 128 : (cout % 64 == 0 ? 64 : (cout % 32 == 0 ? 32 : 0)); }
 
-static int num_sms() {
-  static int n = 0;
-  if (!n) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-    if (n <= 0) n = 148;
-  }
-  return n;
-}
+static int num_sms() { return current_device_sms(); }
 
 static bool fill_params(const ConvP& c, int geo, Params& p) {
   p = Params();
@@ -1311,8 +1302,8 @@ static int launch(Params p, cudaStream_t st) {
     p.trace = (long long*)sym;
     p.trace_cta = 3;
   }
-  static bool attr_set = false;
-  if (!attr_set) {
+  static DeviceOnce attr_set;
+  if (attr_set.first()) {
     DMN_CUDA_CHECK(cudaFuncSetAttribute(conv_tcgen05_kernel<GEO, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemLimit));
     DMN_CUDA_CHECK(cudaFuncSetAttribute(conv_tcgen05_kernel<GEO, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemLimit));
     DMN_CUDA_CHECK(cudaFuncSetAttribute(conv_tcgen05_kernel<GEO, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemLimit));
@@ -1321,7 +1312,6 @@ static int launch(Params p, cudaStream_t st) {
       DMN_CUDA_CHECK(cudaFuncSetAttribute(conv_tcgen05_kernel<GEO_SAME, 64, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemLimit));
       DMN_CUDA_CHECK(cudaFuncSetAttribute(conv_tcgen05_kernel<GEO_SAME, 128, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemLimit));
     }
-    attr_set = true;
   }
   const int grid = p.total_tiles < num_sms() ? p.total_tiles : num_sms();
   // measured rule for the lean issue path: with fewer than DMN_EXP_LEAN_MIN_PASS passes per tile the tile is epilogue-bound and the
@@ -1332,18 +1322,16 @@ static int launch(Params p, cudaStream_t st) {
   if (GEO == GEO_SAME && p.NT == 128 && p.ntap == 1 && p.c.pro == PRO_NONE && !DMN_EXP_NO_ONETAP) {
     // 1x1 convolutions (to_qkv with the folded GroupNorm, to_out, res_conv): table-free producers
     constexpr int G2 = GEO_SAME;
-    static bool one_attr = false;
-    if (!one_attr) {
+    static DeviceOnce one_attr;
+    if (one_attr.first()) {
       DMN_CUDA_CHECK(cudaFuncSetAttribute(conv_tcgen05_kernel<G2, 128, false, false, true, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemLimit));
       DMN_CUDA_CHECK(cudaFuncSetAttribute(conv_tcgen05_kernel<G2, 128, false, false, false, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemLimit));
-      one_attr = true;
     }
     if (DMN_EXP_EW16) {
-      static bool a16 = false;
-      if (!a16) {
+      static DeviceOnce a16;
+      if (a16.first()) {
         DMN_CUDA_CHECK(cudaFuncSetAttribute(conv_tcgen05_kernel<G2, 128, false, false, true, 3, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemLimit));
         DMN_CUDA_CHECK(cudaFuncSetAttribute(conv_tcgen05_kernel<G2, 128, false, false, false, 3, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemLimit));
-        a16 = true;
       }
       if (extra) DMN_CUDA_CHECK(launch_pdl(conv_tcgen05_kernel<G2, 128, false, false, true, 3, 16>, dim3(grid), dim3(kThreads16), smem_bytes(p), st, p));
       else DMN_CUDA_CHECK(launch_pdl(conv_tcgen05_kernel<G2, 128, false, false, false, 3, 16>, dim3(grid), dim3(kThreads16), smem_bytes(p), st, p));
@@ -1356,15 +1344,14 @@ static int launch(Params p, cudaStream_t st) {
   if (GEO != GEO_INIT && p.NT == 128 && !(p.c.pro & PRO_LRELU) && !extra) {
     // the hot instantiations: no residual / fold terms in the epilogue, lean or looped issue
     constexpr int G2 = GEO == GEO_INIT ? GEO_SAME : GEO;
-    static bool hot_attr = false;
-    if (!hot_attr) {
+    static DeviceOnce hot_attr;
+    if (hot_attr.first()) {
       DMN_CUDA_CHECK(cudaFuncSetAttribute(conv_tcgen05_kernel<G2, 128, false, true, false, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemLimit));
       DMN_CUDA_CHECK(cudaFuncSetAttribute(conv_tcgen05_kernel<G2, 128, false, false, false, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemLimit));
       if (G2 == GEO_SAME) {
         DMN_CUDA_CHECK(cudaFuncSetAttribute(conv_tcgen05_kernel<GEO_SAME, 128, false, true, false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemLimit));
         DMN_CUDA_CHECK(cudaFuncSetAttribute(conv_tcgen05_kernel<GEO_SAME, 128, false, false, false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemLimit));
       }
-      hot_attr = true;
     }
     const bool pro = G2 == GEO_SAME && p.c.pro != PRO_NONE;
     if (pro && lean_ok) DMN_CUDA_CHECK(launch_pdl(conv_tcgen05_kernel<GEO_SAME, 128, false, true, false, 1>, dim3(grid), dim3(kThreads), smem_bytes(p), st, p));
@@ -1373,11 +1360,10 @@ static int launch(Params p, cudaStream_t st) {
     else if (DMN_EXP_EW16 && G2 == GEO_SAME) {
       // epilogue-bound plain 3x3 tiles (fewer than 8 passes): 16 epilogue warps; ncu then shows the epilogue waiting for the
       // accumulators 24 % of the time, so these tiles take the lean issue path as well (DMN_EXP_EW16_LEAN)
-      static bool b16 = false;
-      if (!b16) {
+      static DeviceOnce b16;
+      if (b16.first()) {
         DMN_CUDA_CHECK(cudaFuncSetAttribute(conv_tcgen05_kernel<GEO_SAME, 128, false, false, false, 0, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemLimit));
         DMN_CUDA_CHECK(cudaFuncSetAttribute(conv_tcgen05_kernel<GEO_SAME, 128, false, true, false, 0, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemLimit));
-        b16 = true;
       }
       if (DMN_EXP_EW16_LEAN && p.ntap == 9 && p.G == 3)
         DMN_CUDA_CHECK(launch_pdl(conv_tcgen05_kernel<GEO_SAME, 128, false, true, false, 0, 16>, dim3(grid), dim3(kThreads16), smem_bytes(p), st, p));

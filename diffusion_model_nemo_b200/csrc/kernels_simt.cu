@@ -415,14 +415,16 @@ __global__ void __launch_bounds__(128) final_proj_kernel(const FinalProjP p) {
   float* s_sh = fsm + p.C;           // [C] beta - mean*rstd*gamma
   float* s_w = fsm + 2 * p.C;        // [Cout][C]
   const int b = blockIdx.y;
-  const int cpg = p.C / p.groups;
-  const float inv = 1.f / (float)(p.HW * cpg);
-  for (int c = threadIdx.x; c < p.C; c += blockDim.x) {
-    float mean, rstd;
-    gn_mean_rstd(p.stats + ((long)b * p.groups + c / cpg) * 2, inv, kGnEps, mean, rstd);
-    const float sc = rstd * p.gamma[c];
-    s_sc[c] = sc;
-    s_sh[c] = p.beta[c] - mean * sc;
+  if (!p.plain) {
+    const int cpg = p.C / p.groups;
+    const float inv = 1.f / (float)(p.HW * cpg);
+    for (int c = threadIdx.x; c < p.C; c += blockDim.x) {
+      float mean, rstd;
+      gn_mean_rstd(p.stats + ((long)b * p.groups + c / cpg) * 2, inv, kGnEps, mean, rstd);
+      const float sc = rstd * p.gamma[c];
+      s_sc[c] = sc;
+      s_sh[c] = p.beta[c] - mean * sc;
+    }
   }
   for (int i = threadIdx.x; i < p.Cout * p.C; i += blockDim.x) s_w[i] = p.w[i];
   __syncthreads();
@@ -437,7 +439,7 @@ __global__ void __launch_bounds__(128) final_proj_kernel(const FinalProjP p) {
     const float v[4] = {t.x, t.y, t.z, t.w};
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
-      const float a = silu_f(fmaf(v[e], s_sc[c + e], s_sh[c + e]));
+      const float a = p.plain ? v[e] : silu_f(fmaf(v[e], s_sc[c + e], s_sh[c + e]));
 #pragma unroll
       for (int j = 0; j < 8; ++j)
         if (j < p.Cout) acc[j] = fmaf(a, s_w[j * p.C + c + e], acc[j]);
@@ -473,14 +475,16 @@ __global__ void __launch_bounds__(128) final_proj_bf16_kernel(const FinalProjP p
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
   }
-  const int cpg = C / p.groups;
-  const float inv = 1.f / (float)(p.HW * cpg);
-  for (int c = threadIdx.x; c < C; c += 128) {
-    float mean, rstd;
-    gn_mean_rstd(p.stats + ((long)b * p.groups + c / cpg) * 2, inv, kGnEps, mean, rstd);
-    const float sc = rstd * p.gamma[c];
-    s_sc[c] = sc;
-    s_sh[c] = p.beta[c] - mean * sc;
+  if (!p.plain) {
+    const int cpg = C / p.groups;
+    const float inv = 1.f / (float)(p.HW * cpg);
+    for (int c = threadIdx.x; c < C; c += 128) {
+      float mean, rstd;
+      gn_mean_rstd(p.stats + ((long)b * p.groups + c / cpg) * 2, inv, kGnEps, mean, rstd);
+      const float sc = rstd * p.gamma[c];
+      s_sc[c] = sc;
+      s_sh[c] = p.beta[c] - mean * sc;
+    }
   }
   for (int i = threadIdx.x; i < COUT * C; i += 128) s_w[i] = p.w[i];
   asm volatile("cp.async.wait_group 0;" ::: "memory");
@@ -495,7 +499,7 @@ __global__ void __launch_bounds__(128) final_proj_bf16_kernel(const FinalProjP p
     unpack8(*reinterpret_cast<const uint4*>(row + c * 2), v);
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
-      const float a = silu_fast(fmaf(v[e], s_sc[c + e], s_sh[c + e]));
+      const float a = p.plain ? v[e] : silu_fast(fmaf(v[e], s_sc[c + e], s_sh[c + e]));
 #pragma unroll
       for (int j = 0; j < COUT; ++j) acc[j] = fmaf(a, s_w[j * C + c + e], acc[j]);
     }
@@ -512,12 +516,11 @@ int final_proj(const FinalProjP& p, int act, cudaStream_t st) {
   if (act == ACT_BF16 && p.C % 8 == 0 && (p.Cout == 3 || p.Cout == 6 || p.Cout == 1)) {
     const size_t smem2 = (size_t)(2 + p.Cout) * p.C * sizeof(float) + (size_t)128 * (p.C * 2 + 16);
     if (smem2 <= 200 * 1024) {
-      static bool attr = false;
-      if (!attr) {
+      static DeviceOnce attr;
+      if (attr.first()) {
         DMN_CUDA_CHECK(cudaFuncSetAttribute(final_proj_bf16_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         DMN_CUDA_CHECK(cudaFuncSetAttribute(final_proj_bf16_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         DMN_CUDA_CHECK(cudaFuncSetAttribute(final_proj_bf16_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        attr = true;
       }
       if (p.Cout == 3) DMN_CUDA_CHECK(launch_pdl(final_proj_bf16_kernel<3>, grid, dim3(128), smem2, st, p));
       else if (p.Cout == 6) DMN_CUDA_CHECK(launch_pdl(final_proj_bf16_kernel<6>, grid, dim3(128), smem2, st, p));
@@ -669,11 +672,10 @@ int linattn_core(const void* qkv, void* out, int B, int heads, int dh, int N, in
   DMN_REQUIRE(dh == 32 && heads == 4, "linattn_core: heads must be 4 and dim_head 32");
   if (act == ACT_BF16) return linattn_core_bf16_mma(qkv, out, B, N, st);   // tensor-core kernel (linattn_mma.cu)
   const size_t smem = (size_t)(2 * 32 * 132 + 4 * 32 * 32 + 4 * 128) * sizeof(float);
-  static bool attr = false;
-  if (!attr) {
+  static DeviceOnce attr;
+  if (attr.first()) {
     DMN_CUDA_CHECK(cudaFuncSetAttribute(linattn_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     DMN_CUDA_CHECK(cudaFuncSetAttribute(linattn_kernel<bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr = true;
   }
   if (act == ACT_F32) linattn_kernel<float><<<B, 256, smem, st>>>((const float*)qkv, (float*)out, N);
   else linattn_kernel<bf16><<<B, 256, smem, st>>>((const bf16*)qkv, (bf16*)out, N);

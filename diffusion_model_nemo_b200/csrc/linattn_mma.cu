@@ -273,10 +273,9 @@ __global__ void __launch_bounds__(256, 2) linattn_mma_kernel(const bf16* __restr
 }  // namespace la
 
 int linattn_core_bf16_mma(const void* qkv, void* out, int B, int N, cudaStream_t st) {
-  static bool attr = false;
-  if (!attr) {
+  static DeviceOnce attr;
+  if (attr.first()) {
     DMN_CUDA_CHECK(cudaFuncSetAttribute(la::linattn_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, la::kSmem));
-    attr = true;
   }
   DMN_CUDA_CHECK(launch_pdl(la::linattn_mma_kernel, dim3(B), dim3(256), la::kSmem, st, (const bf16*)qkv, (bf16*)out, N));
   count_launch();

@@ -101,6 +101,7 @@ struct FinalProjP {
   const float* bias = nullptr;
   float* out = nullptr;            // [B][Cout][HW]
   int B = 0, HW = 0, C = 0, Cout = 0;
+  int plain = 0;                   // 1: eps = conv1x1(y) only ('conv_bn_act' tail, unet.py:115-116); stats / gamma / beta unused
 };
 int final_proj(const FinalProjP& p, int act, cudaStream_t s);
 

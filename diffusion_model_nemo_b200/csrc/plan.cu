@@ -58,7 +58,7 @@ int launch_bpd_qsample(const float* x0, const float* z, float* xt, long n, const
 int launch_bpd_term(const float* x0, const float* xt, const float* mo, float* terms, int batch, long chw, int learned, int n_cols, int mode,
                     const float* coef, const float* coef2, const int32_t* step_dev, int step, cudaStream_t st);
 int launch_cfg_dup(const float* x, float* x2, long n, cudaStream_t st);
-int launch_cfg_combine(const float* mo2, float* mo, long n, float w, cudaStream_t st);
+int launch_cfg_combine(const float* mo2, float* mo, long n, long per_sample, long guided, float w, cudaStream_t st);
 int launch_langevin(const float* x, const float* mo, const float* z, float* out, float* mean_out, int batch, long chw,
                     float snr, const float* coef, const int32_t* step_dev, int step, int draw, float* scratch, dmn_rng rng,
                     const dmn_rng* rng_dev, cudaStream_t st);
@@ -499,15 +499,21 @@ struct Builder {
     {
       Buf st;
       Buf o1 = X[(cur + 1) % 3];
-      resblock("final_conv.0", x, dim, Buf(), 0, dim, S, H1, H2, R, o1, false, G, &st);
+      resblock("final_conv.0", x, dim, Buf(), 0, dim, S, H1, H2, R, o1, false, c.plain_tail ? 0 : G, &st);
       Op f;
       f.kind = OP_FINALPROJ;
       f.name = "final_conv.tail";
       f.src1 = o1; f.stats = st; f.groups = G; f.C = dim; f.HW = S * S; f.Cout = c.out_dim;
-      f.gamma = add_param("final_conv.1.weight", {dim}, PK_RAW);
-      f.beta = add_param("final_conv.1.bias", {dim}, PK_RAW);
-      f.w = add_param("final_conv.3.weight", {c.out_dim, dim, 1, 1}, PK_RAW);
-      f.bias = add_param("final_conv.3.bias", {c.out_dim}, PK_RAW);
+      if (c.plain_tail) {          // 'conv_bn_act': the ResnetBlock is followed by the bare 1x1 (unet.py:115-116)
+        f.groups = 0;
+        f.w = add_param("final_conv.1.weight", {c.out_dim, dim, 1, 1}, PK_RAW);
+        f.bias = add_param("final_conv.1.bias", {c.out_dim}, PK_RAW);
+      } else {
+        f.gamma = add_param("final_conv.1.weight", {dim}, PK_RAW);
+        f.beta = add_param("final_conv.1.bias", {dim}, PK_RAW);
+        f.w = add_param("final_conv.3.weight", {c.out_dim, dim, 1, 1}, PK_RAW);
+        f.bias = add_param("final_conv.3.bias", {c.out_dim}, PK_RAW);
+      }
       P.ops.push_back(f);
     }
     if (P.stats_bytes > stats_reserve) return fail(DMN_EINVAL, "internal: statistics arena overflow");
@@ -619,6 +625,7 @@ static int run_forward(dmn_plan* P, const float* x_dev, const int32_t* row_dev, 
         q.y = B(o.src1); q.stats = (const stat_t*)B(o.stats); q.groups = o.groups;
         q.gamma = W(o.gamma); q.beta = W(o.beta); q.w = W(o.w); q.bias = W(o.bias);
         q.out = out_dev; q.B = batch; q.HW = o.HW; q.C = o.C; q.Cout = o.Cout;
+        q.plain = o.groups == 0;
         rc = final_proj(q, P->act, st);
         break;
       }
@@ -664,6 +671,7 @@ int dmn_plan_create(const dmn_unet_cfg* cfg, dmn_plan** out) {
               "tcgen05 engine requires bf16 activations");
   DMN_REQUIRE(cfg->with_time_emb == 0 || cfg->with_time_emb == 1, "with_time_emb must be 0 or 1");
   DMN_REQUIRE(cfg->film == 0 || cfg->film == 1, "film must be 0 or 1");
+  DMN_REQUIRE(cfg->plain_tail == 0 || cfg->plain_tail == 1, "plain_tail must be 0 or 1");
   for (int i = 0; i < cfg->n_mults; ++i) DMN_REQUIRE(cfg->dim_mults[i] >= 1, "dim_mults must be positive");
   std::unique_ptr<dmn_plan> p(new dmn_plan());
   p->cfg = *cfg;
@@ -978,13 +986,14 @@ static int enqueue_step(dmn_plan* p, const dmn_loop_desc* d, int32_t* ctr_dev, b
     if ((rc = launch_affine_noise(d->state_dev, mo, zp, d->state_dev, xmean, n, d->coef_dev, step_dev, s, 7, d->rng, rng_dev, st)))
       return rc;
   } else {
-    if (d->cfg_scale != 0.f) {
+    if (d->cfg_on) {
       // classifier-free guidance: one U-Net evaluation on the doubled batch [x ; x] (labels ; null class), then the mix
       float* x2 = lscr + ((2 * d->batch + 16 + 3) & ~3);
       float* mo2 = x2 + 2 * n;
       if ((rc = launch_cfg_dup(d->state_dev, x2, n, st))) return rc;
       if ((rc = run_forward(p, x2, ctr_dev, d->classes_dev, mo2, 2 * d->batch, st))) return rc;
-      if ((rc = launch_cfg_combine(mo2, mo, n_out, d->cfg_scale, st))) return rc;
+      // a learned-variance U-Net returns [eps | v] per sample: only eps is guided, v is the conditional branch's
+      if ((rc = launch_cfg_combine(mo2, mo, n_out, n_out / d->batch, chw, d->cfg_scale, st))) return rc;
     } else if ((rc = run_forward(p, d->state_dev, ctr_dev, d->classes_dev, mo, d->batch, st))) {
       return rc;
     }
@@ -1007,7 +1016,7 @@ static bool same_graph_key(const dmn_loop_desc& a, const dmn_loop_desc& b) {
   return a.kind == b.kind && (!traj || a.n_steps == b.n_steps) && a.batch == b.batch && a.n_corr == b.n_corr && a.snr == b.snr &&
          a.corr_kind == b.corr_kind && a.coef_dev == b.coef_dev && a.coef2_dev == b.coef2_dev && a.classes_dev == b.classes_dev &&
          a.state_dev == b.state_dev && a.scratch_dev == b.scratch_dev && a.traj_dev == b.traj_dev && a.traj_every == b.traj_every &&
-         a.cfg_scale == b.cfg_scale && (a.kind != DMN_LOOP_BPD || (a.aux_dev == b.aux_dev && a.n_steps == b.n_steps));
+         a.cfg_scale == b.cfg_scale && a.cfg_on == b.cfg_on && (a.kind != DMN_LOOP_BPD || (a.aux_dev == b.aux_dev && a.n_steps == b.n_steps));
 }
 
 extern "C" {
@@ -1018,7 +1027,7 @@ int dmn_sample_loop(dmn_plan* p, const dmn_loop_desc* d, void* stream) {
   if (!d) return fail(DMN_EINVAL, "null descriptor");
   const dmn_unet_cfg& c = p->cfg;
   DMN_REQUIRE(d->kind >= DMN_LOOP_DDPM && d->kind <= DMN_LOOP_BPD, "unknown loop kind");
-  DMN_REQUIRE(d->kind != DMN_LOOP_BPD || (d->aux_dev && d->coef2_dev && d->cfg_scale == 0.f && !d->traj_dev),
+  DMN_REQUIRE(d->kind != DMN_LOOP_BPD || (d->aux_dev && d->coef2_dev && !d->cfg_on && !d->traj_dev),
               "BPD loop needs the terms buffer (aux_dev) and the second coefficient table; no guidance / trajectory");
   DMN_REQUIRE(d->batch >= 1 && d->batch <= c.max_batch, "batch exceeds the plan's max_batch");
   DMN_REQUIRE(d->n_steps >= 1 && d->n_steps <= c.max_time_rows, "n_steps exceeds the plan's time table");
@@ -1032,7 +1041,8 @@ int dmn_sample_loop(dmn_plan* p, const dmn_loop_desc* d, void* stream) {
   const long n = (long)d->batch * chw;
   const long n_out = (long)d->batch * c.out_dim * c.image_size * c.image_size;
   DMN_REQUIRE(d->scratch_bytes >= (size_t)(n_out + n + 2 * d->batch + 16) * sizeof(float), "loop scratch too small");
-  if (d->cfg_scale != 0.f) {
+  DMN_REQUIRE(d->state_elems == 0 || d->state_elems == n, "state_dev does not hold batch * channels * image_size^2 floats for this plan");
+  if (d->cfg_on) {
     DMN_REQUIRE(d->kind != DMN_LOOP_PC, "classifier-free guidance is built for the DDPM / learned / DDIM loops");
     DMN_REQUIRE(c.num_classes >= 0 && d->classes_dev, "classifier-free guidance needs a class-conditional U-Net and 2*batch labels");
     DMN_REQUIRE(2 * d->batch <= c.max_batch, "classifier-free guidance doubles the batch: plan max_batch too small");
@@ -1099,7 +1109,7 @@ int dmn_loop_launches_per_step(const dmn_plan* p, const dmn_loop_desc* d) {
   int n = 0;
   if (d->kind == DMN_LOOP_BPD) return per_fwd + 3;
   if (d->kind == DMN_LOOP_PC) n = (d->n_corr + 1) * per_fwd + d->n_corr * (d->corr_kind == 1 ? 1 : 3) + 1;
-  else n = per_fwd + 1 + (d->cfg_scale != 0.f ? 2 : 0);
+  else n = per_fwd + 1 + (d->cfg_on ? 2 : 0);
   if (d->traj_dev && d->traj_every > 0) n += 1;
   return n + 1;   // + advance_counter
 }

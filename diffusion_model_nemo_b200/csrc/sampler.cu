@@ -255,11 +255,16 @@ __global__ void __launch_bounds__(256) cfg_dup_kernel(const float* __restrict__ 
     reinterpret_cast<float4*>(x2)[n4 + i] = v;
   }
 }
-__global__ void __launch_bounds__(256) cfg_combine_kernel(const float* __restrict__ mo2, float* __restrict__ mo, long n4, float w) {
+// per sample the first `guided4` float4 (the eps channels) are mixed; the rest (learned-variance channels) are the conditional branch's
+__global__ void __launch_bounds__(256) cfg_combine_kernel(const float* __restrict__ mo2, float* __restrict__ mo, long n4, long per4, long guided4,
+                                                          float w) {
   for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long)gridDim.x * blockDim.x) {
-    const float4 c = reinterpret_cast<const float4*>(mo2)[i], u = reinterpret_cast<const float4*>(mo2)[n4 + i];
-    float4 o;
-    o.x = u.x + w * (c.x - u.x); o.y = u.y + w * (c.y - u.y); o.z = u.z + w * (c.z - u.z); o.w = u.w + w * (c.w - u.w);
+    const float4 c = reinterpret_cast<const float4*>(mo2)[i];
+    float4 o = c;
+    if (i % per4 < guided4) {
+      const float4 u = reinterpret_cast<const float4*>(mo2)[n4 + i];
+      o.x = u.x + w * (c.x - u.x); o.y = u.y + w * (c.y - u.y); o.z = u.z + w * (c.z - u.z); o.w = u.w + w * (c.w - u.w);
+    }
     reinterpret_cast<float4*>(mo)[i] = o;
   }
 }
@@ -376,8 +381,9 @@ int launch_cfg_dup(const float* x, float* x2, long n, cudaStream_t st) {
   DMN_LAUNCH_CHECK("cfg_dup");
   return 0;
 }
-int launch_cfg_combine(const float* mo2, float* mo, long n, float w, cudaStream_t st) {
-  cfg_combine_kernel<<<grid_for(n / 4), 256, 0, st>>>(mo2, mo, n / 4, w);
+int launch_cfg_combine(const float* mo2, float* mo, long n, long per_sample, long guided, float w, cudaStream_t st) {
+  DMN_REQUIRE(per_sample % 4 == 0 && guided % 4 == 0, "cfg_combine: per-sample sizes must be multiples of 4");
+  cfg_combine_kernel<<<grid_for(n / 4), 256, 0, st>>>(mo2, mo, n / 4, per_sample / 4, guided / 4, w);
   count_launch();
   DMN_LAUNCH_CHECK("cfg_combine");
   return 0;

@@ -36,7 +36,7 @@ class UnetPlan:
     """One (config, image_size, max_batch, dtype, engine) instance of the native U-Net."""
 
     def __init__(self, *, dim, dim_mults, channels, out_dim, groups, num_classes, image_size, max_batch,
-                 act_dtype, conv_engine, max_time_rows, device, with_time_emb=True, film=False):
+                 act_dtype, conv_engine, max_time_rows, device, with_time_emb=True, film=False, plain_tail=False):
         self.lib = L.lib()
         self.device = torch.device(device)
         if self.device.type != "cuda":
@@ -49,6 +49,7 @@ class UnetPlan:
         cfg.channels, cfg.out_dim, cfg.groups = channels, out_dim, groups
         cfg.with_time_emb = 1 if with_time_emb else 0
         cfg.film = 1 if film else 0
+        cfg.plain_tail = 1 if plain_tail else 0
         cfg.num_classes = -1 if num_classes is None else int(num_classes)
         cfg.image_size, cfg.max_batch = image_size, max_batch
         cfg.act_dtype, cfg.conv_engine = act_dtype, conv_engine

@@ -41,7 +41,15 @@ def draw_seed() -> int:
 
 
 def rank_stream_id() -> int:
-    """Independent RNG stream per data-parallel rank."""
+    """Independent RNG stream per data-parallel rank: the process-group rank when torch.distributed is initialised (covers
+    launchers that do not export RANK: mp.spawn, ddp_spawn, init_method=tcp://), else the RANK environment variable."""
+    try:
+        import torch.distributed as dist
+
+        if dist.is_available() and dist.is_initialized():
+            return int(dist.get_rank())
+    except Exception:
+        pass
     return int(os.environ.get("RANK", "0"))
 
 
@@ -64,17 +72,23 @@ def run_native_loop(unet: Unet, *, kind: int, shape: Sequence[int], device, time
                     noise: Optional[torch.Tensor] = None, classes: Optional[torch.Tensor] = None,
                     n_corr: int = 0, corr_kind: int = 0, snr: float = 0.0, denoise: bool = False,
                     seed: Optional[int] = None, traj_every: int = 0, use_graph: bool = True,
-                    init_scale: float = 1.0, n_steps: Optional[int] = None, cfg_scale: float = 0.0) -> LoopResult:
+                    init_scale: float = 1.0, n_steps: Optional[int] = None, cfg_scale: Optional[float] = None) -> LoopResult:
     """Run n_steps of (U-Net + update) natively.  noise: [1 + n_steps*draws, B, C, H, W] injected N(0,1) tensors in
-    the reference's draw order (element 0 = x_T), or None for in-kernel Philox."""
+    the reference's draw order (element 0 = x_T), or None for in-kernel Philox.  cfg_scale: classifier-free guidance weight
+    (None = off; 0.0 is a valid weight and gives the unconditional prediction)."""
     lib = L.lib()
     device = torch.device(device)
     require_cuda(device)
     b, c, h, w = (int(s) for s in shape)
     assert h == w, "square images only"
+    if c != unet.channels:
+        raise ValueError(f"shape has {c} channels but the U-Net was built for {unet.channels} (the reference raises a conv shape error)")
+    for name, t, lead in (("x_init", x_init, 0), ("noise", noise, 1)):
+        if t is not None and tuple(t.shape[lead:]) != (b, c, h, w):
+            raise ValueError(f"{name} has shape {tuple(t.shape)}; expected {'[n, ' if lead else '['}{b}, {c}, {h}, {w}]")
     n_steps = int(times.shape[0]) if n_steps is None else int(n_steps)
     assert 1 <= n_steps <= times.shape[0]
-    guided = cfg_scale != 0.0
+    guided = cfg_scale is not None
     if guided:
         if unet.num_classes is None or classes is None:
             raise ValueError("classifier-free guidance needs a class-conditional Unet and `classes` labels")
@@ -145,7 +159,9 @@ def run_native_loop(unet: Unet, *, kind: int, shape: Sequence[int], device, time
         d.scratch_bytes = scratch.numel() * 4
         d.traj_dev = traj.data_ptr() if traj is not None else None
         d.traj_every = traj_every if traj is not None else 0
-        d.cfg_scale = float(cfg_scale)
+        d.cfg_scale = float(cfg_scale) if guided else 0.0
+        d.cfg_on = 1 if guided else 0
+        d.state_elems = state.numel()
         L.check(lib.dmn_sample_loop(plan.h, C.byref(d), st), "dmn_sample_loop")
         plan.last_loop_launches = lib.dmn_loop_launches_per_step(plan.h, C.byref(d)) * n_steps
         # keep every buffer alive until the stream has consumed it

@@ -143,7 +143,7 @@ class GaussianDiffusion(AbstractDiffusionProcess):
             res = R.run_native_loop(unet, kind=self._loop_kind, shape=shape, device=device, times=times, coef=coef,
                                     x_init=img, noise=noise, classes=classes, seed=self.seed,
                                     traj_every=self.trajectory_every, use_graph=self.use_cuda_graph,
-                                    cfg_scale=float(self.guidance_scale) if (self.guidance_scale is not None and classes is not None) else 0.0)
+                                    cfg_scale=float(self.guidance_scale) if (self.guidance_scale is not None and classes is not None) else None)
             return R.to_image_list(res.final, res.traj)
         # foreign model: call it per step, fuse only the update
         if self.guidance_scale is not None:

@@ -88,8 +88,6 @@ class Unet(nn.Module):
             )
         if resnet_block_order not in ("conv_bn_act", "bn_act_conv"):
             raise ValueError("Valid ordering for block are : ['conv_bn_act', 'bn_act_conv']")
-        if resnet_block_order != "bn_act_conv":
-            raise NotImplementedError("resnet_block_order='conv_bn_act' drops the final GroupNorm/SiLU; not built")
         if dim_mults is None:
             dim_mults = (1, 2, 4, 8)
         self.channels, self.learned_variance, self.dim = channels, learned_variance, dim
@@ -132,8 +130,11 @@ class Unet(nn.Module):
             ]))
         default_out = channels * (2 if learned_variance else 1)
         self.out_dim = out_dim if out_dim is not None else default_out
-        self.final_conv = nn.Sequential(_resnet_block(dim, dim, None, g), nn.GroupNorm(g, dim), nn.SiLU(),
-                                        nn.Conv2d(dim, self.out_dim, kernel_size=1))
+        if resnet_block_order == "bn_act_conv":      # reference unet.py:112-116
+            tail = [nn.GroupNorm(g, dim), nn.SiLU(), nn.Conv2d(dim, self.out_dim, kernel_size=1)]
+        else:                                          # 'conv_bn_act': the ResnetBlock is followed by the bare 1x1
+            tail = [nn.Conv2d(dim, self.out_dim, kernel_size=1)]
+        self.final_conv = nn.Sequential(_resnet_block(dim, dim, None, g), *tail)
         if num_classes is not None:
             self.class_embed = nn.Embedding(num_classes + 1, embedding_dim=dim, padding_idx=num_classes)
         self._film = False
@@ -166,7 +167,8 @@ class Unet(nn.Module):
             p = UnetPlan(dim=self.dim, dim_mults=self.dim_mults, channels=self.channels, out_dim=self.out_dim,
                          groups=self.groups, num_classes=self.num_classes, image_size=image_size, max_batch=mb,
                          act_dtype=act, conv_engine=eng, max_time_rows=rows, device=device,
-                         with_time_emb=self.with_time_emb, film=self._film)
+                         with_time_emb=self.with_time_emb, film=self._film,
+                         plain_tail=self.resnet_block_order == "conv_bn_act")
             self._plans[key] = p
         ver = self._params_version()
         if p._loaded_version != ver:

@@ -32,6 +32,11 @@ class WaveGradDiffusion(GaussianDiffusion):
         self.original_schedule_cfg = copy.deepcopy(schedule_cfg)
         self.compute_constants(self.timesteps)
 
+    def calculate_bits_per_dimension(self, *args, **kwargs):
+        """Not built: the inherited evaluation feeds integer timesteps to the denoiser and uses the DDPM x0 coefficients, both wrong for
+        the continuous-noise-level WaveGrad parameterisation (reference wavegrad_diffusion.py:150-189)."""
+        raise NotImplementedError("bits-per-dimension evaluation is not defined for WaveGradDiffusion in this package")
+
     # ---- tables (reference wavegrad_diffusion.py:101-106) -------------------------------------------------
     def compute_constants(self, timesteps, verbose: bool = True):
         super().compute_constants(timesteps)

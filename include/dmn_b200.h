@@ -69,7 +69,9 @@ typedef struct dmn_unet_cfg {
   int32_t max_time_rows;   /* rows of the time-embedding table (>= max_batch and >= loop steps) */
   int32_t film;            /* 1 = WaveGradUNet (unet.py:171-266): requires with_time_emb = 0; FeatureWiseLinearModulation
                               layers films.0 .. films.{n_mults-1} (parts/film.py:29-61) driven by a continuous noise level */
-  int32_t reserved[2];
+  int32_t plain_tail;      /* 1 = resnet_block_order 'conv_bn_act': final_conv = [ResnetBlock, Conv2d(dim, out_dim, 1)] without the
+                              GroupNorm + SiLU in front of the 1x1 (unet.py:112-116); the 1x1 is then final_conv.1 */
+  int32_t reserved[1];
 } dmn_unet_cfg;
 
 int    dmn_plan_create(const dmn_unet_cfg* cfg, dmn_plan** out);
@@ -215,11 +217,16 @@ typedef struct dmn_loop_desc {
   size_t         scratch_bytes;
   float*         traj_dev;       /* optional [n_traj][batch*C*H*W] trajectory capture, every traj_every steps */
   int32_t        traj_every;
-  float          cfg_scale;      /* != 0: classifier-free guidance (not in the reference: SURVEY.md section 8 config 5a).  Every step
+  float          cfg_scale;      /* guidance weight w, used when cfg_on != 0 (w = 0 is a valid weight: eps = eps_u).
+                                    Classifier-free guidance (not in the reference: SURVEY.md section 8 config 5a).  Every step
                                     evaluates the U-Net on the doubled batch [x ; x] with classes_dev[0..batch) = labels and
                                     classes_dev[batch..2*batch) = num_classes (the null / padding row, unet.py:118-120) and uses
                                     eps = eps_u + cfg_scale * (eps_c - eps_u).  Needs max_batch >= 2*batch and scratch for
-                                    3*out_dim*S*S*batch + 3*C*S*S*batch + 2*batch + 16 floats.  DDPM / learned / DDIM loops only. */
+                                    3*out_dim*S*S*batch + 3*C*S*S*batch + 2*batch + 16 floats.  DDPM / learned / DDIM loops only.
+                                    With a learned-variance U-Net only the eps half is guided; the variance channels are the
+                                    conditional branch's. */
+  int32_t        cfg_on;         /* 1 = classifier-free guidance with weight cfg_scale, 0 = off */
+  int64_t        state_elems;    /* number of floats behind state_dev; must equal batch * cfg.channels * image_size^2 (0 = unchecked) */
 } dmn_loop_desc;
 
 /* Runs the whole loop on `stream`; returns after enqueueing (no host sync unless use_graph needs capture,

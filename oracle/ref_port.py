@@ -245,6 +245,8 @@ def unet_forward(sd: Dict[str, Tensor], cfg: dict, x: Tensor, time: Tensor, clas
         x = residual_prenorm_fwd(sd, f"ups.{i}.2", x, linear_attention_fwd)
         x = F.conv_transpose2d(x, sd[f"ups.{i}.3.weight"], sd[f"ups.{i}.3.bias"], stride=2, padding=1)
     x = resnet_block_fwd(sd, "final_conv.0", x, None, groups)
+    if cfg.get("order", "bn_act_conv") == "conv_bn_act":      # unet.py:112-116: the bare 1x1 follows the ResnetBlock
+        return F.conv2d(x, sd["final_conv.1.weight"], sd["final_conv.1.bias"])
     x = F.silu(_gn(x, sd, "final_conv.1", groups))
     return F.conv2d(x, sd["final_conv.3.weight"], sd["final_conv.3.bias"])
 
@@ -691,10 +693,14 @@ def unet_param_shapes(cfg: dict) -> Dict[str, Sequence[int]]:
         shapes[f"ups.{i}.3.bias"] = (ci,)
     out_dim = cfg.get("out_dim") or ch * (2 if cfg.get("learned_variance") else 1)
     res("final_conv.0", dim, dim, temb=False)
-    shapes["final_conv.1.weight"] = (dim,)
-    shapes["final_conv.1.bias"] = (dim,)
-    shapes["final_conv.3.weight"] = (out_dim, dim, 1, 1)
-    shapes["final_conv.3.bias"] = (out_dim,)
+    if cfg.get("order", "bn_act_conv") == "conv_bn_act":
+        shapes["final_conv.1.weight"] = (out_dim, dim, 1, 1)
+        shapes["final_conv.1.bias"] = (out_dim,)
+    else:
+        shapes["final_conv.1.weight"] = (dim,)
+        shapes["final_conv.1.bias"] = (dim,)
+        shapes["final_conv.3.weight"] = (out_dim, dim, 1, 1)
+        shapes["final_conv.3.bias"] = (out_dim,)
     if cfg.get("num_classes") is not None:
         shapes["class_embed.weight"] = (cfg["num_classes"] + 1, dim)
     if cfg.get("film"):

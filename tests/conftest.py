@@ -32,6 +32,12 @@ def golden():
     return out
 
 
+@pytest.fixture(scope="session")
+def golden_extra():
+    """Round-2 fixtures of the executed reference (tests/golden/make_golden_extra.py)."""
+    return dict(np.load(os.path.join(GOLDEN, "unet_extra.npz")))
+
+
 @pytest.fixture(scope="session", autouse=True)
 def _build_native():
     """The native library is the product; build it in-tree if the .so is stale or missing."""

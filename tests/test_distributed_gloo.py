@@ -36,6 +36,9 @@ def _worker(rank, ws, port, total, q):
     assert (r, w) == (rank, ws)
     from diffusion_model_nemo_b200.modules import _runtime as R
     assert R.rank_stream_id() == rank                      # independent Philox stream per rank
+    os.environ.pop("RANK")                                 # launchers that do not export RANK (mp.spawn, ddp_spawn, tcp:// init):
+    assert R.rank_stream_id() == rank                      # the process-group rank still separates the streams
+    os.environ["RANK"] = str(rank)
     lo, hi = D.shard_range(total, rank, ws)
     local = torch.arange(lo, hi, dtype=torch.float32).reshape(-1, 1, 1, 1).expand(-1, 3, 2, 2).contiguous()
     full = D.all_gather_samples(local, total=total)

@@ -183,6 +183,32 @@ def test_unet_state_dict_is_key_compatible(name):
     assert all(not p.requires_grad for p in u.parameters())
 
 
+def test_plain_tail_conv_bn_act_keys_and_oracle(golden_extra):
+    """resnet_block_order='conv_bn_act' (reference modules/unet.py:112-116): final_conv.1 is the bare 1x1; oracle vs executed reference."""
+    cfg = dict(dim=32, dim_mults=[1, 2], channels=3, groups=8, order="conv_bn_act")
+    u = M.Unet(None, dim=32, dim_mults=[1, 2], channels=3, use_convnext=False, resnet_block_order="conv_bn_act")
+    want = {k: tuple(v) for k, v in O.unet_param_shapes(cfg).items()}
+    assert {k: tuple(v.shape) for k, v in u.state_dict().items()} == want
+    assert want["final_conv.1.weight"] == (3, 32, 1, 1) and "final_conv.3.weight" not in want
+    sd = O.random_state_dict(cfg, seed=0)
+    u.load_state_dict(sd, strict=True)
+    x = torch.randn(2, 3, 16, 16, generator=torch.Generator().manual_seed(11))
+    y = O.unet_forward(sd, cfg, x, torch.from_numpy(golden_extra["tiny_cba/t"]).float())
+    assert torch.equal(y, torch.from_numpy(golden_extra["tiny_cba/y"]))
+
+
+def test_loop_argument_validation_and_guidance_flag():
+    """run_native_loop rejects shapes the U-Net was not built for BEFORE touching the device path (the reference raises a conv shape
+    error); guidance is an explicit on/off (None = off, 0.0 = a valid weight)."""
+    u = make_unet(CFGS["tiny"][0])          # 1 channel
+    s = M.GaussianDiffusion(10, "linear")
+    with pytest.raises((ValueError, L.DmnError)):
+        R.run_native_loop(u, kind=L.LOOP_DDPM, shape=[2, 3, 16, 16], device="cuda:0", times=torch.zeros(10), coef=torch.zeros(10, 8))
+    d = L.LoopDesc()
+    assert hasattr(d, "cfg_on") and hasattr(d, "state_elems")
+    assert s.guidance_scale is None
+
+
 def test_unet_ctor_contract():
     with pytest.raises(NotImplementedError):
         M.Unet(None, dim=32)                      # reference default use_convnext=True: not on the built path
