@@ -50,6 +50,15 @@ class ConvArgs(C.Structure):
     ]
 
 
+class AttnBlockArgs(C.Structure):
+    _fields_ = [
+        ("batch", C.c_int32), ("dim", C.c_int32), ("n_tokens", C.c_int32),
+        ("x", C.c_void_p), ("norm_w", C.c_void_p), ("norm_b", C.c_void_p), ("w_qkv", C.c_void_p), ("w_out", C.c_void_p),
+        ("b_out", C.c_void_p), ("out_norm_w", C.c_void_p), ("out_norm_b", C.c_void_p), ("y", C.c_void_p),
+        ("scratch_dev", C.c_void_p), ("scratch_bytes", C.c_size_t),
+    ]
+
+
 # every symbol include/dmn_b200.h declares: (restype, argtypes)
 _P, _I, _L, _F = C.c_void_p, C.c_int, C.c_int64, C.c_float
 SYMBOLS = {
@@ -91,6 +100,9 @@ SYMBOLS = {
     "dmn_linear_attention_core": (_I, [_P, _P, _I, _I, _I, _I, _I, _P, C.c_size_t, _P]),
     "dmn_attention_core": (_I, [_P, _P, _I, _I, _I, _I, _I, _P, C.c_size_t, _P]),
     "dmn_selftest_umma_gemm": (_I, [_P, _P, _P, _I, _I, _I, _P]),
+    "dmn_selftest_tma_sw128_gemm": (_I, [_P, _P, _P, _I, _I, _I, _P]),
+    "dmn_linear_attention_block": (_I, [C.POINTER(AttnBlockArgs), _P]),
+    "dmn_linear_attention_block_scratch_bytes": (C.c_size_t, [C.POINTER(AttnBlockArgs)]),
 }
 
 _lib = None

@@ -195,4 +195,84 @@ int dmn_selftest_umma_gemm(const void* a_bf16, const void* b_bf16, float* d, int
   return rc;
 }
 
+int dmn_selftest_tma_sw128_gemm(const void* a_bf16, const void* b_bf16, float* d, int M, int N, int K, void* stream) {
+  DMN_REQUIRE(a_bf16 && b_bf16 && d, "null tensor");
+  int rc = selftest_tma_sw128_gemm(a_bf16, b_bf16, d, M, N, K, (cudaStream_t)stream);
+  if (rc) return rc;
+  cudaError_t e = cudaStreamSynchronize((cudaStream_t)stream);
+  if (e != cudaSuccess) return fail(DMN_ECUDA, std::string("selftest_tma_sw128_gemm: ") + cudaGetErrorString(e));
+  return 0;
+}
+
+namespace {
+struct AttnScratch {
+  size_t x, y, wqkv, wo, s12, stats, total;
+};
+AttnScratch attn_layout(const dmn_attn_block_args* a) {
+  AttnScratch s;
+  size_t o = 0;
+  const size_t act = (size_t)a->batch * a->n_tokens * a->dim * 2;
+  s.x = o; o += al(act);
+  s.y = o; o += al(act);
+  s.wqkv = o; o += al((size_t)384 * a->dim * 2);
+  s.wo = o; o += al((size_t)a->dim * 128 * 2);
+  s.s12 = o; o += al((size_t)2 * 384 * 4);
+  s.stats = o; o += al((size_t)a->batch * 2 * 8);
+  s.total = o;
+  return s;
+}
+}  // namespace
+
+size_t dmn_linear_attention_block_scratch_bytes(const dmn_attn_block_args* a) { return a ? attn_layout(a).total : 0; }
+
+int dmn_linear_attention_block(const dmn_attn_block_args* a, void* stream) {
+  if (!a) return fail(DMN_EINVAL, "null args");
+  DMN_REQUIRE(a->x && a->y && a->norm_w && a->norm_b && a->w_qkv && a->w_out && a->b_out && a->out_norm_w && a->out_norm_b && a->scratch_dev,
+              "null tensor");
+  if (!linattn_fused_supported(a->batch, a->n_tokens, a->dim))
+    return fail(DMN_ENOTSUP, "fused LinearAttention block: n_tokens must be a multiple of 128 and dim 128 or 256");
+  const AttnScratch L = attn_layout(a);
+  DMN_REQUIRE(a->scratch_bytes >= L.total, "scratch too small (dmn_linear_attention_block_scratch_bytes)");
+  cudaStream_t st = (cudaStream_t)stream;
+  char* base = (char*)a->scratch_dev;
+  const int C_ = a->dim;
+  int rc;
+  if ((rc = nchw_to_nhwc(a->x, base + L.x, a->batch, C_, a->n_tokens, ACT_BF16, st))) return rc;
+  group_stats_kernel<bf16><<<a->batch, 256, 0, st>>>((const bf16*)(base + L.x), (stat_t*)(base + L.stats), a->n_tokens, C_, 1);
+  DMN_LAUNCH_CHECK("group_stats");
+  // host side: fold the PreNorm gamma / beta through to_qkv exactly as the plan does (plan.cu, dmn_plan_load_param)
+  std::vector<float> g(C_), be(C_), wq((size_t)384 * C_), wo((size_t)C_ * 128);
+  DMN_CUDA_CHECK(cudaMemcpyAsync(g.data(), a->norm_w, C_ * 4, cudaMemcpyDeviceToHost, st));
+  DMN_CUDA_CHECK(cudaMemcpyAsync(be.data(), a->norm_b, C_ * 4, cudaMemcpyDeviceToHost, st));
+  DMN_CUDA_CHECK(cudaMemcpyAsync(wq.data(), a->w_qkv, wq.size() * 4, cudaMemcpyDeviceToHost, st));
+  DMN_CUDA_CHECK(cudaMemcpyAsync(wo.data(), a->w_out, wo.size() * 4, cudaMemcpyDeviceToHost, st));
+  DMN_CUDA_CHECK(cudaStreamSynchronize(st));
+  std::vector<bf16> wqb(wq.size()), wob(wo.size());
+  std::vector<float> s12((size_t)2 * 384);
+  for (int n = 0; n < 384; ++n) {
+    double s1 = 0.0, s2 = 0.0;
+    for (int c = 0; c < C_; ++c) {
+      const bf16 wb = __float2bfloat16_rn(wq[(size_t)n * C_ + c] * g[c]);
+      wqb[(size_t)n * C_ + c] = wb;
+      s1 += (double)__bfloat162float(wb);
+      s2 += (double)wq[(size_t)n * C_ + c] * (double)be[c];
+    }
+    s12[n] = (float)s1;
+    s12[384 + n] = (float)s2;
+  }
+  for (size_t i = 0; i < wo.size(); ++i) wob[i] = __float2bfloat16_rn(wo[i]);
+  DMN_CUDA_CHECK(cudaMemcpyAsync(base + L.wqkv, wqb.data(), wqb.size() * 2, cudaMemcpyHostToDevice, st));
+  DMN_CUDA_CHECK(cudaMemcpyAsync(base + L.wo, wob.data(), wob.size() * 2, cudaMemcpyHostToDevice, st));
+  DMN_CUDA_CHECK(cudaMemcpyAsync(base + L.s12, s12.data(), s12.size() * 4, cudaMemcpyHostToDevice, st));
+  DMN_CUDA_CHECK(cudaStreamSynchronize(st));
+  LinAttnFusedP q;
+  q.x = base + L.x; q.out = base + L.y; q.pstats = (const stat_t*)(base + L.stats);
+  q.wqkv = base + L.wqkv; q.wo = base + L.wo;
+  q.s1 = (const float*)(base + L.s12); q.s2 = q.s1 + 384;
+  q.bo = a->b_out; q.go = a->out_norm_w; q.beo = a->out_norm_b;
+  q.B = a->batch; q.N = a->n_tokens; q.C = C_;
+  if ((rc = linattn_fused(q, st))) return rc;
+  return nhwc_to_nchw(base + L.y, a->y, a->batch, C_, a->n_tokens, ACT_BF16, st);
+}
+
 }  // extern "C"

@@ -1,0 +1,687 @@
+// attn_fused.cu -- Residual(PreNorm(dim, LinearAttention(dim))) as ONE kernel on the 5th-generation tensor cores (sm_100a only).
+//
+//   reference: utils.py:68-93 (Residual, PreNorm = GroupNorm(1, dim)), parts/mha.py:33-59 (LinearAttention: to_qkv 1x1 without bias,
+//   q = softmax_d(q) * scale, k = softmax_n(k), ctx = k v^T, out = ctx^T q, to_out = Conv1x1 + GroupNorm(1, dim)), result + x.
+//
+// One persistent CTA per SM walks whole images; per image (N tokens, C channels, heads 4 x dim_head 32):
+//   phase A, per 128-token tile   GEMM1  [k | v]^T[256 ch x 128 tok] = W_kv[256 x C] . X[128 tok x C]^T        (lane = channel)
+//                                 epilogue: PreNorm fold affine, ONLINE column softmax of k (running max / sum per channel, the
+//                                 context accumulator in TMEM is rescaled when the max moves), P = exp(k - max) and v as bf16 operands
+//                                 GEMM2  ctx[(h,d) x (h',e)] += P[128 x 128 tok] . V[128 x 128 tok]^T            (diagonal blocks used)
+//   phase B, per 128-token tile   GEMM3  q[128 tok x 128] = X . W_q^T ; epilogue: fold affine, softmax over the 32 head channels
+//                                 GEMM4  o[128 tok x 128] = softmax(q) . (ctx * scale / colsum)                  (block-diagonal B operand)
+//                                 GEMM5  y[128 tok x C] = o . W_o^T ; epilogue: + bias, statistics of GroupNorm(1), raw bf16 y -> out
+//   phase C                       out = GroupNorm(1)(y) * gamma + beta + x, in place over the image (y and x come back from L2)
+// The q / k / v tensors never exist in global memory: x is read (HBM once, L2 twice more), out is written.
+//
+// Operands that come from global memory (x tiles, weight slabs of 128 rows x 64 channels) are loaded by TMA tensor copies
+// (cp.async.bulk.tensor.2d, 128-byte swizzle) into mbarrier rings; operands produced by the epilogues (P, V, softmax(q), o, ctx) are
+// written to shared memory in the UMMA K-major no-swizzle canonical layout [k-chunk of 8][row][8] that the convolution engine uses.
+// Weight slabs stay resident in their ring slot while the slab sequence repeats (C = 128: the whole phase), see Loader::w().
+//
+// Warp roles (320 threads): warps 0-7 epilogues (two per TMEM lane quarter), warp 8 TMA loader, warp 9 TMEM allocator + MMA issuer.
+#include <cuda.h>      // CUtensorMap and its enums only: the encoder is fetched through cudaGetDriverEntryPoint (no libcuda link dependency)
+
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <tuple>
+
+#include "common.cuh"
+#include "ops.h"
+#include "tc_ptx.cuh"
+
+namespace dmn {
+namespace fa {
+
+using namespace tc;
+
+// ---------------------------------------------------------------------------------------------------------------------
+// tensor maps
+// ---------------------------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)p;
+  });
+  return fn;
+}
+// row-major bf16 [rows][cols], box = 64 columns (128 bytes) x box_rows rows, 128-byte swizzle; out-of-range rows read as zero
+static int make_map(CUtensorMap* m, const void* base, uint64_t rows, uint64_t cols, uint32_t box_rows) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) return fail(-3, "cuTensorMapEncodeTiled is not available from this driver");
+  cuuint64_t dims[2] = {cols, rows};
+  cuuint64_t strides[1] = {cols * 2};
+  cuuint32_t box[2] = {64, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  const CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(-3, "cuTensorMapEncodeTiled failed (" + std::to_string((int)r) + ")");
+  return 0;
+}
+
+__device__ __forceinline__ void tma_load(uint32_t dst, const CUtensorMap* map, int col, int row, uint32_t bar) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+               ::"r"(dst), "l"(map), "r"(bar), "r"(col), "r"(row)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t* r) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, "
+      "%18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+        "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]),
+        "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]),
+        "r"(r[30]), "r"(r[31])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void sts16(uint32_t addr, unsigned short v) { asm volatile("st.shared.u16 [%0], %1;" ::"r"(addr), "h"(v) : "memory"); }
+__device__ __forceinline__ uint4 ldcg128(const void* p) {
+  uint4 v;
+  asm volatile("ld.global.cg.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ unsigned short bf16_bits(float v) {
+  const bf16 b = __float2bfloat16_rn(v);
+  return *reinterpret_cast<const unsigned short*>(&b);
+}
+
+constexpr uint32_t kSlab = 128u * 128u;        // one TMA slab: 128 rows x 64 bf16 (128-byte rows, 8-row swizzle atoms of 1 KB)
+constexpr uint32_t kOpBytes = 16u * 128u * 16u;   // one epilogue-written operand: 16 k-chunks x 128 rows x 16 bytes = 32 KB
+constexpr uint32_t kOpLbo = 128u * 16u, kOpSbo = 128u;   // no-swizzle K-major: k-chunk stride, 8-row group stride
+constexpr uint32_t kOpK16 = 2u * kOpLbo;       // one MMA k-step = 2 k-chunks
+
+// =====================================================================================================================
+// self-test of the TMA / 128-byte-swizzle plumbing: D[M][N] (fp32) = A[M][K] . B[N][K]^T, one CTA per 128 x 128 output tile
+// =====================================================================================================================
+struct SelfTestP {
+  CUtensorMap ma, mb;
+  float* d;
+  int M, N, K;
+};
+__global__ void __launch_bounds__(128, 1) sw128_gemm_selftest_kernel(const __grid_constant__ SelfTestP p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const uint32_t base0 = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + ((1024u - (base0 & 1023u)) & 1023u);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 2 * kSlab);
+  uint32_t* tslot = reinterpret_cast<uint32_t*>(bars + 4);
+  const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0), lane = tid & 31;
+  if (tid == 0) {
+    mbar_init(smem_u32(&bars[0]), 1);
+    mbar_init(smem_u32(&bars[1]), 1);
+    fence_barrier_init();
+  }
+  if (warp == 0) tmem_alloc(smem_u32(tslot), 128);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tslot;
+  const uint32_t sa = smem_u32(smem), sb = sa + kSlab;
+  const uint32_t idesc = make_idesc(128, 128);
+  const int m0 = blockIdx.x * 128, n0 = blockIdx.y * 128;
+  if (warp == 0) {
+    const bool leader = elect_one();
+    uint32_t ph = 0;
+    for (int kc = 0; kc < p.K / 64; ++kc) {
+      if (leader) {
+        mbar_arrive_expect_tx(smem_u32(&bars[0]), 2 * kSlab);
+        tma_load(sa, &p.ma, kc * 64, m0, smem_u32(&bars[0]));
+        tma_load(sb, &p.mb, kc * 64, n0, smem_u32(&bars[0]));
+      }
+      __syncwarp();
+      mbar_wait(smem_u32(&bars[0]), ph);
+      tc_fence_after();
+      if (leader) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) umma_bf16(tmem, make_desc_sw128(sa + j * 32), make_desc_sw128(sb + j * 32), idesc, (kc | j) ? 1u : 0u);
+        umma_commit(smem_u32(&bars[1]));
+      }
+      __syncwarp();
+      mbar_wait(smem_u32(&bars[1]), ph);      // the slabs are free again (single-buffered: this is a plumbing test, not a fast GEMM)
+      ph ^= 1;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t r[32];
+  for (int c = 0; c < 128; c += 32) {
+    tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)c, r);
+    const int m = m0 + warp * 32 + lane;
+    if (m < p.M)
+      for (int i = 0; i < 32; ++i)
+        if (n0 + c + i < p.N) p.d[(long)m * p.N + n0 + c + i] = __uint_as_float(r[i]);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc(tmem, 128);
+  }
+}
+
+// =====================================================================================================================
+// fused LinearAttention block, N % 128 == 0 (an image is a whole number of 128-token tiles)
+// =====================================================================================================================
+constexpr int kEpiThreads = 256, kLoaderWarp = 8, kMmaWarp = 9, kThreads = 320;
+constexpr int kXS = 3, kWS = 4;                // ring depths in slabs
+
+struct Params {
+  CUtensorMap mx, mw, mo;        // x [B*N][C],  W_qkv (PreNorm gamma folded in) [384][C],  W_o [C][128]
+  const bf16* x;
+  bf16* out;
+  const stat_t* pstats;          // [B][2] fixed-point {sum, sum of squares} of x over the image (PreNorm GroupNorm(1))
+  const float* s1;               // [384] fold vectors (ops.h: ConvP::fold_s1 / fold_s2)
+  const float* s2;
+  const float* bo;               // [C] to_out.0.bias
+  const float* go;               // [C] to_out.1.weight (GroupNorm(1) gamma)
+  const float* beo;              // [C] to_out.1.bias
+  int B, N, C;
+  float inv_cnt;                 // 1 / (N * C)
+};
+
+// barrier indices
+enum { B_FULLX = 0, B_EMPTYX = B_FULLX + kXS, B_FULLW = B_EMPTYX + kXS, B_EMPTYW = B_FULLW + kWS, B_KV = B_EMPTYW + kWS, B_PV, B_CTX, B_Q, B_QS,
+       B_OUT, B_OUTS, B_Y, B_COUNT };
+
+__global__ void __launch_bounds__(kThreads, 1) linattn_fused_kernel(const __grid_constant__ Params p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const uint32_t base0 = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + ((1024u - (base0 & 1023u)) & 1023u);
+  uint8_t* s_x = smem;                                   // kXS slabs
+  uint8_t* s_w = s_x + kXS * kSlab;                      // kWS slabs
+  uint8_t* s_opa = s_w + kWS * kSlab;                    // P (phase A) | softmax(q) (phase B)        A operand
+  uint8_t* s_opb = s_opa + kOpBytes;                     // V (phase A, B operand) | o (phase B, A operand)
+  uint8_t* s_ctx = s_opb + kOpBytes;                     // block-diagonal context, B operand of GEMM4
+  float* s_tq = reinterpret_cast<float*>(s_ctx + kOpBytes);   // [128] per-image additive term of the q fold: c * s1[n] + s2[n]
+  float* s_bo = s_tq + 128;                              // [C]
+  float* s_go = s_bo + 256;                              // [C]
+  float* s_beo = s_go + 256;                             // [C]
+  float* s_red = s_beo + 256;                            // [8][2] statistics partials
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_red + 16);
+  uint32_t* tslot = reinterpret_cast<uint32_t*>(bars + B_COUNT);
+
+  pdl_trigger();
+  pdl_wait();
+  const int tid = threadIdx.x;
+  const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0), lane = tid & 31;
+  const int C = p.C, N = p.N, KC = C >> 6, T = N >> 7, RH = C >> 7;
+  auto bar = [&](int i) { return smem_u32(&bars[i]); };
+
+  if (warp == kLoaderWarp) {
+    if (lane < B_COUNT) {
+      uint32_t cnt = 1;
+      if (lane == B_PV || lane == B_QS || lane == B_OUTS) cnt = kEpiThreads;
+      mbar_init(bar(lane), cnt);
+    }
+    fence_barrier_init();
+  }
+  if (warp == kMmaWarp) tmem_alloc(smem_u32(tslot), 512);
+  if (warp < 8) {
+    // zero the block-diagonal context operand once: the off-diagonal blocks are never written
+    for (uint32_t i = tid; i < kOpBytes / 16; i += kEpiThreads) sts128(smem_u32(s_ctx) + i * 16, make_uint4(0, 0, 0, 0));
+    for (int i = tid; i < C; i += kEpiThreads) {
+      s_bo[i] = p.bo[i];
+      s_go[i] = p.go[i];
+      s_beo[i] = p.beo[i];
+    }
+    fence_proxy_async();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tslot;
+  const uint32_t tDk = tmem, tDv = tmem + 128, tDctx = tmem + 256;      // phase A
+  const uint32_t tDq = tmem, tDo = tmem + 128, tDy = tmem + 256;        // phase B (aliases)
+
+  if (warp == kLoaderWarp) {
+    // =============================================== TMA loader ===============================================
+    const bool leader = elect_one();
+    int xs = 0, ws = 0;
+    uint32_t xph = 1, wph = 1;                 // parity of the "slot is free" waits
+    int wtag[kWS];
+#pragma unroll
+    for (int i = 0; i < kWS; ++i) wtag[i] = -1;
+    auto load_x = [&](int row0, int kc) {
+      mbar_wait_relaxed(bar(B_EMPTYX + xs), xph);
+      if (leader) {
+        mbar_arrive_expect_tx(bar(B_FULLX + xs), kSlab);
+        tma_load(smem_u32(s_x) + xs * kSlab, &p.mx, kc * 64, row0, bar(B_FULLX + xs));
+      }
+      __syncwarp();
+      if (++xs == kXS) { xs = 0; xph ^= 1; }
+    };
+    // weight slab `id`; a slot that already holds the wanted slab (the slab sequence of a phase repeats with a period that
+    // divides the ring depth when C = 128) is handed over without a copy
+    auto load_w = [&](const CUtensorMap* map, int id, int col, int row) {
+      mbar_wait_relaxed(bar(B_EMPTYW + ws), wph);
+      bool hit = false;
+#pragma unroll
+      for (int i = 0; i < kWS; ++i)
+        if (i == ws) { hit = wtag[i] == id; wtag[i] = id; }
+      if (leader) {
+        if (hit) {
+          mbar_arrive(bar(B_FULLW + ws));
+        } else {
+          mbar_arrive_expect_tx(bar(B_FULLW + ws), kSlab);
+          tma_load(smem_u32(s_w) + ws * kSlab, map, col, row, bar(B_FULLW + ws));
+        }
+      }
+      __syncwarp();
+      if (++ws == kWS) { ws = 0; wph ^= 1; }
+    };
+    for (int b = blockIdx.x; b < p.B; b += gridDim.x) {
+      const int row_img = b * N;
+      for (int t = 0; t < T; ++t)
+        for (int kc = 0; kc < KC; ++kc) {
+          load_x(row_img + t * 128, kc);
+          load_w(&p.mw, 8 + kc, kc * 64, 128);       // W_k rows [128, 256)
+          load_w(&p.mw, 16 + kc, kc * 64, 256);      // W_v rows [256, 384)
+        }
+      for (int t = 0; t < T; ++t) {
+        for (int kc = 0; kc < KC; ++kc) {
+          load_x(row_img + t * 128, kc);
+          load_w(&p.mw, kc, kc * 64, 0);             // W_q rows [0, 128)
+        }
+        for (int kc2 = 0; kc2 < 2; ++kc2)
+          for (int rh = 0; rh < RH; ++rh) load_w(&p.mo, 32 + kc2 * 2 + rh, kc2 * 64, rh * 128);
+      }
+    }
+  } else if (warp == kMmaWarp) {
+    // =============================================== MMA issuer ===============================================
+    const bool leader = elect_one();
+    const uint32_t idesc = make_idesc(128, 128);
+    int xs = 0, ws = 0;
+    uint32_t xph = 0, wph = 0;
+    uint32_t ph_pv = 0, ph_qs = 0, ph_outs = 0;
+    const uint32_t opa = smem_u32(s_opa), opb = smem_u32(s_opb), ctxb = smem_u32(s_ctx);
+    auto wait_x = [&]() -> uint32_t {
+      mbar_wait(bar(B_FULLX + xs), xph);
+      return smem_u32(s_x) + xs * kSlab;
+    };
+    auto wait_w = [&]() -> uint32_t {          // the current weight slot (not advanced)
+      mbar_wait(bar(B_FULLW + ws), wph);
+      return smem_u32(s_w) + ws * kSlab;
+    };
+    auto adv_w = [&]() -> int {                // returns the slot that was current
+      const int s0 = ws;
+      if (++ws == kWS) { ws = 0; wph ^= 1; }
+      return s0;
+    };
+    auto free_x = [&]() {                      // the slot is released once the MMAs issued so far have retired
+      if (leader) umma_commit(bar(B_EMPTYX + xs));
+      __syncwarp();
+      if (++xs == kXS) { xs = 0; xph ^= 1; }
+    };
+    auto free_w_slot = [&](int slot) {
+      if (leader) umma_commit(bar(B_EMPTYW + slot));
+      __syncwarp();
+    };
+    for (int b = blockIdx.x; b < p.B; b += gridDim.x) {
+      // ---------------- phase A ----------------
+      for (int t = 0; t < T; ++t) {
+        for (int kc = 0; kc < KC; ++kc) {
+          const uint32_t ax = wait_x();
+          const uint32_t wk = wait_w();
+          const int slot_k = adv_w();
+          const uint32_t wv = wait_w();
+          const int slot_v = adv_w();
+          tc_fence_after();
+          if (leader) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const uint32_t acc = (kc | j) ? 1u : 0u;
+              const uint64_t xd = make_desc_sw128(ax + j * 32);
+              umma_bf16(tDk, make_desc_sw128(wk + j * 32), xd, idesc, acc);
+              umma_bf16(tDv, make_desc_sw128(wv + j * 32), xd, idesc, acc);
+            }
+          }
+          __syncwarp();
+          free_w_slot(slot_k);
+          free_w_slot(slot_v);
+          free_x();
+        }
+        if (leader) umma_commit(bar(B_KV));
+        __syncwarp();
+        mbar_wait(bar(B_PV), ph_pv);
+        ph_pv ^= 1;
+        tc_fence_after();
+        if (leader) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            umma_bf16(tDctx, make_desc(opa + j * kOpK16, kOpLbo, kOpSbo), make_desc(opb + j * kOpK16, kOpLbo, kOpSbo), idesc, (t | j) ? 1u : 0u);
+          if (t == T - 1) umma_commit(bar(B_CTX));
+        }
+        __syncwarp();
+      }
+      // ---------------- phase B ----------------
+      for (int t = 0; t < T; ++t) {
+        for (int kc = 0; kc < KC; ++kc) {
+          const uint32_t ax = wait_x();
+          const uint32_t wq = wait_w();
+          tc_fence_after();
+          if (leader) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) umma_bf16(tDq, make_desc_sw128(ax + j * 32), make_desc_sw128(wq + j * 32), idesc, (kc | j) ? 1u : 0u);
+          }
+          __syncwarp();
+          free_w_slot(adv_w());
+          free_x();
+        }
+        if (leader) umma_commit(bar(B_Q));
+        __syncwarp();
+        mbar_wait(bar(B_QS), ph_qs);
+        ph_qs ^= 1;
+        tc_fence_after();
+        if (leader) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            umma_bf16(tDo, make_desc(opa + j * kOpK16, kOpLbo, kOpSbo), make_desc(ctxb + j * kOpK16, kOpLbo, kOpSbo), idesc, j ? 1u : 0u);
+          umma_commit(bar(B_OUT));
+        }
+        __syncwarp();
+        mbar_wait(bar(B_OUTS), ph_outs);
+        ph_outs ^= 1;
+        tc_fence_after();
+        for (int kc2 = 0; kc2 < 2; ++kc2)
+          for (int rh = 0; rh < RH; ++rh) {
+            const uint32_t wo = wait_w();
+            tc_fence_after();
+            if (leader) {
+#pragma unroll
+              for (int j = 0; j < 4; ++j)
+                umma_bf16(tDy + rh * 128, make_desc(opb + (kc2 * 4 + j) * kOpK16, kOpLbo, kOpSbo), make_desc_sw128(wo + j * 32), idesc,
+                          (kc2 | j) ? 1u : 0u);
+            }
+            __syncwarp();
+            free_w_slot(adv_w());
+          }
+        if (leader) umma_commit(bar(B_Y));
+        __syncwarp();
+      }
+    }
+  } else {
+    // =============================================== epilogues ===============================================
+    const int q4 = warp & 3, half = warp >> 2;                 // TMEM lane quarter of this warp; column half / role
+    const uint32_t lane_base = (uint32_t)(q4 * 32) << 16;
+    const int ch = q4 * 32 + lane;                             // phase A: the channel of this thread (lane = channel)
+    const uint32_t opa = smem_u32(s_opa), opb = smem_u32(s_opb), ctxb = smem_u32(s_ctx);
+    // phase A fold constants of this thread's channel: k -> qkv channel 128 + ch, v -> 256 + ch
+    const float s1c = p.s1[(half ? 256 : 128) + ch], s2c = p.s2[(half ? 256 : 128) + ch];
+    uint32_t ph_kv = 0, ph_ctx = 0, ph_q = 0, ph_out = 0, ph_y = 0;
+    const float qscale = rsqrtf(32.f);
+    for (int b = blockIdx.x; b < p.B; b += gridDim.x) {
+      float mean_x, rstd_x;
+      gn_mean_rstd(p.pstats + (long)b * 2, p.inv_cnt, kGnEps, mean_x, rstd_x);
+      const float fa = rstd_x, fc = -mean_x * rstd_x;          // x_hat = fa * x + fc (gamma / beta live in the weights and s1 / s2)
+      if (tid < 128) s_tq[tid] = fc * p.s1[tid] + p.s2[tid];
+      const float cc = fc * s1c + s2c;
+      float run_max = -INFINITY, run_sum = 0.f;
+      float sy = 0.f, sq = 0.f;
+      // ---------------- phase A ----------------
+      for (int t = 0; t < T; ++t) {
+        mbar_wait_relaxed(bar(B_KV), ph_kv);
+        ph_kv ^= 1;
+        tc_fence_after();
+        uint32_t r[32];
+        if (half == 0) {
+          // ---- k: online column softmax over the tokens ----
+          float tmax = -INFINITY;
+#pragma unroll 1
+          for (int c0 = 0; c0 < 128; c0 += 32) {
+            tmem_ld32(tDk + lane_base + c0, r);
+#pragma unroll
+            for (int i = 0; i < 32; ++i) tmax = fmaxf(tmax, fmaf(fa, __uint_as_float(r[i]), cc));
+          }
+          const float new_max = fmaxf(run_max, tmax);
+          const float f = __expf(run_max - new_max);           // 0 on the first tile (run_max = -inf)
+          float psum = 0.f;
+#pragma unroll 1
+          for (int c0 = 0; c0 < 128; c0 += 32) {
+            tmem_ld32(tDk + lane_base + c0, r);
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              uint32_t w[4];
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const bf16 p0 = __float2bfloat16_rn(__expf(fmaf(fa, __uint_as_float(r[g * 8 + 2 * e]), cc) - new_max));
+                const bf16 p1 = __float2bfloat16_rn(__expf(fmaf(fa, __uint_as_float(r[g * 8 + 2 * e + 1]), cc) - new_max));
+                psum += __bfloat162float(p0) + __bfloat162float(p1);     // sums of the ROUNDED values: numerator and denominator agree
+                w[e] = (uint32_t)(*reinterpret_cast<const unsigned short*>(&p0)) | ((uint32_t)(*reinterpret_cast<const unsigned short*>(&p1)) << 16);
+              }
+              sts128(opa + (uint32_t)((((c0 >> 3) + g) * 128 + ch) * 16), make_uint4(w[0], w[1], w[2], w[3]));
+            }
+          }
+          run_sum = run_sum * f + psum;
+          run_max = new_max;
+          // rescale this channel's row of the context accumulator (its head's diagonal block) when the max moved
+          if (t > 0 && __any_sync(0xffffffffu, f != 1.f)) {
+            tmem_ld32(tDctx + lane_base + (uint32_t)(q4 * 32), r);
+#pragma unroll
+            for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) * f);
+            tmem_st32(tDctx + lane_base + (uint32_t)(q4 * 32), r);
+            tmem_st_wait();
+          }
+        } else {
+          // ---- v ----
+#pragma unroll 1
+          for (int c0 = 0; c0 < 128; c0 += 32) {
+            tmem_ld32(tDv + lane_base + c0, r);
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              uint32_t w[4];
+#pragma unroll
+              for (int e = 0; e < 4; ++e)
+                w[e] = pack_bf16x2(fmaf(fa, __uint_as_float(r[g * 8 + 2 * e]), cc), fmaf(fa, __uint_as_float(r[g * 8 + 2 * e + 1]), cc));
+              sts128(opb + (uint32_t)((((c0 >> 3) + g) * 128 + ch) * 16), make_uint4(w[0], w[1], w[2], w[3]));
+            }
+          }
+        }
+        fence_proxy_async();
+        tc_fence_before();
+        mbar_arrive(bar(B_PV));
+      }
+      // ---- context: ctx[d][e] * scale / colsum[d] -> block-diagonal B operand of GEMM4, element (row (h,e), k (h,d)) ----
+      mbar_wait_relaxed(bar(B_CTX), ph_ctx);
+      ph_ctx ^= 1;
+      tc_fence_after();
+      if (half == 0) {
+        uint32_t r[32];
+        tmem_ld32(tDctx + lane_base + (uint32_t)(q4 * 32), r);
+        const float sc = qscale / run_sum;
+        const uint32_t dst = ctxb + (uint32_t)(((ch >> 3) * 128 + q4 * 32) * 16 + (ch & 7) * 2);
+#pragma unroll
+        for (int e = 0; e < 32; ++e) sts16(dst + e * 16, bf16_bits(__uint_as_float(r[e]) * sc));
+      }
+      bar_sync_named(1, kEpiThreads);            // s_tq (written above by threads 0..127) is visible to everybody
+      // ---------------- phase B ----------------
+      for (int t = 0; t < T; ++t) {
+        const int tok = t * 128 + q4 * 32 + lane;              // phase B: lane = token
+        uint32_t r[32];
+        // ---- q: fold affine, softmax over the 32 channels of each head, (scale lives in the context operand) ----
+        mbar_wait_relaxed(bar(B_Q), ph_q);
+        ph_q ^= 1;
+        tc_fence_after();
+#pragma unroll 1
+        for (int hh = 0; hh < 2; ++hh) {
+          const int col0 = (half * 2 + hh) * 32;
+          tmem_ld32(tDq + lane_base + col0, r);
+          float v[32];
+          float mx = -INFINITY;
+#pragma unroll
+          for (int i = 0; i < 32; i += 4) {
+            const float4 tq = *reinterpret_cast<const float4*>(s_tq + col0 + i);
+            v[i] = fmaf(fa, __uint_as_float(r[i]), tq.x);
+            v[i + 1] = fmaf(fa, __uint_as_float(r[i + 1]), tq.y);
+            v[i + 2] = fmaf(fa, __uint_as_float(r[i + 2]), tq.z);
+            v[i + 3] = fmaf(fa, __uint_as_float(r[i + 3]), tq.w);
+            mx = fmaxf(fmaxf(mx, fmaxf(v[i], v[i + 1])), fmaxf(v[i + 2], v[i + 3]));
+          }
+          float sum = 0.f;
+#pragma unroll
+          for (int i = 0; i < 32; ++i) { v[i] = __expf(v[i] - mx); sum += v[i]; }
+          const float inv = 1.f / sum;
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            uint4 o;
+            o.x = pack_bf16x2(v[g * 8] * inv, v[g * 8 + 1] * inv);
+            o.y = pack_bf16x2(v[g * 8 + 2] * inv, v[g * 8 + 3] * inv);
+            o.z = pack_bf16x2(v[g * 8 + 4] * inv, v[g * 8 + 5] * inv);
+            o.w = pack_bf16x2(v[g * 8 + 6] * inv, v[g * 8 + 7] * inv);
+            sts128(opa + (uint32_t)((((col0 >> 3) + g) * 128 + q4 * 32 + lane) * 16), o);
+          }
+        }
+        fence_proxy_async();
+        tc_fence_before();
+        mbar_arrive(bar(B_QS));
+        // ---- o = softmax(q) . ctx: TMEM -> bf16 A operand of GEMM5 ----
+        mbar_wait_relaxed(bar(B_OUT), ph_out);
+        ph_out ^= 1;
+        tc_fence_after();
+#pragma unroll 1
+        for (int hh = 0; hh < 2; ++hh) {
+          const int col0 = (half * 2 + hh) * 32;
+          tmem_ld32(tDo + lane_base + col0, r);
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            uint4 o;
+            o.x = pack_bf16x2(__uint_as_float(r[g * 8]), __uint_as_float(r[g * 8 + 1]));
+            o.y = pack_bf16x2(__uint_as_float(r[g * 8 + 2]), __uint_as_float(r[g * 8 + 3]));
+            o.z = pack_bf16x2(__uint_as_float(r[g * 8 + 4]), __uint_as_float(r[g * 8 + 5]));
+            o.w = pack_bf16x2(__uint_as_float(r[g * 8 + 6]), __uint_as_float(r[g * 8 + 7]));
+            sts128(opb + (uint32_t)((((col0 >> 3) + g) * 128 + q4 * 32 + lane) * 16), o);
+          }
+        }
+        fence_proxy_async();
+        tc_fence_before();
+        mbar_arrive(bar(B_OUTS));
+        // ---- y = o . W_o^T + bias: statistics of GroupNorm(1), raw bf16 y parked in the output buffer ----
+        mbar_wait_relaxed(bar(B_Y), ph_y);
+        ph_y ^= 1;
+        tc_fence_after();
+        const int ncol = C >> 1;                               // columns of this warp: [half * ncol, (half + 1) * ncol)
+        bf16* yrow = p.out + ((long)b * N + tok) * C + half * ncol;
+#pragma unroll 1
+        for (int c0 = 0; c0 < ncol; c0 += 32) {
+          tmem_ld32(tDy + lane_base + (uint32_t)(half * ncol + c0), r);
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            float y[8];
+#pragma unroll
+            for (int e = 0; e < 8; e += 4) {
+              const float4 bb = *reinterpret_cast<const float4*>(s_bo + half * ncol + c0 + g * 8 + e);
+              y[e] = __uint_as_float(r[g * 8 + e]) + bb.x;
+              y[e + 1] = __uint_as_float(r[g * 8 + e + 1]) + bb.y;
+              y[e + 2] = __uint_as_float(r[g * 8 + e + 2]) + bb.z;
+              y[e + 3] = __uint_as_float(r[g * 8 + e + 3]) + bb.w;
+            }
+#pragma unroll
+            for (int e = 0; e < 8; ++e) { sy += y[e]; sq = fmaf(y[e], y[e], sq); }
+            *reinterpret_cast<uint4*>(yrow + c0 + g * 8) = pack8(y);
+          }
+        }
+        tc_fence_before();
+      }
+      // ---------------- phase C: out = GroupNorm(1)(y) * gamma + beta + x ----------------
+      sy = warp_sum(sy);
+      sq = warp_sum(sq);
+      if (lane == 0) { s_red[warp * 2] = sy; s_red[warp * 2 + 1] = sq; }
+      bar_sync_named(1, kEpiThreads);            // also orders this CTA's global y stores before the reads below
+      float ts = 0.f, tq2 = 0.f;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { ts += s_red[2 * i]; tq2 += s_red[2 * i + 1]; }
+      const float mean_y = ts * p.inv_cnt;
+      float var_y = tq2 * p.inv_cnt - mean_y * mean_y;
+      var_y = var_y < 0.f ? 0.f : var_y;
+      const float rstd_y = rsqrtf(var_y + kGnEps);
+      {
+        const int per_row = C >> 3;                            // 16-byte items per token row (16 or 32: divides 256)
+        const int c8 = (tid % per_row) * 8;
+        float gsc[8], gsh[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          gsc[e] = rstd_y * s_go[c8 + e];
+          gsh[e] = s_beo[c8 + e] - mean_y * gsc[e];
+        }
+        const long base = (long)b * N * C;
+        const int items = N * per_row;
+#pragma unroll 2
+        for (int i = tid; i < items; i += kEpiThreads) {
+          const uint4 yv = ldcg128(p.out + base + (long)i * 8);
+          const uint4 xv = *reinterpret_cast<const uint4*>(p.x + base + (long)i * 8);
+          float y[8], xx[8];
+          unpack8(yv, y);
+          unpack8(xv, xx);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) y[e] = fmaf(y[e], gsc[e], gsh[e]) + xx[e];
+          *reinterpret_cast<uint4*>(p.out + base + (long)i * 8) = pack8(y);
+        }
+      }
+      bar_sync_named(1, kEpiThreads);            // s_red / s_tq are rewritten by the next image
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == kMmaWarp) {
+    tc_fence_after();
+    tmem_dealloc(tmem, 512);
+  }
+}
+
+constexpr size_t kSmemFused = 1024 + (size_t)(kXS + kWS) * kSlab + 3 * (size_t)kOpBytes + (128 + 3 * 256 + 16) * 4 + (B_COUNT + 2) * 8 + 64;
+
+}  // namespace fa
+
+bool linattn_fused_supported(int B, int N, int C) {
+  return B >= 1 && N >= 128 && N % 128 == 0 && (C == 128 || C == 256) && (long)B * N < (1L << 30);
+}
+
+int linattn_fused(const LinAttnFusedP& q, cudaStream_t st) {
+  if (!linattn_fused_supported(q.B, q.N, q.C)) return fail(-2, "linattn_fused: unsupported shape");
+  fa::Params p;
+  memset(&p, 0, sizeof(p));
+  int rc;
+  if ((rc = fa::make_map(&p.mx, q.x, (uint64_t)q.B * q.N, (uint64_t)q.C, 128))) return rc;
+  if ((rc = fa::make_map(&p.mw, q.wqkv, 384, (uint64_t)q.C, 128))) return rc;
+  if ((rc = fa::make_map(&p.mo, q.wo, (uint64_t)q.C, 128, 128))) return rc;
+  p.x = (const bf16*)q.x;
+  p.out = (bf16*)q.out;
+  p.pstats = q.pstats;
+  p.s1 = q.s1; p.s2 = q.s2; p.bo = q.bo; p.go = q.go; p.beo = q.beo;
+  p.B = q.B; p.N = q.N; p.C = q.C;
+  p.inv_cnt = 1.f / ((float)q.N * (float)q.C);
+  static DeviceOnce attr;
+  if (attr.first()) DMN_CUDA_CHECK(cudaFuncSetAttribute(fa::linattn_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fa::kSmemFused));
+  const int grid = q.B < current_device_sms() ? q.B : current_device_sms();
+  DMN_CUDA_CHECK(launch_pdl(fa::linattn_fused_kernel, dim3(grid), dim3(fa::kThreads), fa::kSmemFused, st, p));
+  count_launch();
+  DMN_LAUNCH_CHECK("linattn_fused");
+  return 0;
+}
+
+int selftest_tma_sw128_gemm(const void* a_bf16, const void* b_bf16, float* d, int M, int N, int K, cudaStream_t st) {
+  DMN_REQUIRE(M > 0 && N > 0 && K > 0 && K % 64 == 0, "selftest_tma_sw128_gemm: K must be a multiple of 64");
+  fa::SelfTestP p;
+  memset(&p, 0, sizeof(p));
+  int rc;
+  if ((rc = fa::make_map(&p.ma, a_bf16, (uint64_t)M, (uint64_t)K, 128))) return rc;
+  if ((rc = fa::make_map(&p.mb, b_bf16, (uint64_t)N, (uint64_t)K, 128))) return rc;
+  p.d = d; p.M = M; p.N = N; p.K = K;
+  const size_t smem = 1024 + 2 * fa::kSlab + 64;
+  static DeviceOnce attr;
+  if (attr.first()) DMN_CUDA_CHECK(cudaFuncSetAttribute(fa::sw128_gemm_selftest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  fa::sw128_gemm_selftest_kernel<<<dim3((M + 127) / 128, (N + 127) / 128), 128, smem, st>>>(p);
+  DMN_LAUNCH_CHECK("sw128_gemm_selftest");
+  return 0;
+}
+
+}  // namespace dmn

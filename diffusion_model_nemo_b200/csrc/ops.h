@@ -110,6 +110,27 @@ int attn_core(const void* qkv, void* out, int B, int heads, int dh, int N, int a
 // bf16 tensor-core LinearAttention core (heads = 4, dim_head = 32); linattn_core dispatches to it for ACT_BF16
 int linattn_core_bf16_mma(const void* qkv, void* out, int B, int N, cudaStream_t s);
 
+// Residual(PreNorm(dim, LinearAttention(dim))) as one tcgen05 kernel (attn_fused.cu): out = GroupNorm(1)(to_out(attn(GN1(x)))) + x.
+// bf16 NHWC activations; wqkv = row-major bf16 [384][C] with the PreNorm gamma folded in, wo = row-major bf16 [C][128];
+// s1 / s2 = the fold vectors of ConvP (384 floats each); pstats = GroupNorm(1) statistics of x.
+struct LinAttnFusedP {
+  const void* x = nullptr;
+  void* out = nullptr;
+  const stat_t* pstats = nullptr;
+  const void* wqkv = nullptr;
+  const void* wo = nullptr;
+  const float* s1 = nullptr;
+  const float* s2 = nullptr;
+  const float* bo = nullptr;       // to_out.0.bias [C]
+  const float* go = nullptr;       // to_out.1.weight [C]
+  const float* beo = nullptr;      // to_out.1.bias [C]
+  int B = 0, N = 0, C = 0;
+};
+bool linattn_fused_supported(int B, int N, int C);
+int linattn_fused(const LinAttnFusedP& p, cudaStream_t s);
+// plumbing self-test of the TMA tensor copies + 128-byte-swizzle UMMA descriptors: D[M][N] = A[M][K] . B[N][K]^T (row-major bf16 in, fp32 out)
+int selftest_tma_sw128_gemm(const void* a_bf16, const void* b_bf16, float* d, int M, int N, int K, cudaStream_t s);
+
 // time path
 struct TimeP {
   const float* times = nullptr;    // [rows]

@@ -72,6 +72,7 @@ enum ParamKind {
   PK_LIN_T,      // Linear weight [out][in] -> [in][out]
   PK_BLOCK_MLP_W,  // ResnetBlock.mlp.1.weight [cout][4dim] -> column slice of [4dim][sumC]
   PK_BLOCK_MLP_B,  // ResnetBlock.mlp.1.bias -> slice of [sumC]
+  PK_PLAIN_BF16,   // 1x1 conv weight [out][in][1][1] -> row-major bf16 [out][in] (TMA operand of the fused attention kernel)
 };
 
 struct Param {
@@ -95,7 +96,7 @@ struct Param {
   }
 };
 
-enum OpKind { OP_MEMSET, OP_INIT, OP_CONV, OP_FINALIZE, OP_LINATTN, OP_ATTN, OP_FINALPROJ, OP_MODULATE, OP_CLASSADD };
+enum OpKind { OP_MEMSET, OP_INIT, OP_CONV, OP_FINALIZE, OP_LINATTN, OP_ATTN, OP_FINALPROJ, OP_MODULATE, OP_CLASSADD, OP_ATTN_FUSED };
 
 // Buffers are addressed as (region id, so pointers can be resolved after bind)
 struct Buf {
@@ -124,6 +125,7 @@ struct Op {
   Buf raw, stats;
   // attention
   int heads = 4, dh = 32, N = 0;
+  int wo = -1, bo = -1;             // fused attention block: to_out.0 weight (plain bf16 image) / bias
 };
 
 }  // namespace dmn
@@ -215,6 +217,18 @@ struct Builder {
     if (q.has_simt) q.off = walloc((size_t)q.numel() * sizeof(float));
     q.has_tc = tc;
     if (tc) q.off2 = walloc(conv_tcgen05_weight_bytes(mode, ksize, cin, cout));
+    P.params.push_back(q);
+    P.pidx[name] = (int)P.params.size() - 1;
+    return (int)P.params.size() - 1;
+  }
+
+  int add_plain_param(const std::string& name, int cout, int cin) {
+    Param q;
+    q.name = name;
+    q.shape = {cout, cin, 1, 1};
+    q.kind = PK_PLAIN_BF16;
+    q.cin = cin; q.cout = cout;
+    q.off = walloc((size_t)cout * cin * 2);
     P.params.push_back(q);
     P.pidx[name] = (int)P.params.size() - 1;
     return (int)P.params.size() - 1;
@@ -317,6 +331,30 @@ struct Builder {
     const int hidden = 128;
     int nw = add_param(p + ".fn.norm.weight", {C}, PK_RAW);
     int nb = add_param(p + ".fn.norm.bias", {C}, PK_RAW);
+    static const bool no_fused = [] { const char* e = getenv("DMN_NO_FUSED_ATTN"); return e && e[0] == '1'; }();
+    if (linear && !no_fused && P.engine == DMN_CONV_TCGEN05 && linattn_fused_supported(P.cfg.max_batch, H * H, C)) {
+      // the whole Residual(PreNorm(LinearAttention)) block as one tcgen05 kernel (attn_fused.cu): q / k / v never reach global memory
+      Op a;
+      a.kind = OP_ATTN_FUSED;
+      a.name = p + ".fused";
+      a.src1 = x; a.out = out; a.pstats = xstats; a.C = C; a.N = H * H; a.HW = H * H; a.Hin = H;
+      a.w = add_plain_param(p + ".fn.fn.to_qkv.weight", 3 * hidden, C);
+      a.fold = true;
+      a.fold_gamma = nw;
+      a.fold_beta = nb;
+      a.fold_off = walloc((size_t)2 * 3 * hidden * sizeof(float));
+      a.wo = add_plain_param(p + ".fn.fn.to_out.0.weight", C, hidden);
+      a.bo = add_param(p + ".fn.fn.to_out.0.bias", {C}, PK_RAW);
+      a.gamma = add_param(p + ".fn.fn.to_out.1.weight", {C}, PK_RAW);
+      a.beta = add_param(p + ".fn.fn.to_out.1.bias", {C}, PK_RAW);
+      P.ops.push_back(a);
+      const int ci = (int)P.ops.size() - 1;
+      for (int pi : {a.w, nw, nb}) {
+        P.params[pi].keep_host = true;
+        P.params[pi].fold_op = ci;
+      }
+      return;
+    }
     if (P.engine == DMN_CONV_TCGEN05 && want_tc(CONV_SAME, 1, C, 0, 3 * hidden, H, 0, 0, 0)) {
       // tensor-core engine: GroupNorm(1) folded through the 1x1 conv (raw operand load, affine in the epilogue)
       const int ci = conv(p + ".fn.fn.to_qkv", CONV_SAME, 1, x, C, Buf(), 0, 3 * hidden, H, qkv, false, 0);
@@ -614,6 +652,18 @@ static int run_forward(dmn_plan* P, const float* x_dev, const int32_t* row_dev, 
       case OP_ATTN:
         rc = attn_core(B(o.src1), B(o.out), batch, o.heads, o.dh, o.N, P->act, st);
         break;
+      case OP_ATTN_FUSED: {
+        LinAttnFusedP q;
+        q.x = B(o.src1); q.out = B(o.out); q.pstats = (const stat_t*)B(o.pstats);
+        q.wqkv = P->wbase + P->params[o.w].off;
+        q.wo = P->wbase + P->params[o.wo].off;
+        q.s1 = (const float*)(P->wbase + o.fold_off);
+        q.s2 = q.s1 + 384;
+        q.bo = W(o.bo); q.go = W(o.gamma); q.beo = W(o.beta);
+        q.B = batch; q.N = o.N; q.C = o.C;
+        rc = linattn_fused(q, st);
+        break;
+      }
       case OP_CLASSADD:
         rc = class_embed_add(B(o.src1), W(P->pidx["class_embed.weight"]), classes_dev, c.num_classes, batch, o.HW, o.C, P->act, st);
         break;
@@ -767,6 +817,15 @@ int dmn_plan_load_param(dmn_plan* p, const char* name, const float* host, int64_
       DMN_CUDA_CHECK(cudaMemcpyAsync(p->wbase + p->off_bc + (size_t)q.col * sizeof(float), host, numel * sizeof(float),
                                      cudaMemcpyHostToDevice, st));
       break;
+    case PK_PLAIN_BF16: {
+      if (q.fold_op < 0) {       // folded weights are packed below, once gamma / beta are known too
+        std::vector<bf16> img((size_t)numel);
+        for (int64_t i = 0; i < numel; ++i) img[i] = __float2bfloat16_rn(host[i]);
+        DMN_CUDA_CHECK(cudaMemcpyAsync(p->wbase + q.off, img.data(), img.size() * 2, cudaMemcpyHostToDevice, st));
+        DMN_CUDA_CHECK(cudaStreamSynchronize(st));
+      }
+      break;
+    }
     case PK_CONV: {
       if (q.has_simt) {
         tmp.resize(numel);
@@ -804,11 +863,19 @@ int dmn_plan_load_param(dmn_plan* p, const char* name, const float* host, int64_
         s12[n] = (float)s1;
         s12[cout + n] = (float)s2;
       }
-      std::vector<char> img(conv_tcgen05_weight_bytes(pw.mode, pw.ksize, cin, cout));
-      conv_tcgen05_pack_weights(pw.mode, pw.ksize, cin, cout, wf.data(), img.data());
-      DMN_CUDA_CHECK(cudaMemcpyAsync(p->wbase + pw.off2, img.data(), img.size(), cudaMemcpyHostToDevice, st));
-      DMN_CUDA_CHECK(cudaMemcpyAsync(p->wbase + o.fold_off, s12.data(), s12.size() * sizeof(float), cudaMemcpyHostToDevice, st));
-      DMN_CUDA_CHECK(cudaStreamSynchronize(st));
+      if (pw.kind == PK_PLAIN_BF16) {        // fused attention block: row-major bf16 [cout][cin]
+        std::vector<bf16> img(wf.size());
+        for (size_t i = 0; i < wf.size(); ++i) img[i] = __float2bfloat16_rn(wf[i]);
+        DMN_CUDA_CHECK(cudaMemcpyAsync(p->wbase + pw.off, img.data(), img.size() * 2, cudaMemcpyHostToDevice, st));
+        DMN_CUDA_CHECK(cudaMemcpyAsync(p->wbase + o.fold_off, s12.data(), s12.size() * sizeof(float), cudaMemcpyHostToDevice, st));
+        DMN_CUDA_CHECK(cudaStreamSynchronize(st));
+      } else {
+        std::vector<char> img(conv_tcgen05_weight_bytes(pw.mode, pw.ksize, cin, cout));
+        conv_tcgen05_pack_weights(pw.mode, pw.ksize, cin, cout, wf.data(), img.data());
+        DMN_CUDA_CHECK(cudaMemcpyAsync(p->wbase + pw.off2, img.data(), img.size(), cudaMemcpyHostToDevice, st));
+        DMN_CUDA_CHECK(cudaMemcpyAsync(p->wbase + o.fold_off, s12.data(), s12.size() * sizeof(float), cudaMemcpyHostToDevice, st));
+        DMN_CUDA_CHECK(cudaStreamSynchronize(st));
+      }
     }
   }
   return 0;
@@ -909,13 +976,17 @@ int dmn_plan_op_info(const dmn_plan* p, int i, char* name_out, int name_cap, int
     case OP_LINATTN: fl = 2.0 * 2.0 * o.heads * o.dh * o.dh * o.N; by = esz * (double)o.N * o.heads * o.dh * 4.0; break;
     case OP_ATTN: fl = 2.0 * 2.0 * o.heads * o.dh * (double)o.N * o.N; by = esz * (double)o.N * o.heads * o.dh * 4.0; break;
     case OP_FINALPROJ: fl = 2.0 * o.HW * o.C * o.Cout; by = esz * (double)o.HW * o.C + 4.0 * o.HW * o.Cout; break;
+    case OP_ATTN_FUSED:      // to_qkv + both contractions + to_out; x read once, result written once
+      fl = 2.0 * o.N * (384.0 * o.C + 2.0 * 128.0 * 32.0 + 128.0 * o.C);
+      by = esz * (double)o.N * o.C * 2.0;
+      break;
   }
   if (name_out && name_cap > 0) {
     strncpy(name_out, o.name.c_str(), (size_t)name_cap - 1);
     name_out[name_cap - 1] = 0;
   }
   if (kind) *kind = o.kind;
-  if (engine) *engine = ((o.kind == OP_CONV && o.tc) || (o.kind == OP_INIT && p->init_tc)) ? 1 : 0;
+  if (engine) *engine = ((o.kind == OP_CONV && o.tc) || (o.kind == OP_INIT && p->init_tc) || o.kind == OP_ATTN_FUSED) ? 1 : 0;
   if (flops_per_sample) *flops_per_sample = fl;
   if (bytes_per_sample) *bytes_per_sample = by;
   return 0;

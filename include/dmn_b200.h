@@ -270,6 +270,28 @@ int dmn_attention_core(const float* qkv, float* out, int batch, int heads, int d
  * fp32 out; all device pointers).  Used by tests to pin the UMMA descriptor encodings. */
 int dmn_selftest_umma_gemm(const void* a_bf16, const void* b_bf16, float* d, int M, int N, int K, void* stream);
 
+/* Self-test of the TMA tensor copies (cp.async.bulk.tensor.2d, 128-byte swizzle) + SWIZZLE_128B UMMA descriptors used by the fused
+ * attention kernel: D[M,N] = A[M,K] * B[N,K]^T, row-major bf16 in, fp32 out, K a multiple of 64 (all device pointers). */
+int dmn_selftest_tma_sw128_gemm(const void* a_bf16, const void* b_bf16, float* d, int M, int N, int K, void* stream);
+
+/* Residual(PreNorm(dim, LinearAttention(dim))) (utils.py:68-93, parts/mha.py:33-59) through the fused tcgen05 kernel:
+ *   y = GroupNorm(1)(to_out(linear_attention(to_qkv(GroupNorm(1)(x))))) + x,   heads = 4, dim_head = 32.
+ * x / y fp32 NCHW [batch, dim, H, W] with H*W a multiple of 128 and dim in {128, 256}; parameters fp32 in PyTorch layout (device):
+ * norm_w / norm_b [dim] (PreNorm), w_qkv [384, dim], w_out [dim, 128], b_out [dim], out_norm_w / out_norm_b [dim].
+ * scratch_dev >= dmn_linear_attention_block_scratch_bytes().  Validation path (host repack, sync copies). */
+typedef struct dmn_attn_block_args {
+  int32_t batch, dim, n_tokens;
+  const float* x;
+  const float* norm_w; const float* norm_b;
+  const float* w_qkv;
+  const float* w_out; const float* b_out;
+  const float* out_norm_w; const float* out_norm_b;
+  float* y;
+  void* scratch_dev; size_t scratch_bytes;
+} dmn_attn_block_args;
+int dmn_linear_attention_block(const dmn_attn_block_args* a, void* stream);
+size_t dmn_linear_attention_block_scratch_bytes(const dmn_attn_block_args* a);
+
 #ifdef __cplusplus
 }
 #endif

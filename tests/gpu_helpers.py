@@ -61,3 +61,30 @@ def attention_core(qkv, linear, act=L.ACT_F32, heads=4, dh=32):
         L.check(fn(L.ptr(q), L.ptr(out), b, heads, dh, n, act, C.c_void_p(sp), scratch.numel() - 256, L.stream_ptr(dev)), "attention core")
     torch.cuda.synchronize(dev)
     return out
+
+
+def linear_attention_block(x, sd, prefix):
+    """Residual(PreNorm(LinearAttention)) through the fused tcgen05 kernel.  x fp32 NCHW cuda; sd holds the reference parameter names
+    under `prefix` (fn.norm.*, fn.fn.to_qkv.weight, fn.fn.to_out.0.*, fn.fn.to_out.1.*)."""
+    lib = L.lib()
+    dev = x.device
+    b, c, h, w = x.shape
+    a = L.AttnBlockArgs()
+    a.batch, a.dim, a.n_tokens = b, c, h * w
+    keep = {k: sd[prefix + k].float().contiguous().to(dev) for k in (".fn.norm.weight", ".fn.norm.bias", ".fn.fn.to_qkv.weight",
+                                                                    ".fn.fn.to_out.0.weight", ".fn.fn.to_out.0.bias",
+                                                                    ".fn.fn.to_out.1.weight", ".fn.fn.to_out.1.bias")}
+    xc = x.float().contiguous()
+    y = torch.empty_like(xc)
+    a.x, a.y = xc.data_ptr(), y.data_ptr()
+    a.norm_w, a.norm_b = keep[".fn.norm.weight"].data_ptr(), keep[".fn.norm.bias"].data_ptr()
+    a.w_qkv = keep[".fn.fn.to_qkv.weight"].data_ptr()
+    a.w_out, a.b_out = keep[".fn.fn.to_out.0.weight"].data_ptr(), keep[".fn.fn.to_out.0.bias"].data_ptr()
+    a.out_norm_w, a.out_norm_b = keep[".fn.fn.to_out.1.weight"].data_ptr(), keep[".fn.fn.to_out.1.bias"].data_ptr()
+    scratch = torch.empty(lib.dmn_linear_attention_block_scratch_bytes(C.byref(a)) + 256, dtype=torch.uint8, device=dev)
+    a.scratch_dev = (scratch.data_ptr() + 255) // 256 * 256
+    a.scratch_bytes = scratch.numel() - 256
+    with torch.cuda.device(dev):
+        L.check(lib.dmn_linear_attention_block(C.byref(a), L.stream_ptr(dev)), "dmn_linear_attention_block")
+    torch.cuda.synchronize(dev)
+    return y
