@@ -57,12 +57,18 @@ __global__ void group_stats_kernel(const T* x, stat_t* stats, int HW, int C, int
 }
 }  // namespace
 
-namespace dmn { int conv_tcgen05_read_trace(long long* out, int n); }
+namespace dmn {
+int conv_tcgen05_read_trace(long long* out, int n);
+int fa_read_trace(long long* out, int n);
+}
 
 extern "C" {
 
 /* debug only (not part of the documented ABI): timeline of one CTA of the last tcgen05 conv launched with DMN_TC_TRACE=1 */
 int dmn_debug_conv_trace(long long* out, int n) { return conv_tcgen05_read_trace(out, n); }
+/* debug only: phase timeline of CTA 0 of the last fused attention launch with DMN_FA_TRACE=1 (clock64 at: image start, phase A done,
+ * context built, phase B done, phase C done; slots 0..4 first image, 8..12 last image of the CTA) */
+int dmn_debug_fa_trace(long long* out, int n) { return fa_read_trace(out, n); }
 
 size_t dmn_conv_scratch_bytes(const dmn_conv_args* a) { return a ? conv_layout(a).total : 0; }
 

@@ -22,6 +22,7 @@
 // Warp roles (320 threads): warps 0-7 epilogues (two per TMEM lane quarter), warp 8 TMA loader, warp 9 TMEM allocator + MMA issuer.
 #include <cuda.h>      // CUtensorMap and its enums only: the encoder is fetched through cudaGetDriverEntryPoint (no libcuda link dependency)
 
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <mutex>
@@ -94,10 +95,19 @@ __device__ __forceinline__ unsigned short bf16_bits(float v) {
   return *reinterpret_cast<const unsigned short*>(&b);
 }
 
+__device__ __forceinline__ float ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+constexpr float kLog2e = 1.4426950408889634f;
+
 constexpr uint32_t kSlab = 128u * 128u;        // one TMA slab: 128 rows x 64 bf16 (128-byte rows, 8-row swizzle atoms of 1 KB)
 constexpr uint32_t kOpBytes = 16u * 128u * 16u;   // one epilogue-written operand: 16 k-chunks x 128 rows x 16 bytes = 32 KB
 constexpr uint32_t kOpLbo = 128u * 16u, kOpSbo = 128u;   // no-swizzle K-major: k-chunk stride, 8-row group stride
 constexpr uint32_t kOpK16 = 2u * kOpLbo;       // one MMA k-step = 2 k-chunks
+// per-head context operand of GEMM4: B[N = 32 (e)][K = 32 (d)] no-swizzle K-major = [4 k-chunks][32 rows][16 B] = 2 KB per head
+constexpr uint32_t kCtxHead = 4u * 32u * 16u, kCtxLbo = 32u * 16u;
 
 // =====================================================================================================================
 // self-test of the TMA / 128-byte-swizzle plumbing: D[M][N] (fp32) = A[M][K] . B[N][K]^T, one CTA per 128 x 128 output tile
@@ -186,7 +196,10 @@ struct Params {
   const float* beo;              // [C] to_out.1.bias
   int B, N, C;
   float inv_cnt;                 // 1 / (N * C)
+  long long* trace;              // debug timeline of CTA 0 (DMN_FA_TRACE=1), else null
 };
+__device__ long long g_fa_trace[64];
+#define FA_TRACE(k) do { if (p.trace && blockIdx.x == 0 && tid == 0) p.trace[(k)] = clock64(); } while (0)
 
 // barrier indices
 enum { B_FULLX = 0, B_EMPTYX = B_FULLX + kXS, B_FULLW = B_EMPTYX + kXS, B_EMPTYW = B_FULLW + kWS, B_KV = B_EMPTYW + kWS, B_PV, B_CTX, B_Q, B_QS,
@@ -200,13 +213,15 @@ __global__ void __launch_bounds__(kThreads, 1) linattn_fused_kernel(const __grid
   uint8_t* s_w = s_x + kXS * kSlab;                      // kWS slabs
   uint8_t* s_opa = s_w + kWS * kSlab;                    // P (phase A) | softmax(q) (phase B)        A operand
   uint8_t* s_opb = s_opa + kOpBytes;                     // V (phase A, B operand) | o (phase B, A operand)
-  uint8_t* s_ctx = s_opb + kOpBytes;                     // block-diagonal context, B operand of GEMM4
-  float* s_tq = reinterpret_cast<float*>(s_ctx + kOpBytes);   // [128] per-image additive term of the q fold: c * s1[n] + s2[n]
+  uint8_t* s_ctx = s_opb + kOpBytes;                     // per-head context operands of GEMM4 (4 x 2 KB)
+  float* s_tq = reinterpret_cast<float*>(s_ctx + 4 * kCtxHead);   // [128] per-image additive term of the q fold (log2 domain)
   float* s_bo = s_tq + 128;                              // [C]
   float* s_go = s_bo + 256;                              // [C]
   float* s_beo = s_go + 256;                             // [C]
   float* s_red = s_beo + 256;                            // [8][2] statistics partials
-  uint64_t* bars = reinterpret_cast<uint64_t*>(s_red + 16);
+  float* s_kx = s_red + 16;                              // [2][128] k softmax exchange between the two warps of a lane quarter: tile maxima
+  float* s_ks = s_kx + 256;                              // [2][128] ... column sums
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_ks + 256);
   uint32_t* tslot = reinterpret_cast<uint32_t*>(bars + B_COUNT);
 
   pdl_trigger();
@@ -226,14 +241,11 @@ __global__ void __launch_bounds__(kThreads, 1) linattn_fused_kernel(const __grid
   }
   if (warp == kMmaWarp) tmem_alloc(smem_u32(tslot), 512);
   if (warp < 8) {
-    // zero the block-diagonal context operand once: the off-diagonal blocks are never written
-    for (uint32_t i = tid; i < kOpBytes / 16; i += kEpiThreads) sts128(smem_u32(s_ctx) + i * 16, make_uint4(0, 0, 0, 0));
     for (int i = tid; i < C; i += kEpiThreads) {
       s_bo[i] = p.bo[i];
       s_go[i] = p.go[i];
       s_beo[i] = p.beo[i];
     }
-    fence_proxy_async();
   }
   tc_fence_before();
   __syncthreads();
@@ -286,11 +298,16 @@ __global__ void __launch_bounds__(kThreads, 1) linattn_fused_kernel(const __grid
           load_w(&p.mw, 8 + kc, kc * 64, 128);       // W_k rows [128, 256)
           load_w(&p.mw, 16 + kc, kc * 64, 256);      // W_v rows [256, 384)
         }
-      for (int t = 0; t < T; ++t) {
+      // phase B in the order the MMA issuer consumes: q(0); then per tile q(t + 1), W_o(t)
+      auto q_tile = [&](int t) {
         for (int kc = 0; kc < KC; ++kc) {
           load_x(row_img + t * 128, kc);
           load_w(&p.mw, kc, kc * 64, 0);             // W_q rows [0, 128)
         }
+      };
+      q_tile(0);
+      for (int t = 0; t < T; ++t) {
+        if (t + 1 < T) q_tile(t + 1);
         for (int kc2 = 0; kc2 < 2; ++kc2)
           for (int rh = 0; rh < RH; ++rh) load_w(&p.mo, 32 + kc2 * 2 + rh, kc2 * 64, rh * 128);
       }
@@ -298,7 +315,7 @@ __global__ void __launch_bounds__(kThreads, 1) linattn_fused_kernel(const __grid
   } else if (warp == kMmaWarp) {
     // =============================================== MMA issuer ===============================================
     const bool leader = elect_one();
-    const uint32_t idesc = make_idesc(128, 128);
+    const uint32_t idesc = make_idesc(128, 128), idesc32 = make_idesc(128, 32);
     int xs = 0, ws = 0;
     uint32_t xph = 0, wph = 0;
     uint32_t ph_pv = 0, ph_qs = 0, ph_outs = 0;
@@ -362,8 +379,8 @@ __global__ void __launch_bounds__(kThreads, 1) linattn_fused_kernel(const __grid
         }
         __syncwarp();
       }
-      // ---------------- phase B ----------------
-      for (int t = 0; t < T; ++t) {
+      // ---------------- phase B (software pipelined: GEMM3 of tile t + 1 is issued before GEMM5 of tile t) ----------------
+      auto gemm3 = [&]() {
         for (int kc = 0; kc < KC; ++kc) {
           const uint32_t ax = wait_x();
           const uint32_t wq = wait_w();
@@ -378,16 +395,24 @@ __global__ void __launch_bounds__(kThreads, 1) linattn_fused_kernel(const __grid
         }
         if (leader) umma_commit(bar(B_Q));
         __syncwarp();
+      };
+      gemm3();
+      for (int t = 0; t < T; ++t) {
         mbar_wait(bar(B_QS), ph_qs);
         ph_qs ^= 1;
         tc_fence_after();
         if (leader) {
+          // o[:, head h] = softmax(q)[:, head h] . ctx_h: four M128 x N32 x K32 products
 #pragma unroll
-          for (int j = 0; j < 8; ++j)
-            umma_bf16(tDo, make_desc(opa + j * kOpK16, kOpLbo, kOpSbo), make_desc(ctxb + j * kOpK16, kOpLbo, kOpSbo), idesc, j ? 1u : 0u);
+          for (int h = 0; h < 4; ++h)
+#pragma unroll
+            for (int j = 0; j < 2; ++j)
+              umma_bf16(tDo + h * 32, make_desc(opa + (h * 2 + j) * kOpK16, kOpLbo, kOpSbo),
+                        make_desc(ctxb + h * kCtxHead + j * 2 * kCtxLbo, kCtxLbo, kOpSbo), idesc32, j ? 1u : 0u);
           umma_commit(bar(B_OUT));
         }
         __syncwarp();
+        if (t + 1 < T) gemm3();                 // early: the epilogue of this tile's o / y overlaps the next tile's q product
         mbar_wait(bar(B_OUTS), ph_outs);
         ph_outs ^= 1;
         tc_fence_after();
@@ -410,107 +435,111 @@ __global__ void __launch_bounds__(kThreads, 1) linattn_fused_kernel(const __grid
     }
   } else {
     // =============================================== epilogues ===============================================
-    const int q4 = warp & 3, half = warp >> 2;                 // TMEM lane quarter of this warp; column half / role
+    const int q4 = warp & 3, half = warp >> 2;                 // TMEM lane quarter of this warp; column half
     const uint32_t lane_base = (uint32_t)(q4 * 32) << 16;
     const int ch = q4 * 32 + lane;                             // phase A: the channel of this thread (lane = channel)
     const uint32_t opa = smem_u32(s_opa), opb = smem_u32(s_opb), ctxb = smem_u32(s_ctx);
-    // phase A fold constants of this thread's channel: k -> qkv channel 128 + ch, v -> 256 + ch
-    const float s1c = p.s1[(half ? 256 : 128) + ch], s2c = p.s2[(half ? 256 : 128) + ch];
+    // phase A: both warps of a lane quarter work on k AND v of the quarter's 32 channels, each on one half of the tile's tokens
+    const float s1k = p.s1[128 + ch], s2k = p.s2[128 + ch], s1v = p.s1[256 + ch], s2v = p.s2[256 + ch];
     uint32_t ph_kv = 0, ph_ctx = 0, ph_q = 0, ph_out = 0, ph_y = 0;
     const float qscale = rsqrtf(32.f);
+    const int tcol0 = half * 64;                               // phase A: this thread's token columns [tcol0, tcol0 + 64)
     for (int b = blockIdx.x; b < p.B; b += gridDim.x) {
       float mean_x, rstd_x;
       gn_mean_rstd(p.pstats + (long)b * 2, p.inv_cnt, kGnEps, mean_x, rstd_x);
       const float fa = rstd_x, fc = -mean_x * rstd_x;          // x_hat = fa * x + fc (gamma / beta live in the weights and s1 / s2)
-      if (tid < 128) s_tq[tid] = fc * p.s1[tid] + p.s2[tid];
-      const float cc = fc * s1c + s2c;
-      float run_max = -INFINITY, run_sum = 0.f;
+      const float fa2 = fa * kLog2e;                           // softmax arguments are kept in the log2 domain (one ex2 per element)
+      if (tid < 128) s_tq[tid] = (fc * p.s1[tid] + p.s2[tid]) * kLog2e;
+      const float ck2 = (fc * s1k + s2k) * kLog2e, cv = fc * s1v + s2v;
+      float run_max = -INFINITY, run_sum = 0.f;                // run_sum: this thread's half of the columns
       float sy = 0.f, sq = 0.f;
+      const int tb = (b == (int)blockIdx.x) ? 0 : 8;
+      FA_TRACE(tb + 0);
       // ---------------- phase A ----------------
       for (int t = 0; t < T; ++t) {
         mbar_wait_relaxed(bar(B_KV), ph_kv);
         ph_kv ^= 1;
         tc_fence_after();
         uint32_t r[32];
-        if (half == 0) {
-          // ---- k: online column softmax over the tokens ----
-          float tmax = -INFINITY;
-#pragma unroll 1
-          for (int c0 = 0; c0 < 128; c0 += 32) {
-            tmem_ld32(tDk + lane_base + c0, r);
+        // ---- k: online column softmax over the tokens; pass 1 = maximum of this thread's 64 columns ----
+        float tmax = -INFINITY;
 #pragma unroll
-            for (int i = 0; i < 32; ++i) tmax = fmaxf(tmax, fmaf(fa, __uint_as_float(r[i]), cc));
-          }
-          const float new_max = fmaxf(run_max, tmax);
-          const float f = __expf(run_max - new_max);           // 0 on the first tile (run_max = -inf)
-          float psum = 0.f;
-#pragma unroll 1
-          for (int c0 = 0; c0 < 128; c0 += 32) {
-            tmem_ld32(tDk + lane_base + c0, r);
+        for (int c0 = 0; c0 < 64; c0 += 32) {
+          tmem_ld32(tDk + lane_base + tcol0 + c0, r);
 #pragma unroll
-            for (int g = 0; g < 4; ++g) {
-              uint32_t w[4];
+          for (int i = 0; i < 32; ++i) tmax = fmaxf(tmax, fmaf(fa2, __uint_as_float(r[i]), ck2));
+        }
+        s_kx[half * 128 + ch] = tmax;
+        bar_sync_named(1, kEpiThreads);
+        const float new_max = fmaxf(run_max, fmaxf(tmax, s_kx[(half ^ 1) * 128 + ch]));
+        const float f = ex2(run_max - new_max);                // 0 on the first tile (run_max = -inf)
+        float psum = 0.f;
 #pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                const bf16 p0 = __float2bfloat16_rn(__expf(fmaf(fa, __uint_as_float(r[g * 8 + 2 * e]), cc) - new_max));
-                const bf16 p1 = __float2bfloat16_rn(__expf(fmaf(fa, __uint_as_float(r[g * 8 + 2 * e + 1]), cc) - new_max));
-                psum += __bfloat162float(p0) + __bfloat162float(p1);     // sums of the ROUNDED values: numerator and denominator agree
-                w[e] = (uint32_t)(*reinterpret_cast<const unsigned short*>(&p0)) | ((uint32_t)(*reinterpret_cast<const unsigned short*>(&p1)) << 16);
-              }
-              sts128(opa + (uint32_t)((((c0 >> 3) + g) * 128 + ch) * 16), make_uint4(w[0], w[1], w[2], w[3]));
+        for (int c0 = 0; c0 < 64; c0 += 32) {
+          tmem_ld32(tDk + lane_base + tcol0 + c0, r);
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            uint32_t w[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const bf16 p0 = __float2bfloat16_rn(ex2(fmaf(fa2, __uint_as_float(r[g * 8 + 2 * e]), ck2) - new_max));
+              const bf16 p1 = __float2bfloat16_rn(ex2(fmaf(fa2, __uint_as_float(r[g * 8 + 2 * e + 1]), ck2) - new_max));
+              psum += __bfloat162float(p0) + __bfloat162float(p1);     // sums of the ROUNDED values: numerator and denominator agree
+              w[e] = (uint32_t)(*reinterpret_cast<const unsigned short*>(&p0)) | ((uint32_t)(*reinterpret_cast<const unsigned short*>(&p1)) << 16);
             }
+            sts128(opa + (uint32_t)(((((tcol0 + c0) >> 3) + g) * 128 + ch) * 16), make_uint4(w[0], w[1], w[2], w[3]));
           }
-          run_sum = run_sum * f + psum;
-          run_max = new_max;
-          // rescale this channel's row of the context accumulator (its head's diagonal block) when the max moved
-          if (t > 0 && __any_sync(0xffffffffu, f != 1.f)) {
-            tmem_ld32(tDctx + lane_base + (uint32_t)(q4 * 32), r);
+        }
+        run_sum = run_sum * f + psum;
+        run_max = new_max;
+        // rescale this channel's row of the context accumulator (its head's diagonal block) when the max moved
+        if (half == 0 && t > 0 && __any_sync(0xffffffffu, f != 1.f)) {
+          tmem_ld32(tDctx + lane_base + (uint32_t)(q4 * 32), r);
 #pragma unroll
-            for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) * f);
-            tmem_st32(tDctx + lane_base + (uint32_t)(q4 * 32), r);
-            tmem_st_wait();
-          }
-        } else {
-          // ---- v ----
-#pragma unroll 1
-          for (int c0 = 0; c0 < 128; c0 += 32) {
-            tmem_ld32(tDv + lane_base + c0, r);
+          for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) * f);
+          tmem_st32(tDctx + lane_base + (uint32_t)(q4 * 32), r);
+          tmem_st_wait();
+        }
+        // ---- v ----
 #pragma unroll
-            for (int g = 0; g < 4; ++g) {
-              uint32_t w[4];
+        for (int c0 = 0; c0 < 64; c0 += 32) {
+          tmem_ld32(tDv + lane_base + tcol0 + c0, r);
 #pragma unroll
-              for (int e = 0; e < 4; ++e)
-                w[e] = pack_bf16x2(fmaf(fa, __uint_as_float(r[g * 8 + 2 * e]), cc), fmaf(fa, __uint_as_float(r[g * 8 + 2 * e + 1]), cc));
-              sts128(opb + (uint32_t)((((c0 >> 3) + g) * 128 + ch) * 16), make_uint4(w[0], w[1], w[2], w[3]));
-            }
+          for (int g = 0; g < 4; ++g) {
+            uint32_t w[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+              w[e] = pack_bf16x2(fmaf(fa, __uint_as_float(r[g * 8 + 2 * e]), cv), fmaf(fa, __uint_as_float(r[g * 8 + 2 * e + 1]), cv));
+            sts128(opb + (uint32_t)(((((tcol0 + c0) >> 3) + g) * 128 + ch) * 16), make_uint4(w[0], w[1], w[2], w[3]));
           }
         }
         fence_proxy_async();
         tc_fence_before();
         mbar_arrive(bar(B_PV));
       }
-      // ---- context: ctx[d][e] * scale / colsum[d] -> block-diagonal B operand of GEMM4, element (row (h,e), k (h,d)) ----
+      FA_TRACE(tb + 1);
+      // ---- context: ctx[d][e] * scale / colsum[d] -> per-head B operands of GEMM4, element (row e, k d) ----
+      s_ks[half * 128 + ch] = run_sum;
       mbar_wait_relaxed(bar(B_CTX), ph_ctx);
       ph_ctx ^= 1;
       tc_fence_after();
+      bar_sync_named(1, kEpiThreads);            // both halves of the column sums, and s_tq, are visible
       if (half == 0) {
         uint32_t r[32];
         tmem_ld32(tDctx + lane_base + (uint32_t)(q4 * 32), r);
-        const float sc = qscale / run_sum;
-        const uint32_t dst = ctxb + (uint32_t)(((ch >> 3) * 128 + q4 * 32) * 16 + (ch & 7) * 2);
+        const float sc = qscale / (run_sum + s_ks[128 + ch]);
+        const uint32_t dst = ctxb + (uint32_t)(q4 * kCtxHead + (lane >> 3) * kCtxLbo + (lane & 7) * 2);
 #pragma unroll
         for (int e = 0; e < 32; ++e) sts16(dst + e * 16, bf16_bits(__uint_as_float(r[e]) * sc));
       }
-      bar_sync_named(1, kEpiThreads);            // s_tq (written above by threads 0..127) is visible to everybody
       // ---------------- phase B ----------------
-      for (int t = 0; t < T; ++t) {
-        const int tok = t * 128 + q4 * 32 + lane;              // phase B: lane = token
+      // q: fold affine, softmax over the 32 channels of each head (the scale lives in the context operand) -> A operand of GEMM4
+      auto epi_q = [&]() {
         uint32_t r[32];
-        // ---- q: fold affine, softmax over the 32 channels of each head, (scale lives in the context operand) ----
         mbar_wait_relaxed(bar(B_Q), ph_q);
         ph_q ^= 1;
         tc_fence_after();
-#pragma unroll 1
+#pragma unroll
         for (int hh = 0; hh < 2; ++hh) {
           const int col0 = (half * 2 + hh) * 32;
           tmem_ld32(tDq + lane_base + col0, r);
@@ -519,15 +548,15 @@ __global__ void __launch_bounds__(kThreads, 1) linattn_fused_kernel(const __grid
 #pragma unroll
           for (int i = 0; i < 32; i += 4) {
             const float4 tq = *reinterpret_cast<const float4*>(s_tq + col0 + i);
-            v[i] = fmaf(fa, __uint_as_float(r[i]), tq.x);
-            v[i + 1] = fmaf(fa, __uint_as_float(r[i + 1]), tq.y);
-            v[i + 2] = fmaf(fa, __uint_as_float(r[i + 2]), tq.z);
-            v[i + 3] = fmaf(fa, __uint_as_float(r[i + 3]), tq.w);
+            v[i] = fmaf(fa2, __uint_as_float(r[i]), tq.x);
+            v[i + 1] = fmaf(fa2, __uint_as_float(r[i + 1]), tq.y);
+            v[i + 2] = fmaf(fa2, __uint_as_float(r[i + 2]), tq.z);
+            v[i + 3] = fmaf(fa2, __uint_as_float(r[i + 3]), tq.w);
             mx = fmaxf(fmaxf(mx, fmaxf(v[i], v[i + 1])), fmaxf(v[i + 2], v[i + 3]));
           }
           float sum = 0.f;
 #pragma unroll
-          for (int i = 0; i < 32; ++i) { v[i] = __expf(v[i] - mx); sum += v[i]; }
+          for (int i = 0; i < 32; ++i) { v[i] = ex2(v[i] - mx); sum += v[i]; }
           const float inv = 1.f / sum;
 #pragma unroll
           for (int g = 0; g < 4; ++g) {
@@ -542,11 +571,17 @@ __global__ void __launch_bounds__(kThreads, 1) linattn_fused_kernel(const __grid
         fence_proxy_async();
         tc_fence_before();
         mbar_arrive(bar(B_QS));
+      };
+      FA_TRACE(tb + 2);
+      epi_q();                                   // (the B_QS arrival also publishes the context operands written above)
+      for (int t = 0; t < T; ++t) {
+        const int tok = t * 128 + q4 * 32 + lane;              // phase B: lane = token
+        uint32_t r[32];
         // ---- o = softmax(q) . ctx: TMEM -> bf16 A operand of GEMM5 ----
         mbar_wait_relaxed(bar(B_OUT), ph_out);
         ph_out ^= 1;
         tc_fence_after();
-#pragma unroll 1
+#pragma unroll
         for (int hh = 0; hh < 2; ++hh) {
           const int col0 = (half * 2 + hh) * 32;
           tmem_ld32(tDo + lane_base + col0, r);
@@ -563,6 +598,7 @@ __global__ void __launch_bounds__(kThreads, 1) linattn_fused_kernel(const __grid
         fence_proxy_async();
         tc_fence_before();
         mbar_arrive(bar(B_OUTS));
+        if (t + 1 < T) epi_q();                  // the next tile's q while the tensor core computes this tile's y
         // ---- y = o . W_o^T + bias: statistics of GroupNorm(1), raw bf16 y parked in the output buffer ----
         mbar_wait_relaxed(bar(B_Y), ph_y);
         ph_y ^= 1;
@@ -590,6 +626,7 @@ __global__ void __launch_bounds__(kThreads, 1) linattn_fused_kernel(const __grid
         }
         tc_fence_before();
       }
+      FA_TRACE(tb + 3);
       // ---------------- phase C: out = GroupNorm(1)(y) * gamma + beta + x ----------------
       sy = warp_sum(sy);
       sq = warp_sum(sq);
@@ -612,20 +649,29 @@ __global__ void __launch_bounds__(kThreads, 1) linattn_fused_kernel(const __grid
           gsh[e] = s_beo[c8 + e] - mean_y * gsc[e];
         }
         const long base = (long)b * N * C;
-        const int items = N * per_row;
-#pragma unroll 2
-        for (int i = tid; i < items; i += kEpiThreads) {
-          const uint4 yv = ldcg128(p.out + base + (long)i * 8);
-          const uint4 xv = *reinterpret_cast<const uint4*>(p.x + base + (long)i * 8);
-          float y[8], xx[8];
-          unpack8(yv, y);
-          unpack8(xv, xx);
+        const int items = N * per_row;                         // a multiple of 8 * 256 (N >= 128, per_row >= 16)
+        constexpr int U = 8;                                   // independent 16-byte items in flight per thread
+        for (int i0 = tid; i0 < items; i0 += U * kEpiThreads) {
+          uint4 yv[U], xv[U];
 #pragma unroll
-          for (int e = 0; e < 8; ++e) y[e] = fmaf(y[e], gsc[e], gsh[e]) + xx[e];
-          *reinterpret_cast<uint4*>(p.out + base + (long)i * 8) = pack8(y);
+          for (int u = 0; u < U; ++u) {
+            const long off = base + (long)(i0 + u * kEpiThreads) * 8;
+            yv[u] = ldcg128(p.out + off);
+            xv[u] = ldcg128(p.x + off);
+          }
+#pragma unroll
+          for (int u = 0; u < U; ++u) {
+            float y[8], xx[8];
+            unpack8(yv[u], y);
+            unpack8(xv[u], xx);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) y[e] = fmaf(y[e], gsc[e], gsh[e]) + xx[e];
+            *reinterpret_cast<uint4*>(p.out + base + (long)(i0 + u * kEpiThreads) * 8) = pack8(y);
+          }
         }
       }
-      bar_sync_named(1, kEpiThreads);            // s_red / s_tq are rewritten by the next image
+      FA_TRACE(tb + 4);
+      bar_sync_named(1, kEpiThreads);            // s_red / s_tq / s_ks are rewritten by the next image
     }
   }
 
@@ -637,7 +683,7 @@ __global__ void __launch_bounds__(kThreads, 1) linattn_fused_kernel(const __grid
   }
 }
 
-constexpr size_t kSmemFused = 1024 + (size_t)(kXS + kWS) * kSlab + 3 * (size_t)kOpBytes + (128 + 3 * 256 + 16) * 4 + (B_COUNT + 2) * 8 + 64;
+constexpr size_t kSmemFused = 1024 + (size_t)(kXS + kWS) * kSlab + 2 * (size_t)kOpBytes + 4 * kCtxHead + (128 + 3 * 256 + 16 + 512) * 4 + (B_COUNT + 2) * 8 + 64;
 
 }  // namespace fa
 
@@ -659,12 +705,25 @@ int linattn_fused(const LinAttnFusedP& q, cudaStream_t st) {
   p.s1 = q.s1; p.s2 = q.s2; p.bo = q.bo; p.go = q.go; p.beo = q.beo;
   p.B = q.B; p.N = q.N; p.C = q.C;
   p.inv_cnt = 1.f / ((float)q.N * (float)q.C);
+  static const bool trace_on = [] { const char* e = getenv("DMN_FA_TRACE"); return e && e[0] == '1'; }();
+  if (trace_on) {
+    void* sym = nullptr;
+    DMN_CUDA_CHECK(cudaGetSymbolAddress(&sym, fa::g_fa_trace));
+    p.trace = (long long*)sym;
+  }
   static DeviceOnce attr;
   if (attr.first()) DMN_CUDA_CHECK(cudaFuncSetAttribute(fa::linattn_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fa::kSmemFused));
   const int grid = q.B < current_device_sms() ? q.B : current_device_sms();
   DMN_CUDA_CHECK(launch_pdl(fa::linattn_fused_kernel, dim3(grid), dim3(fa::kThreads), fa::kSmemFused, st, p));
   count_launch();
   DMN_LAUNCH_CHECK("linattn_fused");
+  return 0;
+}
+
+int fa_read_trace(long long* out, int n) {
+  if (n > 64) n = 64;
+  DMN_CUDA_CHECK(cudaDeviceSynchronize());
+  DMN_CUDA_CHECK(cudaMemcpyFromSymbol(out, fa::g_fa_trace, (size_t)n * sizeof(long long)));
   return 0;
 }
 
