@@ -236,7 +236,7 @@ int dmn_linear_attention_block(const dmn_attn_block_args* a, void* stream) {
   DMN_REQUIRE(a->x && a->y && a->norm_w && a->norm_b && a->w_qkv && a->w_out && a->b_out && a->out_norm_w && a->out_norm_b && a->scratch_dev,
               "null tensor");
   if (!linattn_fused_supported(a->batch, a->n_tokens, a->dim))
-    return fail(DMN_ENOTSUP, "fused LinearAttention block: n_tokens must be a multiple of 128 and dim 128 or 256");
+    return fail(DMN_ENOTSUP, "fused LinearAttention block: n_tokens must be a multiple of 128 (or of 8, below 128) and dim 128 or 256");
   const AttnScratch L = attn_layout(a);
   DMN_REQUIRE(a->scratch_bytes >= L.total, "scratch too small (dmn_linear_attention_block_scratch_bytes)");
   cudaStream_t st = (cudaStream_t)stream;

@@ -3,6 +3,8 @@
 //   reference: utils.py:68-93 (Residual, PreNorm = GroupNorm(1, dim)), parts/mha.py:33-59 (LinearAttention: to_qkv 1x1 without bias,
 //   q = softmax_d(q) * scale, k = softmax_n(k), ctx = k v^T, out = ctx^T q, to_out = Conv1x1 + GroupNorm(1, dim)), result + x.
 //
+// Images with fewer than 128 tokens (8x8, 4x4 maps) take one tile each: the TMA box only brings the image's N rows, the rest of the tile
+// stays zero, the padded token columns are masked out of the k softmax and the padded rows are neither counted nor stored.
 // One persistent CTA per SM walks whole images; per image (N tokens, C channels, heads 4 x dim_head 32):
 //   phase A, per 128-token tile   GEMM1  [k | v]^T[256 ch x 128 tok] = W_kv[256 x C] . X[128 tok x C]^T        (lane = channel)
 //                                 epilogue: PreNorm fold affine, ONLINE column softmax of k (running max / sum per channel, the
@@ -228,7 +230,10 @@ __global__ void __launch_bounds__(kThreads, 1) linattn_fused_kernel(const __grid
   pdl_wait();
   const int tid = threadIdx.x;
   const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0), lane = tid & 31;
-  const int C = p.C, N = p.N, KC = C >> 6, T = N >> 7, RH = C >> 7;
+  const int C = p.C, N = p.N, KC = C >> 6, RH = C >> 7;
+  const int T = N >= 128 ? (N >> 7) : 1;         // 128-token tiles per image
+  const int NV = N >= 128 ? 128 : N;             // valid tokens of a tile (N < 128: one zero-padded tile per image)
+  const uint32_t xbytes = (uint32_t)NV * 128u;   // bytes one x slab copy delivers
   auto bar = [&](int i) { return smem_u32(&bars[i]); };
 
   if (warp == kLoaderWarp) {
@@ -241,11 +246,14 @@ __global__ void __launch_bounds__(kThreads, 1) linattn_fused_kernel(const __grid
   }
   if (warp == kMmaWarp) tmem_alloc(smem_u32(tslot), 512);
   if (warp < 8) {
+    if (NV < 128)      // the TMA box only writes the first NV rows of a slab: the padded rows are zero for the whole launch
+      for (uint32_t i = tid; i < kXS * kSlab / 16; i += kEpiThreads) sts128(smem_u32(s_x) + i * 16, make_uint4(0, 0, 0, 0));
     for (int i = tid; i < C; i += kEpiThreads) {
       s_bo[i] = p.bo[i];
       s_go[i] = p.go[i];
       s_beo[i] = p.beo[i];
     }
+    fence_proxy_async();
   }
   tc_fence_before();
   __syncthreads();
@@ -265,7 +273,7 @@ __global__ void __launch_bounds__(kThreads, 1) linattn_fused_kernel(const __grid
     auto load_x = [&](int row0, int kc) {
       mbar_wait_relaxed(bar(B_EMPTYX + xs), xph);
       if (leader) {
-        mbar_arrive_expect_tx(bar(B_FULLX + xs), kSlab);
+        mbar_arrive_expect_tx(bar(B_FULLX + xs), xbytes);
         tma_load(smem_u32(s_x) + xs * kSlab, &p.mx, kc * 64, row0, bar(B_FULLX + xs));
       }
       __syncwarp();
@@ -466,8 +474,10 @@ __global__ void __launch_bounds__(kThreads, 1) linattn_fused_kernel(const __grid
 #pragma unroll
         for (int c0 = 0; c0 < 64; c0 += 32) {
           tmem_ld32(tDk + lane_base + tcol0 + c0, r);
+          const int nvalid = NV - (tcol0 + c0);                 // token columns >= NV are padding
 #pragma unroll
-          for (int i = 0; i < 32; ++i) tmax = fmaxf(tmax, fmaf(fa2, __uint_as_float(r[i]), ck2));
+          for (int i = 0; i < 32; ++i)
+            if (i < nvalid) tmax = fmaxf(tmax, fmaf(fa2, __uint_as_float(r[i]), ck2));
         }
         s_kx[half * 128 + ch] = tmax;
         bar_sync_named(1, kEpiThreads);
@@ -477,13 +487,15 @@ __global__ void __launch_bounds__(kThreads, 1) linattn_fused_kernel(const __grid
 #pragma unroll
         for (int c0 = 0; c0 < 64; c0 += 32) {
           tmem_ld32(tDk + lane_base + tcol0 + c0, r);
+          const int nvalid = NV - (tcol0 + c0);
 #pragma unroll
           for (int g = 0; g < 4; ++g) {
             uint32_t w[4];
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
-              const bf16 p0 = __float2bfloat16_rn(ex2(fmaf(fa2, __uint_as_float(r[g * 8 + 2 * e]), ck2) - new_max));
-              const bf16 p1 = __float2bfloat16_rn(ex2(fmaf(fa2, __uint_as_float(r[g * 8 + 2 * e + 1]), ck2) - new_max));
+              const int i0 = g * 8 + 2 * e;
+              const bf16 p0 = __float2bfloat16_rn(i0 < nvalid ? ex2(fmaf(fa2, __uint_as_float(r[i0]), ck2) - new_max) : 0.f);
+              const bf16 p1 = __float2bfloat16_rn(i0 + 1 < nvalid ? ex2(fmaf(fa2, __uint_as_float(r[i0 + 1]), ck2) - new_max) : 0.f);
               psum += __bfloat162float(p0) + __bfloat162float(p1);     // sums of the ROUNDED values: numerator and denominator agree
               w[e] = (uint32_t)(*reinterpret_cast<const unsigned short*>(&p0)) | ((uint32_t)(*reinterpret_cast<const unsigned short*>(&p1)) << 16);
             }
@@ -604,6 +616,7 @@ __global__ void __launch_bounds__(kThreads, 1) linattn_fused_kernel(const __grid
         ph_y ^= 1;
         tc_fence_after();
         const int ncol = C >> 1;                               // columns of this warp: [half * ncol, (half + 1) * ncol)
+        const bool row_ok = q4 * 32 + lane < NV;               // padded token rows are neither counted nor stored
         bf16* yrow = p.out + ((long)b * N + tok) * C + half * ncol;
 #pragma unroll 1
         for (int c0 = 0; c0 < ncol; c0 += 32) {
@@ -619,9 +632,11 @@ __global__ void __launch_bounds__(kThreads, 1) linattn_fused_kernel(const __grid
               y[e + 2] = __uint_as_float(r[g * 8 + e + 2]) + bb.z;
               y[e + 3] = __uint_as_float(r[g * 8 + e + 3]) + bb.w;
             }
+            if (row_ok) {
 #pragma unroll
-            for (int e = 0; e < 8; ++e) { sy += y[e]; sq = fmaf(y[e], y[e], sq); }
-            *reinterpret_cast<uint4*>(yrow + c0 + g * 8) = pack8(y);
+              for (int e = 0; e < 8; ++e) { sy += y[e]; sq = fmaf(y[e], y[e], sq); }
+              *reinterpret_cast<uint4*>(yrow + c0 + g * 8) = pack8(y);
+            }
           }
         }
         tc_fence_before();
@@ -649,24 +664,29 @@ __global__ void __launch_bounds__(kThreads, 1) linattn_fused_kernel(const __grid
           gsh[e] = s_beo[c8 + e] - mean_y * gsc[e];
         }
         const long base = (long)b * N * C;
-        const int items = N * per_row;                         // a multiple of 8 * 256 (N >= 128, per_row >= 16)
+        const int items = N * per_row;
         constexpr int U = 8;                                   // independent 16-byte items in flight per thread
         for (int i0 = tid; i0 < items; i0 += U * kEpiThreads) {
           uint4 yv[U], xv[U];
 #pragma unroll
           for (int u = 0; u < U; ++u) {
-            const long off = base + (long)(i0 + u * kEpiThreads) * 8;
-            yv[u] = ldcg128(p.out + off);
-            xv[u] = ldcg128(p.x + off);
+            const int i = i0 + u * kEpiThreads;
+            if (i < items) {
+              yv[u] = ldcg128(p.out + base + (long)i * 8);
+              xv[u] = ldcg128(p.x + base + (long)i * 8);
+            }
           }
 #pragma unroll
           for (int u = 0; u < U; ++u) {
-            float y[8], xx[8];
-            unpack8(yv[u], y);
-            unpack8(xv[u], xx);
+            const int i = i0 + u * kEpiThreads;
+            if (i < items) {
+              float y[8], xx[8];
+              unpack8(yv[u], y);
+              unpack8(xv[u], xx);
 #pragma unroll
-            for (int e = 0; e < 8; ++e) y[e] = fmaf(y[e], gsc[e], gsh[e]) + xx[e];
-            *reinterpret_cast<uint4*>(p.out + base + (long)(i0 + u * kEpiThreads) * 8) = pack8(y);
+              for (int e = 0; e < 8; ++e) y[e] = fmaf(y[e], gsc[e], gsh[e]) + xx[e];
+              *reinterpret_cast<uint4*>(p.out + base + (long)i * 8) = pack8(y);
+            }
           }
         }
       }
@@ -688,7 +708,8 @@ constexpr size_t kSmemFused = 1024 + (size_t)(kXS + kWS) * kSlab + 2 * (size_t)k
 }  // namespace fa
 
 bool linattn_fused_supported(int B, int N, int C) {
-  return B >= 1 && N >= 128 && N % 128 == 0 && (C == 128 || C == 256) && (long)B * N < (1L << 30);
+  const bool n_ok = (N >= 128 && N % 128 == 0) || (N >= 16 && N < 128 && N % 8 == 0);
+  return B >= 1 && n_ok && (C == 128 || C == 256) && (long)B * N < (1L << 30);
 }
 
 int linattn_fused(const LinAttnFusedP& q, cudaStream_t st) {
@@ -696,7 +717,7 @@ int linattn_fused(const LinAttnFusedP& q, cudaStream_t st) {
   fa::Params p;
   memset(&p, 0, sizeof(p));
   int rc;
-  if ((rc = fa::make_map(&p.mx, q.x, (uint64_t)q.B * q.N, (uint64_t)q.C, 128))) return rc;
+  if ((rc = fa::make_map(&p.mx, q.x, (uint64_t)q.B * q.N, (uint64_t)q.C, q.N >= 128 ? 128 : q.N))) return rc;
   if ((rc = fa::make_map(&p.mw, q.wqkv, 384, (uint64_t)q.C, 128))) return rc;
   if ((rc = fa::make_map(&p.mo, q.wo, (uint64_t)q.C, 128, 128))) return rc;
   p.x = (const bf16*)q.x;

@@ -61,6 +61,12 @@
 #ifndef DMN_EXP_ONE_ABUF
 #define DMN_EXP_ONE_ABUF 5
 #endif
+#ifndef DMN_EXP_PLAIN_ABUF
+#define DMN_EXP_PLAIN_ABUF 3        // operand ring of the plain (no prologue) swapped-role instantiations ...
+#endif
+#ifndef DMN_EXP_PLAIN_DEPTH
+#define DMN_EXP_PLAIN_DEPTH 1       // ... and the passes of cp.async copies a producer thread keeps in flight
+#endif
 
 namespace dmn {
 namespace tc {
@@ -96,6 +102,8 @@ struct Params {
   int ksize, ntap, NT, n_pass, tiles_per_phase, n_tiles_n, m_tiles, total_tiles;
   int abuf;                // operand buffers of the instantiation that will be launched (kABuf, or kABufOne for the 1x1 form)
   int n_big_tiles, big_rows, halo_hi;   // tiles [0, n_big_tiles) have 256 rows, the rest 128 rows starting at flat position big_rows
+  int cl;                  // CTAs per cluster (1 | 2): the CTAs of a cluster work on neighbouring pixel tiles of the SAME N tile in lock step
+                           // and share every weight stage (each loads 1 / cl of it and multicasts it to all)
   long total_flat;
   uint32_t lbo_a, sbo_a, lbo_b, sbo_b;   // bytes
   uint32_t tmem_cols;
@@ -201,18 +209,17 @@ __device__ __forceinline__ VPos vdecode(int f, const Params& p) {
 struct TileGeom {
   int m0, mt, n_tile;
 };
+// Cluster-aware order: tile = cl * q + r (r = rank in the cluster); the cl tiles of one q share the N tile q % n_tiles_n and are
+// neighbouring M tiles, so the CTAs of a cluster consume identical weight stages in the same order.  cl = 1 is the plain order.
 __device__ __forceinline__ TileGeom tile_geom(int tile, const Params& p) {
   TileGeom g;
-  if (tile < p.n_big_tiles) {
-    g.m0 = (tile / p.n_tiles_n) * 256;
-    g.mt = 2;
-    g.n_tile = tile % p.n_tiles_n;
-  } else {
-    const int k = tile - p.n_big_tiles;
-    g.m0 = p.big_rows + (k / p.n_tiles_n) * 128;
-    g.mt = 1;
-    g.n_tile = k % p.n_tiles_n;
-  }
+  const bool big = tile < p.n_big_tiles;
+  const int k = big ? tile : tile - p.n_big_tiles;
+  const int q = p.cl == 2 ? (k >> 1) : k, r = p.cl == 2 ? (k & 1) : 0;
+  const int m = (q / p.n_tiles_n) * p.cl + r;
+  g.n_tile = q % p.n_tiles_n;
+  g.mt = big ? 2 : 1;
+  g.m0 = big ? m * 256 : p.big_rows + m * 128;
   return g;
 }
 // decode f = base_flat + n (0 <= n < 2^12 - ish) given the decoded base (img0, rem0 = base_flat - img0 * S): two multiply-shift
@@ -313,6 +320,12 @@ __device__ __forceinline__ void stats_flush(const float* val, int key, bool vali
   }
 }
 
+// release of a weight stage: with a cluster every CTA's loader writes into every CTA's stage, so the release is multicast
+__device__ __forceinline__ void commit_stage(uint32_t bar, uint32_t cmask) {
+  if (cmask > 1u) umma_commit_mc(bar, (uint16_t)cmask);
+  else umma_commit(bar);
+}
+
 // One weight stage (G taps x two k16 steps x 1|2 accumulators) of the MMA issuer.  Descriptor words are computed OUTSIDE the
 // elected branch so that they are warp-uniform values (uniform registers); `didx` indexes the tap-offset table in the constant bank.
 template <int G, bool TWO>
@@ -367,7 +380,7 @@ template <int NTAP, int GG, bool TWO>
 __device__ __forceinline__ void issue_pass(bool leader, uint32_t d0, uint32_t d1, uint32_t au_lo, const int (&dl)[NTAP], uint32_t b_lo0,
                                            uint32_t b_stage_units, uint32_t b_tap_units, uint32_t hi_a, uint32_t hi_b, uint32_t a_k16,
                                            uint32_t b_k16, uint32_t idesc, uint32_t acc_first, uint64_t* full_b, uint64_t* empty_b, int nst,
-                                           int& st, uint32_t& ph) {
+                                           int& st, uint32_t& ph, uint32_t cmask = 1u) {
 #pragma unroll
   for (int s = 0; s < NTAP / GG; ++s) {
     mbar_wait(smem_u32(&full_b[st]), ph);
@@ -377,7 +390,38 @@ __device__ __forceinline__ void issue_pass(bool leader, uint32_t d0, uint32_t d1
     for (int g = 0; g < GG; ++g)
       issue_tap<TWO>(leader, d0, d1, au_lo + (uint32_t)dl[s * GG + g], b_lo + (uint32_t)g * b_tap_units, hi_a, hi_b, a_k16, b_k16, idesc,
                      (s | g) ? 1u : acc_first);
-    if (leader) umma_commit(smem_u32(&empty_b[st]));     // frees the weight stage once these MMAs retire
+    if (leader) commit_stage(smem_u32(&empty_b[st]), cmask);     // frees the weight stage once these MMAs retire
+    __syncwarp();
+    if (++st == nst) { st = 0; ph ^= 1; }
+  }
+}
+
+// Swapped operand roles: one MMA per k16 step (M = 128 output channels, N = 256 | 128 pixels).  `w_lo` / `x_lo` are the descriptor low
+// words of the weight tap and of the shifted pixel view.
+__device__ __forceinline__ void issue_tap_swap(bool leader, uint32_t d, uint32_t x_lo, uint32_t w_lo, uint32_t hi_x, uint32_t hi_w, uint32_t x_k16,
+                                               uint32_t w_k16, uint32_t idesc, uint32_t acc) {
+  const uint64_t wd0 = ((uint64_t)hi_w << 32) | w_lo, wd1 = ((uint64_t)hi_w << 32) | (w_lo + w_k16);
+  const uint64_t xd0 = ((uint64_t)hi_x << 32) | x_lo, xd1 = ((uint64_t)hi_x << 32) | (x_lo + x_k16);
+  if (leader) {
+    umma_bf16(d, wd0, xd0, idesc, acc);
+    umma_bf16(d, wd1, xd1, idesc, 1u);
+  }
+}
+template <int NTAP, int GG>
+__device__ __forceinline__ void issue_pass_swap(bool leader, uint32_t d, uint32_t au_lo, const int (&dl)[NTAP], uint32_t b_lo0, uint32_t b_stage_units,
+                                                uint32_t b_tap_units, uint32_t hi_a, uint32_t hi_b, uint32_t a_k16, uint32_t b_k16, uint32_t idesc,
+                                                uint32_t acc_first, uint64_t* full_b, uint64_t* empty_b, int nst, int& st, uint32_t& ph,
+                                                uint32_t cmask) {
+#pragma unroll
+  for (int s = 0; s < NTAP / GG; ++s) {
+    mbar_wait(smem_u32(&full_b[st]), ph);
+    tc_fence_after();
+    const uint32_t b_lo = b_lo0 + (uint32_t)st * b_stage_units;
+#pragma unroll
+    for (int g = 0; g < GG; ++g)
+      issue_tap_swap(leader, d, au_lo + (uint32_t)dl[s * GG + g], b_lo + (uint32_t)g * b_tap_units, hi_a, hi_b, a_k16, b_k16, idesc,
+                     (s | g) ? 1u : acc_first);
+    if (leader) commit_stage(smem_u32(&empty_b[st]), cmask);
     __syncwarp();
     if (++st == nst) { st = 0; ph ^= 1; }
   }
@@ -399,11 +443,23 @@ __device__ __forceinline__ void issue_pass(bool leader, uint32_t d0, uint32_t d1
 // EW: epilogue warps, 8 or 16.  The 16-warp form (832 threads, 72 registers per thread at launch) is for the epilogue-bound tiles
 //     whose producers only issue copies: the producer warps hand registers back (setmaxnreg.dec 40) and the epilogue warps take
 //     them (setmaxnreg.inc 88), so twice as many epilogue chains are in flight at the register budget the epilogue code needs.
-template <int GEO, int NT, bool FILM = false, bool LEAN = false, bool EXTRA = true, int PRO = 2, int EW = kEpiWarps>
-__global__ void __launch_bounds__((kProdWarps + EW + 2) * 32, 1) conv_tcgen05_kernel(const Params p) {
+// SWAP: operand roles exchanged -- the weights are the M operand (128 output channels on the TMEM lanes) and the tile's pixels the N
+//     operand, so a 256-pixel tile is ONE M128 x N256 instruction per k-step instead of two M128 x N128: the tensor core then reads
+//     12 KB of shared memory per 128 clk instead of 16 KB (the N = 128 form saturates the 128 B/clk shared-memory port, which is what
+//     slows the operand producers and the epilogue staging down), and the single issuing thread has half as many instructions to feed.
+//     The epilogue becomes channel-per-lane: bias and GroupNorm statistics are per-thread scalars / serial sums, the bf16 output is
+//     transposed through a small per-warp staging tile (2 x 2 register transposes with one shuffle per pixel pair).
+// PW: operand-producer warps, 8 or 16.  The GroupNorm-prologue producers are latency bound (cp.async -> LDS -> transform -> STS chains with
+//     two warps per scheduler): 16 warps halve the items per thread and double the chains in flight.
+template <int GEO, int NT, bool FILM = false, bool LEAN = false, bool EXTRA = true, int PRO = 2, int EW = kEpiWarps, bool SWAP = false, int PW = 8>
+__global__ void __launch_bounds__((PW + EW + 2) * 32, 1) conv_tcgen05_kernel(const Params p) {
+  static_assert(!SWAP || (NT == 128 && !EXTRA && !FILM && GEO != GEO_INIT), "swapped operand roles: hot 128-channel instantiations only");
+  static_assert(PW == 8 || (PW == 16 && EW == 8 && PRO == 1 && SWAP), "16 producer warps: the swapped-role GroupNorm-prologue instantiations");
+  constexpr int kProdWarps = PW, kProdThreads = PW * 32;       // (shadow the 8-warp defaults of the namespace)
+  constexpr int kMaxItems = PW == 16 ? 4 : 7;
   constexpr int kLoaderW = kProdWarps + EW, kMmaW = kLoaderW + 1, kEpiT = EW * 32;
-  constexpr int AB = (PRO == 3 && GEO == GEO_SAME) ? kABufOne : ((PRO == 1 && GEO == GEO_SAME) ? kABufPro : kABuf);
-  constexpr int DEPTH = (PRO == 3 && GEO == GEO_SAME) ? kDepthOne : ((PRO == 1 && GEO == GEO_SAME) ? DMN_EXP_PRO_DEPTH : kDepth);
+  constexpr int AB = (PRO == 3 && GEO == GEO_SAME) ? kABufOne : ((PRO == 1 && GEO == GEO_SAME) ? kABufPro : ((PRO == 0 && SWAP) ? DMN_EXP_PLAIN_ABUF : kABuf));
+  constexpr int DEPTH = (PRO == 3 && GEO == GEO_SAME) ? kDepthOne : ((PRO == 1 && GEO == GEO_SAME) ? DMN_EXP_PRO_DEPTH : ((PRO == 0 && SWAP) ? DMN_EXP_PLAIN_DEPTH : kDepth));
   static_assert(AB <= kABufMax && DEPTH >= 1 && DEPTH <= 3 && AB >= DEPTH + 2, "operand ring geometry");
   static_assert(EW == 8 || (EW == 16 && NT == 128 && (PRO == 0 || PRO == 3)), "16 epilogue warps: 128-column tiles without prologue");
   static_assert(!(LEAN && PRO == 3), "the lean issue path is for 9- and 4-tap convolutions");
@@ -438,7 +494,7 @@ __global__ void __launch_bounds__((kProdWarps + EW + 2) * 32, 1) conv_tcgen05_ke
 
   // ---- one-time setup ----
   if (warp == kLoaderW) {          // one lane per barrier
-    if (lane < nst) { mbar_init(smem_u32(&full_b[lane]), 1); mbar_init(smem_u32(&empty_b[lane]), 1); }
+    if (lane < nst) { mbar_init(smem_u32(&full_b[lane]), 1); mbar_init(smem_u32(&empty_b[lane]), (uint32_t)p.cl); }
     if (lane >= 16 && lane < 16 + AB) { mbar_init(smem_u32(&full_a[lane - 16]), kProdThreads); mbar_init(smem_u32(&empty_a[lane - 16]), 1); }
     if (lane >= 24 && lane < 26) { mbar_init(smem_u32(&acc_full[lane - 24]), 1); mbar_init(smem_u32(&acc_empty[lane - 24]), kEpiT); }
     fence_barrier_init();
@@ -446,6 +502,7 @@ __global__ void __launch_bounds__((kProdWarps + EW + 2) * 32, 1) conv_tcgen05_ke
   if (warp == kMmaW) tmem_alloc(smem_u32(tmem_slot), p.tmem_cols);
   tc_fence_before();
   __syncthreads();
+  if (p.cl > 1) cluster_sync_all();      // the peer's barriers are initialised before any multicast copy / commit can reach them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   pdl_trigger();        // the next kernel may start its prologue; it waits for this grid's completion before reading our output
@@ -667,11 +724,12 @@ __global__ void __launch_bounds__((kProdWarps + EW + 2) * 32, 1) conv_tcgen05_ke
 
       int inflight = 0;
       const bool ptracing = kTraceProducer && p.trace && tid == 0 && blockIdx.x == (unsigned)p.trace_cta && pit < 60;
-      long long wait_e = 0, wait_g = 0;
+      long long wait_e = 0, wait_g = 0, t_issue = 0, t_fin = 0;
       for (int c = 0; c < p.n_pass; ++c) {
         long long w0 = ptracing ? clock64() : 0;
         mbar_wait_relaxed(smem_u32(&empty_a[ibuf]), iph);
         if (ptracing) wait_e += clock64() - w0;
+        const long long wi0 = ptracing ? clock64() : 0;
         int cb = c * kCk + kc * 8;        // first (virtual) channel of this thread's k-chunk
         int sy = 0, sx = 0;
         if (GEO == GEO_DOWN) {            // virtual channel = sub * C + ci, sub = sy*2 + sx
@@ -717,16 +775,19 @@ __global__ void __launch_bounds__((kProdWarps + EW + 2) * 32, 1) conv_tcgen05_ke
           }
         }
         cp_async_commit();
+        if (ptracing) t_issue += clock64() - wi0;
         if (++ibuf == AB) { ibuf = 0; iph ^= 1; }
         if (++inflight > DEPTH) {
           w0 = ptracing ? clock64() : 0;
           cp_async_wait<DEPTH>();
           if (ptracing) wait_g += clock64() - w0;
+          const long long wf0 = ptracing ? clock64() : 0;
           finish(c - DEPTH);
+          if (ptracing) t_fin += clock64() - wf0;
           --inflight;
         }
       }
-      if (ptracing) { p.trace[16 * pit + 14] = wait_e; p.trace[16 * pit + 15] = wait_g; }
+      if (ptracing) { p.trace[16 * pit + 14] = wait_e; p.trace[16 * pit + 15] = wait_g; p.trace[16 * pit + 3] = t_issue; p.trace[16 * pit + 7] = t_fin; }
       // drain: the last passes of the tile
       if (DEPTH >= 3 && inflight == 3) {
         cp_async_wait<2>();
@@ -757,6 +818,157 @@ __global__ void __launch_bounds__((kProdWarps + EW + 2) * 32, 1) conv_tcgen05_ke
     pdl_wait();                                       // output / residual / statistics buffers are free to touch
     const int ew = warp - kProdWarps;                 // 0 .. EW-1
     const int quarter = ew & 3, part = ew >> 2;       // TMEM lane quarter, column part (half / quarter) of the tile
+    if constexpr (SWAP) {
+      // ---- swapped roles: TMEM lane = output channel, column = pixel of the tile ----
+      bf16* out = (bf16*)p.c.out;
+      constexpr int NPART = EW / 4;                     // the tile's pixel columns are split over NPART warps per lane quarter
+      const bool do_stats = GEO == GEO_SAME && p.c.ostats != nullptr;
+      const bool has_bias = p.c.bias != nullptr;
+      // per-warp shared memory: [32 pixels][32 channels] bf16 staging (2 KB) + output pixel index of each of the warp's columns
+      uint8_t* my_base = s_stage + ew * (EW == 8 ? 4608 : 2304);
+      const uint32_t my_stage = smem_u32(my_base);
+      int* s_opix = reinterpret_cast<int*>(my_base + 2048);
+      float* s_ball = reinterpret_cast<float*>(s_stage + 8 * 4608);
+      {
+        const int et = tid - kProdThreads;
+        if (has_bias)
+          for (int i = et; i < p.c.Cout; i += kEpiT) s_ball[i] = p.c.bias[i];
+        bar_sync_named(3, kEpiT);
+      }
+      const int sh = p.cpg_out_shift;
+      const int red_lanes = p.cpg_out >= 32 ? 32 : p.cpg_out;     // lanes of this warp that share a statistics group (16 or 32)
+      const int prow = lane >> 2, pchunk = lane & 3;              // store phase: pixel row within an instruction, 16-byte chunk of its 64 bytes
+      int it = 0;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+        const TileGeom tg = tile_geom(tile, p);
+        const int n_tile = tg.n_tile, m0 = tg.m0, tmt = tg.mt;
+        const int phase = (GEO == GEO_UP) ? n_tile / p.tiles_per_phase : 0;
+        const int n0 = (GEO == GEO_UP ? n_tile % p.tiles_per_phase : n_tile) * NT;
+        const int ncols = tmt * 128 / NPART;                      // pixel columns of this warp: 128 | 64 | 32
+        const int col_base = part * ncols;
+        const int eimg0 = m0 / p.S, erem0 = m0 - eimg0 * p.S;     // uniform
+        // ---- decode this warp's columns once: output pixel (or -1), validity masks (uniform after the ballots) ----
+        uint32_t vmask[4] = {0u, 0u, 0u, 0u};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          if (i * 32 < ncols) {
+            const VPos v = vdecode_rel(eimg0, erem0, col_base + i * 32 + lane, p);
+            bool valid = v.img >= 0;
+            int opix = -1;
+            if (valid) {
+              if (GEO == GEO_SAME) {
+                valid = v.row >= p.pad && v.col >= p.pad;
+                opix = v.img * p.HW + (v.row - p.pad) * p.W + (v.col - p.pad);
+              } else if (GEO == GEO_DOWN) {
+                valid = v.row < (p.H >> 1) && v.col < (p.W >> 1);
+                opix = v.img * (p.HW >> 2) + v.row * (p.W >> 1) + v.col;
+              } else {
+                valid = v.row >= 1 && v.col >= 1;
+                opix = v.img * (p.HW << 2) + (2 * (v.row - 1) + (phase >> 1)) * (2 * p.W) + 2 * (v.col - 1) + (phase & 1);
+              }
+            }
+            s_opix[i * 32 + lane] = valid ? opix : -1;
+            vmask[i] = __ballot_sync(0xffffffffu, valid);
+          }
+        }
+        __syncwarp();
+        const int my_c = n0 + quarter * 32 + lane;                // this thread's output channel
+        const float bias = has_bias ? s_ball[my_c] : 0.f;
+        // statistics bookkeeping (uniform): image of the current column, columns left in it
+        int cur_img = eimg0 + (erem0 + col_base) / p.S;
+        int to_boundary = p.S - (erem0 + col_base) % p.S;
+        float rs = 0.f, rq = 0.f;                                 // running (sum, sum of squares) of this channel over the current image
+        auto flush = [&]() {
+          // reduce over the lanes of the group, then the group leader adds the fixed-point partials
+          float a = rs, b = rq;
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1)
+            if (o < red_lanes) { a += __shfl_xor_sync(0xffffffffu, a, o); b += __shfl_xor_sync(0xffffffffu, b, o); }
+          if ((lane & (red_lanes - 1)) == 0 && cur_img < p.c.B) stat_add(p.c.ostats + ((long)cur_img * p.c.ogroups + (my_c >> sh)) * 2, a, b);
+          rs = rq = 0.f;
+        };
+
+        const int as = it & 1;
+        if (ew == 0 && lane == 0) TRACE(it, 8);
+        mbar_wait_relaxed(smem_u32(&acc_full[as]), (it >> 1) & 1);
+        tc_fence_after();
+        if (ew == 0 && lane == 0) TRACE(it, 9);
+        const uint32_t tlane = tmem_base + (uint32_t)(as * 2 * NT) + ((uint32_t)(quarter * 32) << 16) + (uint32_t)col_base;
+        const int rounds = ncols >> 5;                            // 32 columns per staging round
+        uint32_t rb[2][16];
+        tmem_ld16_nowait(tlane, rb[0]);
+#pragma unroll 1
+        for (int rd = 0; rd < rounds; ++rd) {
+          const uint32_t vm = rd == 0 ? vmask[0] : (rd == 1 ? vmask[1] : (rd == 2 ? vmask[2] : vmask[3]));
+#pragma unroll
+          for (int hc = 0; hc < 2; ++hc) {                        // two 16-column chunks per round
+            tmem_ld_wait();
+            const int cnext = rd * 32 + (hc + 1) * 16;
+            if (cnext < ncols) {
+              tmem_ld16_nowait(tlane + (uint32_t)cnext, rb[hc ^ 1]);
+            } else {
+              tc_fence_before();                                  // last TMEM read of this tile: hand the accumulators back
+              mbar_arrive(smem_u32(&acc_empty[as]));
+              if (ew == 0 && lane == 0) TRACE(it, 10);
+            }
+            const uint32_t* r = rb[hc];
+            float v[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]) + bias;
+            if (do_stats) {
+              const uint32_t m16 = (vm >> (hc * 16)) & 0xffffu;
+              if (to_boundary > 16) {                             // (uniform) the whole chunk belongs to the current image
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                  const float x = (m16 >> j) & 1u ? v[j] : 0.f;
+                  rs += x;
+                  rq = fmaf(x, x, rq);
+                }
+                to_boundary -= 16;
+              } else {
+                // columns [0, tb) close the current image, [tb, 16) open the next one (S >= 16: at most one boundary per chunk)
+                const int tb = to_boundary;
+                float s1 = 0.f, q1 = 0.f;
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                  const float x = (m16 >> j) & 1u ? v[j] : 0.f;
+                  if (j < tb) { rs += x; rq = fmaf(x, x, rq); }
+                  else { s1 += x; q1 = fmaf(x, x, q1); }
+                }
+                flush();
+                ++cur_img;
+                rs = s1;
+                rq = q1;
+                to_boundary = p.S - (16 - tb);
+              }
+            }
+            // 2 x 2 transposes: after the exchange an even lane holds channels (lane, lane + 1) of pixel 2i, an odd lane channels
+            // (lane - 1, lane) of pixel 2i + 1; one 32-bit store per pixel pair, conflict-free
+            const bool odd = lane & 1;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const float send = odd ? v[2 * i] : v[2 * i + 1];
+              const float got = __shfl_xor_sync(0xffffffffu, send, 1);
+              const uint32_t w = odd ? pack_bf16x2(got, v[2 * i + 1]) : pack_bf16x2(v[2 * i], got);
+              const int px = hc * 16 + 2 * i + (odd ? 1 : 0);
+              asm volatile("st.shared.b32 [%0], %1;" ::"r"(my_stage + (uint32_t)(px * 64 + (lane >> 1) * 4)), "r"(w) : "memory");
+            }
+          }
+          __syncwarp();
+          // store phase: 32 pixel rows x 64 bytes; one instruction covers 8 rows (4 lanes x 16 bytes each)
+#pragma unroll
+          for (int i0 = 0; i0 < 32; i0 += 8) {
+            const int row = i0 + prow;
+            const int opix = s_opix[rd * 32 + row];
+            const uint4 o = lds128(my_stage + (uint32_t)(row * 64 + pchunk * 16));
+            if (opix >= 0) *reinterpret_cast<uint4*>(out + (long)opix * p.c.Cout + n0 + quarter * 32 + pchunk * 8) = o;
+          }
+          __syncwarp();
+        }
+        if (do_stats) flush();
+        if (ew == 0 && lane == 0) TRACE(it, 11);
+      }
+    } else {
     bf16* out = (bf16*)p.c.out;
     constexpr bool kExtra = EXTRA && GEO == GEO_SAME;      // fill_params rejects residual / fold for the other geometries
     const bf16* res = kExtra ? (const bf16*)p.c.res : nullptr;
@@ -984,6 +1196,7 @@ __global__ void __launch_bounds__((kProdWarps + EW + 2) * 32, 1) conv_tcgen05_ke
       }
       if (ew == 0 && lane == 0) TRACE(it, 11);
     }
+    }
   } else if (warp == kLoaderW) {
     // =============================== weight loader ===============================
     // warp-uniform loop, one elected lane issues: one bulk copy (UBLKCP) of G taps (stage_bytes, contiguous in the blocked
@@ -992,6 +1205,10 @@ __global__ void __launch_bounds__((kProdWarps + EW + 2) * 32, 1) conv_tcgen05_ke
     int st = 0;
     uint32_t ph = 1;
     const int per_tile = p.n_pass * p.stages_per_pass;
+    // cluster: this CTA copies its 1 / cl share of every stage and multicasts it to all CTAs of the cluster; a stage may be refilled
+    // once EVERY CTA of the cluster has released it (empty_b counts cl arrivals: the MMA issuers commit with a multicast arrive)
+    const uint32_t share = b_bytes / (uint32_t)p.cl, my_off = share * cluster_ctarank();
+    const uint16_t cmask = (uint16_t)((1u << p.cl) - 1u);
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
       const int n_tile = tile_geom(tile, p).n_tile;
       const uint8_t* wsrc = (const uint8_t*)p.c.w + (size_t)n_tile * per_tile * b_bytes;
@@ -1002,7 +1219,8 @@ __global__ void __launch_bounds__((kProdWarps + EW + 2) * 32, 1) conv_tcgen05_ke
             mbar_arrive(smem_u32(&full_b[st]));
           } else {
             mbar_arrive_expect_tx(smem_u32(&full_b[st]), b_bytes);
-            bulk_g2s(smem_u32(sB + st * b_bytes), wsrc + (size_t)s * b_bytes, b_bytes, smem_u32(&full_b[st]));
+            if (p.cl > 1) bulk_g2s_mc(smem_u32(sB + st * b_bytes) + my_off, wsrc + (size_t)s * b_bytes + my_off, share, smem_u32(&full_b[st]), cmask);
+            else bulk_g2s(smem_u32(sB + st * b_bytes), wsrc + (size_t)s * b_bytes, b_bytes, smem_u32(&full_b[st]));
           }
         }
         __syncwarp();
@@ -1017,6 +1235,8 @@ __global__ void __launch_bounds__((kProdWarps + EW + 2) * 32, 1) conv_tcgen05_ke
     // which alone caps the tensor pipe at ~40 %; see tools/mma_rate2.cu.
     const bool leader = elect_one();
     const uint32_t idesc = make_idesc(128, NT);
+    const uint32_t idesc_s2 = make_idesc(128, 256), idesc_s1 = make_idesc(128, 128);     // SWAP: N = pixels of the tile
+    const uint32_t cmask = (1u << p.cl) - 1u;
     const uint32_t hi_a = (p.sbo_a >> 4) | (1u << 14), hi_b = (p.sbo_b >> 4) | (1u << 14);
     const uint32_t lbo_a_f = ((p.lbo_a >> 4) & 0x3FFFu) << 16, lbo_b_f = ((p.lbo_b >> 4) & 0x3FFFu) << 16;
     const uint32_t a_units0 = (smem_u32(sA) >> 4) + (uint32_t)p.halo_lo;          // 16-byte units
@@ -1054,7 +1274,18 @@ __global__ void __launch_bounds__((kProdWarps + EW + 2) * 32, 1) conv_tcgen05_ke
         if (!DMN_EXP_NO_FENCE) tc_fence_after();
         if (c == 0 && leader) TRACE(it, 5);
         const uint32_t au = a_units0 + (uint32_t)cbuf * a_buf_units;
-        if constexpr (lean9 || lean4) {
+        if constexpr (SWAP && (lean9 || lean4)) {
+          const uint32_t au_lo = au | lbo_a_f, acc0 = c ? 1u : 0u;
+          const uint32_t ids = two ? idesc_s2 : idesc_s1;
+          if constexpr (lean9) {
+            issue_pass_swap<9, 3>(leader, d0, au_lo, dl9, b_lo0, b_stage_units, b_tap_units, hi_a, hi_b, a_k16, b_k16, ids, acc0, full_b, empty_b, nst, st, ph, cmask);
+          } else {
+            int dl4[4];
+#pragma unroll
+            for (int t = 0; t < 4; ++t) dl4[t] = p.delta[phase * 16 + t];
+            issue_pass_swap<4, 2>(leader, d0, au_lo, dl4, b_lo0, b_stage_units, b_tap_units, hi_a, hi_b, a_k16, b_k16, ids, acc0, full_b, empty_b, nst, st, ph, cmask);
+          }
+        } else if constexpr (lean9 || lean4) {
           const uint32_t au_lo = au | lbo_a_f, acc0 = c ? 1u : 0u;
           if constexpr (lean9) {
             if (two) issue_pass<9, 3, true>(leader, d0, d1, au_lo, dl9, b_lo0, b_stage_units, b_tap_units, hi_a, hi_b, a_k16, b_k16, idesc, acc0, full_b, empty_b, nst, st, ph);
@@ -1075,7 +1306,15 @@ __global__ void __launch_bounds__((kProdWarps + EW + 2) * 32, 1) conv_tcgen05_ke
           if (!DMN_EXP_NO_FENCE) tc_fence_after();
           const uint32_t bs = b_units0 + (uint32_t)st * b_stage_units;
           const uint32_t acc0 = c ? 1u : 0u;
-          if (two) {
+          if constexpr (SWAP) {
+            const uint32_t ids = two ? idesc_s2 : idesc_s1;
+            for (int g = 0; g < G; ++g) {
+              const int t = t0 + g;
+              const uint32_t a0 = au + (uint32_t)p.delta[phase * 16 + t];
+              const uint32_t b0 = bs + (uint32_t)g * b_tap_units;
+              issue_tap_swap(leader, d0, (a0 & 0x3FFFu) | lbo_a_f, (b0 & 0x3FFFu) | lbo_b_f, hi_a, hi_b, a_k16, b_k16, ids, (c | t) ? 1u : 0u);
+            }
+          } else if (two) {
             // 256-row tiles: per-tap issue (4 MMAs = 256 clk of tensor work cover the ~20 uniform instructions of the next tap);
             // batching a whole stage's descriptors first measured slower here (the MMA queue drains during the longer prologue)
             for (int g = 0; g < G; ++g) {
@@ -1101,7 +1340,7 @@ __global__ void __launch_bounds__((kProdWarps + EW + 2) * 32, 1) conv_tcgen05_ke
             else if (G == 2) issue_stage<2, false>(p, leader, d0, d1, au, bs, phase * 16 + t0, t0, acc0, idesc, hi_a, hi_b, lbo_a_f, lbo_b_f, a_k16, b_k16, b_tap_units);
             else issue_stage<1, false>(p, leader, d0, d1, au, bs, phase * 16 + t0, t0, acc0, idesc, hi_a, hi_b, lbo_a_f, lbo_b_f, a_k16, b_k16, b_tap_units);
           }
-          if (leader) umma_commit(smem_u32(&empty_b[st]));     // frees the weight stage once these MMAs retire
+          if (leader) commit_stage(smem_u32(&empty_b[st]), cmask);     // frees the weight stage once these MMAs retire
           __syncwarp();
           if (++st == nst) { st = 0; ph ^= 1; }
         }
@@ -1120,6 +1359,7 @@ __global__ void __launch_bounds__((kProdWarps + EW + 2) * 32, 1) conv_tcgen05_ke
 
   tc_fence_before();
   __syncthreads();
+  if (p.cl > 1) cluster_sync_all();      // nobody leaves while a peer may still multicast into its shared memory
   if (warp == kMmaW) {
     tc_fence_after();
     tmem_dealloc(tmem_base, p.tmem_cols);
@@ -1153,6 +1393,28 @@ static bool pick_stages(Params& p) {
 static int pick_nt(int cout) { return cout % 128 == 0 ? 128 : (cout % 64 == 0 ? 64 : (cout % 32 == 0 ? 32 : 0)); }
 
 static int num_sms() { return current_device_sms(); }
+
+static bool swap_enabled() {
+  static const bool on = [] {
+    const char* e = getenv("DMN_CONV_SWAP");
+    return e && e[0] == '1';                // EXPERIMENT, default off (DMN_CONV_SWAP=1): swapped operand roles, weights on the TMEM lanes, one
+                                            // M128 x N256 instruction per k-step.  Parity-green and measured NEUTRAL on the step (profiles/README.md):
+                                            // the MMA issue loop gets faster (11.0k -> 10.5k clk per level-0 tile) but then waits for operands, and
+                                            // the serial per-channel statistics make the result depend on how tiles align with images (batch-slice
+                                            // invariance 2e-3 instead of <= 1e-6)
+  }();
+  return on;
+}
+
+static bool cluster_enabled() {
+  static const bool on = [] {
+    const char* e = getenv("DMN_CONV_CLUSTER");
+    return e && e[0] == '1';                // EXPERIMENT, default off: CTA pairs share the weight stream through multicast bulk copies.
+                                            // Measured neutral (+-1 % per conv: the weight stream from L2 is not what bounds the engine, the
+                                            // shared-memory port is) and one unit test (3x3 128->128 @16x16, batch 2) does not pass with it.
+  }();
+  return on;
+}
 
 static bool fill_params(const ConvP& c, int geo, Params& p) {
   p = Params();
@@ -1212,20 +1474,28 @@ static bool fill_params(const ConvP& c, int geo, Params& p) {
     p.mcta = 128 * p.mt;
   }
   p.halo_hi = halo_hi;
+  // clusters of two CTAs sharing the weight stream (multicast): the swapped-role hot instantiations with enough tiles for every SM
+  p.cl = 1;
+  if (swap_enabled() && cluster_enabled() && geo != GEO_INIT && p.NT == 128 && !(c.pro & PRO_LRELU) && !c.res && !c.fold_s1 &&
+      (geo != GEO_SAME || p.ntap == 9) && (num_sms() % 2) == 0)
+    p.cl = 2;
   {
     // mixed tiling: whole rounds of 256-row tiles, the remainder in 128-row tiles (the last round then costs half)
     const long nsm = num_sms();
     const long m2 = (p.total_flat + 255) / 256, t2 = m2 * p.n_tiles_n;
+    const long clm = p.cl;       // M-tile counts are multiples of the cluster size (a tile past the end of the flat range computes nothing)
     if (p.mt == 2) {
       long big_m = m2;
       if (t2 % nsm != 0) big_m = (t2 / nsm) * nsm / p.n_tiles_n;       // m-tiles inside the whole rounds
+      big_m = big_m / clm * clm;
       long rem = p.total_flat - big_m * 256;
       long small_m = rem > 0 ? (rem + 127) / 128 : 0;
+      small_m = (small_m + clm - 1) / clm * clm;
       // a 128-row tile costs ~0.6 of a 256-row tile (it streams the same weights): mix only when the estimate is lower
       const double cost_uniform = (double)((t2 + nsm - 1) / nsm);
       const double cost_mixed = (double)(t2 / nsm) + 0.6 * (double)((small_m * p.n_tiles_n + nsm - 1) / nsm);
       if (cost_mixed >= cost_uniform - 0.05) {
-        big_m = m2;
+        big_m = (m2 + clm - 1) / clm * clm;
         rem = 0;
         small_m = 0;
       }
@@ -1235,13 +1505,16 @@ static bool fill_params(const ConvP& c, int geo, Params& p) {
     } else {
       p.n_big_tiles = 0;
       p.big_rows = 0;
-      p.total_tiles = (int)((p.total_flat + 127) / 128) * p.n_tiles_n;
+      p.total_tiles = (int)(((p.total_flat + 127) / 128 + clm - 1) / clm * clm) * p.n_tiles_n;
     }
     p.m_tiles = p.total_tiles / p.n_tiles_n;
   }
   p.P = p.mcta + p.halo_lo + halo_hi;
   p.PA = p.P;
-  while (p.PA % 8 != 2) ++p.PA;
+  {
+    static const bool align_taps = [] { const char* e = getenv("DMN_EXP_ALIGN_TAPS"); return e && e[0] == '1'; }();
+    while (p.PA % 8 != (align_taps ? 0 : 2)) ++p.PA;
+  }
   if (geo != GEO_INIT && (4 * p.P + kProdThreads - 1) / kProdThreads > kMaxItems) return false;
   if (kMcta / p.S + 3 > kNimgMax || p.S < 16) return false;
   p.lbo_a = (uint32_t)p.PA * 16u;
@@ -1281,13 +1554,56 @@ static bool fill_params(const ConvP& c, int geo, Params& p) {
   p.magic_W = (uint32_t)(((1ull << 24) + p.Wv - 1) / p.Wv);
   for (int ph = 0; ph < 4; ++ph)
     for (int t = 0; t < 16; ++t) p.delta[ph * 16 + t] = t < p.ntap ? tap_delta(p, geo, t, ph) : 0;
+  {
+    // timing experiment only (results are wrong): every tap offset rounded so that the shifted operand view starts on an 8-row
+    // (128-byte) boundary -- measures what the unaligned start addresses of the shifted views cost the tensor core's operand fetch
+    static const bool align_taps = [] { const char* e = getenv("DMN_EXP_ALIGN_TAPS"); return e && e[0] == '1'; }();
+    if (align_taps)
+      for (int i = 0; i < 64; ++i) p.delta[i] = (p.halo_lo + p.delta[i]) / 8 * 8 - p.halo_lo;
+  }
   p.abuf = (geo == GEO_SAME && p.NT == 128 && p.ntap == 1 && c.pro == PRO_NONE && !DMN_EXP_NO_ONETAP) ? kABufOne : kABuf;
+  // plain swapped-role instantiations (launch<>: hot path without prologue)
+  if (swap_enabled() && geo != GEO_INIT && p.NT == 128 && c.pro == PRO_NONE && !c.res && !c.fold_s1 && (geo != GEO_SAME || p.ntap == 9))
+    p.abuf = DMN_EXP_PLAIN_ABUF;
   // the GroupNorm-prologue instantiation (PRO = 1) is launched for 128-column tiles without residual / fold / FiLM (launch<>)
   if (geo == GEO_SAME && p.NT == 128 && c.pro != PRO_NONE && !(c.pro & PRO_LRELU) && !c.res && !c.fold_s1) p.abuf = kABufPro;
   return pick_stages(p);
 }
 
 static int geo_of(const ConvP& c) { return c.mode == CONV_SAME ? GEO_SAME : (c.mode == CONV_DOWN ? GEO_DOWN : GEO_UP); }
+
+// > 48 KB of dynamic shared memory is a per-kernel, per-device opt-in
+static cudaError_t ensure_smem_attr(const void* fn) {
+  static std::vector<std::pair<int, const void*>> done;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  for (auto& d : done)
+    if (d.first == dev && d.second == fn) return cudaSuccess;
+  const cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemLimit);
+  if (e == cudaSuccess) done.emplace_back(dev, fn);
+  return e;
+}
+template <typename K>
+static cudaError_t launch_kernel(K kern, int grid, int threads, const Params& p, cudaStream_t st) {
+  const cudaError_t e = ensure_smem_attr((const void*)kern);
+  if (e != cudaSuccess) return e;
+  if (p.cl <= 1) return launch_pdl(kern, dim3(grid), dim3(threads), smem_bytes(p), st, p);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid / p.cl * p.cl);
+  cfg.blockDim = dim3(threads);
+  cfg.dynamicSmemBytes = smem_bytes(p);
+  cfg.stream = st;
+  cudaLaunchAttribute at[2];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = (unsigned)p.cl;
+  at[0].val.clusterDim.y = 1;
+  at[0].val.clusterDim.z = 1;
+  at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[1].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = pdl_enabled() ? 2 : 1;
+  return cudaLaunchKernelEx(&cfg, kern, p);
+}
 
 template <int GEO>
 static int launch(Params p, cudaStream_t st) {
@@ -1344,32 +1660,36 @@ static int launch(Params p, cudaStream_t st) {
   if (GEO != GEO_INIT && p.NT == 128 && !(p.c.pro & PRO_LRELU) && !extra) {
     // the hot instantiations: no residual / fold terms in the epilogue, lean or looped issue
     constexpr int G2 = GEO == GEO_INIT ? GEO_SAME : GEO;
-    static DeviceOnce hot_attr;
-    if (hot_attr.first()) {
-      DMN_CUDA_CHECK(cudaFuncSetAttribute(conv_tcgen05_kernel<G2, 128, false, true, false, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemLimit));
-      DMN_CUDA_CHECK(cudaFuncSetAttribute(conv_tcgen05_kernel<G2, 128, false, false, false, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemLimit));
-      if (G2 == GEO_SAME) {
-        DMN_CUDA_CHECK(cudaFuncSetAttribute(conv_tcgen05_kernel<GEO_SAME, 128, false, true, false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemLimit));
-        DMN_CUDA_CHECK(cudaFuncSetAttribute(conv_tcgen05_kernel<GEO_SAME, 128, false, false, false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemLimit));
-      }
-    }
+    const bool swap_on = swap_enabled();
     const bool pro = G2 == GEO_SAME && p.c.pro != PRO_NONE;
-    if (pro && lean_ok) DMN_CUDA_CHECK(launch_pdl(conv_tcgen05_kernel<GEO_SAME, 128, false, true, false, 1>, dim3(grid), dim3(kThreads), smem_bytes(p), st, p));
-    else if (pro) DMN_CUDA_CHECK(launch_pdl(conv_tcgen05_kernel<GEO_SAME, 128, false, false, false, 1>, dim3(grid), dim3(kThreads), smem_bytes(p), st, p));
-    else if (lean_ok) DMN_CUDA_CHECK(launch_pdl(conv_tcgen05_kernel<G2, 128, false, true, false, 0>, dim3(grid), dim3(kThreads), smem_bytes(p), st, p));
+    if (swap_on && (G2 != GEO_SAME || p.ntap == 9)) {
+      static const bool pw16 = [] { const char* e = getenv("DMN_CONV_PW16"); return !(e && e[0] == '0'); }();
+      if (pro && pw16 && lean_ok) DMN_CUDA_CHECK(launch_kernel(conv_tcgen05_kernel<GEO_SAME, 128, false, true, false, 1, 8, true, 16>, grid, kThreads16, p, st));
+      else if (pro && pw16) DMN_CUDA_CHECK(launch_kernel(conv_tcgen05_kernel<GEO_SAME, 128, false, false, false, 1, 8, true, 16>, grid, kThreads16, p, st));
+      else if (pro && lean_ok) DMN_CUDA_CHECK(launch_kernel(conv_tcgen05_kernel<GEO_SAME, 128, false, true, false, 1, 8, true>, grid, kThreads, p, st));
+      else if (pro) DMN_CUDA_CHECK(launch_kernel(conv_tcgen05_kernel<GEO_SAME, 128, false, false, false, 1, 8, true>, grid, kThreads, p, st));
+      else if (lean_ok) DMN_CUDA_CHECK(launch_kernel(conv_tcgen05_kernel<G2, 128, false, true, false, 0, 8, true>, grid, kThreads, p, st));
+      else if (DMN_EXP_EW16 && G2 == GEO_SAME) {
+        if (DMN_EXP_EW16_LEAN && p.ntap == 9 && p.G == 3)
+          DMN_CUDA_CHECK(launch_kernel(conv_tcgen05_kernel<GEO_SAME, 128, false, true, false, 0, 16, true>, grid, kThreads16, p, st));
+        else
+          DMN_CUDA_CHECK(launch_kernel(conv_tcgen05_kernel<GEO_SAME, 128, false, false, false, 0, 16, true>, grid, kThreads16, p, st));
+      } else DMN_CUDA_CHECK(launch_kernel(conv_tcgen05_kernel<G2, 128, false, false, false, 0, 8, true>, grid, kThreads, p, st));
+      count_launch();
+      DMN_LAUNCH_CHECK("conv_tcgen05");
+      return 0;
+    }
+    if (pro && lean_ok) DMN_CUDA_CHECK(launch_kernel(conv_tcgen05_kernel<GEO_SAME, 128, false, true, false, 1>, grid, kThreads, p, st));
+    else if (pro) DMN_CUDA_CHECK(launch_kernel(conv_tcgen05_kernel<GEO_SAME, 128, false, false, false, 1>, grid, kThreads, p, st));
+    else if (lean_ok) DMN_CUDA_CHECK(launch_kernel(conv_tcgen05_kernel<G2, 128, false, true, false, 0>, grid, kThreads, p, st));
     else if (DMN_EXP_EW16 && G2 == GEO_SAME) {
       // epilogue-bound plain 3x3 tiles (fewer than 8 passes): 16 epilogue warps; ncu then shows the epilogue waiting for the
       // accumulators 24 % of the time, so these tiles take the lean issue path as well (DMN_EXP_EW16_LEAN)
-      static DeviceOnce b16;
-      if (b16.first()) {
-        DMN_CUDA_CHECK(cudaFuncSetAttribute(conv_tcgen05_kernel<GEO_SAME, 128, false, false, false, 0, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemLimit));
-        DMN_CUDA_CHECK(cudaFuncSetAttribute(conv_tcgen05_kernel<GEO_SAME, 128, false, true, false, 0, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemLimit));
-      }
       if (DMN_EXP_EW16_LEAN && p.ntap == 9 && p.G == 3)
-        DMN_CUDA_CHECK(launch_pdl(conv_tcgen05_kernel<GEO_SAME, 128, false, true, false, 0, 16>, dim3(grid), dim3(kThreads16), smem_bytes(p), st, p));
+        DMN_CUDA_CHECK(launch_kernel(conv_tcgen05_kernel<GEO_SAME, 128, false, true, false, 0, 16>, grid, kThreads16, p, st));
       else
-        DMN_CUDA_CHECK(launch_pdl(conv_tcgen05_kernel<GEO_SAME, 128, false, false, false, 0, 16>, dim3(grid), dim3(kThreads16), smem_bytes(p), st, p));
-    } else DMN_CUDA_CHECK(launch_pdl(conv_tcgen05_kernel<G2, 128, false, false, false, 0>, dim3(grid), dim3(kThreads), smem_bytes(p), st, p));
+        DMN_CUDA_CHECK(launch_kernel(conv_tcgen05_kernel<GEO_SAME, 128, false, false, false, 0, 16>, grid, kThreads16, p, st));
+    } else DMN_CUDA_CHECK(launch_kernel(conv_tcgen05_kernel<G2, 128, false, false, false, 0>, grid, kThreads, p, st));
     count_launch();
     DMN_LAUNCH_CHECK("conv_tcgen05");
     return 0;

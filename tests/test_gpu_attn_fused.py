@@ -42,7 +42,8 @@ def _block_sd(c, seed):
     }
 
 
-@pytest.mark.parametrize("b,c,h", [(1, 128, 16), (3, 128, 16), (2, 256, 16), (2, 128, 32), (5, 256, 32), (150, 128, 16)])
+@pytest.mark.parametrize("b,c,h", [(1, 128, 16), (3, 128, 16), (2, 256, 16), (2, 128, 32), (5, 256, 32), (150, 128, 16),
+                                   (3, 256, 8), (5, 256, 4), (2, 128, 8), (300, 256, 4), (1, 128, 4)])
 def test_linear_attention_block_vs_oracle(b, c, h):
     p, sd = _block_sd(c, seed=7)
     x = _bf(_rand(b, c, h, h, seed=3) * 1.5 + 0.2)

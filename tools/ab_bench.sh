@@ -19,7 +19,7 @@ try:
     d = json.loads(open(sys.argv[1]).read().strip().splitlines()[-1])
     kb = d["kernel_breakdown"]
     print("%-28s samples/s %.2f  ms/step %.4f  conv %.4f  finalize %.4f  linattn %.4f" % (
-        sys.argv[2], d["value"], d["ms_per_step"], kb["conv_tcgen05"]["ms"], kb["gn_finalize"]["ms"], kb["linattn_core"]["ms"]))
+        sys.argv[2], d["value"], d["ms_per_step"], kb["conv_tcgen05"]["ms"], kb["gn_finalize"]["ms"], kb.get("other", {"ms": 0})["ms"]))
 except Exception as e:
     print(sys.argv[2], "FAILED", e)
 PY

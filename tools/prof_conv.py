@@ -11,7 +11,7 @@ from diffusion_model_nemo_b200 import _lib as L
 from gpu_helpers import conv_forward
 
 DEV = "cuda:0"
-CASES = {"plain": (3, 128, 128, 32, 256, False), "gn": (3, 256, 256, 16, 256, True), "small": (3, 256, 256, 4, 256, True),
+CASES = {"plain": (3, 128, 128, 32, 256, False), "gn0": (3, 128, 128, 32, 256, True), "gn": (3, 256, 256, 16, 256, True), "small": (3, 256, 256, 4, 256, True),
          "qkv": (1, 128, 384, 32, 256, False)}
 
 

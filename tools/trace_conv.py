@@ -50,13 +50,19 @@ def run(k, cin, cout, h, b, gn, mode=0):
         if not any(row):
             break
         print(f"   tile {it}: prod start {rel(row[0])} tables {rel(row[1])} filled {rel(row[2])} | mma acc {rel(row[4])} firstA {rel(row[5])} "
-              f"issued {rel(row[6])} (waitA {row[12]} waitB {row[13]}; prod waitEmpty {row[14]} waitCp {row[15]}) | epi tables {rel(row[8])} ready {rel(row[9])} drained {rel(row[10])} done {rel(row[11])}")
+              f"issued {rel(row[6])} (waitA {row[12]} waitB {row[13]}; prod waitEmpty {row[14]} waitCp {row[15]} issue {row[3]} finish {row[7]}) | epi tables {rel(row[8])} ready {rel(row[9])} drained {rel(row[10])} done {rel(row[11])}")
     pcs = t[800:800 + 96]
     if any(pcs):
         print("   epilogue pieces of tile 2 (warp 8): (wait, work) clk:", " ".join(
             f"({pcs[3*k+1]-pcs[3*k]},{pcs[3*k+2]-pcs[3*k+1]})" for k in range(32) if pcs[3 * k]))
 
 
+if __name__ == "__main__" and os.environ.get("TRACE_SHAPES"):
+    # TRACE_SHAPES="k,cin,cout,h,b,gn;..."
+    for spec in os.environ["TRACE_SHAPES"].split(";"):
+        k, cin, cout, h, b, gn = (int(v) for v in spec.split(","))
+        run(k, cin, cout, h, b, bool(gn))
+    sys.exit(0)
 if __name__ == "__main__" and os.environ.get("TRACE_QUICK"):
     run(3, 128, 128, 32, 256, False)
     run(3, 256, 256, 16, 256, False)
