@@ -635,7 +635,8 @@ __global__ void __launch_bounds__(kThreads, 1) linattn_fused_kernel(const __grid
             if (row_ok) {
 #pragma unroll
               for (int e = 0; e < 8; ++e) { sy += y[e]; sq = fmaf(y[e], y[e], sq); }
-              *reinterpret_cast<uint4*>(yrow + c0 + g * 8) = pack8(y);
+              *reinterpret_cast<uint4*>(yrow + c0 + g * 8) = pack8(y);     // (finishing single-tile images straight from TMEM measured slower:
+                                                                           //  per-row residual loads are uncoalesced, the coalesced pass below wins)
             }
           }
         }

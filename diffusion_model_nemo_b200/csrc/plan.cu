@@ -52,6 +52,9 @@ int launch_learned(const float* x, const float* mo, const float* z, float* out, 
                    const int32_t* step_dev, int step, dmn_rng rng, const dmn_rng* rng_dev, cudaStream_t st);
 int launch_ddim(const float* x, const float* eps, const float* z, float* out, long n, const float* coef, const int32_t* step_dev,
                 int step, dmn_rng rng, const dmn_rng* rng_dev, cudaStream_t st);
+bool fused_tail_supported(const FinalProjP& p, int act);
+int launch_final_proj_ddpm(const FinalProjP& p, const float* x, const float* z, float* out, const float* coef, const int32_t* step_dev,
+                           int step, dmn_rng rng, const dmn_rng* rng_dev, int32_t* advance, cudaStream_t st);
 int launch_traj(const float* x, float* traj, long n, const int32_t* step_dev, int every, int n_steps, cudaStream_t st);
 int launch_bpd_qsample(const float* x0, const float* z, float* xt, long n, const float* coef, const int32_t* step_dev, int step, dmn_rng rng,
                        const dmn_rng* rng_dev, cudaStream_t st);
@@ -575,8 +578,39 @@ struct Builder {
   }
 };
 
+// DDPM loop: the final_conv tail, the posterior update and the step counter as ONE launch (sampler.cu: final_proj_ddpm_kernel)
+struct TailFuse {
+  const float* x = nullptr;          // x_t (also the U-Net input of this step)
+  const float* z = nullptr;          // injected noise of this step or null (in-kernel Philox)
+  float* out = nullptr;              // x_{t-1} (may alias x)
+  const float* coef = nullptr;
+  const int32_t* step_dev = nullptr;
+  int step = 0;
+  dmn_rng rng = {0, 0};
+  const dmn_rng* rng_dev = nullptr;
+  int32_t* advance = nullptr;        // loop counters when this launch also advances the step counter
+};
+
+static FinalProjP final_proj_params(const dmn_plan* P, const Op& o, float* out_dev, int batch) {
+  auto W = [&](int pi) -> const float* { return pi < 0 ? nullptr : (const float*)(P->wbase + P->params[pi].off); };
+  FinalProjP q;
+  q.y = o.src1.valid() ? (void*)(P->wsbase + o.src1.off) : nullptr;
+  q.stats = o.stats.valid() ? (const stat_t*)(P->wsbase + o.stats.off) : nullptr;
+  q.groups = o.groups;
+  q.gamma = W(o.gamma); q.beta = W(o.beta); q.w = W(o.w); q.bias = W(o.bias);
+  q.out = out_dev; q.B = batch; q.HW = o.HW; q.C = o.C; q.Cout = o.Cout;
+  q.plain = o.groups == 0;
+  return q;
+}
+
+static bool tail_fusable(const dmn_plan* P) {
+  static const bool off = [] { const char* e = getenv("DMN_NO_FUSED_TAIL"); return e && e[0] == '1'; }();
+  if (off || P->ops.empty() || P->ops.back().kind != OP_FINALPROJ || P->cfg.out_dim != P->cfg.channels) return false;
+  return fused_tail_supported(final_proj_params(P, P->ops.back(), nullptr, 1), P->act);
+}
+
 static int run_forward(dmn_plan* P, const float* x_dev, const int32_t* row_dev, const int64_t* classes_dev, float* out_dev,
-                       int batch, cudaStream_t st, std::vector<cudaEvent_t>* evs = nullptr) {
+                       int batch, cudaStream_t st, std::vector<cudaEvent_t>* evs = nullptr, const TailFuse* tail = nullptr) {
   const dmn_unet_cfg& c = P->cfg;
   auto W = [&](int pi) -> const float* { return pi < 0 ? nullptr : (const float*)(P->wbase + P->params[pi].off); };
   auto B = [&](const Buf& b) -> void* { return b.valid() ? (void*)(P->wsbase + b.off) : nullptr; };
@@ -671,12 +705,9 @@ static int run_forward(dmn_plan* P, const float* x_dev, const int32_t* row_dev, 
         rc = film_modulate(B(o.src1), B(o.src2), B(o.res), B(o.out), (long)batch * o.HW * o.C, P->act, st);
         break;
       case OP_FINALPROJ: {
-        FinalProjP q;
-        q.y = B(o.src1); q.stats = (const stat_t*)B(o.stats); q.groups = o.groups;
-        q.gamma = W(o.gamma); q.beta = W(o.beta); q.w = W(o.w); q.bias = W(o.bias);
-        q.out = out_dev; q.B = batch; q.HW = o.HW; q.C = o.C; q.Cout = o.Cout;
-        q.plain = o.groups == 0;
-        rc = final_proj(q, P->act, st);
+        const FinalProjP q = final_proj_params(P, o, out_dev, batch);
+        if (tail) rc = launch_final_proj_ddpm(q, tail->x, tail->z, tail->out, tail->coef, tail->step_dev, tail->step, tail->rng, tail->rng_dev, tail->advance, st);
+        else rc = final_proj(q, P->act, st);
         break;
       }
     }
@@ -1065,6 +1096,17 @@ static int enqueue_step(dmn_plan* p, const dmn_loop_desc* d, int32_t* ctr_dev, b
       if ((rc = run_forward(p, x2, ctr_dev, d->classes_dev, mo2, 2 * d->batch, st))) return rc;
       // a learned-variance U-Net returns [eps | v] per sample: only eps is guided, v is the conditional branch's
       if ((rc = launch_cfg_combine(mo2, mo, n_out, n_out / d->batch, chw, d->cfg_scale, st))) return rc;
+    } else if (d->kind == DMN_LOOP_DDPM && tail_fusable(p)) {
+      // final_conv tail + posterior update (+ step counter unless a trajectory copy still has to see this step's index) in one launch
+      TailFuse tf;
+      tf.x = d->state_dev; tf.z = z0; tf.out = d->state_dev; tf.coef = d->coef_dev; tf.step_dev = step_dev; tf.step = s;
+      tf.rng = d->rng; tf.rng_dev = rng_dev;
+      const bool traj = d->traj_dev && d->traj_every > 0;
+      tf.advance = traj ? nullptr : ctr_dev;
+      if ((rc = run_forward(p, d->state_dev, ctr_dev, d->classes_dev, mo, d->batch, st, nullptr, &tf))) return rc;
+      if (!traj) return 0;
+      if ((rc = launch_traj(d->state_dev, d->traj_dev, n, ctr_dev, d->traj_every, d->n_steps, st))) return rc;
+      return launch_advance_counter(ctr_dev, st);
     } else if ((rc = run_forward(p, d->state_dev, ctr_dev, d->classes_dev, mo, d->batch, st))) {
       return rc;
     }
@@ -1180,7 +1222,10 @@ int dmn_loop_launches_per_step(const dmn_plan* p, const dmn_loop_desc* d) {
   int n = 0;
   if (d->kind == DMN_LOOP_BPD) return per_fwd + 3;
   if (d->kind == DMN_LOOP_PC) n = (d->n_corr + 1) * per_fwd + d->n_corr * (d->corr_kind == 1 ? 1 : 3) + 1;
-  else n = per_fwd + 1 + (d->cfg_on ? 2 : 0);
+  else if (d->kind == DMN_LOOP_DDPM && !d->cfg_on && tail_fusable(p)) {
+    // fused tail: the update (and, without trajectory capture, the counter) ride on the last launch of the forward program
+    return (d->traj_dev && d->traj_every > 0) ? per_fwd + 2 : per_fwd;
+  } else n = per_fwd + 1 + (d->cfg_on ? 2 : 0);
   if (d->traj_dev && d->traj_every > 0) n += 1;
   return n + 1;   // + advance_counter
 }

@@ -4,6 +4,7 @@
 // with in-kernel Philox noise = 12 B.  These kernels are HBM/launch bound (about 2 us at B = 256, 3x32x32).
 #include "../../include/dmn_b200.h"
 #include "common.cuh"
+#include "ops.h"
 
 namespace dmn {
 
@@ -231,10 +232,117 @@ __global__ void __launch_bounds__(256) randn_kernel(float* __restrict__ out, lon
     reinterpret_cast<float4*>(out)[i] = Philox::normal4(rng.seed, rng.stream_id, sw, (uint64_t)i);
 }
 __global__ void advance_counter_kernel(int32_t* c) { *c += 1; }
-// loop state: int32 step counter at [0], dmn_rng at byte offset 16
+// loop state: int32 step counter at [0], block ticket of the fused tail at [1], dmn_rng at byte offset 16
 __global__ void set_counter_kernel(int32_t* c, int v, dmn_rng rng) {
-  *c = v;
+  c[0] = v;
+  c[1] = 0;
   *reinterpret_cast<dmn_rng*>(c + 4) = rng;
+}
+
+// =====================================================================================================
+// Fused tail of one DDPM step (reference modules/unet.py:109-116 + gaussian_diffusion.py:118-167):
+//   eps = conv1x1(SiLU(GroupNorm(y)))   (final_conv tail)   ->   x0 prediction, clamp, posterior mean, + sigma_t * z   ->   x_{t-1}
+// and the step counter of the loop.  The model output never reaches global memory.  One block = 128 pixels of one sample: the
+// projection is the staged bf16 path of final_proj_bf16_kernel (kernels_simt.cu), eps goes through shared memory to 3 x 32 threads
+// that each update 4 consecutive pixels of one channel with the SAME Philox quads ddpm_step_kernel draws (bit-identical results).
+// =====================================================================================================
+template <int COUT>
+__global__ void __launch_bounds__(128) final_proj_ddpm_kernel(const FinalProjP p, const float* __restrict__ x, const float* __restrict__ z,
+                                                              float* __restrict__ xout, const float* __restrict__ coef, const int32_t* step_dev,
+                                                              int step, dmn_rng rng_v, const dmn_rng* rng_dev, int32_t* advance) {
+  pdl_trigger();
+  pdl_wait();
+  extern __shared__ __align__(16) unsigned char fsmb[];
+  const int C = p.C, ld = C * 2 + 16;                       // bytes per staged pixel row
+  float* s_sc = reinterpret_cast<float*>(fsmb);             // [C] rstd*gamma
+  float* s_sh = s_sc + C;                                   // [C] beta - mean*rstd*gamma
+  float* s_w = s_sh + C;                                    // [COUT][C]
+  float* s_eps = s_w + COUT * C;                            // [COUT][128]
+  unsigned char* s_tile = fsmb + (size_t)(2 + COUT) * C * 4 + (size_t)COUT * 128 * 4;
+  const int b = blockIdx.y, pix0 = blockIdx.x * 128;
+  const int npix = min(128, p.HW - pix0);
+  {
+    const bf16* y = (const bf16*)p.y + ((long)b * p.HW + pix0) * C;
+    const int chunks = C / 8;
+    const uint32_t tile_u = (uint32_t)__cvta_generic_to_shared(s_tile);
+    for (int i = threadIdx.x; i < npix * chunks; i += 128) {
+      const int r = i / chunks, c16 = i - r * chunks;
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(tile_u + (uint32_t)(r * ld + c16 * 16)), "l"(y + (long)r * C + c16 * 8) : "memory");
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  }
+  const dmn_rng rng = pick_rng(rng_v, rng_dev);
+  const float* cr = coef_row(coef, step_dev, step);
+  const float c0 = cr[0], c1 = cr[1], c2 = cr[2], c3 = cr[3], c4 = cr[4];
+  const bool pred_x0 = cr[5] != 0.f;
+  const uint32_t sw = step_word(step_dev, step, 0);
+  if (!p.plain) {
+    const int cpg = C / p.groups;
+    const float inv = 1.f / (float)(p.HW * cpg);
+    for (int c = threadIdx.x; c < C; c += 128) {
+      float mean, rstd;
+      gn_mean_rstd(p.stats + ((long)b * p.groups + c / cpg) * 2, inv, kGnEps, mean, rstd);
+      const float sc = rstd * p.gamma[c];
+      s_sc[c] = sc;
+      s_sh[c] = p.beta[c] - mean * sc;
+    }
+  }
+  for (int i = threadIdx.x; i < COUT * C; i += 128) s_w[i] = p.w[i];
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  __syncthreads();
+  if ((int)threadIdx.x < npix) {
+    const unsigned char* row = s_tile + (size_t)threadIdx.x * ld;
+    float acc[COUT];
+#pragma unroll
+    for (int j = 0; j < COUT; ++j) acc[j] = 0.f;
+    for (int c = 0; c < C; c += 8) {
+      float v[8];
+      unpack8(*reinterpret_cast<const uint4*>(row + c * 2), v);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const float a = p.plain ? v[e] : silu_fast(fmaf(v[e], s_sc[c + e], s_sh[c + e]));
+#pragma unroll
+        for (int j = 0; j < COUT; ++j) acc[j] = fmaf(a, s_w[j * C + c + e], acc[j]);
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < COUT; ++j) s_eps[j * 128 + threadIdx.x] = acc[j] + (p.bias ? p.bias[j] : 0.f);
+  }
+  __syncthreads();
+  // ---- posterior update: thread u -> channel u / 32, pixels pix0 + 4 * (u % 32) .. + 3 ----
+  if ((int)threadIdx.x < COUT * 32) {
+    const int j = threadIdx.x >> 5, g4 = threadIdx.x & 31;
+    if (4 * g4 < npix) {
+      const long e0 = ((long)b * COUT + j) * p.HW + pix0 + 4 * g4;      // first element (HW and pix0 are multiples of 4)
+      const long i = e0 >> 2;                                            // the Philox quad ddpm_step_kernel uses for these 4 elements
+      const float4 xv = reinterpret_cast<const float4*>(x)[i];
+      const float4 ev = *reinterpret_cast<const float4*>(s_eps + j * 128 + 4 * g4);
+      const float4 zv = z ? reinterpret_cast<const float4*>(z)[i] : Philox::normal4(rng.seed, rng.stream_id, sw, (uint64_t)i);
+      float4 o;
+#define DMN_DDPM(f)                                                    \
+  {                                                                    \
+    float x0 = pred_x0 ? ev.f : (c0 * xv.f - c1 * ev.f);               \
+    x0 = clamp1(x0);                                                   \
+    const float mean = c2 * x0 + c3 * xv.f;                            \
+    o.f = mean + c4 * zv.f;                                            \
+  }
+      DMN_DDPM(x) DMN_DDPM(y) DMN_DDPM(z) DMN_DDPM(w)
+#undef DMN_DDPM
+      reinterpret_cast<float4*>(xout)[i] = o;
+    }
+  }
+  // ---- step counter: the last block to finish advances it (every block has read the step index above) ----
+  if (advance) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      __threadfence();
+      const int total = (int)(gridDim.x * gridDim.y);
+      if (atomicAdd(advance + 1, 1) == total - 1) {
+        advance[1] = 0;
+        advance[0] += 1;
+      }
+    }
+  }
 }
 // copy every `every`-th step's state into the trajectory buffer (device-side decision => graph friendly)
 __global__ void __launch_bounds__(256) traj_kernel(const float* __restrict__ x, float* __restrict__ traj, long n4,
@@ -434,6 +542,27 @@ int launch_ddpm(const float* x, const float* eps, const float* z, float* out, lo
   DMN_LAUNCH_CHECK("ddpm_step");
   return 0;
 }
+bool fused_tail_supported(const FinalProjP& p, int act) {
+  const size_t smem = (size_t)(2 + p.Cout) * p.C * 4 + (size_t)p.Cout * 128 * 4 + (size_t)128 * (p.C * 2 + 16);
+  return act == ACT_BF16 && p.C % 8 == 0 && (p.Cout == 3 || p.Cout == 1) && p.HW % 4 == 0 && smem <= 200 * 1024;
+}
+// eps = final_conv tail (never stored) + DDPM update + (optionally) the loop's step counter, one launch
+int launch_final_proj_ddpm(const FinalProjP& p, const float* x, const float* z, float* out, const float* coef, const int32_t* step_dev,
+                           int step, dmn_rng rng, const dmn_rng* rng_dev, int32_t* advance, cudaStream_t st) {
+  const size_t smem = (size_t)(2 + p.Cout) * p.C * 4 + (size_t)p.Cout * 128 * 4 + (size_t)128 * (p.C * 2 + 16);
+  static DeviceOnce attr;
+  if (attr.first()) {
+    DMN_CUDA_CHECK(cudaFuncSetAttribute(final_proj_ddpm_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    DMN_CUDA_CHECK(cudaFuncSetAttribute(final_proj_ddpm_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  }
+  dim3 grid((unsigned)((p.HW + 127) / 128), (unsigned)p.B);
+  if (p.Cout == 3) DMN_CUDA_CHECK(launch_pdl(final_proj_ddpm_kernel<3>, grid, dim3(128), smem, st, p, x, z, out, coef, step_dev, step, rng, rng_dev, advance));
+  else DMN_CUDA_CHECK(launch_pdl(final_proj_ddpm_kernel<1>, grid, dim3(128), smem, st, p, x, z, out, coef, step_dev, step, rng, rng_dev, advance));
+  count_launch();
+  DMN_LAUNCH_CHECK("final_proj_ddpm");
+  return 0;
+}
+
 int launch_learned(const float* x, const float* mo, const float* z, float* out, int batch, long chw, const float* coef,
                    const int32_t* step_dev, int step, dmn_rng rng, const dmn_rng* rng_dev, cudaStream_t st) {
   DMN_REQUIRE(chw % 4 == 0 && chw > 0 && batch > 0, "learned_step: C*H*W must be a positive multiple of 4");
