@@ -451,8 +451,13 @@ __device__ __forceinline__ void issue_pass_swap(bool leader, uint32_t d, uint32_
 //     transposed through a small per-warp staging tile (2 x 2 register transposes with one shuffle per pixel pair).
 // PW: operand-producer warps, 8 or 16.  The GroupNorm-prologue producers are latency bound (cp.async -> LDS -> transform -> STS chains with
 //     two warps per scheduler): 16 warps halve the items per thread and double the chains in flight.
-template <int GEO, int NT, bool FILM = false, bool LEAN = false, bool EXTRA = true, int PRO = 2, int EW = kEpiWarps, bool SWAP = false, int PW = 8>
+// TAIL: the ResnetBlock tail fused behind a grid-wide barrier (cooperative launch: every CTA of the persistent grid is resident): once all
+//     tiles of the launch are stored and their GroupNorm statistics complete, each CTA walks its own tiles again (they are still in L2)
+//     and writes SiLU(GroupNorm(out)) + residual -- the pass that used to be a separate gn_finalize launch reading the raw output from HBM.
+template <int GEO, int NT, bool FILM = false, bool LEAN = false, bool EXTRA = true, int PRO = 2, int EW = kEpiWarps, bool SWAP = false, int PW = 8,
+          bool TAIL = false>
 __global__ void __launch_bounds__((PW + EW + 2) * 32, 1) conv_tcgen05_kernel(const Params p) {
+  static_assert(!TAIL || (GEO == GEO_SAME && NT == 128 && PRO == 1 && !EXTRA && !SWAP), "fused block tail: the GroupNorm-prologue 3x3 instantiations");
   static_assert(!SWAP || (NT == 128 && !EXTRA && !FILM && GEO != GEO_INIT), "swapped operand roles: hot 128-channel instantiations only");
   static_assert(PW == 8 || (PW == 16 && EW == 8 && PRO == 1 && SWAP), "16 producer warps: the swapped-role GroupNorm-prologue instantiations");
   constexpr int kProdWarps = PW, kProdThreads = PW * 32;       // (shadow the 8-warp defaults of the namespace)
@@ -1357,6 +1362,134 @@ __global__ void __launch_bounds__((PW + EW + 2) * 32, 1) conv_tcgen05_kernel(con
     }
   }
 
+  if constexpr (TAIL) {
+    if (p.c.fin_out) {
+      // ---- grid barrier: every tile of the launch is stored, every statistics atomic has landed ----
+      __threadfence();
+      __syncthreads();
+      if (tid == 0) {
+        atomicAdd(p.c.fin_sync, 1u);
+        const long long t0 = clock64();
+        unsigned int seen;
+        do {
+          __nanosleep(64);
+          asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(p.c.fin_sync) : "memory");
+          if (clock64() - t0 > 4000000000LL) __trap();
+        } while (seen < gridDim.x);
+      }
+      __syncthreads();
+      // ---- finalise this CTA's tiles: y = SiLU(GroupNorm(raw)) + res, 16-byte items, coalesced rows ----
+      constexpr int kAll = (PW + EW + 2) * 32;
+      float2* t_gn = reinterpret_cast<float2*>(smem);                          // [kNimgMax][8] (mean, rstd) of (image, group of this N tile)
+      float* t_gb = reinterpret_cast<float*>(t_gn + kNimgMax * 8);             // [2][128] gamma | beta of this N tile
+      unsigned long long* t_st = reinterpret_cast<unsigned long long*>(t_gb + 256);   // [kNimgMax][8][2] statistics of y (fixed point)
+      const int sh = p.cpg_out_shift, gpt = NT >> sh;                          // groups per N tile (<= 8)
+      const float inv_cnt_out = 1.f / (float)(p.HW * p.cpg_out);
+      const bf16* raw = (const bf16*)p.c.out;
+      const bf16* res = (const bf16*)p.c.fin_res;
+      bf16* fout = (bf16*)p.c.fin_out;
+      const int fog = p.c.fin_ostats ? p.c.fin_ogroups : 0;
+      const int fcpg = fog ? p.c.Cout / fog : 1;                               // channels per statistics group of y (>= 16)
+      const int chunk = tid & 15, row0 = tid >> 4;                             // this thread's 8 channels of the N tile; first row
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        const TileGeom tg = tile_geom(tile, p);
+        const int m0 = tg.m0, rows = tg.mt * 128, n0 = tg.n_tile * NT;
+        const int img0 = m0 / p.S, rem0 = m0 - img0 * p.S;
+        for (int i = tid; i < kNimgMax * gpt; i += kAll) {
+          const int il = i / gpt, g = i - il * gpt, img = img0 + il;
+          float mean = 0.f, rstd = 0.f;
+          if (img < p.c.B) gn_mean_rstd(p.c.ostats + ((long)img * p.c.ogroups + (n0 >> sh) + g) * 2, inv_cnt_out, kGnEps, mean, rstd);
+          t_gn[il * 8 + g] = make_float2(mean, rstd);
+        }
+        for (int i = tid; i < NT; i += kAll) {
+          t_gb[i] = p.c.fin_gamma[n0 + i];
+          t_gb[128 + i] = p.c.fin_beta[n0 + i];
+        }
+        if (fog)
+          for (int i = tid; i < kNimgMax * 16; i += kAll) t_st[i] = 0ull;
+        __syncthreads();
+        float ga[8], be[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) { ga[e] = t_gb[chunk * 8 + e]; be[e] = t_gb[128 + chunk * 8 + e]; }
+        const int gl = (chunk * 8) >> sh;                                      // group of this thread's channels within the N tile
+        constexpr int RS = kAll / 16, U = 4;                                   // row stride between a thread's rows; rows in flight
+        for (int rb = row0; rb < rows; rb += U * RS) {
+          long off[U];
+          int iml[U];
+          uint4 rv[U], sv[U];
+#pragma unroll
+          for (int u = 0; u < U; ++u) {
+            const int r = rb + u * RS;
+            off[u] = -1;
+            iml[u] = 0;
+            if (r < rows) {
+              const VPos v = vdecode_rel(img0, rem0, r, p);
+              if (v.img >= 0 && v.row >= p.pad && v.col >= p.pad) {
+                off[u] = ((long)v.img * p.HW + (v.row - p.pad) * p.W + (v.col - p.pad)) * p.c.Cout + n0 + chunk * 8;
+                iml[u] = v.img - img0;
+              }
+            }
+          }
+#pragma unroll
+          for (int u = 0; u < U; ++u)
+            if (off[u] >= 0) {
+              asm volatile("ld.global.cg.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(rv[u].x), "=r"(rv[u].y), "=r"(rv[u].z), "=r"(rv[u].w) : "l"(raw + off[u]));
+              asm volatile("ld.global.cg.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(sv[u].x), "=r"(sv[u].y), "=r"(sv[u].z), "=r"(sv[u].w) : "l"(res + off[u]));
+            }
+#pragma unroll
+          for (int u = 0; u < U; ++u) {
+            const bool valid = off[u] >= 0;
+            float y[8];
+            float s8 = 0.f, q8 = 0.f;
+            if (valid) {
+              float xr[8], xs[8];
+              unpack8(rv[u], xr);
+              unpack8(sv[u], xs);
+              const float2 mr = t_gn[iml[u] * 8 + gl];
+#pragma unroll
+              for (int e = 0; e < 8; ++e) {
+                const float sc = mr.y * ga[e];
+                y[e] = silu_fast(fmaf(xr[e], sc, be[e] - mr.x * sc)) + xs[e];
+                s8 += y[e];
+                q8 = fmaf(y[e], y[e], q8);
+              }
+              *reinterpret_cast<uint4*>(fout + off[u]) = pack8(y);
+            }
+            if (fog) {
+              // lanes 0-15 / 16-31 of a warp hold one pixel row each: reduce over the lanes that share a statistics group of y, then one
+              // fixed-point shared-memory atomic per (row, group): order independent => deterministic
+              const int span = fcpg >= 128 ? 16 : (fcpg >> 3);                 // lanes (8-channel chunks) per group inside the N tile
+#pragma unroll
+              for (int o = 8; o > 0; o >>= 1)
+                if (o < span) { s8 += __shfl_xor_sync(0xffffffffu, s8, o); q8 += __shfl_xor_sync(0xffffffffu, q8, o); }
+              if (valid && (chunk & (span - 1)) == 0) {
+                const int og = (n0 + chunk * 8) / fcpg;                        // statistics group of y (global index)
+                const int slot = (iml[u] * 8 + (og & 7)) * 2;
+                atomicAdd(&t_st[slot], (unsigned long long)__float2ll_rn(s8 * kStatScaleSum));
+                atomicAdd(&t_st[slot + 1], (unsigned long long)__float2ll_rn(q8 * kStatScaleSq));
+              }
+            }
+          }
+        }
+        __syncthreads();
+        if (fog) {
+          // flush the tile's partial statistics: slot (image, og & 7) -> global (image, og); with fog == 1 only slot 0 of an image is used
+          const int og_base = fog == 1 ? 0 : (n0 / fcpg);
+          const int nog = fog == 1 ? 1 : NT / fcpg;
+          for (int i = tid; i < kNimgMax * nog; i += kAll) {
+            const int il = i / nog, k = i - il * nog, img = img0 + il;
+            const int og = og_base + k;
+            const unsigned long long a = t_st[(il * 8 + (og & 7)) * 2], b2 = t_st[(il * 8 + (og & 7)) * 2 + 1];
+            if (img < p.c.B && (a | b2)) {
+              atomicAdd(reinterpret_cast<unsigned long long*>(p.c.fin_ostats) + ((long)img * fog + og) * 2, a);
+              atomicAdd(reinterpret_cast<unsigned long long*>(p.c.fin_ostats) + ((long)img * fog + og) * 2 + 1, b2);
+            }
+          }
+          __syncthreads();
+        }
+      }
+    }
+  }
   tc_fence_before();
   __syncthreads();
   if (p.cl > 1) cluster_sync_all();      // nobody leaves while a peer may still multicast into its shared memory
@@ -1584,9 +1717,22 @@ static cudaError_t ensure_smem_attr(const void* fn) {
   return e;
 }
 template <typename K>
-static cudaError_t launch_kernel(K kern, int grid, int threads, const Params& p, cudaStream_t st) {
+static cudaError_t launch_kernel(K kern, int grid, int threads, const Params& p, cudaStream_t st, bool cooperative = false) {
   const cudaError_t e = ensure_smem_attr((const void*)kern);
   if (e != cudaSuccess) return e;
+  if (cooperative) {      // grid-wide barrier inside the kernel: the runtime guarantees (or refuses) co-residency of the whole grid
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(threads);
+    cfg.dynamicSmemBytes = smem_bytes(p);
+    cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeCooperative;
+    at[0].val.cooperative = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kern, p);
+  }
   if (p.cl <= 1) return launch_pdl(kern, dim3(grid), dim3(threads), smem_bytes(p), st, p);
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(grid / p.cl * p.cl);
@@ -1662,6 +1808,15 @@ static int launch(Params p, cudaStream_t st) {
     constexpr int G2 = GEO == GEO_INIT ? GEO_SAME : GEO;
     const bool swap_on = swap_enabled();
     const bool pro = G2 == GEO_SAME && p.c.pro != PRO_NONE;
+    if (G2 == GEO_SAME && p.c.fin_out) {
+      // ResnetBlock.block2 with the block tail fused behind a grid barrier (cooperative launch)
+      if (!pro || p.ntap != 9) return fail(-2, "conv_tcgen05: the fused block tail needs the GroupNorm-prologue 3x3 instantiation");
+      if (lean_ok) DMN_CUDA_CHECK(launch_kernel(conv_tcgen05_kernel<GEO_SAME, 128, false, true, false, 1, 8, false, 8, true>, grid, kThreads, p, st, true));
+      else DMN_CUDA_CHECK(launch_kernel(conv_tcgen05_kernel<GEO_SAME, 128, false, false, false, 1, 8, false, 8, true>, grid, kThreads, p, st, true));
+      count_launch();
+      DMN_LAUNCH_CHECK("conv_tcgen05");
+      return 0;
+    }
     if (swap_on && (G2 != GEO_SAME || p.ntap == 9)) {
       static const bool pw16 = [] { const char* e = getenv("DMN_CONV_PW16"); return !(e && e[0] == '0'); }();
       if (pro && pw16 && lean_ok) DMN_CUDA_CHECK(launch_kernel(conv_tcgen05_kernel<GEO_SAME, 128, false, true, false, 1, 8, true, 16>, grid, kThreads16, p, st));
@@ -1711,6 +1866,23 @@ static int launch(Params p, cudaStream_t st) {
 bool conv_tcgen05_supported(const ConvP& c) {
   tc::Params p;
   return tc::fill_params(c, tc::geo_of(c), p);
+}
+// can this convolution carry the fused block tail (ConvP::fin_*)?  fin_ogroups = statistics groups of the tail's output (0 = none)
+bool conv_tcgen05_tail_supported(const ConvP& c) {
+  tc::Params p;
+  if (c.mode != CONV_SAME || c.ksize != 3 || !tc::fill_params(c, tc::GEO_SAME, p)) return false;
+  if (p.NT != 128 || !(c.pro & PRO_GN) || (c.pro & PRO_LRELU) || c.res || c.fold_s1 || c.ogroups <= 0 || p.cpg_out < 16) return false;
+  if (c.fin_ogroups < 0 || (c.fin_ogroups > 0 && c.Cout % c.fin_ogroups)) return false;
+  if (c.fin_ogroups > 0) {
+    const int fcpg = c.Cout / c.fin_ogroups;
+    if (fcpg < 16 || (fcpg < 128 && (fcpg & (fcpg - 1))) || (fcpg >= 128 && fcpg % 128)) return false;
+    if (fcpg >= 128 && c.fin_ogroups != 1) return false;      // a group wider than the N tile: only the single-group (GroupNorm(1)) form
+  }
+  // EXPERIMENT, default off (DMN_FUSED_FINALIZE=1): parity-green, but measured SLOWER than the separate gn_finalize launch -- level-0
+  // block2 conv + tail 0.168 ms against 0.101 + 0.044 ms: the pass over the CTA's own tiles runs at ~12 B/clk/SM behind the grid barrier
+  // (576 threads per SM, tiles no longer L2-resident after 8 rounds), the stand-alone kernel streams at 4.5 TB/s with 3 x 256 threads per SM
+  static const bool on = [] { const char* e = getenv("DMN_FUSED_FINALIZE"); return e && e[0] == '1'; }();
+  return on;
 }
 bool init_conv_tcgen05_supported(int Cin, int S, int Cout, int B) {
   ConvP c;
