@@ -52,7 +52,7 @@ class ConvArgs(C.Structure):
 
 class AttnBlockArgs(C.Structure):
     _fields_ = [
-        ("batch", C.c_int32), ("dim", C.c_int32), ("n_tokens", C.c_int32),
+        ("batch", C.c_int32), ("dim", C.c_int32), ("n_tokens", C.c_int32), ("softmax", C.c_int32),
         ("x", C.c_void_p), ("norm_w", C.c_void_p), ("norm_b", C.c_void_p), ("w_qkv", C.c_void_p), ("w_out", C.c_void_p),
         ("b_out", C.c_void_p), ("out_norm_w", C.c_void_p), ("out_norm_b", C.c_void_p), ("y", C.c_void_p),
         ("scratch_dev", C.c_void_p), ("scratch_bytes", C.c_size_t),

@@ -233,10 +233,10 @@ size_t dmn_linear_attention_block_scratch_bytes(const dmn_attn_block_args* a) { 
 
 int dmn_linear_attention_block(const dmn_attn_block_args* a, void* stream) {
   if (!a) return fail(DMN_EINVAL, "null args");
-  DMN_REQUIRE(a->x && a->y && a->norm_w && a->norm_b && a->w_qkv && a->w_out && a->b_out && a->out_norm_w && a->out_norm_b && a->scratch_dev,
-              "null tensor");
-  if (!linattn_fused_supported(a->batch, a->n_tokens, a->dim))
-    return fail(DMN_ENOTSUP, "fused LinearAttention block: n_tokens must be a multiple of 128 (or of 8, below 128) and dim 128 or 256");
+  DMN_REQUIRE(a->x && a->y && a->norm_w && a->norm_b && a->w_qkv && a->w_out && a->b_out && a->scratch_dev, "null tensor");
+  DMN_REQUIRE(a->softmax || (a->out_norm_w && a->out_norm_b), "null tensor (to_out GroupNorm parameters)");
+  if (a->softmax ? !attn_softmax_fused_supported(a->batch, a->n_tokens, a->dim) : !linattn_fused_supported(a->batch, a->n_tokens, a->dim))
+    return fail(DMN_ENOTSUP, "fused attention block: n_tokens must be a multiple of 128 (or of 8, below 128; softmax form: at most 64) and dim 128 or 256");
   const AttnScratch L = attn_layout(a);
   DMN_REQUIRE(a->scratch_bytes >= L.total, "scratch too small (dmn_linear_attention_block_scratch_bytes)");
   cudaStream_t st = (cudaStream_t)stream;
@@ -277,7 +277,7 @@ int dmn_linear_attention_block(const dmn_attn_block_args* a, void* stream) {
   q.s1 = (const float*)(base + L.s12); q.s2 = q.s1 + 384;
   q.bo = a->b_out; q.go = a->out_norm_w; q.beo = a->out_norm_b;
   q.B = a->batch; q.N = a->n_tokens; q.C = C_;
-  if ((rc = linattn_fused(q, st))) return rc;
+  if ((rc = a->softmax ? attn_softmax_fused(q, st) : linattn_fused(q, st))) return rc;
   return nhwc_to_nchw(base + L.y, a->y, a->batch, C_, a->n_tokens, ACT_BF16, st);
 }
 

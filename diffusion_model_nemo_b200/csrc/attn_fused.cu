@@ -706,6 +706,341 @@ __global__ void __launch_bounds__(kThreads, 1) linattn_fused_kernel(const __grid
 
 constexpr size_t kSmemFused = 1024 + (size_t)(kXS + kWS) * kSlab + 2 * (size_t)kOpBytes + 4 * kCtxHead + (128 + 3 * 256 + 16 + 512) * 4 + (B_COUNT + 2) * 8 + 64;
 
+// =====================================================================================================================
+// fused softmax Attention block (the U-Net bottleneck): Residual(PreNorm(dim, Attention(dim)))   (reference parts/mha.py:8-30)
+//   out = to_out(softmax_j(scale * q_i . k_j) v_j) + x,  heads 4 x dim_head 32, at most 64 tokens per image (one zero-padded tile)
+// Per image:  GEMM  q[tok x 128] = X W_q^T,  k^T | v^T [128 ch x tok] = W_k | W_v . X^T          (TMA operands, as above)
+//             epilogue: fold affine; q * scale (log2 domain), k as the B operand [tok_j][(h,d)], v as the B operand [(h,e)][tok_j]
+//             GEMM  S_h[tok_i x tok_j] = q_h k_h^T  (4 heads, N = padded token count)   ->   row softmax  ->  P_h as A operand
+//             GEMM  o_h[tok_i x 32] = P_h v_h       ->  A operand of   GEMM  y = o W_o^T   ->   + bias + x, stored
+// =====================================================================================================================
+enum { S_FULLX = 0, S_EMPTYX = S_FULLX + kXS, S_FULLW = S_EMPTYX + kXS, S_EMPTYW = S_FULLW + kWS, S_QKV = S_EMPTYW + kWS, S_OPS, S_S, S_P, S_OUT,
+       S_OUTS, S_Y, S_FREE, S_COUNT };
+
+__global__ void __launch_bounds__(kThreads, 1) attn_softmax_fused_kernel(const __grid_constant__ Params p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const uint32_t base0 = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + ((1024u - (base0 & 1023u)) & 1023u);
+  uint8_t* s_x = smem;
+  uint8_t* s_w = s_x + kXS * kSlab;
+  uint8_t* s_opa = s_w + kWS * kSlab;                    // q operand (A of the S products); with s_kop it later holds P (A of the o products)
+  uint8_t* s_kop = s_opa + kOpBytes;                     // k operand (B of the S products)
+  uint8_t* s_opb = s_kop + kOpBytes;                     // v operand (B of the o products), then o (A of the to_out product)
+  float* s_tq = reinterpret_cast<float*>(s_opb + kOpBytes);   // [128] additive fold term of q, already times scale * log2(e)
+  float* s_bo = s_tq + 128;                              // [C]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_bo + 256);
+  uint32_t* tslot = reinterpret_cast<uint32_t*>(bars + S_COUNT);
+
+  pdl_trigger();
+  pdl_wait();
+  const int tid = threadIdx.x;
+  const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0), lane = tid & 31;
+  const int C = p.C, N = p.N, KC = C >> 6, RH = C >> 7;
+  const int NV = N;                                      // valid tokens (<= 64)
+  const int NVp = (NV + 15) & ~15;                       // token count padded to the MMA granularity
+  const uint32_t xbytes = (uint32_t)NV * 128u;
+  auto bar = [&](int i) { return smem_u32(&bars[i]); };
+
+  if (warp == kLoaderWarp) {
+    if (lane < S_COUNT) {
+      uint32_t cnt = 1;
+      if (lane == S_OPS || lane == S_P || lane == S_OUTS || lane == S_FREE) cnt = kEpiThreads;
+      mbar_init(bar(lane), cnt);
+    }
+    fence_barrier_init();
+  }
+  if (warp == kMmaWarp) tmem_alloc(smem_u32(tslot), 512);
+  if (warp < 8) {
+    for (uint32_t i = tid; i < kXS * kSlab / 16; i += kEpiThreads) sts128(smem_u32(s_x) + i * 16, make_uint4(0, 0, 0, 0));
+    // the k operand's rows beyond the image (tok_j >= NV, up to NVp) must be finite: zero the buffer once
+    for (uint32_t i = tid; i < kOpBytes / 16; i += kEpiThreads) sts128(smem_u32(s_kop) + i * 16, make_uint4(0, 0, 0, 0));
+    for (int i = tid; i < C; i += kEpiThreads) s_bo[i] = p.bo[i];
+    fence_proxy_async();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tslot;
+  const uint32_t tDk = tmem, tDv = tmem + 128, tDq = tmem + 256, tDo = tmem + 384;
+  const uint32_t tS = tmem, tDy = tmem;                  // aliases of the k^T | v^T columns (dead once their operands are in shared memory)
+  const uint32_t pHead = (uint32_t)(NVp >> 3) * kOpLbo;  // bytes of one head's P operand: NVp / 8 k-chunks
+
+  if (warp == kLoaderWarp) {
+    const bool leader = elect_one();
+    int xs = 0, ws = 0;
+    uint32_t xph = 1, wph = 1;
+    auto load_x = [&](int row0, int kc) {
+      mbar_wait_relaxed(bar(S_EMPTYX + xs), xph);
+      if (leader) {
+        mbar_arrive_expect_tx(bar(S_FULLX + xs), xbytes);
+        tma_load(smem_u32(s_x) + xs * kSlab, &p.mx, kc * 64, row0, bar(S_FULLX + xs));
+      }
+      __syncwarp();
+      if (++xs == kXS) { xs = 0; xph ^= 1; }
+    };
+    auto load_w = [&](const CUtensorMap* map, int col, int row) {
+      mbar_wait_relaxed(bar(S_EMPTYW + ws), wph);
+      if (leader) {
+        mbar_arrive_expect_tx(bar(S_FULLW + ws), kSlab);
+        tma_load(smem_u32(s_w) + ws * kSlab, map, col, row, bar(S_FULLW + ws));
+      }
+      __syncwarp();
+      if (++ws == kWS) { ws = 0; wph ^= 1; }
+    };
+    for (int b = blockIdx.x; b < p.B; b += gridDim.x) {
+      for (int kc = 0; kc < KC; ++kc) {
+        load_x(b * N, kc);
+        load_w(&p.mw, kc * 64, 0);
+        load_w(&p.mw, kc * 64, 128);
+        load_w(&p.mw, kc * 64, 256);
+      }
+      for (int kc2 = 0; kc2 < 2; ++kc2)
+        for (int rh = 0; rh < RH; ++rh) load_w(&p.mo, kc2 * 64, rh * 128);
+    }
+  } else if (warp == kMmaWarp) {
+    const bool leader = elect_one();
+    const uint32_t idesc = make_idesc(128, 128), idesc32 = make_idesc(128, 32), idescS = make_idesc(128, NVp);
+    int xs = 0, ws = 0;
+    uint32_t xph = 0, wph = 0, ph_ops = 0, ph_p = 0, ph_outs = 0, ph_free = 1;
+    const uint32_t opa = smem_u32(s_opa), kop = smem_u32(s_kop), opb = smem_u32(s_opb);
+    auto wait_w = [&]() -> uint32_t {
+      mbar_wait(bar(S_FULLW + ws), wph);
+      tc_fence_after();
+      return smem_u32(s_w) + ws * kSlab;
+    };
+    auto free_w = [&]() {
+      if (leader) umma_commit(bar(S_EMPTYW + ws));
+      __syncwarp();
+      if (++ws == kWS) { ws = 0; wph ^= 1; }
+    };
+    for (int b = blockIdx.x; b < p.B; b += gridDim.x) {
+      mbar_wait(bar(S_FREE), ph_free);                   // the previous image's y has been read out of the aliased columns
+      ph_free ^= 1;
+      tc_fence_after();
+      for (int kc = 0; kc < KC; ++kc) {
+        mbar_wait(bar(S_FULLX + xs), xph);
+        tc_fence_after();
+        const uint32_t ax = smem_u32(s_x) + xs * kSlab;
+        const uint32_t wq = wait_w();
+        if (leader) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) umma_bf16(tDq, make_desc_sw128(ax + j * 32), make_desc_sw128(wq + j * 32), idesc, (kc | j) ? 1u : 0u);
+        }
+        __syncwarp();
+        free_w();
+        const uint32_t wk = wait_w();
+        if (leader) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) umma_bf16(tDk, make_desc_sw128(wk + j * 32), make_desc_sw128(ax + j * 32), idesc, (kc | j) ? 1u : 0u);
+        }
+        __syncwarp();
+        free_w();
+        const uint32_t wv = wait_w();
+        if (leader) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) umma_bf16(tDv, make_desc_sw128(wv + j * 32), make_desc_sw128(ax + j * 32), idesc, (kc | j) ? 1u : 0u);
+        }
+        __syncwarp();
+        free_w();
+        if (leader) umma_commit(bar(S_EMPTYX + xs));
+        __syncwarp();
+        if (++xs == kXS) { xs = 0; xph ^= 1; }
+      }
+      if (leader) umma_commit(bar(S_QKV));
+      __syncwarp();
+      // S_h = q_h k_h^T : M128 x N(NVp) x K32 per head
+      mbar_wait(bar(S_OPS), ph_ops);
+      ph_ops ^= 1;
+      tc_fence_after();
+      if (leader) {
+#pragma unroll
+        for (int h = 0; h < 4; ++h)
+#pragma unroll
+          for (int j = 0; j < 2; ++j)
+            umma_bf16(tS + h * NVp, make_desc(opa + (h * 2 + j) * kOpK16, kOpLbo, kOpSbo), make_desc(kop + (h * 2 + j) * kOpK16, kOpLbo, kOpSbo),
+                      idescS, j ? 1u : 0u);
+        umma_commit(bar(S_S));
+      }
+      __syncwarp();
+      // o_h = P_h v_h : M128 x N32 x K(NVp) per head
+      mbar_wait(bar(S_P), ph_p);
+      ph_p ^= 1;
+      tc_fence_after();
+      if (leader) {
+        for (int h = 0; h < 4; ++h)
+          for (int j = 0; j < (NVp >> 4); ++j)
+            umma_bf16(tDo + h * 32, make_desc(opa + h * pHead + j * kOpK16, kOpLbo, kOpSbo),
+                      make_desc(opb + (uint32_t)(h * 32) * 16u + j * kOpK16, kOpLbo, kOpSbo), idesc32, j ? 1u : 0u);
+        umma_commit(bar(S_OUT));
+      }
+      __syncwarp();
+      mbar_wait(bar(S_OUTS), ph_outs);
+      ph_outs ^= 1;
+      tc_fence_after();
+      for (int kc2 = 0; kc2 < 2; ++kc2)
+        for (int rh = 0; rh < RH; ++rh) {
+          const uint32_t wo = wait_w();
+          if (leader) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              umma_bf16(tDy + rh * 128, make_desc(opb + (kc2 * 4 + j) * kOpK16, kOpLbo, kOpSbo), make_desc_sw128(wo + j * 32), idesc, (kc2 | j) ? 1u : 0u);
+          }
+          __syncwarp();
+          free_w();
+        }
+      if (leader) umma_commit(bar(S_Y));
+      __syncwarp();
+    }
+  } else {
+    const int q4 = warp & 3, half = warp >> 2;
+    const uint32_t lane_base = (uint32_t)(q4 * 32) << 16;
+    const int ch = q4 * 32 + lane;
+    const uint32_t opa = smem_u32(s_opa), kop = smem_u32(s_kop), opb = smem_u32(s_opb);
+    const float s1k = p.s1[128 + ch], s2k = p.s2[128 + ch], s1v = p.s1[256 + ch], s2v = p.s2[256 + ch];
+    const float qs = rsqrtf(32.f) * kLog2e;                    // q * scale, softmax in the log2 domain
+    uint32_t ph_qkv = 0, ph_s = 0, ph_out = 0, ph_y = 0;
+    for (int b = blockIdx.x; b < p.B; b += gridDim.x) {
+      float mean_x, rstd_x;
+      gn_mean_rstd(p.pstats + (long)b * 2, p.inv_cnt, kGnEps, mean_x, rstd_x);
+      const float fa = rstd_x, fc = -mean_x * rstd_x;
+      if (tid < 128) s_tq[tid] = (fc * p.s1[tid] + p.s2[tid]) * qs;
+      const float ck = fc * s1k + s2k, cv = fc * s1v + s2v;
+      bar_sync_named(1, kEpiThreads);
+      mbar_wait_relaxed(bar(S_QKV), ph_qkv);
+      ph_qkv ^= 1;
+      tc_fence_after();
+      uint32_t r[32];
+      // ---- q operand: [tok_i][(h,d)] (lane = token), two heads per warp ----
+      const float faq = fa * qs;
+#pragma unroll
+      for (int hh = 0; hh < 2; ++hh) {
+        const int col0 = (half * 2 + hh) * 32;
+        tmem_ld32(tDq + lane_base + col0, r);
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          float v[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) v[e] = fmaf(faq, __uint_as_float(r[g * 8 + e]), s_tq[col0 + g * 8 + e]);
+          sts128(opa + (uint32_t)((((col0 >> 3) + g) * 128 + q4 * 32 + lane) * 16), pack8(v));
+        }
+      }
+      // ---- k operand [tok_j][(h,d)] (warps 0-3) / v operand [(h,e)][tok_j] (warps 4-7): lane = channel ----
+      for (int c0 = 0; c0 < NVp; c0 += 32) {
+        tmem_ld32((half ? tDv : tDk) + lane_base + c0, r);
+        if (half == 0) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (c0 + i < NV) sts16(kop + (uint32_t)(((ch >> 3) * 128 + c0 + i) * 16 + (ch & 7) * 2), bf16_bits(fmaf(fa, __uint_as_float(r[i]), ck)));
+        } else {
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            if (c0 + g * 8 < NVp) {
+              float v[8];
+#pragma unroll
+              for (int e = 0; e < 8; ++e) v[e] = fmaf(fa, __uint_as_float(r[g * 8 + e]), cv);
+              sts128(opb + (uint32_t)((((c0 >> 3) + g) * 128 + ch) * 16), pack8(v));
+            }
+          }
+        }
+      }
+      fence_proxy_async();
+      tc_fence_before();
+      mbar_arrive(bar(S_OPS));
+      // ---- row softmax of S_h over the image's tokens -> P_h [tok_i][tok_j] (A operand; overwrites the q / k operands) ----
+      mbar_wait_relaxed(bar(S_S), ph_s);
+      ph_s ^= 1;
+      tc_fence_after();
+#pragma unroll 1
+      for (int hh = 0; hh < 2; ++hh) {
+        const int h = half * 2 + hh;
+        float mx = -INFINITY, sum = 0.f;
+        float e[64];
+#pragma unroll
+        for (int c0 = 0; c0 < 64; c0 += 32) {
+          if (c0 < NVp) {
+            tmem_ld32(tS + lane_base + (uint32_t)(h * NVp + c0), r);      // (columns beyond NVp belong to the next head: masked below)
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              e[c0 + i] = c0 + i < NV ? __uint_as_float(r[i]) : -INFINITY;
+              mx = fmaxf(mx, e[c0 + i]);
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) e[c0 + i] = -INFINITY;
+          }
+        }
+#pragma unroll
+        for (int i = 0; i < 64; ++i) { e[i] = ex2(e[i] - mx); sum += e[i]; }
+        const float inv = 1.f / sum;
+#pragma unroll
+        for (int g = 0; g < 8; ++g) {
+          if (g * 8 < NVp) {
+            float v[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[i] = e[g * 8 + i] * inv;
+            sts128(opa + h * pHead + (uint32_t)((g * 128 + q4 * 32 + lane) * 16), pack8(v));
+          }
+        }
+      }
+      fence_proxy_async();
+      tc_fence_before();
+      mbar_arrive(bar(S_P));
+      // ---- o -> A operand of the to_out product (overwrites the v operand) ----
+      mbar_wait_relaxed(bar(S_OUT), ph_out);
+      ph_out ^= 1;
+      tc_fence_after();
+#pragma unroll
+      for (int hh = 0; hh < 2; ++hh) {
+        const int col0 = (half * 2 + hh) * 32;
+        tmem_ld32(tDo + lane_base + col0, r);
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          float v[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[g * 8 + i]);
+          sts128(opb + (uint32_t)((((col0 >> 3) + g) * 128 + q4 * 32 + lane) * 16), pack8(v));
+        }
+      }
+      fence_proxy_async();
+      tc_fence_before();
+      mbar_arrive(bar(S_OUTS));
+      // ---- y = o W_o^T + bias + x ----
+      mbar_wait_relaxed(bar(S_Y), ph_y);
+      ph_y ^= 1;
+      tc_fence_after();
+      {
+        const int ncol = C >> 1;
+        const bool row_ok = q4 * 32 + lane < NV;
+        const long roff = ((long)b * N + q4 * 32 + lane) * C + half * ncol;
+#pragma unroll 1
+        for (int c0 = 0; c0 < ncol; c0 += 32) {
+          tmem_ld32(tDy + lane_base + (uint32_t)(half * ncol + c0), r);
+          if (row_ok) {
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              float xx[8], y[8];
+              unpack8(ldcg128(p.x + roff + c0 + g * 8), xx);
+#pragma unroll
+              for (int i = 0; i < 8; ++i) y[i] = __uint_as_float(r[g * 8 + i]) + s_bo[half * ncol + c0 + g * 8 + i] + xx[i];
+              *reinterpret_cast<uint4*>(p.out + roff + c0 + g * 8) = pack8(y);
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(bar(S_FREE));
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == kMmaWarp) {
+    tc_fence_after();
+    tmem_dealloc(tmem, 512);
+  }
+}
+
+constexpr size_t kSmemSoftmax = 1024 + (size_t)(kXS + kWS) * kSlab + 3 * (size_t)kOpBytes + (128 + 256) * 4 + (S_COUNT + 2) * 8 + 64;
+
 }  // namespace fa
 
 bool linattn_fused_supported(int B, int N, int C) {
@@ -739,6 +1074,34 @@ int linattn_fused(const LinAttnFusedP& q, cudaStream_t st) {
   DMN_CUDA_CHECK(launch_pdl(fa::linattn_fused_kernel, dim3(grid), dim3(fa::kThreads), fa::kSmemFused, st, p));
   count_launch();
   DMN_LAUNCH_CHECK("linattn_fused");
+  return 0;
+}
+
+bool attn_softmax_fused_supported(int B, int N, int C) {
+  return B >= 1 && N >= 16 && N <= 64 && N % 8 == 0 && (C == 128 || C == 256) && (long)B * N < (1L << 30);
+}
+
+// Residual(PreNorm(Attention)): same parameter block as the linear form; go / beo are unused (to_out is a bare 1x1 here)
+int attn_softmax_fused(const LinAttnFusedP& q, cudaStream_t st) {
+  if (!attn_softmax_fused_supported(q.B, q.N, q.C)) return fail(-2, "attn_softmax_fused: unsupported shape");
+  fa::Params p;
+  memset(&p, 0, sizeof(p));
+  int rc;
+  if ((rc = fa::make_map(&p.mx, q.x, (uint64_t)q.B * q.N, (uint64_t)q.C, q.N))) return rc;
+  if ((rc = fa::make_map(&p.mw, q.wqkv, 384, (uint64_t)q.C, 128))) return rc;
+  if ((rc = fa::make_map(&p.mo, q.wo, (uint64_t)q.C, 128, 128))) return rc;
+  p.x = (const bf16*)q.x;
+  p.out = (bf16*)q.out;
+  p.pstats = q.pstats;
+  p.s1 = q.s1; p.s2 = q.s2; p.bo = q.bo; p.go = q.go; p.beo = q.beo;
+  p.B = q.B; p.N = q.N; p.C = q.C;
+  p.inv_cnt = 1.f / ((float)q.N * (float)q.C);
+  static DeviceOnce attr;
+  if (attr.first()) DMN_CUDA_CHECK(cudaFuncSetAttribute(fa::attn_softmax_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fa::kSmemSoftmax));
+  const int grid = q.B < current_device_sms() ? q.B : current_device_sms();
+  DMN_CUDA_CHECK(launch_pdl(fa::attn_softmax_fused_kernel, dim3(grid), dim3(fa::kThreads), fa::kSmemSoftmax, st, p));
+  count_launch();
+  DMN_LAUNCH_CHECK("attn_softmax_fused");
   return 0;
 }
 

@@ -470,6 +470,7 @@ __global__ void __launch_bounds__((PW + EW + 2) * 32, 1) conv_tcgen05_kernel(con
   static_assert(!(LEAN && PRO == 3), "the lean issue path is for 9- and 4-tap convolutions");
   extern __shared__ __align__(128) uint8_t smem[];
   const int tid = threadIdx.x;
+  if (DMN_TC_TRACE_BUILD && p.trace && blockIdx.x == (unsigned)p.trace_cta && tid == 0) p.trace[1000] = clock64();     // kernel entry
   // broadcast => ptxas knows the role branches below are warp-uniform and may use the uniform datapath inside them
   const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0), lane = tid & 31;
   const int nst = p.nstage;
@@ -1497,6 +1498,7 @@ __global__ void __launch_bounds__((PW + EW + 2) * 32, 1) conv_tcgen05_kernel(con
     tc_fence_after();
     tmem_dealloc(tmem_base, p.tmem_cols);
   }
+  if (DMN_TC_TRACE_BUILD && p.trace && blockIdx.x == (unsigned)p.trace_cta && tid == 0) p.trace[1001] = clock64();     // kernel exit
 }
 
 static size_t smem_fixed_bytes(const Params& p) {

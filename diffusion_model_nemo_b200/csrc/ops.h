@@ -139,6 +139,9 @@ struct LinAttnFusedP {
 };
 bool linattn_fused_supported(int B, int N, int C);
 int linattn_fused(const LinAttnFusedP& p, cudaStream_t s);
+// Residual(PreNorm(dim, Attention(dim))) (the bottleneck softmax attention, at most 64 tokens): same parameter block, go / beo unused
+bool attn_softmax_fused_supported(int B, int N, int C);
+int attn_softmax_fused(const LinAttnFusedP& p, cudaStream_t s);
 // plumbing self-test of the TMA tensor copies + 128-byte-swizzle UMMA descriptors: D[M][N] = A[M][K] . B[N][K]^T (row-major bf16 in, fp32 out)
 int selftest_tma_sw128_gemm(const void* a_bf16, const void* b_bf16, float* d, int M, int N, int K, cudaStream_t s);
 

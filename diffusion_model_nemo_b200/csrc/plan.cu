@@ -133,6 +133,7 @@ struct Op {
   // attention
   int heads = 4, dh = 32, N = 0;
   int wo = -1, bo = -1;             // fused attention block: to_out.0 weight (plain bf16 image) / bias
+  bool softmax = false;             // fused attention block: the bottleneck softmax Attention instead of LinearAttention
 };
 
 }  // namespace dmn
@@ -374,6 +375,28 @@ struct Builder {
       a.bo = add_param(p + ".fn.fn.to_out.0.bias", {C}, PK_RAW);
       a.gamma = add_param(p + ".fn.fn.to_out.1.weight", {C}, PK_RAW);
       a.beta = add_param(p + ".fn.fn.to_out.1.bias", {C}, PK_RAW);
+      P.ops.push_back(a);
+      const int ci = (int)P.ops.size() - 1;
+      for (int pi : {a.w, nw, nb}) {
+        P.params[pi].keep_host = true;
+        P.params[pi].fold_op = ci;
+      }
+      return;
+    }
+    if (!linear && !no_fused && P.engine == DMN_CONV_TCGEN05 && attn_softmax_fused_supported(P.cfg.max_batch, H * H, C)) {
+      // Residual(PreNorm(Attention)) (the bottleneck softmax attention) as one tcgen05 kernel
+      Op a;
+      a.kind = OP_ATTN_FUSED;
+      a.name = p + ".fused";
+      a.softmax = true;
+      a.src1 = x; a.out = out; a.pstats = xstats; a.C = C; a.N = H * H; a.HW = H * H; a.Hin = H;
+      a.w = add_plain_param(p + ".fn.fn.to_qkv.weight", 3 * hidden, C);
+      a.fold = true;
+      a.fold_gamma = nw;
+      a.fold_beta = nb;
+      a.fold_off = walloc((size_t)2 * 3 * hidden * sizeof(float));
+      a.wo = add_plain_param(p + ".fn.fn.to_out.weight", C, hidden);
+      a.bo = add_param(p + ".fn.fn.to_out.bias", {C}, PK_RAW);
       P.ops.push_back(a);
       const int ci = (int)P.ops.size() - 1;
       for (int pi : {a.w, nw, nb}) {
@@ -724,7 +747,7 @@ static int run_forward(dmn_plan* P, const float* x_dev, const int32_t* row_dev, 
         q.s2 = q.s1 + 384;
         q.bo = W(o.bo); q.go = W(o.gamma); q.beo = W(o.beta);
         q.B = batch; q.N = o.N; q.C = o.C;
-        rc = linattn_fused(q, st);
+        rc = o.softmax ? attn_softmax_fused(q, st) : linattn_fused(q, st);
         break;
       }
       case OP_CLASSADD:
@@ -1038,7 +1061,7 @@ int dmn_plan_op_info(const dmn_plan* p, int i, char* name_out, int name_cap, int
     case OP_ATTN: fl = 2.0 * 2.0 * o.heads * o.dh * (double)o.N * o.N; by = esz * (double)o.N * o.heads * o.dh * 4.0; break;
     case OP_FINALPROJ: fl = 2.0 * o.HW * o.C * o.Cout; by = esz * (double)o.HW * o.C + 4.0 * o.HW * o.Cout; break;
     case OP_ATTN_FUSED:      // to_qkv + both contractions + to_out; x read once, result written once
-      fl = 2.0 * o.N * (384.0 * o.C + 2.0 * 128.0 * 32.0 + 128.0 * o.C);
+      fl = 2.0 * o.N * (384.0 * o.C + (o.softmax ? 2.0 * 128.0 * o.N : 2.0 * 128.0 * 32.0) + 128.0 * o.C);
       by = esz * (double)o.N * o.C * 2.0;
       break;
   }

@@ -281,6 +281,9 @@ int dmn_selftest_tma_sw128_gemm(const void* a_bf16, const void* b_bf16, float* d
  * scratch_dev >= dmn_linear_attention_block_scratch_bytes().  Validation path (host repack, sync copies). */
 typedef struct dmn_attn_block_args {
   int32_t batch, dim, n_tokens;
+  int32_t softmax;         /* 0: LinearAttention block (above).  1: Residual(PreNorm(Attention)) (parts/mha.py:8-30, the bottleneck softmax
+                              attention): y = to_out(softmax attention) + x, at most 64 tokens; w_out / b_out are to_out.weight / .bias,
+                              out_norm_w / out_norm_b are unused */
   const float* x;
   const float* norm_w; const float* norm_b;
   const float* w_qkv;

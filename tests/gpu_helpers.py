@@ -63,24 +63,29 @@ def attention_core(qkv, linear, act=L.ACT_F32, heads=4, dh=32):
     return out
 
 
-def linear_attention_block(x, sd, prefix):
-    """Residual(PreNorm(LinearAttention)) through the fused tcgen05 kernel.  x fp32 NCHW cuda; sd holds the reference parameter names
-    under `prefix` (fn.norm.*, fn.fn.to_qkv.weight, fn.fn.to_out.0.*, fn.fn.to_out.1.*)."""
+def linear_attention_block(x, sd, prefix, softmax=False):
+    """Residual(PreNorm(LinearAttention)) -- or, with softmax=True, Residual(PreNorm(Attention)) -- through the fused tcgen05 kernel.
+    x fp32 NCHW cuda; sd holds the reference parameter names under `prefix` (fn.norm.*, fn.fn.to_qkv.weight, fn.fn.to_out.0.* and
+    fn.fn.to_out.1.* for the linear form, fn.fn.to_out.* for the softmax form)."""
     lib = L.lib()
     dev = x.device
     b, c, h, w = x.shape
     a = L.AttnBlockArgs()
-    a.batch, a.dim, a.n_tokens = b, c, h * w
-    keep = {k: sd[prefix + k].float().contiguous().to(dev) for k in (".fn.norm.weight", ".fn.norm.bias", ".fn.fn.to_qkv.weight",
-                                                                    ".fn.fn.to_out.0.weight", ".fn.fn.to_out.0.bias",
-                                                                    ".fn.fn.to_out.1.weight", ".fn.fn.to_out.1.bias")}
+    a.batch, a.dim, a.n_tokens, a.softmax = b, c, h * w, int(softmax)
+    names = [".fn.norm.weight", ".fn.norm.bias", ".fn.fn.to_qkv.weight"]
+    names += [".fn.fn.to_out.weight", ".fn.fn.to_out.bias"] if softmax else [".fn.fn.to_out.0.weight", ".fn.fn.to_out.0.bias",
+                                                                              ".fn.fn.to_out.1.weight", ".fn.fn.to_out.1.bias"]
+    keep = {k: sd[prefix + k].float().contiguous().to(dev) for k in names}
     xc = x.float().contiguous()
     y = torch.empty_like(xc)
     a.x, a.y = xc.data_ptr(), y.data_ptr()
     a.norm_w, a.norm_b = keep[".fn.norm.weight"].data_ptr(), keep[".fn.norm.bias"].data_ptr()
     a.w_qkv = keep[".fn.fn.to_qkv.weight"].data_ptr()
-    a.w_out, a.b_out = keep[".fn.fn.to_out.0.weight"].data_ptr(), keep[".fn.fn.to_out.0.bias"].data_ptr()
-    a.out_norm_w, a.out_norm_b = keep[".fn.fn.to_out.1.weight"].data_ptr(), keep[".fn.fn.to_out.1.bias"].data_ptr()
+    if softmax:
+        a.w_out, a.b_out = keep[".fn.fn.to_out.weight"].data_ptr(), keep[".fn.fn.to_out.bias"].data_ptr()
+    else:
+        a.w_out, a.b_out = keep[".fn.fn.to_out.0.weight"].data_ptr(), keep[".fn.fn.to_out.0.bias"].data_ptr()
+        a.out_norm_w, a.out_norm_b = keep[".fn.fn.to_out.1.weight"].data_ptr(), keep[".fn.fn.to_out.1.bias"].data_ptr()
     scratch = torch.empty(lib.dmn_linear_attention_block_scratch_bytes(C.byref(a)) + 256, dtype=torch.uint8, device=dev)
     a.scratch_dev = (scratch.data_ptr() + 255) // 256 * 256
     a.scratch_bytes = scratch.numel() - 256

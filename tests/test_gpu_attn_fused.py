@@ -65,3 +65,18 @@ def test_linear_attention_block_large_k_logits():
     ref = O.residual_prenorm_fwd(sd, p, x, O.linear_attention_fwd)
     y = linear_attention_block(x.to(DEV), sd, p).cpu()
     assert rel_l2(y - x, ref - x) <= 3e-2
+
+
+@pytest.mark.parametrize("b,c,h", [(1, 256, 4), (5, 256, 4), (3, 128, 4), (2, 256, 8), (300, 256, 4)])
+def test_softmax_attention_block_vs_oracle(b, c, h):
+    """The bottleneck Residual(PreNorm(Attention)) (reference parts/mha.py:8-30) on the fused tcgen05 kernel."""
+    p, sd = _block_sd(c, seed=11)
+    sd[p + ".fn.fn.to_out.weight"] = sd.pop(p + ".fn.fn.to_out.0.weight")
+    sd[p + ".fn.fn.to_out.bias"] = sd.pop(p + ".fn.fn.to_out.0.bias")
+    sd[p + ".fn.fn.to_qkv.weight"] = sd[p + ".fn.fn.to_qkv.weight"] * 3.0      # logits of order 1: a non-trivial softmax
+    x = _bf(_rand(b, c, h, h, seed=5) * 1.5 + 0.2)
+    ref = O.residual_prenorm_fwd(sd, p, x, O.attention_fwd)
+    y = linear_attention_block(x.to(DEV), sd, p, softmax=True).cpu()
+    assert torch.isfinite(y).all()
+    assert rel_l2(y, ref) <= 1e-2
+    assert rel_l2(y - x, ref - x) <= 2e-2

@@ -39,7 +39,11 @@ def run(k, cin, cout, h, b, gn, mode=0):
     buf = (C.c_longlong * 1024)()
     lib.dmn_debug_conv_trace(buf, 1024)
     t = list(buf)
-    t0 = min(v for v in t if v > 10 ** 7)
+    if t[1000] and t[1001]:
+        first = min(v for v in t[:960] if v > 10 ** 7)
+        last = max(t[:960])
+        print(f"   kernel entry -> first stamp {first - t[1000]} clk, last stamp -> exit {t[1001] - last} clk, entry -> exit {t[1001] - t[1000]} clk")
+    t0 = min(v for v in t[:960] if v > 10 ** 7)
     rel = lambda v: (v - t0) if v else None
     per = [(t[16 * i + 6] - t[16 * i + 5]) for i in range(1, 10) if t[16 * i + 6] and t[16 * i + 16 + 6]]
     if per:
