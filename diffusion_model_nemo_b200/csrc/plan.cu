@@ -656,14 +656,23 @@ static bool tail_fusable(const dmn_plan* P) {
   return fused_tail_supported(final_proj_params(P, P->ops.back(), nullptr, 1), P->act);
 }
 
+// device time stamp (nanoseconds) between the launches of a captured forward program (dmn_plan_profile_forward_graph)
+__global__ void stamp_kernel(unsigned long long* t) {
+  unsigned long long v;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(v));
+  *t = v;
+}
+
 static int run_forward(dmn_plan* P, const float* x_dev, const int32_t* row_dev, const int64_t* classes_dev, float* out_dev,
-                       int batch, cudaStream_t st, std::vector<cudaEvent_t>* evs = nullptr, const TailFuse* tail = nullptr) {
+                       int batch, cudaStream_t st, std::vector<cudaEvent_t>* evs = nullptr, const TailFuse* tail = nullptr,
+                       unsigned long long* stamps = nullptr) {
   const dmn_unet_cfg& c = P->cfg;
   auto W = [&](int pi) -> const float* { return pi < 0 ? nullptr : (const float*)(P->wbase + P->params[pi].off); };
   auto B = [&](const Buf& b) -> void* { return b.valid() ? (void*)(P->wsbase + b.off) : nullptr; };
   const long launches0 = g_launches;
   size_t op_i = 0;
   if (evs) cudaEventRecord((*evs)[0], st);
+  if (stamps) stamp_kernel<<<1, 1, 0, st>>>(stamps);
   for (const Op& o : P->ops) {
     int rc = 0;
     switch (o.kind) {
@@ -769,7 +778,9 @@ static int run_forward(dmn_plan* P, const float* x_dev, const int32_t* row_dev, 
     }
     ++op_i;
     if (evs) cudaEventRecord((*evs)[op_i], st);
+    if (stamps) stamp_kernel<<<1, 1, 0, st>>>(stamps + op_i);
   }
+  if (stamps) stamp_kernel<<<1, 1, 0, st>>>(stamps + op_i + 1);      // two stamps back to back: the cost of a stamp itself
   P->launches_per_forward = (int)(g_launches - launches0);
   return 0;
 }
@@ -1093,6 +1104,59 @@ int dmn_plan_profile_forward(dmn_plan* p, const float* x_dev, const int32_t* row
   if (!rc)
     for (size_t i = 0; i < p->ops.size(); ++i) cudaEventElapsedTime(&ms_out[i], evs[i], evs[i + 1]);
   for (auto& e : evs) cudaEventDestroy(e);
+  return rc;
+}
+
+/* Same measurement inside ONE CUDA graph: the forward program is stream-captured with an event-record node between
+ * consecutive launches, the graph is replayed (once warm, once timed) and the per-launch times are the event differences.
+ * Unlike plain stream launches the kernels run back to back as they do in the sampling loop (no exposed launch latency). */
+int dmn_plan_profile_forward_graph(dmn_plan* p, const float* x_dev, const int32_t* row_dev, const int64_t* classes_dev,
+                                   float* out_dev, int batch, void* stream, float* ms_out, int max_ops) {
+  int rc = check_ready(p);
+  if (rc) return rc;
+  DMN_REQUIRE(x_dev && out_dev && ms_out, "null tensor");
+  DMN_REQUIRE(batch >= 1 && batch <= p->cfg.max_batch, "batch exceeds the plan's max_batch");
+  DMN_REQUIRE(max_ops >= (int)p->ops.size(), "ms_out too small (dmn_plan_num_ops)");
+  const size_t n = p->ops.size();
+  // CUDA events recorded by graph nodes cannot be timed (cudaEventElapsedTime: invalid argument), so the stamps are %globaltimer
+  // reads of one-thread kernels between the launches; the cost of a stamp (two of them back to back at the end) is subtracted.
+  // Measurement aid only: the one other place (besides the GEMM self-test) where the library allocates device memory itself.
+  unsigned long long* stamps = nullptr;
+  DMN_CUDA_CHECK(cudaMalloc(&stamps, (n + 2) * sizeof(unsigned long long)));
+  cudaStream_t cs;
+  DMN_CUDA_CHECK(cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking));
+  cudaGraph_t graph = nullptr;
+  cudaGraphExec_t exec = nullptr;
+  const char* where = "begin capture";
+  cudaError_t e = cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal);
+  if (e == cudaSuccess) {
+    rc = run_forward(p, x_dev, row_dev, classes_dev, out_dev, batch, cs, nullptr, nullptr, stamps);
+    where = "end capture";
+    e = cudaStreamEndCapture(cs, &graph);
+  }
+  if (!rc && e == cudaSuccess) { where = "instantiate"; e = cudaGraphInstantiate(&exec, graph, 0); }
+  std::vector<unsigned long long> host(n + 2);
+  if (!rc && e == cudaSuccess) {
+    cudaStream_t st = (cudaStream_t)stream;
+    where = "launch";
+    e = cudaGraphLaunch(exec, st);
+    if (e == cudaSuccess) e = cudaGraphLaunch(exec, st);
+    if (e == cudaSuccess) { where = "synchronize"; e = cudaStreamSynchronize(st); }
+    if (e == cudaSuccess) { where = "copy"; e = cudaMemcpy(host.data(), stamps, (n + 2) * sizeof(unsigned long long), cudaMemcpyDeviceToHost); }
+    if (e == cudaSuccess) {
+      const double stamp_ns = (double)(host[n + 1] - host[n]);
+      for (size_t i = 0; i < n; ++i) {
+        double ns = (double)(host[i + 1] - host[i]) - stamp_ns;
+        ms_out[i] = (float)((ns > 0 ? ns : 0) * 1e-6);
+      }
+    }
+  }
+  if (exec) cudaGraphExecDestroy(exec);
+  if (graph) cudaGraphDestroy(graph);
+  cudaStreamDestroy(cs);
+  cudaFree(stamps);
+  if (!rc && e != cudaSuccess) rc = fail(DMN_ECUDA, std::string("profile_forward_graph (") + where + "): " + cudaGetErrorString(e));
+  cudaGetLastError();
   return rc;
 }
 

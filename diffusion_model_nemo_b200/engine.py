@@ -132,14 +132,16 @@ class UnetPlan:
             out.append((name.value.decode(), kind.value, eng.value, fl.value, by.value))
         return out
 
-    def profile_forward(self, x: torch.Tensor, row_dev: Optional[torch.Tensor] = None):
-        """Per-launch milliseconds of one forward (CUDA events around every launch); time table must be filled."""
+    def profile_forward(self, x: torch.Tensor, row_dev: Optional[torch.Tensor] = None, in_graph: bool = False):
+        """Per-launch milliseconds of one forward (CUDA events around every launch); time table must be filled.
+        in_graph=True measures inside one CUDA graph (event-record nodes): back-to-back kernels as in the sampling loop."""
         n = self.lib.dmn_plan_num_ops(self.h)
         ms = (C.c_float * n)()
         out = torch.empty((x.shape[0], self.out_dim, self.image_size, self.image_size), dtype=torch.float32, device=self.device)
+        fn = self.lib.dmn_plan_profile_forward_graph if in_graph else self.lib.dmn_plan_profile_forward
         with torch.cuda.device(self.device):
-            L.check(self.lib.dmn_plan_profile_forward(self.h, L.ptr(x), L.ptr(row_dev), None, L.ptr(out), x.shape[0],
-                                                      L.stream_ptr(self.device), ms, n), "dmn_plan_profile_forward")
+            L.check(fn(self.h, L.ptr(x), L.ptr(row_dev), None, L.ptr(out), x.shape[0], L.stream_ptr(self.device), ms, n),
+                    "dmn_plan_profile_forward")
         return list(ms)
 
     def launches_per_forward(self) -> int:

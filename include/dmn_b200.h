@@ -123,6 +123,10 @@ int dmn_plan_op_info(const dmn_plan* p, int i, char* name_out, int name_cap, int
                      double* flops_per_sample, double* bytes_per_sample);
 int dmn_plan_profile_forward(dmn_plan* p, const float* x_dev, const int32_t* row_dev, const int64_t* classes_dev,
                              float* out_dev, int batch, void* stream, float* ms_out, int max_ops);
+/* the same per-launch times measured INSIDE one CUDA graph (event-record nodes between the launches): the kernels run back to back
+ * as in the sampling loop, without the launch latency plain stream launches expose between dependent kernels. */
+int dmn_plan_profile_forward_graph(dmn_plan* p, const float* x_dev, const int32_t* row_dev, const int64_t* classes_dev,
+                                   float* out_dev, int batch, void* stream, float* ms_out, int max_ops);
 
 /* ------------------------------------------------------------------------------------------------------
  * Sampler updates: ONE fused elementwise kernel per step.  Coefficients live in a device table

@@ -7,7 +7,9 @@ python __graft_entry__.py smoke > $O/${T}_smoke.log 2>&1; tail -2 $O/${T}_smoke.
 python bench.py --impl reference --steps 3 --warmup 1 > $O/${T}_bench_reference.json 2> $O/${T}_bench_reference.err
 python bench.py --dump-ops $O/${T}_ops.txt > $O/${T}_bench.json 2> $O/${T}_bench.err; cut -c1-300 $O/${T}_bench.json
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $O/${T}_launches.csv \
-    python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-e2e > $O/${T}_ncu_launches.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:conv_tcgen05 -s 244 -c 14 -f -o $O/${T}_conv_full \
-    python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-e2e > $O/${T}_ncu_full.log 2>&1
+    python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-e2e --no-library-bar > $O/${T}_ncu_launches.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:conv_tcgen05 -s 200 -c 14 -f -o $O/${T}_conv_full \
+    python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-e2e --no-library-bar > $O/${T}_ncu_full.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:fused -s 32 -c 8 -f -o $O/${T}_attn_full \
+    python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-e2e --no-library-bar > $O/${T}_ncu_attn.log 2>&1
 ls -la $O/${T}_*
