@@ -158,6 +158,10 @@ constexpr bool kTraceProducer = DMN_TC_TRACE_PRODUCER != 0;
 #ifndef DMN_EXP_NO_ONETAP
 #define DMN_EXP_NO_ONETAP 0
 #endif
+#ifndef DMN_EXP_PRO_COST
+#define DMN_EXP_PRO_COST 0          // timing probes of the prologue transform (results are wrong): 1 = no tanh, 2 = LDS + STS only (no math),
+                                    // 3 = nothing at all (copies, fence and barrier arrival only)
+#endif
 #ifndef DMN_EXP_EW16_LEAN
 #define DMN_EXP_EW16_LEAN 1
 #endif
@@ -459,7 +463,7 @@ template <int GEO, int NT, bool FILM = false, bool LEAN = false, bool EXTRA = tr
 __global__ void __launch_bounds__((PW + EW + 2) * 32, 1) conv_tcgen05_kernel(const Params p) {
   static_assert(!TAIL || (GEO == GEO_SAME && NT == 128 && PRO == 1 && !EXTRA && !SWAP), "fused block tail: the GroupNorm-prologue 3x3 instantiations");
   static_assert(!SWAP || (NT == 128 && !EXTRA && !FILM && GEO != GEO_INIT), "swapped operand roles: hot 128-channel instantiations only");
-  static_assert(PW == 8 || (PW == 16 && EW == 8 && PRO == 1 && SWAP), "16 producer warps: the swapped-role GroupNorm-prologue instantiations");
+  static_assert(PW == 8 || (PW == 16 && EW == 8 && PRO == 1), "16 producer warps: the GroupNorm-prologue instantiations");
   constexpr int kProdWarps = PW, kProdThreads = PW * 32;       // (shadow the 8-warp defaults of the namespace)
   constexpr int kMaxItems = PW == 16 ? 4 : 7;
   constexpr int kLoaderW = kProdWarps + EW, kMmaW = kLoaderW + 1, kEpiT = EW * 32;
@@ -516,6 +520,7 @@ __global__ void __launch_bounds__((PW + EW + 2) * 32, 1) conv_tcgen05_kernel(con
   if (warp < kProdWarps) {
     // =============================== operand producers ===============================
     if (EW == 16) asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+    if (PW == 16 && !SWAP) asm volatile("setmaxnreg.dec.sync.aligned.u32 64;");     // 512 x 8 registers handed to the 8 epilogue warps
     // Each thread owns up to kMaxItems 16-byte items (pixel, k-chunk) of every pass.  A pass is ISSUED as cp.async (LDGSTS)
     // copies straight into the operand buffer (padding is stored as zeros), and FINISHED kDepth passes later: wait for the
     // thread's own copies, apply the fused prologue in place (GroupNorm-apply, SiLU, time-embedding add), make the writes
@@ -671,8 +676,10 @@ __global__ void __launch_bounds__((PW + EW + 2) * 32, 1) conv_tcgen05_kernel(con
           // their chains; only the store is predicated, padding stays zero AFTER the transform); the tail slots keep the branch so
           // that slots outside the window cost nothing
           auto do_item = [&](int j, bool check) {
+            if (DMN_EXP_PRO_COST == 3) return;
             if (check && goff[j] < 0) return;
             uint4* slot = reinterpret_cast<uint4*>(base + (px0 + (kProdThreads / 4) * j) * 16);
+            if (DMN_EXP_PRO_COST == 2) { uint4 t = *slot; t.x ^= 0x00010001u; *slot = t; return; }
             const float2 mr = FILM ? make_float2(0.f, 1.f) : s_gn[imgl[j] * kGroupsMax + g];
             if ((p.c.pro & PRO_TEMB) && !temb_shared) {
               const float* tp = temb_base + (long)(img_lo + imgl[j]) * p.c.temb_bstride + cb;
@@ -695,7 +702,9 @@ __global__ void __launch_bounds__((PW + EW + 2) * 32, 1) conv_tcgen05_kernel(con
                 unsigned long long x2 = fma2(pack2(v[2 * e], v[2 * e + 1]), sc2, sh2);
                 x2 = fma2(x2, gah2[e], beh2[e]);                       // hx
                 unsigned long long y2;
-                if (p.c.pro & PRO_SILU) {
+                if (DMN_EXP_PRO_COST == 1) {
+                  y2 = fma2(x2, x2, x2);
+                } else if (p.c.pro & PRO_SILU) {
                   float h0, h1, t0, t1;
                   unpack2(x2, h0, h1);
                   asm("tanh.approx.f32 %0, %1;" : "=f"(t0) : "f"(h0));
@@ -816,6 +825,7 @@ __global__ void __launch_bounds__((PW + EW + 2) * 32, 1) conv_tcgen05_kernel(con
     // register pool of the CTA: the 8 producer warps release 8 x 32 x (72 - 40) = 8192 registers, exactly what 16 epilogue warps need to
     // grow from 72 to 88 (setmaxnreg only moves registers inside the CTA's launch allocation; asking for 96 here deadlocks)
     if (EW == 16) asm volatile("setmaxnreg.inc.sync.aligned.u32 88;");
+    if (PW == 16 && !SWAP) asm volatile("setmaxnreg.inc.sync.aligned.u32 88;");
     // Warps are independent: no shared tables and no block barriers.  Each thread decodes its own accumulator rows
     // (flat position -> output pixel / image), reads 32-column chunks from TMEM, adds bias (+ class embedding, + residual),
     // stores bf16 and accumulates the GroupNorm statistics of its rows; a warp then reduces 8 partials at a time with a
@@ -1836,7 +1846,10 @@ static int launch(Params p, cudaStream_t st) {
       DMN_LAUNCH_CHECK("conv_tcgen05");
       return 0;
     }
-    if (pro && lean_ok) DMN_CUDA_CHECK(launch_kernel(conv_tcgen05_kernel<GEO_SAME, 128, false, true, false, 1>, grid, kThreads, p, st));
+    static const bool pw16n = [] { const char* e = getenv("DMN_CONV_PW16"); return e && e[0] == '1'; }();
+    if (pro && pw16n && lean_ok) DMN_CUDA_CHECK(launch_kernel(conv_tcgen05_kernel<GEO_SAME, 128, false, true, false, 1, 8, false, 16>, grid, kThreads16, p, st));
+    else if (pro && pw16n) DMN_CUDA_CHECK(launch_kernel(conv_tcgen05_kernel<GEO_SAME, 128, false, false, false, 1, 8, false, 16>, grid, kThreads16, p, st));
+    else if (pro && lean_ok) DMN_CUDA_CHECK(launch_kernel(conv_tcgen05_kernel<GEO_SAME, 128, false, true, false, 1>, grid, kThreads, p, st));
     else if (pro) DMN_CUDA_CHECK(launch_kernel(conv_tcgen05_kernel<GEO_SAME, 128, false, false, false, 1>, grid, kThreads, p, st));
     else if (lean_ok) DMN_CUDA_CHECK(launch_kernel(conv_tcgen05_kernel<G2, 128, false, true, false, 0>, grid, kThreads, p, st));
     else if (DMN_EXP_EW16 && G2 == GEO_SAME) {
