@@ -23,9 +23,11 @@ def init(backend: str = None):
         backend = backend or ("nccl" if torch.cuda.is_available() else "gloo")
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         os.environ.setdefault("MASTER_PORT", "29500")
+        kw = {}
         if backend == "nccl":
             torch.cuda.set_device(local)
-        dist.init_process_group(backend=backend, rank=rank, world_size=ws)
+            kw["device_id"] = torch.device("cuda", local)      # binds the communicator to this rank's GPU (no device guessing)
+        dist.init_process_group(backend=backend, rank=rank, world_size=ws, **kw)
     return rank, ws, local
 
 
