@@ -131,6 +131,9 @@ __device__ long long g_trace[1024];
 #define DMN_TC_TRACE_PRODUCER 0     // 1: also account the producers' wait clocks (slots 14 / 15); costs registers in the hot role
 #endif
 constexpr bool kTraceProducer = DMN_TC_TRACE_PRODUCER != 0;
+#ifndef DMN_EXP_ZFILL_PLAIN
+#define DMN_EXP_ZFILL_PLAIN 0
+#endif
 #ifndef DMN_EXP_ZFILL
 #define DMN_EXP_ZFILL 1
 #endif
@@ -760,7 +763,7 @@ __global__ void __launch_bounds__((PW + EW + 2) * 32, 1) conv_tcgen05_kernel(con
         const uint32_t dst0 = sA_u + ibuf * a_bytes + (uint32_t)kc * p.lbo_a + (uint32_t)px0 * 16u;
         // measured: the predicated zero-fill form wins when the fused prologue follows (-0.003 ms on the level-0 GroupNorm convs)
         // and loses for plain copies (+0.004 ms), so plain operands keep the branchy issue
-        if (GEO == GEO_DOWN || !DMN_EXP_ZFILL || !has_pro) {
+        if (GEO == GEO_DOWN || !DMN_EXP_ZFILL || (!has_pro && !DMN_EXP_ZFILL_PLAIN)) {
 #pragma unroll
           for (int j = 0; j < kMaxItems; ++j) {
             if (goff[j] < -1) continue;                  // outside the window

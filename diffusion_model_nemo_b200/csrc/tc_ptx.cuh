@@ -83,7 +83,11 @@ __device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t cols) {
 __device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols) {
   asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
 }
+#ifndef DMN_EXP_NO_MMA
+#define DMN_EXP_NO_MMA 0     // timing probe (results are wrong): the issuer runs every handshake but no tcgen05.mma is issued
+#endif
 __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  if (DMN_EXP_NO_MMA) return;
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
       "setp.ne.b32 p, %4, 0;\n\t"

@@ -64,8 +64,8 @@ def run(k, cin, cout, h, b, gn, mode=0):
 if __name__ == "__main__" and os.environ.get("TRACE_SHAPES"):
     # TRACE_SHAPES="k,cin,cout,h,b,gn;..."
     for spec in os.environ["TRACE_SHAPES"].split(";"):
-        k, cin, cout, h, b, gn = (int(v) for v in spec.split(","))
-        run(k, cin, cout, h, b, bool(gn))
+        k, cin, cout, h, b, gn, *rest = (int(v) for v in spec.split(","))
+        run(k, cin, cout, h, b, bool(gn), mode=rest[0] if rest else 0)
     sys.exit(0)
 if __name__ == "__main__" and os.environ.get("TRACE_QUICK"):
     run(3, 128, 128, 32, 256, False)
