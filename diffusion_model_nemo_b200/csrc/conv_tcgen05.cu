@@ -40,6 +40,7 @@
 //
 // Garbage rows: flat positions that fall on a pad column/row are computed and discarded (1 - HW/S of the MMA
 // work for 3x3: 6 % at 32x32, 11 % at 16x16, 21 % at 8x8, 36 % at 4x4).
+#include <cuda.h>     // CUtensorMap (type and enums only; the encoder is fetched through cudaGetDriverEntryPoint)
 #include <cstdlib>
 #include <cstring>
 #include <type_traits>
@@ -119,6 +120,12 @@ struct Params {
   const float* cls_w;
   const int64_t* classes;
   int pad_class;
+  // TMA operand path (ATMA instantiations): the window of a pass is ONE cp.async.bulk.tensor im2col copy of P pixels x 32 channels into
+  // a SWIZZLE_64B tile [P rows][64 B]; tap offsets / descriptor strides below are then in that layout
+  int atma;                // 1: launch an ATMA instantiation
+  uint32_t a_bytes;        // one operand buffer (both layouts)
+  uint32_t a_half;         // 16-byte units between the two 128-row halves of a 256-row tile (128 | 512)
+  alignas(64) CUtensorMap tm_a1, tm_a2;   // im2col views of src1 / src2
 };
 
 // debug timeline (DMN_TC_TRACE=1): CTA `trace_cta` records clock64 per role and tile: slot = 16*tile_iter + k
@@ -338,7 +345,7 @@ __device__ __forceinline__ void commit_stage(uint32_t bar, uint32_t cmask) {
 template <int G, bool TWO>
 __device__ __forceinline__ void issue_stage(const Params& p, bool leader, uint32_t d0, uint32_t d1, uint32_t au, uint32_t bs, int didx, int t0,
                                             uint32_t acc0, uint32_t idesc, uint32_t hi_a, uint32_t hi_b, uint32_t lbo_a_f, uint32_t lbo_b_f,
-                                            uint32_t a_k16, uint32_t b_k16, uint32_t b_tap_units) {
+                                            uint32_t a_k16, uint32_t b_k16, uint32_t b_tap_units, uint32_t a_half) {
   uint64_t ad[G][4], bd[G][2];
 #pragma unroll
   for (int g = 0; g < G; ++g) {
@@ -347,9 +354,9 @@ __device__ __forceinline__ void issue_stage(const Params& p, bool leader, uint32
     bd[g][0] = ((uint64_t)hi_b << 32) | ((b0 & 0x3FFFu) | lbo_b_f);
     bd[g][1] = ((uint64_t)hi_b << 32) | (((b0 + b_k16) & 0x3FFFu) | lbo_b_f);
     ad[g][0] = ((uint64_t)hi_a << 32) | ((a0 & 0x3FFFu) | lbo_a_f);
-    ad[g][1] = ((uint64_t)hi_a << 32) | (((a0 + 128u) & 0x3FFFu) | lbo_a_f);
+    ad[g][1] = ((uint64_t)hi_a << 32) | (((a0 + a_half) & 0x3FFFu) | lbo_a_f);
     ad[g][2] = ((uint64_t)hi_a << 32) | (((a0 + a_k16) & 0x3FFFu) | lbo_a_f);
-    ad[g][3] = ((uint64_t)hi_a << 32) | (((a0 + a_k16 + 128u) & 0x3FFFu) | lbo_a_f);
+    ad[g][3] = ((uint64_t)hi_a << 32) | (((a0 + a_k16 + a_half) & 0x3FFFu) | lbo_a_f);
   }
   if (leader) {
 #pragma unroll
@@ -371,10 +378,10 @@ __device__ __forceinline__ void issue_stage(const Params& p, bool leader, uint32
 // is < 256 KB, so (address >> 4) never carries into the LBO field and no masking is needed.
 template <bool TWO>
 __device__ __forceinline__ void issue_tap(bool leader, uint32_t d0, uint32_t d1, uint32_t a_lo, uint32_t b_lo, uint32_t hi_a, uint32_t hi_b,
-                                          uint32_t a_k16, uint32_t b_k16, uint32_t idesc, uint32_t acc) {
+                                          uint32_t a_k16, uint32_t b_k16, uint32_t idesc, uint32_t acc, uint32_t a_half) {
   const uint64_t bd0 = ((uint64_t)hi_b << 32) | b_lo, bd1 = ((uint64_t)hi_b << 32) | (b_lo + b_k16);
   const uint64_t ad00 = ((uint64_t)hi_a << 32) | a_lo, ad10 = ((uint64_t)hi_a << 32) | (a_lo + a_k16);
-  const uint64_t ad01 = ((uint64_t)hi_a << 32) | (a_lo + 128u), ad11 = ((uint64_t)hi_a << 32) | (a_lo + a_k16 + 128u);
+  const uint64_t ad01 = ((uint64_t)hi_a << 32) | (a_lo + a_half), ad11 = ((uint64_t)hi_a << 32) | (a_lo + a_k16 + a_half);
   if (leader) {
     umma_bf16(d0, ad00, bd0, idesc, acc);
     if (TWO) umma_bf16(d1, ad01, bd0, idesc, acc);
@@ -387,7 +394,7 @@ template <int NTAP, int GG, bool TWO>
 __device__ __forceinline__ void issue_pass(bool leader, uint32_t d0, uint32_t d1, uint32_t au_lo, const int (&dl)[NTAP], uint32_t b_lo0,
                                            uint32_t b_stage_units, uint32_t b_tap_units, uint32_t hi_a, uint32_t hi_b, uint32_t a_k16,
                                            uint32_t b_k16, uint32_t idesc, uint32_t acc_first, uint64_t* full_b, uint64_t* empty_b, int nst,
-                                           int& st, uint32_t& ph, uint32_t cmask = 1u) {
+                                           int& st, uint32_t& ph, uint32_t a_half, uint32_t cmask = 1u) {
 #pragma unroll
   for (int s = 0; s < NTAP / GG; ++s) {
     mbar_wait(smem_u32(&full_b[st]), ph);
@@ -396,7 +403,7 @@ __device__ __forceinline__ void issue_pass(bool leader, uint32_t d0, uint32_t d1
 #pragma unroll
     for (int g = 0; g < GG; ++g)
       issue_tap<TWO>(leader, d0, d1, au_lo + (uint32_t)dl[s * GG + g], b_lo + (uint32_t)g * b_tap_units, hi_a, hi_b, a_k16, b_k16, idesc,
-                     (s | g) ? 1u : acc_first);
+                     (s | g) ? 1u : acc_first, a_half);
     if (leader) commit_stage(smem_u32(&empty_b[st]), cmask);     // frees the weight stage once these MMAs retire
     __syncwarp();
     if (++st == nst) { st = 0; ph ^= 1; }
@@ -462,8 +469,10 @@ __device__ __forceinline__ void issue_pass_swap(bool leader, uint32_t d, uint32_
 //     tiles of the launch are stored and their GroupNorm statistics complete, each CTA walks its own tiles again (they are still in L2)
 //     and writes SiLU(GroupNorm(out)) + residual -- the pass that used to be a separate gn_finalize launch reading the raw output from HBM.
 template <int GEO, int NT, bool FILM = false, bool LEAN = false, bool EXTRA = true, int PRO = 2, int EW = kEpiWarps, bool SWAP = false, int PW = 8,
-          bool TAIL = false>
-__global__ void __launch_bounds__((PW + EW + 2) * 32, 1) conv_tcgen05_kernel(const Params p) {
+          bool TAIL = false, bool ATMA = false>
+__global__ void __launch_bounds__((PW + EW + 2) * 32, 1) conv_tcgen05_kernel(const __grid_constant__ Params p) {
+  static_assert(!ATMA || (NT == 128 && !FILM && !EXTRA && !SWAP && !TAIL && PW == 8 && (PRO == 0 || PRO == 1) && GEO != GEO_INIT),
+                "TMA operand path: the hot 128-column instantiations");
   static_assert(!TAIL || (GEO == GEO_SAME && NT == 128 && PRO == 1 && !EXTRA && !SWAP), "fused block tail: the GroupNorm-prologue 3x3 instantiations");
   static_assert(!SWAP || (NT == 128 && !EXTRA && !FILM && GEO != GEO_INIT), "swapped operand roles: hot 128-channel instantiations only");
   static_assert(PW == 8 || (PW == 16 && EW == 8 && PRO == 1), "16 producer warps: the GroupNorm-prologue instantiations");
@@ -475,7 +484,7 @@ __global__ void __launch_bounds__((PW + EW + 2) * 32, 1) conv_tcgen05_kernel(con
   static_assert(AB <= kABufMax && DEPTH >= 1 && DEPTH <= 3 && AB >= DEPTH + 2, "operand ring geometry");
   static_assert(EW == 8 || (EW == 16 && NT == 128 && (PRO == 0 || PRO == 3)), "16 epilogue warps: 128-column tiles without prologue");
   static_assert(!(LEAN && PRO == 3), "the lean issue path is for 9- and 4-tap convolutions");
-  extern __shared__ __align__(128) uint8_t smem[];
+  extern __shared__ __align__(1024) uint8_t smem[];
   const int tid = threadIdx.x;
   if (DMN_TC_TRACE_BUILD && p.trace && blockIdx.x == (unsigned)p.trace_cta && tid == 0) p.trace[1000] = clock64();     // kernel entry
   // broadcast => ptxas knows the role branches below are warp-uniform and may use the uniform datapath inside them
@@ -483,7 +492,7 @@ __global__ void __launch_bounds__((PW + EW + 2) * 32, 1) conv_tcgen05_kernel(con
   const int nst = p.nstage;
 
   // ---- shared memory carve-up ----
-  const uint32_t a_bytes = 4u * p.PA * 16u;           // one A buffer (4 k-chunks)
+  const uint32_t a_bytes = p.a_bytes;                 // one A buffer (4 k-chunks x PA rows x 16 B, or P rows x 64 B rounded to 1 KB)
   const uint32_t tap_bytes = 4u * NT * 16u;           // weights of one tap of one pass
   const uint32_t b_bytes = p.stage_bytes;             // one B stage (G taps)
   uint8_t* sA = smem;
@@ -493,7 +502,8 @@ __global__ void __launch_bounds__((PW + EW + 2) * 32, 1) conv_tcgen05_kernel(con
   uint64_t* empty_b = bars + kStagesMax;
   uint64_t* full_a = bars + 2 * kStagesMax;
   uint64_t* empty_a = full_a + kABufMax;
-  uint64_t* acc_full = empty_a + kABufMax;
+  uint64_t* raw_a = empty_a + kABufMax;               // ATMA with prologue: "the TMA copy of this buffer has landed"
+  uint64_t* acc_full = raw_a + kABufMax;
   uint64_t* acc_empty = acc_full + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
   float2* s_gn = reinterpret_cast<float2*>(tmem_slot + 2);                                  // [kNimgMax][kGroupsMax] (mean, rstd)
@@ -508,7 +518,11 @@ __global__ void __launch_bounds__((PW + EW + 2) * 32, 1) conv_tcgen05_kernel(con
   // ---- one-time setup ----
   if (warp == kLoaderW) {          // one lane per barrier
     if (lane < nst) { mbar_init(smem_u32(&full_b[lane]), 1); mbar_init(smem_u32(&empty_b[lane]), (uint32_t)p.cl); }
-    if (lane >= 16 && lane < 16 + AB) { mbar_init(smem_u32(&full_a[lane - 16]), kProdThreads); mbar_init(smem_u32(&empty_a[lane - 16]), 1); }
+    if (lane >= 16 && lane < 16 + AB) {
+      mbar_init(smem_u32(&full_a[lane - 16]), (ATMA && PRO == 0) ? 1 : kProdThreads);
+      mbar_init(smem_u32(&empty_a[lane - 16]), 1);
+      mbar_init(smem_u32(&raw_a[lane - 16]), 1);
+    }
     if (lane >= 24 && lane < 26) { mbar_init(smem_u32(&acc_full[lane - 24]), 1); mbar_init(smem_u32(&acc_empty[lane - 24]), kEpiT); }
     fence_barrier_init();
   }
@@ -530,7 +544,10 @@ __global__ void __launch_bounds__((PW + EW + 2) * 32, 1) conv_tcgen05_kernel(con
     // visible to the tensor core (async proxy) and arrive on the buffer's barrier.  Global latency is thereby covered by
     // kDepth passes in flight without staging the raw data in registers.
     pdl_wait();                                       // activations / statistics of the previous kernel are complete
-    const int kc = tid & 3, px0 = tid >> 2;          // k-chunk, first window pixel of this thread (step 64)
+    const int pc = tid & 3, px0 = tid >> 2;          // 16-byte chunk position in the row / k-chunk plane, first window pixel (step 64)
+    // ATMA: the SWIZZLE_64B tile holds k-chunk (pc ^ ((row >> 1) & 3)) at chunk position pc of a row; the thread's rows are px0 + 64 j,
+    // so that is one k-chunk for all of its items
+    const int kc = ATMA ? (pc ^ ((px0 >> 1) & 3)) : pc;
     const bf16* src1 = (const bf16*)p.c.src1;
     const bf16* src2 = (const bf16*)p.c.src2;
     const float* temb_base = nullptr;
@@ -546,13 +563,57 @@ __global__ void __launch_bounds__((PW + EW + 2) * 32, 1) conv_tcgen05_kernel(con
       }
     }
     const uint32_t sA_u = smem_u32(sA);
+    // ATMA: one im2col copy per pass.  (w, h, n) = tensor coordinates of the window's first position (decoded per tile)
+    int tw = 0, th = 0, tn = 0;
+    auto tma_window = [&](int c, int buf, uint64_t* bars_) {
+      int cb = c * kCk;
+      uint16_t ow = 0, oh = 0;
+      const void* map = &p.tm_a1;
+      if (GEO == GEO_DOWN) {
+        const int sub = cb / p.c.C1;
+        cb -= sub * p.c.C1;
+        oh = (uint16_t)(sub >> 1);
+        ow = (uint16_t)(sub & 1);
+      } else if (cb >= p.c.C1) {
+        cb -= p.c.C1;
+        map = &p.tm_a2;
+      }
+      const uint32_t bar = smem_u32(&bars_[buf]);
+      mbar_arrive_expect_tx(bar, (uint32_t)p.P * 64u);
+      tma_load_im2col_4d(sA_u + (uint32_t)buf * a_bytes, map, cb, tw, th, tn, bar, ow, oh);
+    };
+    auto tma_tile_coords = [&](int m0) {
+      const int f = m0 - p.halo_lo;
+      tn = f >= 0 ? f / p.S : -1;                      // halo_lo < S: a negative start lies in "image -1" (all zeros)
+      const int rem = f - tn * p.S;
+      const int row = rem / p.Wv, col = rem - row * p.Wv;
+      if (GEO == GEO_DOWN) { tw = 2 * col - 1; th = 2 * row - 1; }
+      else { tw = col - p.pad; th = row - p.pad; }
+    };
+    if constexpr (ATMA && PRO == 0) {
+      // plain operands: nothing to transform -- one thread feeds the ring, the tensor core consumes the tiles as the copies land
+      if (tid == 0) {
+        int ibuf = 0;
+        uint32_t iph = 1;
+        for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+          tma_tile_coords(tile_geom(tile, p).m0);
+          for (int c = 0; c < p.n_pass; ++c) {
+            mbar_wait_relaxed(smem_u32(&empty_a[ibuf]), iph);
+            tma_window(c, ibuf, full_a);
+            if (++ibuf == AB) { ibuf = 0; iph ^= 1; }
+          }
+        }
+      }
+    } else {
     int ibuf = 0, fbuf = 0;
+    uint32_t rph = 0;                                  // ATMA: parity of the "copy has landed" wait
     uint32_t iph = 1;                                  // parity of the "buffer is free" wait; flips when the ring wraps
     int pit = 0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++pit) {
       if (tid == 0) TRACE(pit, 0);
       const TileGeom tg = tile_geom(tile, p);
       const int m0 = tg.m0;
+      if constexpr (ATMA) tma_tile_coords(m0);
       const int Pt = tg.mt * 128 + p.halo_lo + p.halo_hi;       // window of THIS tile
       int f_lo = m0 - p.halo_lo;
       if (f_lo < 0) f_lo = 0;
@@ -652,6 +713,7 @@ __global__ void __launch_bounds__((PW + EW + 2) * 32, 1) conv_tcgen05_kernel(con
 
       // finish pass c (in buffer fbuf): prologue in place on this thread's own items, publish to the tensor core
       auto finish = [&](int c) {
+        if constexpr (ATMA) mbar_wait(smem_u32(&raw_a[fbuf]), rph);      // the window of this pass has landed
         if (has_pro) {
           const int cb = c * kCk + kc * 8;
           float ga[8], be[8], te[8];
@@ -664,7 +726,7 @@ __global__ void __launch_bounds__((PW + EW + 2) * 32, 1) conv_tcgen05_kernel(con
             te[0] = t0.x; te[1] = t0.y; te[2] = t0.z; te[3] = t0.w; te[4] = t1.x; te[5] = t1.y; te[6] = t1.z; te[7] = t1.w;
           }
           const int g = cb >> p.cpg_in_shift;
-          uint8_t* base = sA + fbuf * a_bytes + (uint32_t)kc * p.lbo_a;
+          uint8_t* base = ATMA ? sA + fbuf * a_bytes + (uint32_t)pc * 16u : sA + fbuf * a_bytes + (uint32_t)kc * p.lbo_a;
           // packed fp32x2 arithmetic (FFMA2 / FADD2).  hx = t / 2 with t = GroupNorm affine: the halving is folded into gamma / beta
           // (exact: a power of two), SiLU(t) = hx * tanh(hx) + hx is one MUFU per element
           unsigned long long gah2[4], beh2[4], te2[4];
@@ -681,7 +743,7 @@ __global__ void __launch_bounds__((PW + EW + 2) * 32, 1) conv_tcgen05_kernel(con
           auto do_item = [&](int j, bool check) {
             if (DMN_EXP_PRO_COST == 3) return;
             if (check && goff[j] < 0) return;
-            uint4* slot = reinterpret_cast<uint4*>(base + (px0 + (kProdThreads / 4) * j) * 16);
+            uint4* slot = reinterpret_cast<uint4*>(base + (px0 + (kProdThreads / 4) * j) * (ATMA ? 64 : 16));
             if (DMN_EXP_PRO_COST == 2) { uint4 t = *slot; t.x ^= 0x00010001u; *slot = t; return; }
             const float2 mr = FILM ? make_float2(0.f, 1.f) : s_gn[imgl[j] * kGroupsMax + g];
             if ((p.c.pro & PRO_TEMB) && !temb_shared) {
@@ -737,7 +799,7 @@ __global__ void __launch_bounds__((PW + EW + 2) * 32, 1) conv_tcgen05_kernel(con
         }
         if (DMN_EXP_FENCE_MODE == 0) fence_proxy_async();
         mbar_arrive(smem_u32(&full_a[fbuf]));
-        if (++fbuf == AB) fbuf = 0;
+        if (++fbuf == AB) { fbuf = 0; rph ^= 1; }
       };
 
       int inflight = 0;
@@ -745,6 +807,14 @@ __global__ void __launch_bounds__((PW + EW + 2) * 32, 1) conv_tcgen05_kernel(con
       long long wait_e = 0, wait_g = 0, t_issue = 0, t_fin = 0;
       for (int c = 0; c < p.n_pass; ++c) {
         long long w0 = ptracing ? clock64() : 0;
+        if constexpr (ATMA) {
+          // one thread waits for the free buffer and issues the window copy; everybody meets the data at the raw_a barrier in finish()
+          if (tid == 0) {
+            mbar_wait_relaxed(smem_u32(&empty_a[ibuf]), iph);
+            if (ptracing) wait_e += clock64() - w0;
+            tma_window(c, ibuf, raw_a);
+          }
+        } else {
         mbar_wait_relaxed(smem_u32(&empty_a[ibuf]), iph);
         if (ptracing) wait_e += clock64() - w0;
         const long long wi0 = ptracing ? clock64() : 0;
@@ -794,10 +864,11 @@ __global__ void __launch_bounds__((PW + EW + 2) * 32, 1) conv_tcgen05_kernel(con
         }
         cp_async_commit();
         if (ptracing) t_issue += clock64() - wi0;
+        }   // !ATMA
         if (++ibuf == AB) { ibuf = 0; iph ^= 1; }
         if (++inflight > DEPTH) {
           w0 = ptracing ? clock64() : 0;
-          cp_async_wait<DEPTH>();
+          if constexpr (!ATMA) cp_async_wait<DEPTH>();
           if (ptracing) wait_g += clock64() - w0;
           const long long wf0 = ptracing ? clock64() : 0;
           finish(c - DEPTH);
@@ -808,21 +879,22 @@ __global__ void __launch_bounds__((PW + EW + 2) * 32, 1) conv_tcgen05_kernel(con
       if (ptracing) { p.trace[16 * pit + 14] = wait_e; p.trace[16 * pit + 15] = wait_g; p.trace[16 * pit + 3] = t_issue; p.trace[16 * pit + 7] = t_fin; }
       // drain: the last passes of the tile
       if (DEPTH >= 3 && inflight == 3) {
-        cp_async_wait<2>();
+        if constexpr (!ATMA) cp_async_wait<2>();
         finish(p.n_pass - 3);
         --inflight;
       }
       if (DEPTH >= 2 && inflight == 2) {
-        cp_async_wait<1>();
+        if constexpr (!ATMA) cp_async_wait<1>();
         finish(p.n_pass - 2);
         --inflight;
       }
       if (inflight == 1) {
-        cp_async_wait<0>();
+        if constexpr (!ATMA) cp_async_wait<0>();
         finish(p.n_pass - 1);
       }
       if (tid == 0) TRACE(pit, 2);
     }
+    }   // !(ATMA && PRO == 0)
   } else if (warp < kLoaderW) {
     // =============================== epilogue ===============================
     // register pool of the CTA: the 8 producer warps release 8 x 32 x (72 - 40) = 8192 registers, exactly what 16 epilogue warps need to
@@ -1256,11 +1328,15 @@ __global__ void __launch_bounds__((PW + EW + 2) * 32, 1) conv_tcgen05_kernel(con
     const uint32_t idesc = make_idesc(128, NT);
     const uint32_t idesc_s2 = make_idesc(128, 256), idesc_s1 = make_idesc(128, 128);     // SWAP: N = pixels of the tile
     const uint32_t cmask = (1u << p.cl) - 1u;
-    const uint32_t hi_a = (p.sbo_a >> 4) | (1u << 14), hi_b = (p.sbo_b >> 4) | (1u << 14);
-    const uint32_t lbo_a_f = ((p.lbo_a >> 4) & 0x3FFFu) << 16, lbo_b_f = ((p.lbo_b >> 4) & 0x3FFFu) << 16;
-    const uint32_t a_units0 = (smem_u32(sA) >> 4) + (uint32_t)p.halo_lo;          // 16-byte units
+    // ATMA: the operand tile is [P rows][64 B] SWIZZLE_64B (layout type 4 in descriptor bits 61-63, SBO = 512 B between 8-row groups,
+    // LBO unused); a k16 step is 32 B inside the row, a tap offset of d rows is d * 64 B.  The swizzle is a function of the absolute
+    // shared-memory address (buffers are 1 KB aligned), so the shifted views need no base-offset field (tools/micro/im2col_umma_test.cu)
+    const uint32_t hi_a = ATMA ? ((512u >> 4) | (1u << 14) | (4u << 29)) : ((p.sbo_a >> 4) | (1u << 14)), hi_b = (p.sbo_b >> 4) | (1u << 14);
+    const uint32_t lbo_a_f = ATMA ? (1u << 16) : (((p.lbo_a >> 4) & 0x3FFFu) << 16), lbo_b_f = ((p.lbo_b >> 4) & 0x3FFFu) << 16;
+    const uint32_t a_units0 = (smem_u32(sA) >> 4) + (uint32_t)p.halo_lo * (ATMA ? 4u : 1u);          // 16-byte units
     const uint32_t a_buf_units = a_bytes >> 4;
-    const uint32_t a_k16 = 2u * (p.lbo_a >> 4);
+    const uint32_t a_k16 = ATMA ? 2u : 2u * (p.lbo_a >> 4);
+    const uint32_t a_half = p.a_half;
     const uint32_t b_units0 = smem_u32(sB) >> 4, b_stage_units = b_bytes >> 4, b_tap_units = tap_bytes >> 4, b_k16 = 2u * (p.lbo_b >> 4);
     const int G = p.G;
     int st = 0, cbuf = 0, it = 0;
@@ -1307,14 +1383,14 @@ __global__ void __launch_bounds__((PW + EW + 2) * 32, 1) conv_tcgen05_kernel(con
         } else if constexpr (lean9 || lean4) {
           const uint32_t au_lo = au | lbo_a_f, acc0 = c ? 1u : 0u;
           if constexpr (lean9) {
-            if (two) issue_pass<9, 3, true>(leader, d0, d1, au_lo, dl9, b_lo0, b_stage_units, b_tap_units, hi_a, hi_b, a_k16, b_k16, idesc, acc0, full_b, empty_b, nst, st, ph);
-            else issue_pass<9, 3, false>(leader, d0, d1, au_lo, dl9, b_lo0, b_stage_units, b_tap_units, hi_a, hi_b, a_k16, b_k16, idesc, acc0, full_b, empty_b, nst, st, ph);
+            if (two) issue_pass<9, 3, true>(leader, d0, d1, au_lo, dl9, b_lo0, b_stage_units, b_tap_units, hi_a, hi_b, a_k16, b_k16, idesc, acc0, full_b, empty_b, nst, st, ph, a_half);
+            else issue_pass<9, 3, false>(leader, d0, d1, au_lo, dl9, b_lo0, b_stage_units, b_tap_units, hi_a, hi_b, a_k16, b_k16, idesc, acc0, full_b, empty_b, nst, st, ph, a_half);
           } else {
             int dl4[4];
 #pragma unroll
             for (int t = 0; t < 4; ++t) dl4[t] = p.delta[phase * 16 + t];
-            if (two) issue_pass<4, 2, true>(leader, d0, d1, au_lo, dl4, b_lo0, b_stage_units, b_tap_units, hi_a, hi_b, a_k16, b_k16, idesc, acc0, full_b, empty_b, nst, st, ph);
-            else issue_pass<4, 2, false>(leader, d0, d1, au_lo, dl4, b_lo0, b_stage_units, b_tap_units, hi_a, hi_b, a_k16, b_k16, idesc, acc0, full_b, empty_b, nst, st, ph);
+            if (two) issue_pass<4, 2, true>(leader, d0, d1, au_lo, dl4, b_lo0, b_stage_units, b_tap_units, hi_a, hi_b, a_k16, b_k16, idesc, acc0, full_b, empty_b, nst, st, ph, a_half);
+            else issue_pass<4, 2, false>(leader, d0, d1, au_lo, dl4, b_lo0, b_stage_units, b_tap_units, hi_a, hi_b, a_k16, b_k16, idesc, acc0, full_b, empty_b, nst, st, ph, a_half);
           }
         } else
         for (int s = 0; s < p.stages_per_pass; ++s) {
@@ -1344,9 +1420,9 @@ __global__ void __launch_bounds__((PW + EW + 2) * 32, 1) conv_tcgen05_kernel(con
               const uint64_t bd0 = ((uint64_t)hi_b << 32) | ((b0 & 0x3FFFu) | lbo_b_f);
               const uint64_t bd1 = ((uint64_t)hi_b << 32) | (((b0 + b_k16) & 0x3FFFu) | lbo_b_f);
               const uint64_t ad00 = ((uint64_t)hi_a << 32) | ((a0 & 0x3FFFu) | lbo_a_f);
-              const uint64_t ad01 = ((uint64_t)hi_a << 32) | (((a0 + 128u) & 0x3FFFu) | lbo_a_f);
+              const uint64_t ad01 = ((uint64_t)hi_a << 32) | (((a0 + a_half) & 0x3FFFu) | lbo_a_f);
               const uint64_t ad10 = ((uint64_t)hi_a << 32) | (((a0 + a_k16) & 0x3FFFu) | lbo_a_f);
-              const uint64_t ad11 = ((uint64_t)hi_a << 32) | (((a0 + a_k16 + 128u) & 0x3FFFu) | lbo_a_f);
+              const uint64_t ad11 = ((uint64_t)hi_a << 32) | (((a0 + a_k16 + a_half) & 0x3FFFu) | lbo_a_f);
               if (leader) {
                 umma_bf16(d0, ad00, bd0, idesc, acc);
                 umma_bf16(d1, ad01, bd0, idesc, acc);
@@ -1355,9 +1431,9 @@ __global__ void __launch_bounds__((PW + EW + 2) * 32, 1) conv_tcgen05_kernel(con
               }
             }
           } else {
-            if (G == 3) issue_stage<3, false>(p, leader, d0, d1, au, bs, phase * 16 + t0, t0, acc0, idesc, hi_a, hi_b, lbo_a_f, lbo_b_f, a_k16, b_k16, b_tap_units);
-            else if (G == 2) issue_stage<2, false>(p, leader, d0, d1, au, bs, phase * 16 + t0, t0, acc0, idesc, hi_a, hi_b, lbo_a_f, lbo_b_f, a_k16, b_k16, b_tap_units);
-            else issue_stage<1, false>(p, leader, d0, d1, au, bs, phase * 16 + t0, t0, acc0, idesc, hi_a, hi_b, lbo_a_f, lbo_b_f, a_k16, b_k16, b_tap_units);
+            if (G == 3) issue_stage<3, false>(p, leader, d0, d1, au, bs, phase * 16 + t0, t0, acc0, idesc, hi_a, hi_b, lbo_a_f, lbo_b_f, a_k16, b_k16, b_tap_units, a_half);
+            else if (G == 2) issue_stage<2, false>(p, leader, d0, d1, au, bs, phase * 16 + t0, t0, acc0, idesc, hi_a, hi_b, lbo_a_f, lbo_b_f, a_k16, b_k16, b_tap_units, a_half);
+            else issue_stage<1, false>(p, leader, d0, d1, au, bs, phase * 16 + t0, t0, acc0, idesc, hi_a, hi_b, lbo_a_f, lbo_b_f, a_k16, b_k16, b_tap_units, a_half);
           }
           if (leader) commit_stage(smem_u32(&empty_b[st]), cmask);     // frees the weight stage once these MMAs retire
           __syncwarp();
@@ -1516,7 +1592,7 @@ __global__ void __launch_bounds__((PW + EW + 2) * 32, 1) conv_tcgen05_kernel(con
 
 static size_t smem_fixed_bytes(const Params& p) {
   const int ncol = p.NT >= 64 ? p.NT / 2 : p.NT;
-  return (size_t)p.abuf * 4 * p.PA * 16 + (2 * kStagesMax + 2 * kABufMax + 4) * 8 + 16 + (size_t)kNimgMax * kGroupsMax * 8 +
+  return (size_t)p.abuf * p.a_bytes + (2 * kStagesMax + 3 * kABufMax + 4) * 8 + 16 + (size_t)kNimgMax * kGroupsMax * 8 +
          2 * (size_t)p.P * 4 + 128 + (p.c.pro != PRO_NONE ? 3 * (size_t)p.c.C1 * 4 + 16 : 0) + (size_t)kEpiWarps * (32 * ncol * 2 + ncol * 8) + 128 +
          2 * (size_t)p.c.Cout * 4 + (p.c.fold_s1 ? (size_t)p.c.B * 8 : 0) + 32;
 }
@@ -1562,6 +1638,41 @@ static bool cluster_enabled() {
                                             // shared-memory port is) and one unit test (3x3 128->128 @16x16, batch 2) does not pass with it.
   }();
   return on;
+}
+
+// ---- TMA operand path ----
+typedef CUresult (*EncodeIm2colFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const int*, const int*, cuuint32_t,
+                                   cuuint32_t, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeIm2colFn im2col_encoder() {
+  static const EncodeIm2colFn fn = [] {
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeIm2col", &f, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) f = nullptr;
+    return (EncodeIm2colFn)f;
+  }();
+  return fn;
+}
+static bool atma_enabled() {
+  static const bool on = [] {
+    const char* e = getenv("DMN_CONV_TMA");
+    return !(e && e[0] == '0') && im2col_encoder() != nullptr;      // DMN_CONV_TMA=0: the cp.async operand producers (A/B comparison)
+  }();
+  return on;
+}
+// im2col view of one NHWC bf16 source whose traversal order IS the engine's flat padded position order: the bounding box adds the pad
+// column / row in front (lower corner -1; nothing behind: upper corner 0), stride-2 traversal for the k4s2 form; positions outside the
+// tensor (pads, images < 0 or >= B) arrive as zeros.  One copy = P positions x 32 channels, SWIZZLE_64B rows of 64 bytes
+static bool encode_window_map(CUtensorMap* m, const void* src, int C, int B, int H, int W, int geo, int pad, int P) {
+  EncodeIm2colFn fn = im2col_encoder();
+  if (!fn || !src || (reinterpret_cast<uintptr_t>(src) & 15)) return false;
+  cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+  cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
+  const int lo = geo == GEO_DOWN ? -1 : -pad;
+  int lower[2] = {lo, lo}, upper[2] = {0, 0};
+  const cuuint32_t step = geo == GEO_DOWN ? 2 : 1;
+  cuuint32_t estr[4] = {1, step, step, 1};
+  return fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(src), dims, strides, lower, upper, (cuuint32_t)kCk, (cuuint32_t)P, estr,
+            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
 static bool fill_params(const ConvP& c, int geo, Params& p) {
@@ -1667,6 +1778,9 @@ static bool fill_params(const ConvP& c, int geo, Params& p) {
   if (kMcta / p.S + 3 > kNimgMax || p.S < 16) return false;
   p.lbo_a = (uint32_t)p.PA * 16u;
   p.sbo_a = 128u;
+  p.a_bytes = 4u * (uint32_t)p.PA * 16u;
+  p.a_half = 128u;
+  p.atma = 0;
   p.lbo_b = (uint32_t)p.NT * 16u;
   p.sbo_b = 128u;
   p.tmem_cols = 32;
@@ -1715,6 +1829,25 @@ static bool fill_params(const ConvP& c, int geo, Params& p) {
     p.abuf = DMN_EXP_PLAIN_ABUF;
   // the GroupNorm-prologue instantiation (PRO = 1) is launched for 128-column tiles without residual / fold / FiLM (launch<>)
   if (geo == GEO_SAME && p.NT == 128 && c.pro != PRO_NONE && !(c.pro & PRO_LRELU) && !c.res && !c.fold_s1) p.abuf = kABufPro;
+  // TMA operand path: the hot instantiations (launch<>: 128-column tiles, 3x3 / k4s2 / transposed k4s2, no FiLM / residual / fold terms)
+  const bool hot = geo != GEO_INIT && p.NT == 128 && !(c.pro & PRO_LRELU) && !c.res && !c.fold_s1 && !c.fin_out && !swap_enabled() &&
+                   ((geo == GEO_SAME && p.ntap == 9) || geo == GEO_DOWN || geo == GEO_UP);
+  if (hot && atma_enabled() && p.P <= 1024 && p.halo_lo < p.S) {
+    Params q = p;
+    q.atma = 1;
+    q.a_bytes = ((uint32_t)q.P * 64u + 1023u) & ~1023u;
+    q.a_half = 512u;
+    for (int i = 0; i < 64; ++i) q.delta[i] *= 4;               // tap offsets in 16-byte units: one row of the tile is 64 bytes
+    bool ok = pick_stages(q);
+    if (ok && c.src1) {          // (shape queries come without pointers)
+      ok = encode_window_map(&q.tm_a1, c.src1, c.C1, c.B, c.Hin, c.Win, geo, q.pad, q.P);
+      if (ok && c.C2 > 0) ok = encode_window_map(&q.tm_a2, c.src2, c.C2, c.B, c.Hin, c.Win, geo, q.pad, q.P);
+    }
+    if (ok) {
+      p = q;
+      return true;
+    }
+  }
   return pick_stages(p);
 }
 
@@ -1845,6 +1978,21 @@ static int launch(Params p, cudaStream_t st) {
         else
           DMN_CUDA_CHECK(launch_kernel(conv_tcgen05_kernel<GEO_SAME, 128, false, false, false, 0, 16, true>, grid, kThreads16, p, st));
       } else DMN_CUDA_CHECK(launch_kernel(conv_tcgen05_kernel<G2, 128, false, false, false, 0, 8, true>, grid, kThreads, p, st));
+      count_launch();
+      DMN_LAUNCH_CHECK("conv_tcgen05");
+      return 0;
+    }
+    if (p.atma) {
+      // TMA operand path (fill_params): same choice of issue loop / epilogue width as below
+      if (pro && lean_ok) DMN_CUDA_CHECK(launch_kernel(conv_tcgen05_kernel<GEO_SAME, 128, false, true, false, 1, 8, false, 8, false, true>, grid, kThreads, p, st));
+      else if (pro) DMN_CUDA_CHECK(launch_kernel(conv_tcgen05_kernel<GEO_SAME, 128, false, false, false, 1, 8, false, 8, false, true>, grid, kThreads, p, st));
+      else if (lean_ok) DMN_CUDA_CHECK(launch_kernel(conv_tcgen05_kernel<G2, 128, false, true, false, 0, 8, false, 8, false, true>, grid, kThreads, p, st));
+      else if (DMN_EXP_EW16 && G2 == GEO_SAME) {
+        if (DMN_EXP_EW16_LEAN && p.ntap == 9 && p.G == 3)
+          DMN_CUDA_CHECK(launch_kernel(conv_tcgen05_kernel<GEO_SAME, 128, false, true, false, 0, 16, false, 8, false, true>, grid, kThreads16, p, st));
+        else
+          DMN_CUDA_CHECK(launch_kernel(conv_tcgen05_kernel<GEO_SAME, 128, false, false, false, 0, 16, false, 8, false, true>, grid, kThreads16, p, st));
+      } else DMN_CUDA_CHECK(launch_kernel(conv_tcgen05_kernel<G2, 128, false, false, false, 0, 8, false, 8, false, true>, grid, kThreads, p, st));
       count_launch();
       DMN_LAUNCH_CHECK("conv_tcgen05");
       return 0;

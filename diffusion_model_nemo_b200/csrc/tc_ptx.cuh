@@ -184,6 +184,13 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const void* tmap, int 
                ::"r"(dst), "l"(tmap), "r"(bar), "r"(c0), "r"(c1)
                : "memory");
 }
+// im2col mode (4-D NHWC tensor): `pixelsPerColumn` consecutive positions of the map's bounding box starting at (w, h, n), channels
+// [c, c + channelsPerPixel); (ow, oh) is the filter-tap offset added to every position; out-of-tensor elements arrive as zeros
+__device__ __forceinline__ void tma_load_im2col_4d(uint32_t dst, const void* tmap, int c, int w, int h, int n, uint32_t bar, uint16_t ow, uint16_t oh) {
+  asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.im2col.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2], {%7, %8};"
+               ::"r"(dst), "l"(tmap), "r"(bar), "r"(c), "r"(w), "r"(h), "r"(n), "h"(ow), "h"(oh)
+               : "memory");
+}
 __device__ __forceinline__ void tma_prefetch_desc(const void* tmap) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(tmap) : "memory");
 }
