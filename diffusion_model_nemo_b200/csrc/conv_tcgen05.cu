@@ -471,7 +471,7 @@ __device__ __forceinline__ void issue_pass_swap(bool leader, uint32_t d, uint32_
 template <int GEO, int NT, bool FILM = false, bool LEAN = false, bool EXTRA = true, int PRO = 2, int EW = kEpiWarps, bool SWAP = false, int PW = 8,
           bool TAIL = false, bool ATMA = false>
 __global__ void __launch_bounds__((PW + EW + 2) * 32, 1) conv_tcgen05_kernel(const __grid_constant__ Params p) {
-  static_assert(!ATMA || (NT == 128 && !FILM && !EXTRA && !SWAP && !TAIL && PW == 8 && (PRO == 0 || PRO == 1) && GEO != GEO_INIT),
+  static_assert(!ATMA || (NT == 128 && !FILM && !EXTRA && !SWAP && !TAIL && (PRO == 0 || PRO == 1 || PRO == 3) && GEO != GEO_INIT),
                 "TMA operand path: the hot 128-column instantiations");
   static_assert(!TAIL || (GEO == GEO_SAME && NT == 128 && PRO == 1 && !EXTRA && !SWAP), "fused block tail: the GroupNorm-prologue 3x3 instantiations");
   static_assert(!SWAP || (NT == 128 && !EXTRA && !FILM && GEO != GEO_INIT), "swapped operand roles: hot 128-channel instantiations only");
@@ -519,7 +519,7 @@ __global__ void __launch_bounds__((PW + EW + 2) * 32, 1) conv_tcgen05_kernel(con
   if (warp == kLoaderW) {          // one lane per barrier
     if (lane < nst) { mbar_init(smem_u32(&full_b[lane]), 1); mbar_init(smem_u32(&empty_b[lane]), (uint32_t)p.cl); }
     if (lane >= 16 && lane < 16 + AB) {
-      mbar_init(smem_u32(&full_a[lane - 16]), (ATMA && PRO == 0) ? 1 : kProdThreads);
+      mbar_init(smem_u32(&full_a[lane - 16]), (ATMA && PRO != 1) ? 1 : kProdThreads);
       mbar_init(smem_u32(&empty_a[lane - 16]), 1);
       mbar_init(smem_u32(&raw_a[lane - 16]), 1);
     }
@@ -590,7 +590,7 @@ __global__ void __launch_bounds__((PW + EW + 2) * 32, 1) conv_tcgen05_kernel(con
       if (GEO == GEO_DOWN) { tw = 2 * col - 1; th = 2 * row - 1; }
       else { tw = col - p.pad; th = row - p.pad; }
     };
-    if constexpr (ATMA && PRO == 0) {
+    if constexpr (ATMA && PRO != 1) {
       // plain operands: nothing to transform -- one thread feeds the ring, the tensor core consumes the tiles as the copies land
       if (tid == 0) {
         int ibuf = 0;
@@ -894,7 +894,7 @@ __global__ void __launch_bounds__((PW + EW + 2) * 32, 1) conv_tcgen05_kernel(con
       }
       if (tid == 0) TRACE(pit, 2);
     }
-    }   // !(ATMA && PRO == 0)
+    }   // !(ATMA && PRO != 1)
   } else if (warp < kLoaderW) {
     // =============================== epilogue ===============================
     // register pool of the CTA: the 8 producer warps release 8 x 32 x (72 - 40) = 8192 registers, exactly what 16 epilogue warps need to
@@ -1831,7 +1831,7 @@ static bool fill_params(const ConvP& c, int geo, Params& p) {
   if (geo == GEO_SAME && p.NT == 128 && c.pro != PRO_NONE && !(c.pro & PRO_LRELU) && !c.res && !c.fold_s1) p.abuf = kABufPro;
   // TMA operand path: the hot instantiations (launch<>: 128-column tiles, 3x3 / k4s2 / transposed k4s2, no FiLM / residual / fold terms)
   const bool hot = geo != GEO_INIT && p.NT == 128 && !(c.pro & PRO_LRELU) && !c.res && !c.fold_s1 && !c.fin_out && !swap_enabled() &&
-                   ((geo == GEO_SAME && p.ntap == 9) || geo == GEO_DOWN || geo == GEO_UP);
+                   ((geo == GEO_SAME && (p.ntap == 9 || (p.ntap == 1 && c.pro == PRO_NONE))) || geo == GEO_DOWN || geo == GEO_UP);
   if (hot && atma_enabled() && p.P <= 1024 && p.halo_lo < p.S) {
     Params q = p;
     q.atma = 1;
@@ -1937,6 +1937,13 @@ static int launch(Params p, cudaStream_t st) {
       DMN_CUDA_CHECK(cudaFuncSetAttribute(conv_tcgen05_kernel<G2, 128, false, false, true, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemLimit));
       DMN_CUDA_CHECK(cudaFuncSetAttribute(conv_tcgen05_kernel<G2, 128, false, false, false, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemLimit));
     }
+    if (p.atma && !extra) {
+      if (DMN_EXP_EW16) DMN_CUDA_CHECK(launch_kernel(conv_tcgen05_kernel<G2, 128, false, false, false, 3, 16, false, 8, false, true>, grid, kThreads16, p, st));
+      else DMN_CUDA_CHECK(launch_kernel(conv_tcgen05_kernel<G2, 128, false, false, false, 3, 8, false, 8, false, true>, grid, kThreads, p, st));
+      count_launch();
+      DMN_LAUNCH_CHECK("conv_tcgen05");
+      return 0;
+    }
     if (DMN_EXP_EW16) {
       static DeviceOnce a16;
       if (a16.first()) {
@@ -1984,7 +1991,11 @@ static int launch(Params p, cudaStream_t st) {
     }
     if (p.atma) {
       // TMA operand path (fill_params): same choice of issue loop / epilogue width as below
-      if (pro && lean_ok) DMN_CUDA_CHECK(launch_kernel(conv_tcgen05_kernel<GEO_SAME, 128, false, true, false, 1, 8, false, 8, false, true>, grid, kThreads, p, st));
+      // 16 producer warps: the in-place transform is a latency-bound chain per item (level-0 GroupNorm conv 0.0914 -> 0.0849 ms)
+      static const bool pw16a = [] { const char* e = getenv("DMN_CONV_PW16"); return !(e && e[0] == '0'); }();
+      if (pro && pw16a && lean_ok) DMN_CUDA_CHECK(launch_kernel(conv_tcgen05_kernel<GEO_SAME, 128, false, true, false, 1, 8, false, 16, false, true>, grid, kThreads16, p, st));
+      else if (pro && pw16a) DMN_CUDA_CHECK(launch_kernel(conv_tcgen05_kernel<GEO_SAME, 128, false, false, false, 1, 8, false, 16, false, true>, grid, kThreads16, p, st));
+      else if (pro && lean_ok) DMN_CUDA_CHECK(launch_kernel(conv_tcgen05_kernel<GEO_SAME, 128, false, true, false, 1, 8, false, 8, false, true>, grid, kThreads, p, st));
       else if (pro) DMN_CUDA_CHECK(launch_kernel(conv_tcgen05_kernel<GEO_SAME, 128, false, false, false, 1, 8, false, 8, false, true>, grid, kThreads, p, st));
       else if (lean_ok) DMN_CUDA_CHECK(launch_kernel(conv_tcgen05_kernel<G2, 128, false, true, false, 0, 8, false, 8, false, true>, grid, kThreads, p, st));
       else if (DMN_EXP_EW16 && G2 == GEO_SAME) {
