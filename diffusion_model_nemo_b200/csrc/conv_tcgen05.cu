@@ -471,7 +471,7 @@ __device__ __forceinline__ void issue_pass_swap(bool leader, uint32_t d, uint32_
 template <int GEO, int NT, bool FILM = false, bool LEAN = false, bool EXTRA = true, int PRO = 2, int EW = kEpiWarps, bool SWAP = false, int PW = 8,
           bool TAIL = false, bool ATMA = false>
 __global__ void __launch_bounds__((PW + EW + 2) * 32, 1) conv_tcgen05_kernel(const __grid_constant__ Params p) {
-  static_assert(!ATMA || (NT == 128 && !FILM && !EXTRA && !SWAP && !TAIL && (PRO == 0 || PRO == 1 || PRO == 3) && GEO != GEO_INIT),
+  static_assert(!ATMA || (NT == 128 && !FILM && !EXTRA && !TAIL && (PRO == 0 || PRO == 1 || PRO == 3) && GEO != GEO_INIT),
                 "TMA operand path: the hot 128-column instantiations");
   static_assert(!TAIL || (GEO == GEO_SAME && NT == 128 && PRO == 1 && !EXTRA && !SWAP), "fused block tail: the GroupNorm-prologue 3x3 instantiations");
   static_assert(!SWAP || (NT == 128 && !EXTRA && !FILM && GEO != GEO_INIT), "swapped operand roles: hot 128-channel instantiations only");
@@ -669,7 +669,9 @@ __global__ void __launch_bounds__((PW + EW + 2) * 32, 1) conv_tcgen05_kernel(con
         }
       } else {
       // ---- per-tile tables: operand source per window pixel, GroupNorm (mean, rstd) per touched image ----
+      if (DMN_TC_TRACE_BUILD && p.trace && tid == 0 && pit == 2 && blockIdx.x == (unsigned)p.trace_cta) p.trace[900] = clock64();
       bar_sync_named(2, kProdThreads);                 // everyone is done with the previous tile's tables
+      if (DMN_TC_TRACE_BUILD && p.trace && tid == 0 && pit == 2 && blockIdx.x == (unsigned)p.trace_cta) p.trace[901] = clock64();
       const int pbase = m0 - p.halo_lo > 0 ? m0 - p.halo_lo : 0;            // uniform: decode base of the window
       const int pimg0 = pbase / p.S, prem0 = pbase - pimg0 * p.S;
       for (int pixel = tid; pixel < Pt; pixel += kProdThreads) {
@@ -688,6 +690,7 @@ __global__ void __launch_bounds__((PW + EW + 2) * 32, 1) conv_tcgen05_kernel(con
         s_pix[pixel] = g;
         s_pimg[pixel] = il;
       }
+      if (DMN_TC_TRACE_BUILD && p.trace && tid == 0 && pit == 2 && blockIdx.x == (unsigned)p.trace_cta) p.trace[902] = clock64();
       if (GEO == GEO_SAME && (p.c.pro & PRO_GN)) {
         for (int i = tid; i < kNimgMax * p.c.pgroups; i += kProdThreads) {
           const int il = i / p.c.pgroups, g = i - il * p.c.pgroups;
@@ -697,6 +700,7 @@ __global__ void __launch_bounds__((PW + EW + 2) * 32, 1) conv_tcgen05_kernel(con
           s_gn[il * kGroupsMax + g] = make_float2(mean, rstd);
         }
       }
+      if (DMN_TC_TRACE_BUILD && p.trace && tid == 0 && pit == 2 && blockIdx.x == (unsigned)p.trace_cta) p.trace[903] = clock64();
       bar_sync_named(2, kProdThreads);
       if (tid == 0) TRACE(pit, 1);
 #pragma unroll
@@ -1830,7 +1834,7 @@ static bool fill_params(const ConvP& c, int geo, Params& p) {
   // the GroupNorm-prologue instantiation (PRO = 1) is launched for 128-column tiles without residual / fold / FiLM (launch<>)
   if (geo == GEO_SAME && p.NT == 128 && c.pro != PRO_NONE && !(c.pro & PRO_LRELU) && !c.res && !c.fold_s1) p.abuf = kABufPro;
   // TMA operand path: the hot instantiations (launch<>: 128-column tiles, 3x3 / k4s2 / transposed k4s2, no FiLM / residual / fold terms)
-  const bool hot = geo != GEO_INIT && p.NT == 128 && !(c.pro & PRO_LRELU) && !c.res && !c.fold_s1 && !c.fin_out && !swap_enabled() &&
+  const bool hot = geo != GEO_INIT && p.NT == 128 && !(c.pro & PRO_LRELU) && !c.res && !c.fold_s1 && !c.fin_out &&
                    ((geo == GEO_SAME && (p.ntap == 9 || (p.ntap == 1 && c.pro == PRO_NONE))) || geo == GEO_DOWN || geo == GEO_UP);
   if (hot && atma_enabled() && p.P <= 1024 && p.halo_lo < p.S) {
     Params q = p;
@@ -1974,6 +1978,22 @@ static int launch(Params p, cudaStream_t st) {
     }
     if (swap_on && (G2 != GEO_SAME || p.ntap == 9)) {
       static const bool pw16 = [] { const char* e = getenv("DMN_CONV_PW16"); return !(e && e[0] == '0'); }();
+      if (p.atma) {
+        if (pro && pw16 && lean_ok) DMN_CUDA_CHECK(launch_kernel(conv_tcgen05_kernel<GEO_SAME, 128, false, true, false, 1, 8, true, 16, false, true>, grid, kThreads16, p, st));
+        else if (pro && pw16) DMN_CUDA_CHECK(launch_kernel(conv_tcgen05_kernel<GEO_SAME, 128, false, false, false, 1, 8, true, 16, false, true>, grid, kThreads16, p, st));
+        else if (pro && lean_ok) DMN_CUDA_CHECK(launch_kernel(conv_tcgen05_kernel<GEO_SAME, 128, false, true, false, 1, 8, true, 8, false, true>, grid, kThreads, p, st));
+        else if (pro) DMN_CUDA_CHECK(launch_kernel(conv_tcgen05_kernel<GEO_SAME, 128, false, false, false, 1, 8, true, 8, false, true>, grid, kThreads, p, st));
+        else if (lean_ok) DMN_CUDA_CHECK(launch_kernel(conv_tcgen05_kernel<G2, 128, false, true, false, 0, 8, true, 8, false, true>, grid, kThreads, p, st));
+        else if (DMN_EXP_EW16 && G2 == GEO_SAME) {
+          if (DMN_EXP_EW16_LEAN && p.ntap == 9 && p.G == 3)
+            DMN_CUDA_CHECK(launch_kernel(conv_tcgen05_kernel<GEO_SAME, 128, false, true, false, 0, 16, true, 8, false, true>, grid, kThreads16, p, st));
+          else
+            DMN_CUDA_CHECK(launch_kernel(conv_tcgen05_kernel<GEO_SAME, 128, false, false, false, 0, 16, true, 8, false, true>, grid, kThreads16, p, st));
+        } else DMN_CUDA_CHECK(launch_kernel(conv_tcgen05_kernel<G2, 128, false, false, false, 0, 8, true, 8, false, true>, grid, kThreads, p, st));
+        count_launch();
+        DMN_LAUNCH_CHECK("conv_tcgen05");
+        return 0;
+      }
       if (pro && pw16 && lean_ok) DMN_CUDA_CHECK(launch_kernel(conv_tcgen05_kernel<GEO_SAME, 128, false, true, false, 1, 8, true, 16>, grid, kThreads16, p, st));
       else if (pro && pw16) DMN_CUDA_CHECK(launch_kernel(conv_tcgen05_kernel<GEO_SAME, 128, false, false, false, 1, 8, true, 16>, grid, kThreads16, p, st));
       else if (pro && lean_ok) DMN_CUDA_CHECK(launch_kernel(conv_tcgen05_kernel<GEO_SAME, 128, false, true, false, 1, 8, true>, grid, kThreads, p, st));
@@ -1990,7 +2010,10 @@ static int launch(Params p, cudaStream_t st) {
       return 0;
     }
     if (p.atma) {
-      // TMA operand path (fill_params): same choice of issue loop / epilogue width as below
+      // TMA operand path (fill_params).  The 2x2 forms take the unrolled issue loop whatever the pass count (transposed 16x16 -> 32x32 conv
+      // 0.0392 -> 0.0299 ms); the GroupNorm-prologue 3x3 keeps the round-1 rule (level-0: 0.0843 ms looped, 0.0877 ms unrolled)
+      const bool lean4 = !DMN_EXP_NO_LEAN && (GEO == GEO_DOWN || GEO == GEO_UP) && p.ntap == 4 && p.G == 2;
+      const bool lean_ok = lean4 || (!DMN_EXP_NO_LEAN && GEO == GEO_SAME && p.n_pass >= DMN_EXP_LEAN_MIN_PASS && p.ntap == 9 && p.G == 3);
       // 16 producer warps: the in-place transform is a latency-bound chain per item (level-0 GroupNorm conv 0.0914 -> 0.0849 ms)
       static const bool pw16a = [] { const char* e = getenv("DMN_CONV_PW16"); return !(e && e[0] == '0'); }();
       if (pro && pw16a && lean_ok) DMN_CUDA_CHECK(launch_kernel(conv_tcgen05_kernel<GEO_SAME, 128, false, true, false, 1, 8, false, 16, false, true>, grid, kThreads16, p, st));
