@@ -138,6 +138,13 @@ __device__ long long g_trace[1024];
 #define DMN_TC_TRACE_PRODUCER 0     // 1: also account the producers' wait clocks (slots 14 / 15); costs registers in the hot role
 #endif
 constexpr bool kTraceProducer = DMN_TC_TRACE_PRODUCER != 0;
+#ifndef DMN_EXP_PRO_GROUP
+#define DMN_EXP_PRO_GROUP 3        // items of a thread transformed side by side in one basic block (TMA tiles)
+#endif
+constexpr int kGS = DMN_EXP_PRO_GROUP;
+#ifndef DMN_EXP_SERIAL_PRO
+#define DMN_EXP_SERIAL_PRO 0       // 1: the item-by-item prologue transform of the TMA tiles (A/B)
+#endif
 #ifndef DMN_EXP_ZFILL_PLAIN
 #define DMN_EXP_ZFILL_PLAIN 0
 #endif
@@ -519,7 +526,7 @@ __global__ void __launch_bounds__((PW + EW + 2) * 32, 1) conv_tcgen05_kernel(con
   if (warp == kLoaderW) {          // one lane per barrier
     if (lane < nst) { mbar_init(smem_u32(&full_b[lane]), 1); mbar_init(smem_u32(&empty_b[lane]), (uint32_t)p.cl); }
     if (lane >= 16 && lane < 16 + AB) {
-      mbar_init(smem_u32(&full_a[lane - 16]), (ATMA && PRO != 1) ? 1 : kProdThreads);
+      mbar_init(smem_u32(&full_a[lane - 16]), (ATMA && PRO != 1) ? 1 : kProdWarps);     // one arrival per producer WARP (see finish())
       mbar_init(smem_u32(&empty_a[lane - 16]), 1);
       mbar_init(smem_u32(&raw_a[lane - 16]), 1);
     }
@@ -652,7 +659,8 @@ __global__ void __launch_bounds__((PW + EW + 2) * 32, 1) conv_tcgen05_kernel(con
           *reinterpret_cast<uint4*>(sA + ibuf * a_bytes + (uint32_t)kc * p.lbo_a + pixel * 16) = pack8(f);
         }
         if (DMN_EXP_FENCE_MODE == 0) fence_proxy_async();
-        mbar_arrive(smem_u32(&full_a[ibuf]));
+        __syncwarp();
+        if (lane == 0) mbar_arrive(smem_u32(&full_a[ibuf]));
         if (++ibuf == AB) { ibuf = 0; iph ^= 1; }
         fbuf = ibuf;
         continue;
@@ -717,7 +725,10 @@ __global__ void __launch_bounds__((PW + EW + 2) * 32, 1) conv_tcgen05_kernel(con
 
       // finish pass c (in buffer fbuf): prologue in place on this thread's own items, publish to the tensor core
       auto finish = [&](int c) {
+        const bool fst = DMN_TC_TRACE_BUILD && p.trace && tid == 0 && pit == 2 && c == 1 && blockIdx.x == (unsigned)p.trace_cta;
+        if (fst) p.trace[910] = clock64();
         if constexpr (ATMA) mbar_wait(smem_u32(&raw_a[fbuf]), rph);      // the window of this pass has landed
+        if (fst) p.trace[911] = clock64();
         if (has_pro) {
           const int cb = c * kCk + kc * 8;
           float ga[8], be[8], te[8];
@@ -793,6 +804,70 @@ __global__ void __launch_bounds__((PW + EW + 2) * 32, 1) conv_tcgen05_kernel(con
 #pragma unroll
             for (int j = 0; j < kMaxItems; ++j) do_item(j, j >= NF);
           };
+          // TMA tiles: groups of three items as ONE basic block -- all loads first (an item slot outside the window reads the thread's
+          // first slot instead), then the three arithmetic chains side by side, then stores predicated in the instruction itself
+          // (padding stays zero).  With a per-item `if` ptxas skips the whole chain of a padding item, which makes every item its own
+          // branch region and serialises LDS -> FFMA2 -> MUFU -> STS item after item (SASS of the round-2 build)
+          auto do_group = [&](auto j0_tag, auto silu_tag) {
+            constexpr int J0 = decltype(j0_tag)::value;
+            constexpr bool SILU = decltype(silu_tag)::value;
+            constexpr int N = (kMaxItems - J0) < kGS ? (kMaxItems - J0) : kGS;
+            const uint32_t base_u = smem_u32(base);
+            uint4 raw[N];
+            float2 mr[N];
+#pragma unroll
+            for (int i = 0; i < N; ++i) {
+              const int j = J0 + i;
+              const int px = goff[j] >= -1 ? px0 + (kProdThreads / 4) * j : px0;
+              raw[i] = lds128(base_u + (uint32_t)px * 64u);
+              mr[i] = s_gn[imgl[j] * kGroupsMax + g];
+            }
+#pragma unroll
+            for (int i = 0; i < N; ++i) {
+              float v[8];
+              unpack8(raw[i], v);
+              const float sc = mr[i].y, sh = -mr[i].x * mr[i].y;
+              const unsigned long long sc2 = pack2(sc, sc), sh2 = pack2(sh, sh);
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                unsigned long long x2 = fma2(pack2(v[2 * e], v[2 * e + 1]), sc2, sh2);
+                x2 = fma2(x2, gah2[e], beh2[e]);                       // hx
+                unsigned long long y2;
+                if (SILU) {
+                  float h0, h1, t0, t1;
+                  unpack2(x2, h0, h1);
+                  asm("tanh.approx.f32 %0, %1;" : "=f"(t0) : "f"(h0));
+                  asm("tanh.approx.f32 %0, %1;" : "=f"(t1) : "f"(h1));
+                  y2 = fma2(x2, pack2(t0, t1), x2);
+                } else {
+                  y2 = add2(x2, x2);
+                }
+                y2 = add2(y2, te2[e]);
+                unpack2(y2, v[2 * e], v[2 * e + 1]);
+              }
+              raw[i] = pack8(v);
+            }
+#pragma unroll
+            for (int i = 0; i < N; ++i) {
+              const int j = J0 + i;
+              asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %5, 0;\n\t@p st.shared.v4.b32 [%0], {%1, %2, %3, %4};\n\t}" ::"r"(
+                               base_u + (uint32_t)(px0 + (kProdThreads / 4) * j) * 64u),
+                           "r"(raw[i].x), "r"(raw[i].y), "r"(raw[i].z), "r"(raw[i].w), "r"((uint32_t)(goff[j] >= 0))
+                           : "memory");
+            }
+          };
+          if (fst) p.trace[912] = clock64();
+          if (ATMA && !FILM && DMN_EXP_PRO_COST == 0 && !DMN_EXP_SERIAL_PRO && !((p.c.pro & PRO_TEMB) && !temb_shared)) {
+            const int n_it = (Pt + kProdThreads / 4 - 1) / (kProdThreads / 4);     // item slots that reach into the window (uniform)
+            auto all_groups = [&](auto silu_tag) {
+              do_group(std::integral_constant<int, 0>(), silu_tag);
+              if (kMaxItems > kGS && n_it > kGS) do_group(std::integral_constant<int, (kMaxItems > kGS ? kGS : 0)>(), silu_tag);
+              if (kMaxItems > 2 * kGS && n_it > 2 * kGS) do_group(std::integral_constant<int, (kMaxItems > 2 * kGS ? 2 * kGS : 0)>(), silu_tag);
+              if (kMaxItems > 3 * kGS && n_it > 3 * kGS) do_group(std::integral_constant<int, (kMaxItems > 3 * kGS ? 3 * kGS : 0)>(), silu_tag);
+            };
+            if (p.c.pro & PRO_SILU) all_groups(std::true_type());
+            else all_groups(std::false_type());
+          } else
           switch (DMN_EXP_BRANCHY_PRO ? 0 : nfull) {
             // the window sizes of the U-Net's 3x3 convs: 256-row tiles at 32x32 (5 full slots), at 16x16 / 8x8 (4), 128-row tiles (2)
             case 7: case 6: case 5: run(std::integral_constant<int, 5>()); break;
@@ -801,8 +876,14 @@ __global__ void __launch_bounds__((PW + EW + 2) * 32, 1) conv_tcgen05_kernel(con
             default: run(std::integral_constant<int, 0>()); break;
           }
         }
+        // every writer fences its own stores towards the async proxy, then ONE lane per warp arrives: 256 / 512 arrivals on one
+        // mbarrier serialise (measured: a pass that only loads and stores its items took 1.6k clk with per-thread arrivals)
+        if (fst) p.trace[913] = clock64();
         if (DMN_EXP_FENCE_MODE == 0) fence_proxy_async();
-        mbar_arrive(smem_u32(&full_a[fbuf]));
+        if (fst) p.trace[914] = clock64();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(smem_u32(&full_a[fbuf]));
+        if (fst) p.trace[915] = clock64();
         if (++fbuf == AB) { fbuf = 0; rph ^= 1; }
       };
 
@@ -2014,8 +2095,7 @@ static int launch(Params p, cudaStream_t st) {
       // 0.0392 -> 0.0299 ms); the GroupNorm-prologue 3x3 keeps the round-1 rule (level-0: 0.0843 ms looped, 0.0877 ms unrolled)
       const bool lean4 = !DMN_EXP_NO_LEAN && (GEO == GEO_DOWN || GEO == GEO_UP) && p.ntap == 4 && p.G == 2;
       const bool lean_ok = lean4 || (!DMN_EXP_NO_LEAN && GEO == GEO_SAME && p.n_pass >= DMN_EXP_LEAN_MIN_PASS && p.ntap == 9 && p.G == 3);
-      // 16 producer warps: the in-place transform is a latency-bound chain per item (level-0 GroupNorm conv 0.0914 -> 0.0849 ms)
-      static const bool pw16a = [] { const char* e = getenv("DMN_CONV_PW16"); return !(e && e[0] == '0'); }();
+      static const bool pw16a = [] { const char* e = getenv("DMN_CONV_PW16"); return e && e[0] == '1'; }();     // (64 registers per producer spill the grouped transform)
       if (pro && pw16a && lean_ok) DMN_CUDA_CHECK(launch_kernel(conv_tcgen05_kernel<GEO_SAME, 128, false, true, false, 1, 8, false, 16, false, true>, grid, kThreads16, p, st));
       else if (pro && pw16a) DMN_CUDA_CHECK(launch_kernel(conv_tcgen05_kernel<GEO_SAME, 128, false, false, false, 1, 8, false, 16, false, true>, grid, kThreads16, p, st));
       else if (pro && lean_ok) DMN_CUDA_CHECK(launch_kernel(conv_tcgen05_kernel<GEO_SAME, 128, false, true, false, 1, 8, false, 8, false, true>, grid, kThreads, p, st));

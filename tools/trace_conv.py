@@ -57,6 +57,8 @@ def run(k, cin, cout, h, b, gn, mode=0):
               f"issued {rel(row[6])} (waitA {row[12]} waitB {row[13]}; prod waitEmpty {row[14]} waitCp {row[15]} issue {row[3]} finish {row[7]}) | epi tables {rel(row[8])} ready {rel(row[9])} drained {rel(row[10])} done {rel(row[11])}")
     if t[900]:
         print(f"   tile-2 setup (producer thread 0): enter {t[900]-t[32]} | first barrier {t[901]-t[900]} | pixel table {t[902]-t[901]} | gn table {t[903]-t[902]} | second barrier {t[16*2+1]-t[903]}")
+    if t[910]:
+        print(f"   tile-2 finish of pass 1 (producer thread 0): wait for the window {t[911]-t[910]} | coefficients {t[912]-t[911]} | items {t[913]-t[912]} | fence {t[914]-t[913]} | arrive {t[915]-t[914]}")
     pcs = t[800:800 + 96]
     if any(pcs):
         print("   epilogue pieces of tile 2 (warp 8): (wait, work) clk:", " ".join(
