@@ -32,7 +32,9 @@ def run(k, cin, cout, h, b, gn, mode=0):
     bias = torch.zeros(cout)
     kw = {}
     if gn:
-        kw = dict(gn=(8, torch.ones(cin).to(DEV), torch.zeros(cin).to(DEV)), silu=True, temb=torch.zeros(b, cin).to(DEV))
+        kw = dict(gn=(8, torch.ones(cin).to(DEV), torch.zeros(cin).to(DEV)), silu=True)
+        if os.environ.get("TRACE_TEMB"):      # per-image embedding rows (the layer API's form; the sampling loop shares one row)
+            kw["temb"] = torch.zeros(b, cin).to(DEV)
     for _ in range(2):
         conv_forward(x.to(DEV), w.to(DEV), bias.to(DEV), mode=mode, ksize=k, out_groups=8 if mode == 0 and k == 3 else 0,
                      act=L.ACT_BF16, engine=L.CONV_TCGEN05, **kw)
