@@ -113,6 +113,8 @@ struct Params {
   uint32_t stage_bytes;    // G * 4 * NT * 16
   int delta[64];           // [4 phases][16 taps] tap offsets in flat positions (constant bank => uniform registers in the issuer)
   uint32_t magic_S, magic_W;   // ceil(2^26 / S), ceil(2^24 / Wv): exact small-number division in vdecode_rel
+  unsigned long long magic64_S;   // ceil(2^64 / S): f / S == umul64hi(f, magic64_S) for every 32-bit f (the per-tile decodes of the TMA path)
+  int pg_shift;                // log2(pgroups) (TMA prologue instantiations: pgroups is a power of two)
   float inv_cnt_in;
   long long* trace;        // debug timeline (null in production)
   int trace_cta;
@@ -138,6 +140,12 @@ __device__ long long g_trace[1024];
 #define DMN_TC_TRACE_PRODUCER 0     // 1: also account the producers' wait clocks (slots 14 / 15); costs registers in the hot role
 #endif
 constexpr bool kTraceProducer = DMN_TC_TRACE_PRODUCER != 0;
+#ifndef DMN_EXP_LEAN_MIN_PASS_TMA_PRO
+#define DMN_EXP_LEAN_MIN_PASS_TMA_PRO 8
+#endif
+#ifndef DMN_EXP_TMA_REGTABLES
+#define DMN_EXP_TMA_REGTABLES 0
+#endif
 #ifndef DMN_EXP_PRO_GROUP
 #define DMN_EXP_PRO_GROUP 3        // items of a thread transformed side by side in one basic block (TMA tiles)
 #endif
@@ -591,9 +599,9 @@ __global__ void __launch_bounds__((PW + EW + 2) * 32, 1) conv_tcgen05_kernel(con
     };
     auto tma_tile_coords = [&](int m0) {
       const int f = m0 - p.halo_lo;
-      tn = f >= 0 ? f / p.S : -1;                      // halo_lo < S: a negative start lies in "image -1" (all zeros)
+      tn = f >= 0 ? (int)__umul64hi((unsigned long long)(unsigned)f, p.magic64_S) : -1;     // halo_lo < S: a negative start lies in "image -1" (all zeros)
       const int rem = f - tn * p.S;
-      const int row = rem / p.Wv, col = rem - row * p.Wv;
+      const int row = (int)(((unsigned long long)(unsigned)rem * p.magic_W) >> 24), col = rem - row * p.Wv;
       if (GEO == GEO_DOWN) { tw = 2 * col - 1; th = 2 * row - 1; }
       else { tw = col - p.pad; th = row - p.pad; }
     };
@@ -667,6 +675,9 @@ __global__ void __launch_bounds__((PW + EW + 2) * 32, 1) conv_tcgen05_kernel(con
       }
       int goff[kMaxItems];      // SAME/UP: img*HW + pix (or -1 = padding); DOWN: packed (img, u, v) (or -1); -2 = outside the window
       int imgl[kMaxItems];
+      float2* s_gn_cur = s_gn;
+      stat_t nx_s0 = 0, nx_s1 = 0;       // ATMA: this thread's statistics entry of the next tile's table (loaded early, used late)
+      bool nx_have = false, nx_tile = false;
       const int nfull = Pt / (kProdThreads / 4);      // item slots that are inside the window for EVERY thread (uniform)
       if constexpr (kOneTap) {
 #pragma unroll
@@ -675,6 +686,51 @@ __global__ void __launch_bounds__((PW + EW + 2) * 32, 1) conv_tcgen05_kernel(con
           imgl[j] = 0;
           goff[j] = (pixel < Pt && m0 + pixel < (int)p.total_flat) ? m0 + pixel : -2;
         }
+      } else if constexpr (ATMA && DMN_EXP_TMA_REGTABLES) {
+        // TMA operands: per item the producers only need "is it a real pixel" (padding stays zero) and its image -- decoded in
+        // registers with multiply-shift divisions, no shared tables.  The (mean, rstd) table is double buffered in the unused half of
+        // each image's 32-slot row (pgroups <= 16): this thread's entry of the NEXT tile's table is loaded here and turned into
+        // (mean, rstd) after this tile's passes, so neither its L2 latency nor a second barrier sits in front of the first pass
+        const int fs = m0 - p.halo_lo, fl = fs > 0 ? fs : 0;
+        const int il0 = (int)__umul64hi((unsigned long long)(unsigned)fl, p.magic64_S), rl0 = fl - il0 * p.S;      // == img_lo
+#pragma unroll
+        for (int j = 0; j < kMaxItems; ++j) {
+          const int pixel = px0 + (kProdThreads / 4) * j;
+          goff[j] = -2;
+          imgl[j] = 0;
+          if (pixel < Pt) {
+            goff[j] = -1;
+            if (fs + pixel >= 0) {
+              const VPos v = vdecode_rel(il0, rl0, fs + pixel - fl, p);
+              if (v.img >= 0 && v.row >= p.pad && v.col >= p.pad) { goff[j] = 0; imgl[j] = v.img - il0; }
+            }
+          }
+        }
+        s_gn_cur = s_gn + (pit & 1) * 16;
+        const int t_il = tid >> p.pg_shift, t_g = tid & (p.c.pgroups - 1);
+        const bool t_ent = tid < kNimgMax * p.c.pgroups;
+        if (pit == 0) {                                   // first tile of this CTA: its own table, synchronously
+          if (t_ent) {
+            float mean = 0.f, rstd = 0.f;
+            if (il0 + t_il < p.c.B) gn_mean_rstd(p.c.pstats + ((long)(il0 + t_il) * p.c.pgroups + t_g) * 2, p.inv_cnt_in, kGnEps, mean, rstd);
+            s_gn_cur[t_il * kGroupsMax + t_g] = make_float2(mean, rstd);
+          }
+          bar_sync_named(2, kProdThreads);
+        }
+        nx_have = false;
+        nx_tile = tile + (int)gridDim.x < p.total_tiles;
+        if (nx_tile && t_ent) {
+          int f2 = tile_geom(tile + (int)gridDim.x, p).m0 - p.halo_lo;
+          if (f2 < 0) f2 = 0;
+          const int img = (int)__umul64hi((unsigned long long)(unsigned)f2, p.magic64_S) + t_il;
+          if (img < p.c.B) {
+            const stat_t* sp = p.c.pstats + ((long)img * p.c.pgroups + t_g) * 2;
+            nx_s0 = __ldcg(sp);
+            nx_s1 = __ldcg(sp + 1);
+            nx_have = true;
+          }
+        }
+        if (tid == 0) TRACE(pit, 1);
       } else {
       // ---- per-tile tables: operand source per window pixel, GroupNorm (mean, rstd) per touched image ----
       if (DMN_TC_TRACE_BUILD && p.trace && tid == 0 && pit == 2 && blockIdx.x == (unsigned)p.trace_cta) p.trace[900] = clock64();
@@ -760,7 +816,7 @@ __global__ void __launch_bounds__((PW + EW + 2) * 32, 1) conv_tcgen05_kernel(con
             if (check && goff[j] < 0) return;
             uint4* slot = reinterpret_cast<uint4*>(base + (px0 + (kProdThreads / 4) * j) * (ATMA ? 64 : 16));
             if (DMN_EXP_PRO_COST == 2) { uint4 t = *slot; t.x ^= 0x00010001u; *slot = t; return; }
-            const float2 mr = FILM ? make_float2(0.f, 1.f) : s_gn[imgl[j] * kGroupsMax + g];
+            const float2 mr = FILM ? make_float2(0.f, 1.f) : s_gn_cur[imgl[j] * kGroupsMax + g];
             if ((p.c.pro & PRO_TEMB) && !temb_shared) {
               const float* tp = temb_base + (long)(img_lo + imgl[j]) * p.c.temb_bstride + cb;
               const float4 t0 = *reinterpret_cast<const float4*>(tp), t1 = *reinterpret_cast<const float4*>(tp + 4);
@@ -820,7 +876,7 @@ __global__ void __launch_bounds__((PW + EW + 2) * 32, 1) conv_tcgen05_kernel(con
               const int j = J0 + i;
               const int px = goff[j] >= -1 ? px0 + (kProdThreads / 4) * j : px0;
               raw[i] = lds128(base_u + (uint32_t)px * 64u);
-              mr[i] = s_gn[imgl[j] * kGroupsMax + g];
+              mr[i] = s_gn_cur[imgl[j] * kGroupsMax + g];
             }
 #pragma unroll
             for (int i = 0; i < N; ++i) {
@@ -976,6 +1032,19 @@ __global__ void __launch_bounds__((PW + EW + 2) * 32, 1) conv_tcgen05_kernel(con
       if (inflight == 1) {
         if constexpr (!ATMA) cp_async_wait<0>();
         finish(p.n_pass - 1);
+      }
+      if constexpr (ATMA && DMN_EXP_TMA_REGTABLES) {
+        if (nx_tile) {                   // (uniform) the next tile's table, in the other half of the rows
+          if (tid < kNimgMax * p.c.pgroups) {
+            float mean = 0.f, rstd = 0.f;
+            if (nx_have) {
+              const stat_t st2[2] = {nx_s0, nx_s1};
+              gn_mean_rstd(st2, p.inv_cnt_in, kGnEps, mean, rstd);
+            }
+            s_gn[((pit + 1) & 1) * 16 + (tid >> p.pg_shift) * kGroupsMax + (tid & (p.c.pgroups - 1))] = make_float2(mean, rstd);
+          }
+          bar_sync_named(2, kProdThreads);      // table complete; everybody is done reading this tile's
+        }
       }
       if (tid == 0) TRACE(pit, 2);
     }
@@ -1899,6 +1968,9 @@ static bool fill_params(const ConvP& c, int geo, Params& p) {
   if (p.S > 8192 - 1024 || p.Wv > 128) return false;     // vdecode_rel exactness
   p.magic_S = (uint32_t)(((1ull << 26) + p.S - 1) / p.S);
   p.magic_W = (uint32_t)(((1ull << 24) + p.Wv - 1) / p.Wv);
+  p.magic64_S = ~0ull / (unsigned long long)p.S + 1ull;
+  p.pg_shift = 0;
+  while (c.pgroups > 0 && (1 << p.pg_shift) < c.pgroups) ++p.pg_shift;
   for (int ph = 0; ph < 4; ++ph)
     for (int t = 0; t < 16; ++t) p.delta[ph * 16 + t] = t < p.ntap ? tap_delta(p, geo, t, ph) : 0;
   {
@@ -1917,7 +1989,9 @@ static bool fill_params(const ConvP& c, int geo, Params& p) {
   // TMA operand path: the hot instantiations (launch<>: 128-column tiles, 3x3 / k4s2 / transposed k4s2, no FiLM / residual / fold terms)
   const bool hot = geo != GEO_INIT && p.NT == 128 && !(c.pro & PRO_LRELU) && !c.res && !c.fold_s1 && !c.fin_out &&
                    ((geo == GEO_SAME && (p.ntap == 9 || (p.ntap == 1 && c.pro == PRO_NONE))) || geo == GEO_DOWN || geo == GEO_UP);
-  if (hot && atma_enabled() && p.P <= 1024 && p.halo_lo < p.S) {
+  // (prologue form: power-of-two group count <= 16 and one table entry per producer thread -- the double-buffered (mean, rstd) table)
+  const bool pro_ok = c.pro == PRO_NONE || ((c.pro & PRO_GN) && kNimgMax * c.pgroups <= kProdThreads && c.pgroups <= 16 && (c.pgroups & (c.pgroups - 1)) == 0);
+  if (hot && pro_ok && atma_enabled() && p.P <= 1024 && p.halo_lo < p.S) {
     Params q = p;
     q.atma = 1;
     q.a_bytes = ((uint32_t)q.P * 64u + 1023u) & ~1023u;
@@ -2094,7 +2168,7 @@ static int launch(Params p, cudaStream_t st) {
       // TMA operand path (fill_params).  The 2x2 forms take the unrolled issue loop whatever the pass count (transposed 16x16 -> 32x32 conv
       // 0.0392 -> 0.0299 ms); the GroupNorm-prologue 3x3 keeps the round-1 rule (level-0: 0.0843 ms looped, 0.0877 ms unrolled)
       const bool lean4 = !DMN_EXP_NO_LEAN && (GEO == GEO_DOWN || GEO == GEO_UP) && p.ntap == 4 && p.G == 2;
-      const bool lean_ok = lean4 || (!DMN_EXP_NO_LEAN && GEO == GEO_SAME && p.n_pass >= DMN_EXP_LEAN_MIN_PASS && p.ntap == 9 && p.G == 3);
+      const bool lean_ok = lean4 || (!DMN_EXP_NO_LEAN && GEO == GEO_SAME && p.n_pass >= (pro ? DMN_EXP_LEAN_MIN_PASS_TMA_PRO : DMN_EXP_LEAN_MIN_PASS) && p.ntap == 9 && p.G == 3);
       static const bool pw16a = [] { const char* e = getenv("DMN_CONV_PW16"); return e && e[0] == '1'; }();     // (64 registers per producer spill the grouped transform)
       if (pro && pw16a && lean_ok) DMN_CUDA_CHECK(launch_kernel(conv_tcgen05_kernel<GEO_SAME, 128, false, true, false, 1, 8, false, 16, false, true>, grid, kThreads16, p, st));
       else if (pro && pw16a) DMN_CUDA_CHECK(launch_kernel(conv_tcgen05_kernel<GEO_SAME, 128, false, false, false, 1, 8, false, 16, false, true>, grid, kThreads16, p, st));
