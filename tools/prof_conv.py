@@ -22,7 +22,9 @@ def main(which):
     w = torch.randn(cout, cin, k, k, generator=g) * 0.05
     kw = {}
     if gn:
-        kw = dict(gn=(8, torch.ones(cin).to(DEV), torch.zeros(cin).to(DEV)), silu=True, temb=torch.zeros(b, cin).to(DEV))
+        kw = dict(gn=(8, torch.ones(cin).to(DEV), torch.zeros(cin).to(DEV)), silu=True)
+        if os.environ.get("PROF_TEMB"):       # per-image embedding rows (the layer API's form; the sampling loop shares one row)
+            kw["temb"] = torch.zeros(b, cin).to(DEV)
     for _ in range(3):
         conv_forward(x.to(DEV), w.to(DEV), torch.zeros(cout).to(DEV), ksize=k, out_groups=8 if k == 3 else 0, act=L.ACT_BF16,
                      engine=L.CONV_TCGEN05, **kw)
