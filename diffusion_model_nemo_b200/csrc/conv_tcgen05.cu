@@ -541,6 +541,7 @@ __global__ void __launch_bounds__((PW + EW + 2) * 32, 1) conv_tcgen05_kernel(con
     if (lane >= 24 && lane < 26) { mbar_init(smem_u32(&acc_full[lane - 24]), 1); mbar_init(smem_u32(&acc_empty[lane - 24]), kEpiT); }
     fence_barrier_init();
   }
+  if (ATMA && tid == 0 && (smem_u32(sA) & 1023u)) __trap();      // SWIZZLE_64B tiles: the XOR pattern is keyed on absolute address bits 7-8
   if (warp == kMmaW) tmem_alloc(smem_u32(tmem_slot), p.tmem_cols);
   tc_fence_before();
   __syncthreads();
