@@ -490,9 +490,9 @@ __global__ void __launch_bounds__((PW + EW + 2) * 32, 1) conv_tcgen05_kernel(con
                 "TMA operand path: the hot 128-column instantiations");
   static_assert(!TAIL || (GEO == GEO_SAME && NT == 128 && PRO == 1 && !EXTRA && !SWAP), "fused block tail: the GroupNorm-prologue 3x3 instantiations");
   static_assert(!SWAP || (NT == 128 && !EXTRA && !FILM && GEO != GEO_INIT), "swapped operand roles: hot 128-channel instantiations only");
-  static_assert(PW == 8 || (PW == 16 && EW == 8 && PRO == 1), "16 producer warps: the GroupNorm-prologue instantiations");
+  static_assert(PW == 8 || ((PW == 16 || PW == 12) && EW == 8 && PRO == 1), "12 / 16 producer warps: the GroupNorm-prologue instantiations");
   constexpr int kProdWarps = PW, kProdThreads = PW * 32;       // (shadow the 8-warp defaults of the namespace)
-  constexpr int kMaxItems = PW == 16 ? 4 : 7;
+  constexpr int kMaxItems = PW == 16 ? 4 : (PW == 12 ? 5 : 7);
   constexpr int kLoaderW = kProdWarps + EW, kMmaW = kLoaderW + 1, kEpiT = EW * 32;
   constexpr int AB = (PRO == 3 && GEO == GEO_SAME) ? kABufOne : ((PRO == 1 && GEO == GEO_SAME) ? kABufPro : ((PRO == 0 && SWAP) ? DMN_EXP_PLAIN_ABUF : kABuf));
   constexpr int DEPTH = (PRO == 3 && GEO == GEO_SAME) ? kDepthOne : ((PRO == 1 && GEO == GEO_SAME) ? DMN_EXP_PRO_DEPTH : ((PRO == 0 && SWAP) ? DMN_EXP_PLAIN_DEPTH : kDepth));
@@ -2171,7 +2171,15 @@ static int launch(Params p, cudaStream_t st) {
       const bool lean4 = !DMN_EXP_NO_LEAN && (GEO == GEO_DOWN || GEO == GEO_UP) && p.ntap == 4 && p.G == 2;
       const bool lean_ok = lean4 || (!DMN_EXP_NO_LEAN && GEO == GEO_SAME && p.n_pass >= (pro ? DMN_EXP_LEAN_MIN_PASS_TMA_PRO : DMN_EXP_LEAN_MIN_PASS) && p.ntap == 9 && p.G == 3);
       static const bool pw16a = [] { const char* e = getenv("DMN_CONV_PW16"); return e && e[0] == '1'; }();     // (64 registers per producer spill the grouped transform)
-      if (pro && pw16a && lean_ok) DMN_CUDA_CHECK(launch_kernel(conv_tcgen05_kernel<GEO_SAME, 128, false, true, false, 1, 8, false, 16, false, true>, grid, kThreads16, p, st));
+      // EXPERIMENT (DMN_CONV_PW=12): 12 producer warps (704 threads leave 88 registers per thread, enough for the grouped transform);
+      // DMN_CONV_PRO_LEAN=1: the unrolled issue loop for the prologue convs at any pass count
+      static const bool pw12 = [] { const char* e = getenv("DMN_CONV_PW"); return e && !strcmp(e, "12"); }();
+      static const bool pro_lean = [] { const char* e = getenv("DMN_CONV_PRO_LEAN"); return e && e[0] == '1'; }();
+      const bool lean_pro = lean_ok || (pro_lean && pro && p.ntap == 9 && p.G == 3);
+      if (pro && pw12 && lean_pro) DMN_CUDA_CHECK(launch_kernel(conv_tcgen05_kernel<GEO_SAME, 128, false, true, false, 1, 8, false, 12, false, true>, grid, (12 + 8 + 2) * 32, p, st));
+      else if (pro && pw12) DMN_CUDA_CHECK(launch_kernel(conv_tcgen05_kernel<GEO_SAME, 128, false, false, false, 1, 8, false, 12, false, true>, grid, (12 + 8 + 2) * 32, p, st));
+      else if (pro && pro_lean && lean_pro && !pw16a) DMN_CUDA_CHECK(launch_kernel(conv_tcgen05_kernel<GEO_SAME, 128, false, true, false, 1, 8, false, 8, false, true>, grid, kThreads, p, st));
+      else if (pro && pw16a && lean_ok) DMN_CUDA_CHECK(launch_kernel(conv_tcgen05_kernel<GEO_SAME, 128, false, true, false, 1, 8, false, 16, false, true>, grid, kThreads16, p, st));
       else if (pro && pw16a) DMN_CUDA_CHECK(launch_kernel(conv_tcgen05_kernel<GEO_SAME, 128, false, false, false, 1, 8, false, 16, false, true>, grid, kThreads16, p, st));
       else if (pro && lean_ok) DMN_CUDA_CHECK(launch_kernel(conv_tcgen05_kernel<GEO_SAME, 128, false, true, false, 1, 8, false, 8, false, true>, grid, kThreads, p, st));
       else if (pro) DMN_CUDA_CHECK(launch_kernel(conv_tcgen05_kernel<GEO_SAME, 128, false, false, false, 1, 8, false, 8, false, true>, grid, kThreads, p, st));
