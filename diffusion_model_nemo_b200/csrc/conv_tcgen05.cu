@@ -124,6 +124,7 @@ struct Params {
   int pad_class;
   // TMA operand path (ATMA instantiations): the window of a pass is ONE cp.async.bulk.tensor im2col copy of P pixels x 32 channels into
   // a SWIZZLE_64B tile [P rows][64 B]; tap offsets / descriptor strides below are then in that layout
+  int swap;                // 1: launch a swapped-role (SWAP) instantiation
   int atma;                // 1: launch an ATMA instantiation
   uint32_t a_bytes;        // one operand buffer (both layouts)
   uint32_t a_half;         // 16-byte units between the two 128-row halves of a 256-row tile (128 | 512)
@@ -1123,15 +1124,18 @@ __global__ void __launch_bounds__((PW + EW + 2) * 32, 1) conv_tcgen05_kernel(con
         // statistics bookkeeping (uniform): image of the current column, columns left in it
         int cur_img = eimg0 + (erem0 + col_base) / p.S;
         int to_boundary = p.S - (erem0 + col_base) % p.S;
-        float rs = 0.f, rq = 0.f;                                 // running (sum, sum of squares) of this channel over the current image
+        // Running (sum, sum of squares) of this channel over the current image in FIXED POINT: every 16-column chunk (an absolute
+        // 16-position block of the flat index space, whatever the tiling) is summed in fp32 in a fixed order, converted, and added as an
+        // integer -- so the statistics do not depend on how tiles align with images (batch-slice invariance, graph == plain launches)
+        long long rs = 0, rq = 0;
         auto flush = [&]() {
-          // reduce over the lanes of the group, then the group leader adds the fixed-point partials
-          float a = rs, b = rq;
+          // integer reduction over the lanes of the group, then the group leader adds the partials
+          long long a = rs, b = rq;
 #pragma unroll
           for (int o = 16; o > 0; o >>= 1)
             if (o < red_lanes) { a += __shfl_xor_sync(0xffffffffu, a, o); b += __shfl_xor_sync(0xffffffffu, b, o); }
-          if ((lane & (red_lanes - 1)) == 0 && cur_img < p.c.B) stat_add(p.c.ostats + ((long)cur_img * p.c.ogroups + (my_c >> sh)) * 2, a, b);
-          rs = rq = 0.f;
+          if ((lane & (red_lanes - 1)) == 0 && cur_img < p.c.B) stat_add_fixed(p.c.ostats + ((long)cur_img * p.c.ogroups + (my_c >> sh)) * 2, a, b);
+          rs = rq = 0;
         };
 
         const int as = it & 1;
@@ -1164,27 +1168,32 @@ __global__ void __launch_bounds__((PW + EW + 2) * 32, 1) conv_tcgen05_kernel(con
             if (do_stats) {
               const uint32_t m16 = (vm >> (hc * 16)) & 0xffffu;
               if (to_boundary > 16) {                             // (uniform) the whole chunk belongs to the current image
+                float s0 = 0.f, q0 = 0.f;
 #pragma unroll
                 for (int j = 0; j < 16; ++j) {
                   const float x = (m16 >> j) & 1u ? v[j] : 0.f;
-                  rs += x;
-                  rq = fmaf(x, x, rq);
+                  s0 += x;
+                  q0 = fmaf(x, x, q0);
                 }
+                rs += __float2ll_rn(s0 * kStatScaleSum);
+                rq += __float2ll_rn(q0 * kStatScaleSq);
                 to_boundary -= 16;
               } else {
                 // columns [0, tb) close the current image, [tb, 16) open the next one (S >= 16: at most one boundary per chunk)
                 const int tb = to_boundary;
-                float s1 = 0.f, q1 = 0.f;
+                float s0 = 0.f, q0 = 0.f, s1 = 0.f, q1 = 0.f;
 #pragma unroll
                 for (int j = 0; j < 16; ++j) {
                   const float x = (m16 >> j) & 1u ? v[j] : 0.f;
-                  if (j < tb) { rs += x; rq = fmaf(x, x, rq); }
+                  if (j < tb) { s0 += x; q0 = fmaf(x, x, q0); }
                   else { s1 += x; q1 = fmaf(x, x, q1); }
                 }
+                rs += __float2ll_rn(s0 * kStatScaleSum);
+                rq += __float2ll_rn(q0 * kStatScaleSq);
                 flush();
                 ++cur_img;
-                rs = s1;
-                rq = q1;
+                rs = __float2ll_rn(s1 * kStatScaleSum);
+                rq = __float2ll_rn(q1 * kStatScaleSq);
                 to_boundary = p.S - (16 - tb);
               }
             }
@@ -1773,18 +1782,17 @@ static int pick_nt(int cout) { return cout % 128 == 0 ? 128 : (cout % 64 == 0 ? 
 
 static int num_sms() { return current_device_sms(); }
 
-static bool swap_enabled() {
-  static const bool on = [] {
+// Swapped operand roles (weights on the TMEM lanes, ONE M128 x N256 instruction per k-step of a 256-position tile: the tensor core reads
+// 12 KB instead of 16 KB of shared memory per 128 clk).  DMN_CONV_SWAP = 1: every eligible conv, 0: none, unset: the measured rule in
+// fill_params (maps of at least 64 positions per image with >= 8 passes, or plain 3x3) -- on the TMA operand feed the form
+// is 4-9 % faster there and slower for single-round 4x4 maps and the 4-pass GroupNorm-prologue / transposed convs (profiles/README.md)
+static int swap_mode() {
+  static const int m = [] {
     const char* e = getenv("DMN_CONV_SWAP");
-    return e && e[0] == '1';                // EXPERIMENT, default off (DMN_CONV_SWAP=1): swapped operand roles, weights on the TMEM lanes, one
-                                            // M128 x N256 instruction per k-step.  Parity-green and measured NEUTRAL on the step (profiles/README.md):
-                                            // the MMA issue loop gets faster (11.0k -> 10.5k clk per level-0 tile) but then waits for operands, and
-                                            // the serial per-channel statistics make the result depend on how tiles align with images (batch-slice
-                                            // invariance 2e-3 instead of <= 1e-6)
+    return !e ? 2 : (e[0] == '1' ? 1 : (e[0] == '0' ? 0 : 2));
   }();
-  return on;
+  return m;
 }
-
 static bool cluster_enabled() {
   static const bool on = [] {
     const char* e = getenv("DMN_CONV_CLUSTER");
@@ -1890,7 +1898,7 @@ static bool fill_params(const ConvP& c, int geo, Params& p) {
   p.halo_hi = halo_hi;
   // clusters of two CTAs sharing the weight stream (multicast): the swapped-role hot instantiations with enough tiles for every SM
   p.cl = 1;
-  if (swap_enabled() && cluster_enabled() && geo != GEO_INIT && p.NT == 128 && !(c.pro & PRO_LRELU) && !c.res && !c.fold_s1 &&
+  if (swap_mode() == 1 && cluster_enabled() && geo != GEO_INIT && p.NT == 128 && !(c.pro & PRO_LRELU) && !c.res && !c.fold_s1 &&
       (geo != GEO_SAME || p.ntap == 9) && (num_sms() % 2) == 0)
     p.cl = 2;
   {
@@ -1983,8 +1991,14 @@ static bool fill_params(const ConvP& c, int geo, Params& p) {
   }
   p.abuf = (geo == GEO_SAME && p.NT == 128 && p.ntap == 1 && c.pro == PRO_NONE && !DMN_EXP_NO_ONETAP) ? kABufOne : kABuf;
   // plain swapped-role instantiations (launch<>: hot path without prologue)
-  if (swap_enabled() && geo != GEO_INIT && p.NT == 128 && c.pro == PRO_NONE && !c.res && !c.fold_s1 && (geo != GEO_SAME || p.ntap == 9))
-    p.abuf = DMN_EXP_PLAIN_ABUF;
+  {
+    const bool eligible = geo != GEO_INIT && p.NT == 128 && !(c.pro & PRO_LRELU) && !c.res && !c.fold_s1 && !c.fin_out && (geo != GEO_SAME || p.ntap == 9);
+    // the rule depends on the per-image geometry only, never on the batch: the two forms sum the GroupNorm statistics in different
+    // fp32 orders, so a sample must meet the same form whatever batch it is part of (batch-slice invariance)
+    const bool rule = atma_enabled() && p.S >= 64 && (p.n_pass >= 8 || (geo == GEO_SAME && c.pro == PRO_NONE));
+    p.swap = eligible && (swap_mode() == 1 || (swap_mode() == 2 && rule));
+  }
+  if (p.swap && c.pro == PRO_NONE) p.abuf = DMN_EXP_PLAIN_ABUF;
   // the GroupNorm-prologue instantiation (PRO = 1) is launched for 128-column tiles without residual / fold / FiLM (launch<>)
   if (geo == GEO_SAME && p.NT == 128 && c.pro != PRO_NONE && !(c.pro & PRO_LRELU) && !c.res && !c.fold_s1) p.abuf = kABufPro;
   // TMA operand path: the hot instantiations (launch<>: 128-column tiles, 3x3 / k4s2 / transposed k4s2, no FiLM / residual / fold terms)
@@ -2121,7 +2135,7 @@ static int launch(Params p, cudaStream_t st) {
   if (GEO != GEO_INIT && p.NT == 128 && !(p.c.pro & PRO_LRELU) && !extra) {
     // the hot instantiations: no residual / fold terms in the epilogue, lean or looped issue
     constexpr int G2 = GEO == GEO_INIT ? GEO_SAME : GEO;
-    const bool swap_on = swap_enabled();
+    const bool swap_on = p.swap != 0;
     const bool pro = G2 == GEO_SAME && p.c.pro != PRO_NONE;
     if (G2 == GEO_SAME && p.c.fin_out) {
       // ResnetBlock.block2 with the block tail fused behind a grid barrier (cooperative launch)
@@ -2133,7 +2147,7 @@ static int launch(Params p, cudaStream_t st) {
       return 0;
     }
     if (swap_on && (G2 != GEO_SAME || p.ntap == 9)) {
-      static const bool pw16 = [] { const char* e = getenv("DMN_CONV_PW16"); return !(e && e[0] == '0'); }();
+      static const bool pw16 = [] { const char* e = getenv("DMN_CONV_PW16"); return e && e[0] == '1'; }();
       if (p.atma) {
         if (pro && pw16 && lean_ok) DMN_CUDA_CHECK(launch_kernel(conv_tcgen05_kernel<GEO_SAME, 128, false, true, false, 1, 8, true, 16, false, true>, grid, kThreads16, p, st));
         else if (pro && pw16) DMN_CUDA_CHECK(launch_kernel(conv_tcgen05_kernel<GEO_SAME, 128, false, false, false, 1, 8, true, 16, false, true>, grid, kThreads16, p, st));
