@@ -2149,6 +2149,13 @@ static int launch(Params p, cudaStream_t st) {
     if (swap_on && (G2 != GEO_SAME || p.ntap == 9)) {
       static const bool pw16 = [] { const char* e = getenv("DMN_CONV_PW16"); return e && e[0] == '1'; }();
       if (p.atma) {
+        static const bool pro_lean_s = [] { const char* e = getenv("DMN_CONV_PRO_LEAN"); return e && e[0] == '1'; }();
+        if (pro && !pw16 && pro_lean_s && p.ntap == 9 && p.G == 3) {
+          DMN_CUDA_CHECK(launch_kernel(conv_tcgen05_kernel<GEO_SAME, 128, false, true, false, 1, 8, true, 8, false, true>, grid, kThreads, p, st));
+          count_launch();
+          DMN_LAUNCH_CHECK("conv_tcgen05");
+          return 0;
+        }
         if (pro && pw16 && lean_ok) DMN_CUDA_CHECK(launch_kernel(conv_tcgen05_kernel<GEO_SAME, 128, false, true, false, 1, 8, true, 16, false, true>, grid, kThreads16, p, st));
         else if (pro && pw16) DMN_CUDA_CHECK(launch_kernel(conv_tcgen05_kernel<GEO_SAME, 128, false, false, false, 1, 8, true, 16, false, true>, grid, kThreads16, p, st));
         else if (pro && lean_ok) DMN_CUDA_CHECK(launch_kernel(conv_tcgen05_kernel<GEO_SAME, 128, false, true, false, 1, 8, true, 8, false, true>, grid, kThreads, p, st));
