@@ -15,12 +15,20 @@
 //             (virtual channel = kx*Cin + ch, 7*Cin <= 32), 3 zero rows shared between images, delta = (ky-3)*W.
 //
 // A tile is 256 (or 128) consecutive flat positions x one N tile (two / one 128-row accumulators).  Its input window is
-// loaded ONCE per 32-channel pass into shared memory by the producer warps -- which also apply the fused prologue
-// (GroupNorm-apply of the producing conv, SiLU, time-embedding add; padding is written as zero) -- in the UMMA K-major,
-// no-swizzle canonical layout
-//   A_smem[kchunk (8 channels = 16 B)][pixel]      (LBO = PA*16 B between k-chunks, SBO = 128 B between 8-row groups)
-// so the operand of tap t is the same buffer with the start address advanced by delta*16 B: all taps of a k-step read
-// one resident tile and nothing is re-fetched from L2.  Weights are pre-blocked on the host into
+// loaded ONCE per 32-channel pass into shared memory; the operand of tap t is the same buffer with the start address advanced
+// by delta rows: all taps of a k-step read one resident tile and nothing is re-fetched from L2.  Two operand feeds:
+//   TMA (ATMA instantiations: the hot 128-column 3x3 / 1x1 / k4s2 / transposed convs): ONE cp.async.bulk.tensor im2col copy per
+//     pass -- the tensor map's traversal order over (w, h, n) with the pad row / column inside its bounding box IS the flat padded
+//     position order, out-of-tensor positions arrive as zeros -- into a SWIZZLE_64B tile [P rows][64 B]; tap t = start address
+//     + delta * 64 B (the swizzle is keyed on absolute address bits, buffers are 1 KB aligned, so any row offset works).  The
+//     GroupNorm prologue (GroupNorm-apply of the producing conv, SiLU, time-embedding add) transforms the landed tile in place.
+//     Measured: 16-byte global -> shared transfers run at 16 B/clk/SM however they are issued, TMA rows of 64 B at 42 B/clk/SM
+//     (tools/micro/), which is what had capped the engine.
+//   cp.async (everything else: N tiles of 32 / 64, FiLM, residual / fold epilogues, the stem): the producer warps gather 16-byte
+//     items into the UMMA K-major, no-swizzle canonical layout
+//       A_smem[kchunk (8 channels = 16 B)][pixel]      (LBO = PA*16 B between k-chunks, SBO = 128 B between 8-row groups)
+//     (tap t = start address + delta * 16 B) and apply the prologue to their own items one pass later.
+// Weights are pre-blocked on the host into
 // [n_tile][pass][tap][kchunk][n] 16-byte items and streamed with 1-D bulk async copies (cp.async.bulk -> UBLKCP, the TMA
 // engine's non-tensor mode) through an mbarrier ring.
 //
@@ -32,7 +40,8 @@
 // The accumulators are double buffered in TMEM (2 x mt x NT <= 512 columns), so the epilogue of tile i overlaps the main
 // loop of tile i+1 and the per-CTA setup is paid once per launch.
 //
-// The kernel is a template over <geometry, N tile, FiLM prologue, lean issue, rare epilogue terms, prologue mode, epilogue warps>:
+// The kernel is a template over <geometry, N tile, FiLM prologue, lean issue, rare epilogue terms, prologue mode, epilogue warps,
+// swapped operand roles, producer warps, fused block tail, TMA operand feed>:
 // the engine is sensitive to the amount of code around its inner loops, so every launch picks the smallest instantiation that
 // covers it (launch<>() below).  Compile-time switches DMN_EXP_* keep the measured alternatives buildable
 // (python -m diffusion_model_nemo_b200._build --variant <lib.so> -DDMN_EXP_...=1; select with DMN_LIB_PATH); profiles/README.md
