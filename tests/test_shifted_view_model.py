@@ -255,3 +255,89 @@ def test_stem_7x7_with_kx_packed_into_channels(B, H, Cin, Cout):
 
     _run_generic(B, S, Wv, 3 * Wv, 3 * Wv, 1, 7, NT, Cout // NT, fill_a, lambda t, nt: (t - 3) * Wv, wblock, store)
     assert np.abs(out - ref).max() < 1e-4
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# TMA operand feed (round 2): the im2col traversal and the SWIZZLE_64B tile, modelled on the CPU
+# ---------------------------------------------------------------------------------------------------------------------
+def im2col_window(x_nhwc, tn, th, tw, P, lower, stride=1, off=(0, 0)):
+    """What ONE cp.async.bulk.tensor...im2col copy delivers (tools/micro/im2col_umma_test.cu pins this on the GPU): P base positions of
+    the bounding box [lower, dim - 1] x [lower, dim - 1] (upper corner 0) in (w, h, n) order starting at (tw, th, tn), step `stride`;
+    element = x[n][h + off_h][w + off_w], zero outside the tensor."""
+    B, H, W, C = x_nhwc.shape
+    out = np.zeros((P, C), np.float32)
+    n, h, w = tn, th, tw
+    for i in range(P):
+        hh, ww = h + off[1], w + off[0]
+        if 0 <= n < B and 0 <= hh < H and 0 <= ww < W:
+            out[i] = x_nhwc[n, hh, ww]
+        w += stride
+        if w > W - 1:
+            w, h = lower, h + stride
+            if h > H - 1:
+                h, n = lower, n + 1
+    return out
+
+
+def tile_coords(m0, halo_lo, S, Wv, pad, down):
+    """conv_tcgen05.cu tma_tile_coords: tensor coordinates of the window's first flat position (image -1 = zeros in front)."""
+    f = m0 - halo_lo
+    tn = f // S if f >= 0 else -1
+    rem = f - tn * S
+    row, col = divmod(rem, Wv)
+    return (tn, 2 * row - 1, 2 * col - 1) if down else (tn, row - pad, col - pad)
+
+
+@pytest.mark.parametrize("H,B,m0", [(8, 3, 0), (8, 3, 128), (4, 9, 128), (16, 2, 256), (5, 4, 0)])
+def test_im2col_window_is_the_flat_padded_window_3x3(H, B, m0):
+    rng = np.random.default_rng(0)
+    x = rng.standard_normal((B, H, H, 4)).astype(np.float32)
+    pad, Wv = 1, H + 1
+    S, halo = (H + 1) * Wv, Wv + 1
+    P = 128 + 2 * halo
+    tn, th, tw = tile_coords(m0, halo, S, Wv, pad, False)
+    got = im2col_window(x, tn, th, tw, P, lower=-1)
+    for i in range(P):                      # flat padded index: row 0 / col 0 of every image block are the shared pads
+        f = m0 - halo + i
+        want = np.zeros(4, np.float32)
+        if f >= 0:
+            img, rem = divmod(f, S)
+            row, col = divmod(rem, Wv)
+            if img < B and row >= 1 and col >= 1:
+                want = x[img, row - 1, col - 1]
+        assert np.array_equal(got[i], want), (i, f)
+
+
+@pytest.mark.parametrize("H,B,m0,sub", [(8, 3, 0, 0), (8, 3, 0, 3), (16, 2, 128, 1), (4, 20, 128, 2)])
+def test_im2col_window_of_the_k4s2_form(H, B, m0, sub):
+    """Virtual position (u, v) of the (H/2+1) x (W/2+1) grid holds pixel (2u-1+sy, 2v-1+sx): traversal stride 2 from lower corner -1,
+    the sub-position (sy, sx) is the instruction's (w, h) offset."""
+    rng = np.random.default_rng(1)
+    x = rng.standard_normal((B, H, H, 4)).astype(np.float32)
+    Wv = H // 2 + 1
+    S, P = Wv * Wv, 96
+    sy, sx = sub >> 1, sub & 1
+    tn, th, tw = tile_coords(m0, 0, S, Wv, 0, True)
+    got = im2col_window(x, tn, th, tw, P, lower=-1, stride=2, off=(sx, sy))
+    for i in range(P):
+        img, rem = divmod(m0 + i, S)
+        u, v = divmod(rem, Wv)
+        iy, ix = 2 * u - 1 + sy, 2 * v - 1 + sx
+        want = x[img, iy, ix] if img < B and 0 <= iy < H and 0 <= ix < H else np.zeros(4, np.float32)
+        assert np.array_equal(got[i], want), (i, img, u, v)
+
+
+def test_swizzle64_chunk_of_a_producer_thread_is_constant():
+    """SWIZZLE_64B tile [row][64 B]: 16-byte chunk position pc of row r holds k-chunk pc ^ ((r >> 1) & 3) (address bits 4-5 ^= bits 7-8 of a
+    1 KB aligned buffer).  A producer thread owns chunk position pc of rows px0 + 64 j (8 warps) / + 96 j / + 128 j: one k-chunk for all."""
+    for step in (64, 96, 128):
+        for px0 in range(step):
+            for pc in range(4):
+                ks = {pc ^ (((px0 + step * j) >> 1) & 3) for j in range(8)}
+                assert len(ks) == 1
+    # and the address form: byte offset r * 64 + pc * 16, XOR of bits [4:6) with bits [7:9)
+    for r in range(64):
+        for kc in range(4):
+            addr = r * 64 + kc * 16
+            sw = addr ^ (((addr >> 7) & 3) << 4)
+            assert sw == r * 64 + ((kc ^ ((r >> 1) & 3)) * 16)
