@@ -800,9 +800,12 @@ __global__ void __launch_bounds__((PW + EW + 2) * 32, 1) conv_tcgen05_kernel(con
           const int cb = c * kCk + kc * 8;
           float ga[8], be[8], te[8];
           {
-            const float4 g0 = *reinterpret_cast<const float4*>(s_coef + cb), g1 = *reinterpret_cast<const float4*>(s_coef + cb + 4);
-            const float4 b0 = *reinterpret_cast<const float4*>(s_coef + ncoef + cb), b1 = *reinterpret_cast<const float4*>(s_coef + ncoef + cb + 4);
-            const float4 t0 = *reinterpret_cast<const float4*>(s_coef + 2 * ncoef + cb), t1 = *reinterpret_cast<const float4*>(s_coef + 2 * ncoef + cb + 4);
+            // (explicit shared-space loads: through the integer-cast pointer these compiled to generic LD.E.128)
+            const uint32_t cu = smem_u32(s_coef) + (uint32_t)cb * 4u, nb = (uint32_t)ncoef * 4u;
+            auto ldf4 = [](uint32_t a) { const uint4 u = lds128(a); return make_float4(__uint_as_float(u.x), __uint_as_float(u.y), __uint_as_float(u.z), __uint_as_float(u.w)); };
+            const float4 g0 = ldf4(cu), g1 = ldf4(cu + 16u);
+            const float4 b0 = ldf4(cu + nb), b1 = ldf4(cu + nb + 16u);
+            const float4 t0 = ldf4(cu + 2u * nb), t1 = ldf4(cu + 2u * nb + 16u);
             ga[0] = g0.x; ga[1] = g0.y; ga[2] = g0.z; ga[3] = g0.w; ga[4] = g1.x; ga[5] = g1.y; ga[6] = g1.z; ga[7] = g1.w;
             be[0] = b0.x; be[1] = b0.y; be[2] = b0.z; be[3] = b0.w; be[4] = b1.x; be[5] = b1.y; be[6] = b1.z; be[7] = b1.w;
             te[0] = t0.x; te[1] = t0.y; te[2] = t0.z; te[3] = t0.w; te[4] = t1.x; te[5] = t1.y; te[6] = t1.z; te[7] = t1.w;
