@@ -308,6 +308,7 @@ def main():
     clk.mark_begin()
     ms_total, res = timed(args.steps)
     clocks = clk.stop()
+    loop_launches = getattr(plan, "last_loop_launches", 0)      # kernels launched inside the timed region (launches per step x K)
     # the single collective of the job: all-gather of the final samples (timed once, amortised over T steps)
     ag_ms = 0.0
     gather_check = None
@@ -432,7 +433,6 @@ def main():
     if rank == 0 and ws == 1 and not args.no_library_bar:
         lib_bar = library_bar(dev, B)
 
-    loop_launches = getattr(plan, "last_loop_launches", 0)
     if rank == 0:
         line = {
             "metric": "ddpm_samples_per_sec_32x32_unet_1000_steps", "value": value, "unit": "samples/s", "n_gpus": ws,
