@@ -65,3 +65,36 @@ def test_swapped_operand_roles_equal_plain_roles(tmp_path):
             assert np.allclose(a[k], b[k], rtol=1e-5, atol=1e-6), k
         else:
             assert np.array_equal(a[k], b[k]), f"{k}: max abs diff {np.abs(a[k] - b[k]).max()}"
+
+
+UNET_CHILD = r"""
+import sys, numpy as np, torch
+sys.path.insert(0, sys.argv[1]); sys.path.insert(0, sys.argv[1] + "/tests")
+from conftest import make_unet
+from oracle import ref_port as O
+import diffusion_model_nemo_b200.modules as M
+cfg = dict(dim=128, dim_mults=[1, 2, 2, 2], channels=3, groups=8)
+u = make_unet(cfg, O.random_state_dict(cfg, seed=0), dtype="bf16", engine="tcgen05", device="cuda:0")
+g = torch.Generator().manual_seed(5)
+x = torch.randn(6, 3, 32, 32, generator=g).cuda()
+t = torch.tensor([999, 500, 250, 3, 1, 0]).cuda()
+eps = u(x, t)
+# and a short free-running DDPM loop with injected noise (graph replay of the same kernels)
+s = M.GaussianDiffusion(6, "linear")
+noise = torch.stack([torch.randn(6, 3, 32, 32, generator=g) for _ in range(7)])
+img = s.sample(u, [6, 3, 32, 32], device="cuda:0", noise=noise)[-1]
+np.savez(sys.argv[2], eps=eps.float().cpu().numpy(), img=img.float().cpu().numpy())
+"""
+
+
+def test_whole_unet_and_loop_do_not_depend_on_the_operand_feed(tmp_path):
+    """configs[1] U-Net (bf16, tcgen05) and a 6-step DDPM loop: TMA feed == cp.async feed bit for bit (same issue form in both)."""
+    out = []
+    for tma in ("1", "0"):
+        path = str(tmp_path / f"unet_{tma}.npz")
+        env = dict(os.environ, DMN_CONV_TMA=tma, DMN_CONV_SWAP="0")
+        subprocess.run([sys.executable, "-c", UNET_CHILD, ROOT, path], check=True, env=env, timeout=900)
+        out.append(np.load(path))
+    for k in ("eps", "img"):
+        assert np.isfinite(out[0][k]).all()
+        assert np.array_equal(out[0][k], out[1][k]), f"{k}: max abs diff {np.abs(out[0][k] - out[1][k]).max()}"
